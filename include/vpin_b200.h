@@ -1,0 +1,204 @@
+/* vpin_b200.h — C ABI of the B200-native Spartan prover backend for vPIN's proof_generation crate.
+ *
+ * Drop-in boundary: the Rust functions vPIN's driver calls (vPIN_proof_generation/src/proof_point_add.rs:39-107,
+ * proof_point_mult.rs:39-107) — SNARKGens::new, Instance::new, SNARK::encode, DensePolynomial::commit,
+ * my_dense_mlpoly_commit, my_lib_prove — each get one entry point here with the same argument meaning.
+ * A Rust shim binds these with `extern "C"`; in this repository the same symbols are bound by
+ * vpin_b200/api.py through ctypes. "SP/" = Spartan/src/, "VP/" = vPIN_proof_generation/src/ in the reference tree.
+ *
+ * Conventions
+ *   - scalars cross the ABI as 32-byte little-endian CANONICAL values (what Scalar::to_bytes / Instance::new use),
+ *     never Montgomery form; group elements as 32-byte compressed ristretto255 (CompressedRistretto).
+ *   - proofs and commitments-to-computations are bincode 1.3.3 byte strings identical to bincode::serialize(&SNARK) /
+ *     (&ComputationCommitment) in the reference (VP/proof_point_add.rs:96).
+ *   - the caller owns every input buffer for the duration of the call; outputs are written to caller buffers with an
+ *     explicit capacity and a length out-parameter. Opaque handles own device (HBM) state.
+ *   - every function returns a vpin_status; no function aborts. There is no CPU fallback: if no CUDA device is
+ *     usable, vpin_ctx_create fails with VPIN_ERR_CUDA.
+ *   - one context per host thread (the reference API is single-threaded: &mut Transcript, &mut RandomTape).
+ *   - determinism hook: the reference seeds its RandomTapes from OsRng (SP/random.rs:16-18); here the 32-byte
+ *     `init_randomness` scalar of each tape is an explicit argument.
+ */
+#ifndef VPIN_B200_H
+#define VPIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t vpin_status;
+enum {
+  VPIN_OK = 0,
+  VPIN_ERR_INVALID_SCALAR = 1,    /* R1CSError::InvalidScalar            SP/errors.rs:42 */
+  VPIN_ERR_INVALID_INDEX = 2,     /* R1CSError::InvalidIndex             SP/errors.rs:44 */
+  VPIN_ERR_INVALID_NUM_INPUTS = 3,/* R1CSError::InvalidNumberOfInputs    SP/errors.rs:40 */
+  VPIN_ERR_SIZE_MISMATCH = 4,     /* the reference's assert_eq! on lengths (e.g. SP/commitments.rs:95) */
+  VPIN_ERR_BUFFER_TOO_SMALL = 5,
+  VPIN_ERR_CUDA = 6,
+  VPIN_ERR_OOM = 7,
+  VPIN_ERR_PROVER = 8,            /* a prover-side assert! of the reference failed (unsatisfied witness, ...) */
+  VPIN_ERR_BAD_ARGUMENT = 9
+};
+
+typedef struct vpin_ctx vpin_ctx;
+typedef struct vpin_gens vpin_gens;         /* SNARKGens                    SP/lib.rs:295-327 */
+typedef struct vpin_instance vpin_instance; /* Instance                     SP/lib.rs:130-244 */
+typedef struct vpin_decomm vpin_decomm;     /* ComputationDecommitment      SP/lib.rs:66-69   */
+typedef struct vpin_witness vpin_witness;   /* (vars, poly_vars, comm_vars, blinds_vars) resident in HBM */
+
+/* one COO triple of Instance::new: (row, col, 32-byte LE canonical value)   SP/lib.rs:142-144 */
+typedef struct vpin_coo_entry {
+  uint64_t row;
+  uint64_t col;
+  uint8_t val[32];
+} vpin_coo_entry;
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out);
+void vpin_ctx_destroy(vpin_ctx *ctx);
+/* message of the last failure on this context (never NULL) */
+const char *vpin_last_error(const vpin_ctx *ctx);
+/* number of this library's kernels launched on the context so far (bench.py's gpu_launches) */
+uint64_t vpin_kernel_launches(const vpin_ctx *ctx);
+
+/* ---- public parameters: SNARKGens::new(num_cons, num_vars, num_inputs, num_nz_entries)   SP/lib.rs:305 ---------- */
+vpin_status vpin_gens_create(vpin_ctx *ctx, uint64_t num_cons, uint64_t num_vars, uint64_t num_inputs,
+                             uint64_t num_nz_entries, vpin_gens **out);
+void vpin_gens_destroy(vpin_gens *gens);
+/* L (rows) and R (columns) of the Hyrax grid of the witness polynomial (SP/dense_mlpoly.rs:96-98) */
+vpin_status vpin_gens_witness_grid(const vpin_gens *gens, uint64_t *L, uint64_t *R);
+
+/* ---- Instance::new(num_cons, num_vars, num_inputs, &A, &B, &C)   SP/lib.rs:138-244 ------------------------------ */
+vpin_status vpin_instance_create(vpin_ctx *ctx, uint64_t num_cons, uint64_t num_vars, uint64_t num_inputs,
+                                 const vpin_coo_entry *A, uint64_t nA, const vpin_coo_entry *B, uint64_t nB,
+                                 const vpin_coo_entry *C, uint64_t nC, vpin_instance **out);
+void vpin_instance_destroy(vpin_instance *inst);
+/* padded sizes (inst.inst.get_num_cons / get_num_vars) */
+vpin_status vpin_instance_dims(const vpin_instance *inst, uint64_t *num_cons_padded, uint64_t *num_vars_padded,
+                               uint64_t *num_inputs);
+/* Instance::is_sat(&vars, &inputs)   SP/lib.rs:247-276 ; vars may be shorter than the padded size */
+vpin_status vpin_instance_is_sat(vpin_ctx *ctx, const vpin_instance *inst, const uint8_t *vars32, uint64_t n_vars,
+                                 const uint8_t *inputs32, uint64_t n_inputs, int32_t *sat);
+
+/* ---- SNARK::encode(&inst, &gens)   SP/lib.rs:347-358 -------------------------------------------------------------
+ * comm_out receives bincode(ComputationCommitment); *decomm keeps the dense representation in HBM. */
+vpin_status vpin_encode(vpin_ctx *ctx, const vpin_instance *inst, const vpin_gens *gens, uint8_t *comm_out,
+                        uint64_t comm_cap, uint64_t *comm_len, vpin_decomm **decomm);
+void vpin_decomm_destroy(vpin_decomm *decomm);
+
+/* ---- DensePolynomial::commit(&gens.gens_r1cs_sat.gens_pc, Some(&mut tape))   SP/dense_mlpoly.rs:193-218 ----------
+ * Z: n = 2^ell canonical scalars (the padded assignment). Blinds are drawn from a RandomTape exactly as the
+ * reference does: `tape_state` is an opaque 256-byte buffer initialised by vpin_tape_init and advanced by each call,
+ * so two consecutive commits on one tape reproduce VP/proof_point_add.rs:44-52. Pass tape_state = NULL for zero
+ * blinds. points_out: L x 32 bytes, blinds_out: L x 32 bytes (may be NULL). */
+vpin_status vpin_tape_init(uint8_t tape_state[256], const uint8_t *name, uint64_t name_len,
+                           const uint8_t init_randomness32[32]);
+vpin_status vpin_poly_commit(vpin_ctx *ctx, const vpin_gens *gens, const uint8_t *Z32, uint64_t n,
+                             uint8_t *tape_state, uint8_t *points_out, uint8_t *blinds_out);
+/* my_dense_mlpoly_commit(&poly, &gens_pc, blind_1, blind_2)   VP/commit_test.rs:27-57 (blinds = blind_1 + blind_2) */
+vpin_status vpin_poly_commit_with_blinds(vpin_ctx *ctx, const vpin_gens *gens, const uint8_t *Z32, uint64_t n,
+                                         const uint8_t *blind1_32, const uint8_t *blind2_32, uint64_t L,
+                                         uint8_t *points_out, uint8_t *blinds_out);
+/* row-wise C1[i] + C2[i] on compressed points (VP/proof_point_add.rs:75-80, VP/commit_test.rs:355-358).
+ * Fails with VPIN_ERR_BAD_ARGUMENT if a point does not decompress. */
+vpin_status vpin_commitments_add(vpin_ctx *ctx, const uint8_t *c1, const uint8_t *c2, uint64_t L, uint8_t *out);
+
+/* ---- my_lib_prove(&inst, &decomm, vars, &inputs, &gens, &mut transcript, poly_vars, comm_vars, blinds_vars)
+ *      VP/commit_test.rs:59-133 ------------------------------------------------------------------------------------
+ * vars32: the padded assignment (num_vars_padded scalars) — also the evaluations of poly_vars.
+ * transcript_label: the label of Transcript::new (b"snark_example" in VP/proof_point_add.rs:83).
+ * tape_seed32: init_randomness of RandomTape::new(b"proof") (VP/commit_test.rs:74).
+ * proof_out receives bincode(SNARK). */
+vpin_status vpin_prove(vpin_ctx *ctx, const vpin_instance *inst, const vpin_decomm *decomm, const uint8_t *vars32,
+                       uint64_t n_vars, const uint8_t *inputs32, uint64_t n_inputs, const vpin_gens *gens,
+                       const uint8_t *transcript_label, uint64_t label_len, const uint8_t *comm_vars_points,
+                       const uint8_t *blinds_vars32, uint64_t L, const uint8_t tape_seed32[32], uint8_t *proof_out,
+                       uint64_t proof_cap, uint64_t *proof_len);
+/* same proof with the witness already resident in HBM (what bench.py times as `value`) */
+vpin_status vpin_witness_upload(vpin_ctx *ctx, const vpin_gens *gens, const uint8_t *vars32, uint64_t n_vars,
+                                const uint8_t *comm_vars_points, const uint8_t *blinds_vars32, uint64_t L,
+                                vpin_witness **out);
+void vpin_witness_destroy(vpin_witness *w);
+vpin_status vpin_prove_resident(vpin_ctx *ctx, const vpin_instance *inst, const vpin_decomm *decomm,
+                                const vpin_witness *w, const uint8_t *inputs32, uint64_t n_inputs,
+                                const vpin_gens *gens, const uint8_t *transcript_label, uint64_t label_len,
+                                const uint8_t tape_seed32[32], uint8_t *proof_out, uint64_t proof_cap,
+                                uint64_t *proof_len);
+/* milliseconds (CUDA events + host clock) of the last vpin_prove* under the reference's timer labels
+ * (SP/timer.rs; VP/commit_test.rs:70,101,147,153,159,249,283; SP/sparse_mlpoly.rs:1491,1504,1514).
+ * names_out[i] points at static strings; returns the number of phases written (<= cap). */
+uint32_t vpin_last_phase_times(const vpin_ctx *ctx, const char **names_out, double *ms_out, uint32_t cap);
+
+/* ---- vPIN's R1CS builders (fixture generators; VP/point_addition.rs:5-326, VP/point_mult.rs:7-704) ---------------
+ * Inputs are what VP/load_data.rs / load_data_add.rs read from the JSON files. Outputs: the instance plus the three
+ * UNPADDED assignments (vars_para, vars_input, vars: num_vars x 32 bytes each), the inputs assignment, and the
+ * (num_cons, num_vars, num_inputs, num_non_zero_entries) tuple the driver passes to SNARKGens::new. */
+vpin_status vpin_build_point_mult(vpin_ctx *ctx, uint64_t m, const uint64_t *weights_lo_hi, const uint8_t *px32,
+                                  const uint8_t *py32, vpin_instance **inst, uint64_t dims_out[4],
+                                  uint8_t *vars_para32, uint8_t *vars_input32, uint8_t *vars32, uint8_t *inputs32);
+vpin_status vpin_build_point_add(vpin_ctx *ctx, uint64_t n, const uint8_t *px32, const uint8_t *py32,
+                                 const uint8_t *rx32, const uint8_t *ry32, const int64_t *rz_flags,
+                                 vpin_instance **inst, uint64_t dims_out[4], uint8_t *vars_para32,
+                                 uint8_t *vars_input32, uint8_t *vars32);
+/* sizes only (to allocate the buffers above): dims_out = num_cons, num_vars, num_inputs, num_non_zero_entries */
+void vpin_point_mult_dims(uint64_t m, uint64_t dims_out[4]);
+void vpin_point_add_dims(uint64_t n, uint64_t dims_out[4]);
+
+/* ---- kernel-level entry points (parity tests and roofline benches) -------------------------
+ * Host-buffer forms: canonical scalars in, canonical scalars / compressed points out. */
+/* sum_i s_i * G_i over the first n generators of the SHAKE256 stream `label` (SP/commitments.rs:20-38,
+ * SP/group.rs:103-121) */
+vpin_status vpin_msm(vpin_ctx *ctx, const char *label, const uint8_t *scalars32, uint64_t n, uint8_t out_point[32]);
+/* Hyrax commitment of 2^ell scalars with PolyCommitmentGens::new(ell, label) (SP/dense_mlpoly.rs:36-40,160-175);
+ * blinds32 may be NULL */
+vpin_status vpin_hyrax_commit(vpin_ctx *ctx, const char *label, const uint8_t *Z32, uint64_t n, const uint8_t *blinds32,
+                              uint8_t *points_out);
+/* n+1 generators of MultiCommitGens::new(n, label), compressed (the last one is h) */
+vpin_status vpin_derive_gens(vpin_ctx *ctx, const char *label, uint64_t n, uint8_t *points_out);
+/* (Az, Bz, Cz) = inst.multiply_vec(z)   SP/r1csinstance.rs:272-286; z has 2*num_vars_padded entries */
+vpin_status vpin_spmv_abc(vpin_ctx *ctx, const vpin_instance *inst, const uint8_t *z32, uint8_t *Az32, uint8_t *Bz32,
+                          uint8_t *Cz32);
+/* (A^T x, B^T x, C^T x) = inst.compute_eval_table_sparse(x)   SP/r1csinstance.rs:288-302 */
+vpin_status vpin_spmv_t_abc(vpin_ctx *ctx, const vpin_instance *inst, const uint8_t *x32, uint8_t *At32, uint8_t *Bt32,
+                            uint8_t *Ct32);
+/* EqPolynomial::new(r).evals()   SP/dense_mlpoly.rs:78-94 */
+vpin_status vpin_eq_evals(vpin_ctx *ctx, const uint8_t *r32, uint32_t ell, uint8_t *out32);
+/* eval_point_0, _2, _3 of one round with comb = A*(B*C - D)   SP/sumcheck.rs:619-652, SP/r1csproof.rs:104-108 */
+vpin_status vpin_sumcheck_cubic_round(vpin_ctx *ctx, const uint8_t *A32, const uint8_t *B32, const uint8_t *C32,
+                                      const uint8_t *D32, uint64_t len, uint8_t out96[96]);
+/* eval_point_0, _2 with comb = A*B   SP/sumcheck.rs:456-469 */
+vpin_status vpin_sumcheck_quad_round(vpin_ctx *ctx, const uint8_t *A32, const uint8_t *B32, uint64_t len,
+                                     uint8_t out64[64]);
+/* eval_point_0, _2, _3 with comb = A*B*C   SP/sumcheck.rs:296-320 */
+vpin_status vpin_sumcheck_cubic3_round(vpin_ctx *ctx, const uint8_t *A32, const uint8_t *B32, const uint8_t *C32,
+                                       uint64_t len, uint8_t out96[96]);
+/* bound_poly_var_top   SP/dense_mlpoly.rs:229-236; Z32 (len scalars) is overwritten, first len/2 are the result */
+vpin_status vpin_bind_top(vpin_ctx *ctx, uint8_t *Z32, uint64_t len, const uint8_t r32[32]);
+/* DensePolynomial::bound(L)   SP/dense_mlpoly.rs:220-227: out has R = 2^ceil(ell/2) scalars */
+vpin_status vpin_bound(vpin_ctx *ctx, const uint8_t *Z32, uint64_t len, const uint8_t *L32, uint8_t *out32);
+
+/* Device-resident forms for benchmarks: pointers are CUDA device pointers to 32-byte MONTGOMERY elements (the
+ * in-HBM table format, identical to the reference's serde of Scalar, SP/scalar/ristretto255.rs:199-200).
+ * They enqueue on the context stream; call vpin_sync (or record CUDA events on vpin_stream) to wait. */
+void *vpin_stream(vpin_ctx *ctx); /* cudaStream_t */
+vpin_status vpin_sync(vpin_ctx *ctx);
+vpin_status vpin_dev_to_mont(vpin_ctx *ctx, const void *d_in, uint64_t n, void *d_out);
+vpin_status vpin_dev_from_mont(vpin_ctx *ctx, const void *d_in, uint64_t n, void *d_out);
+vpin_status vpin_dev_hyrax_commit(vpin_ctx *ctx, const char *label, const void *d_Z, uint64_t n, const void *d_blinds,
+                                  void *d_points_out);
+vpin_status vpin_dev_cubic_round(vpin_ctx *ctx, const void *dA, const void *dB, const void *dC, const void *dD,
+                                 uint64_t len, void *d_out3);
+vpin_status vpin_dev_quad_round(vpin_ctx *ctx, const void *dA, const void *dB, uint64_t len, void *d_out2);
+vpin_status vpin_dev_bind_top(vpin_ctx *ctx, void *dZ, uint64_t len, const void *d_r);
+vpin_status vpin_dev_eq_evals(vpin_ctx *ctx, const void *d_r, uint32_t ell, void *d_out);
+vpin_status vpin_dev_spmv_abc(vpin_ctx *ctx, const vpin_instance *inst, const void *d_z, void *dAz, void *dBz, void *dCz);
+/* dependency-free mad.wide.u32 microbenchmark: returns multiply-accumulates per second (the integer roofline) */
+vpin_status vpin_imad_peak(vpin_ctx *ctx, double *macs_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPIN_B200_H */

@@ -1,0 +1,143 @@
+"""Parity of every kernel-level C-ABI entry point with the CPU oracle (bit-exact: integer work)."""
+import pytest
+
+import helpers as H
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_derive_gens_matches_oracle(ctx):
+    for label, n in ((b"gens_r1cs_sat", 37), (b"gens_r1cs_eval", 130)):
+        assert ctx.derive_gens(label, n) == O.derive_gens(label, n)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 64, 65, 300])
+def test_msm_matches_oracle(ctx, n):
+    s = H.rand_scalars(n, seed=100 + n)
+    gens = O.derive_gens(b"gens_r1cs_eval", n)[: 32 * n]
+    assert ctx.msm(b"gens_r1cs_eval", O.ints_to_bytes(s)) == O.msm(s, gens)
+
+
+def test_msm_small_and_negative_scalars(ctx):
+    n = 200
+    s = H.rand_scalars(n, seed=7, edge=False, small=True)
+    s[3] = O.L_ORDER - 1
+    s[4] = O.L_ORDER - 5
+    s[9] = 0
+    gens = O.derive_gens(b"gens_r1cs_eval", n)[: 32 * n]
+    assert ctx.msm(b"gens_r1cs_eval", O.ints_to_bytes(s)) == O.msm(s, gens)
+
+
+@pytest.mark.parametrize("ell,blinds", [(2, False), (5, True), (8, True), (10, False), (13, True)])
+def test_hyrax_commit_matches_oracle(ctx, ell, blinds):
+    n = 1 << ell
+    Z = H.rand_scalars(n, seed=ell)
+    bl = H.rand_scalars(1 << (ell // 2), seed=50 + ell, edge=False) if blinds else None
+    got = ctx.hyrax_commit(b"gens_r1cs_sat", O.ints_to_bytes(Z), O.ints_to_bytes(bl) if bl else None)
+    assert got == O.hyrax_commit(Z, b"gens_r1cs_sat", bl)
+
+
+def test_hyrax_commit_is_linear(ctx):
+    """size-independent property: commit(Z1 + Z2; b1 + b2) = commit(Z1; b1) + commit(Z2; b2) row-wise
+    (the homomorphism vPIN's driver asserts, proof_point_add.rs:69-73)"""
+    ell = 12
+    n = 1 << ell
+    Z1, Z2 = H.rand_scalars(n, 1), H.rand_scalars(n, 2)
+    b1, b2 = H.rand_scalars(64, 3, edge=False), H.rand_scalars(64, 4, edge=False)
+    Zs = [(a + b) % O.L_ORDER for a, b in zip(Z1, Z2)]
+    bs = [(a + b) % O.L_ORDER for a, b in zip(b1, b2)]
+    c1 = ctx.hyrax_commit(b"gens_r1cs_sat", O.ints_to_bytes(Z1), O.ints_to_bytes(b1))
+    c2 = ctx.hyrax_commit(b"gens_r1cs_sat", O.ints_to_bytes(Z2), O.ints_to_bytes(b2))
+    cs = ctx.hyrax_commit(b"gens_r1cs_sat", O.ints_to_bytes(Zs), O.ints_to_bytes(bs))
+    assert ctx.commitments_add(c1, c2) == cs
+
+
+@pytest.mark.parametrize("ell", [0, 1, 3, 9, 12, 13, 17])
+def test_eq_evals(ctx, ell):
+    r = H.rand_scalars(ell, seed=ell, edge=False)
+    got = O.bytes_to_ints(ctx.eq_evals(O.ints_to_bytes(r)))
+    assert got == O.eq_evals(r)
+
+
+@pytest.mark.parametrize("len_", [2, 8, 1024, 1 << 15])
+def test_sumcheck_rounds_and_bind(ctx, len_):
+    A, B, Cc, D = (H.rand_scalars(len_, seed=s + len_) for s in (1, 2, 3, 4))
+    b = lambda v: O.ints_to_bytes(v)
+    assert O.bytes_to_ints(ctx.sumcheck_cubic_round(b(A), b(B), b(Cc), b(D))) == O.cubic_round(A, B, Cc, D)
+    assert O.bytes_to_ints(ctx.sumcheck_quad_round(b(A), b(B))) == O.quad_round(A, B)
+    assert O.bytes_to_ints(ctx.sumcheck_cubic3_round(b(A), b(B), b(Cc))) == O.cubic3_round(A, B, Cc)
+    r = H.rand_scalars(1, seed=99, edge=False)[0]
+    assert O.bytes_to_ints(ctx.bind_top(b(A), O.le32(r))) == O.bind_top(A, r)
+
+
+def test_sumcheck_claim_consistency(ctx):
+    """size-independent property at a larger size: after binding with r, eval_0 + eval_1 of the next round equals
+    the previous round polynomial at r (the verifier's check, sumcheck.rs:46)."""
+    n = 1 << 16
+    A, B = H.rand_scalars(n, 11), H.rand_scalars(n, 12)
+    L = O.L_ORDER
+    e0, e2 = O.bytes_to_ints(ctx.sumcheck_quad_round(O.ints_to_bytes(A), O.ints_to_bytes(B)))
+    claim = sum(a * b for a, b in zip(A, B)) % L
+    e1 = (claim - e0) % L
+    # quadratic through (0,e0),(1,e1),(2,e2)
+    r = 123456789
+    inv2 = pow(2, -1, L)
+    a = inv2 * (e2 - 2 * e1 + e0) % L
+    bq = (e1 - e0 - a) % L
+    at_r = (a * r * r + bq * r + e0) % L
+    A2 = O.bytes_to_ints(ctx.bind_top(O.ints_to_bytes(A), O.le32(r)))
+    B2 = O.bytes_to_ints(ctx.bind_top(O.ints_to_bytes(B), O.le32(r)))
+    assert sum(x * y for x, y in zip(A2, B2)) % L == at_r
+
+
+@pytest.mark.parametrize("ell", [4, 7, 12])
+def test_bound(ctx, ell):
+    n = 1 << ell
+    Z = H.rand_scalars(n, seed=ell)
+    Lv = H.rand_scalars(1 << (ell // 2), seed=ell + 1, edge=False)
+    assert O.bytes_to_ints(ctx.bound(O.ints_to_bytes(Z), O.ints_to_bytes(Lv))) == O.bound(Z, Lv)
+
+
+def test_spmv_and_transpose(ctx):
+    from vpin_b200 import api
+
+    num_cons, num_vars, num_inputs = 256, 128, 3
+    A, B, Cm, _, _, vars_, inputs = H.synthetic_r1cs(num_cons, num_vars, num_inputs, seed=5)
+    # add a heavy column (constant-1 column referenced by every row) and duplicate entries
+    import numpy as np
+
+    extra = np.zeros(num_cons + 2, O.COO_DTYPE)
+    for i in range(num_cons):
+        extra[i] = (i, num_vars, np.frombuffer(O.le32(i + 5), dtype=np.uint8))
+    extra[num_cons] = (3, 7, np.frombuffer(O.le32(O.L_ORDER - 1), dtype=np.uint8))
+    extra[num_cons + 1] = (3, 7, np.frombuffer(O.le32(9), dtype=np.uint8))
+    A2 = np.concatenate([A, extra])
+    inst = api.Instance(ctx, num_cons, num_vars, num_inputs, A2, B, Cm)
+    z = O.bytes_to_ints(vars_) + [1] + O.bytes_to_ints(inputs)
+    z += [0] * (2 * num_vars - len(z))
+    got = inst.spmv_abc(O.ints_to_bytes(z))
+    for g, M in zip(got, (A2, B, Cm)):
+        assert O.bytes_to_ints(g) == O.spmv(M, num_cons, 2 * num_vars, z)
+    x = H.rand_scalars(num_cons, seed=77)
+    got = inst.spmv_t_abc(O.ints_to_bytes(x))
+    for g, M in zip(got, (A2, B, Cm)):
+        assert O.bytes_to_ints(g) == O.spmv(M, num_cons, 2 * num_vars, x, transposed=True)
+
+
+def test_instance_errors(ctx):
+    """error behaviour of Instance::new (Spartan/src/lib.rs:649-692 tests)"""
+    import numpy as np
+    from vpin_b200 import api
+
+    one = np.frombuffer(O.le32(1), dtype=np.uint8)
+    ok = np.array([(0, 0, one)], dtype=O.COO_DTYPE)
+    bad_idx = np.array([(100, 0, one)], dtype=O.COO_DTYPE)
+    with pytest.raises(api.VpinError) as e:
+        api.Instance(ctx, 4, 4, 1, bad_idx, ok, ok)
+    assert e.value.name == "InvalidIndex"
+    big = np.frombuffer(bytes([0xFF] * 32), dtype=np.uint8)
+    bad_val = np.array([(0, 0, big)], dtype=O.COO_DTYPE)
+    with pytest.raises(api.VpinError) as e:
+        api.Instance(ctx, 4, 4, 1, ok, bad_val, ok)
+    assert e.value.name == "InvalidScalar"

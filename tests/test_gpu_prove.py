@@ -1,0 +1,80 @@
+"""End-to-end parity: the CUDA prover behind the C ABI must emit the same commitments and the same bincode proof bytes as
+the CPU oracle under the same tape seeds, and the oracle's my_lib_verify must accept the CUDA proof."""
+import pytest
+
+import helpers as H
+import oracle_lib as O
+from vpin_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, built, dims, inst, vp, vi, v, inputs):
+    from vpin_b200 import api
+
+    sq, sp = W.tape_seeds()
+    ref = O.Flow(built, sq, sp, verify=True)
+    assert ref.verified
+    got = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp)
+    assert got["comm"] == ref.comm, "SNARK::encode commitment differs"
+    assert got["comm_vars_para"] == ref.comm_vars_para
+    assert got["comm_vars_input"] == ref.comm_vars_input
+    assert got["comm_vars"] == ref.comm_vars
+    if got["proof"] != ref.proof:
+        n = min(len(got["proof"]), len(ref.proof))
+        first = next((i for i in range(n) if got["proof"][i] != ref.proof[i]), n)
+        raise AssertionError(f"proof bytes differ at offset {first} (lengths {len(got['proof'])} vs {len(ref.proof)})")
+    assert O.verify(dims, got["proof"], got["comm"], inputs, got["comm_vars_para"], got["comm_vars_input"]) == 1
+    # a corrupted proof must be rejected
+    bad = bytearray(got["proof"])
+    bad[len(bad) // 2] ^= 1
+    assert O.verify(dims, bytes(bad), got["comm"], inputs, got["comm_vars_para"], got["comm_vars_input"]) != 1
+
+
+@pytest.mark.parametrize("n,inf", [(4, 3), (16, 0)])
+def test_point_add_flow(ctx, n, inf):
+    from vpin_b200 import api
+
+    px, py, rx, ry, rz = W.synth_point_add(n, infinity_every=inf)
+    built = O.build_point_add(px, py, rx, ry, rz)
+    dims, inst, vp, vi, v, inputs = api.point_addition(ctx, px, py, rx, ry, rz)
+    assert dims == built.dims
+    A, B, Cm, ovp, ovi, ov, oin = built.arrays()
+    assert (vp, vi, v) == (ovp, ovi, ov)
+    _check(ctx, built, dims, inst, vp, vi, v, inputs)
+
+
+def test_point_mult_flow_m7(ctx):
+    """smallest point-mult count whose hard-coded nnz table rounds to the true padded nnz"""
+    from vpin_b200 import api
+
+    weights, px, py = W.synth_point_mult(7)
+    built = O.build_point_mult(weights, px, py)
+    dims, inst, vp, vi, v, inputs = api.point_mult(ctx, weights, px, py)
+    assert dims == built.dims
+    A, B, Cm, ovp, ovi, ov, oin = built.arrays()
+    assert (vp, vi, v, inputs) == (ovp, ovi, ov, oin)
+    assert inst.is_sat(v, inputs)
+    _check(ctx, built, dims, inst, vp, vi, v, inputs)
+
+
+@pytest.mark.parametrize("num_cons,num_vars,num_inputs", [(1, 2, 1), (16, 16, 3), (64, 32, 5), (1024, 1024, 10), (37, 50, 2)])
+def test_synthetic_r1cs_flow(ctx, num_cons, num_vars, num_inputs):
+    """shapes of the reference's own round-trip tests (Spartan/src/lib.rs:615-774, r1csproof.rs:586-619) incl. padding"""
+    from vpin_b200 import api
+
+    A, B, Cm, vp, vi, v, inputs = H.synthetic_r1cs(num_cons, num_vars, num_inputs, seed=num_cons)
+    nnz = max(len(A), 2) if num_cons > 1 else 2
+    built = O.build_custom(num_cons, num_vars, num_inputs, nnz, A, B, Cm, vp, vi, v, inputs)
+    inst = api.Instance(ctx, num_cons, num_vars, num_inputs, A, B, Cm)
+    _check(ctx, built, (num_cons, num_vars, num_inputs, nnz), inst, vp, vi, v, inputs)
+
+
+def test_unsatisfied_witness_is_reported(ctx):
+    from vpin_b200 import api
+
+    A, B, Cm, vp, vi, v, inputs = H.synthetic_r1cs(16, 16, 2, seed=3)
+    inst = api.Instance(ctx, 16, 16, 2, A, B, Cm)
+    bad = bytearray(v)
+    bad[0] ^= 1
+    assert inst.is_sat(v, inputs) and not inst.is_sat(bytes(bad), inputs)

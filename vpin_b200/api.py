@@ -1,0 +1,374 @@
+"""ctypes binding of libvpin_b200.so (include/vpin_b200.h) mirroring the reference's Rust interface for the prover
+path: SNARKGens::new, Instance::new, SNARK::encode, DensePolynomial::commit, my_dense_mlpoly_commit, my_lib_prove
+(Spartan/src/lib.rs:138-358, vPIN_proof_generation/src/commit_test.rs:27-133).
+
+This is the host side a Rust shim would replace one-for-one. There is NO CPU fallback: the
+library must be built (`python -c "import __graft_entry__ as g; g.build()"`) and a CUDA device must be present, or the
+calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvpin_b200.so")
+
+COO_DTYPE = np.dtype([("row", "<u8"), ("col", "<u8"), ("val", "u1", (32,))])
+
+STATUS = {
+    0: "OK", 1: "InvalidScalar", 2: "InvalidIndex", 3: "InvalidNumberOfInputs", 4: "SizeMismatch", 5: "BufferTooSmall",
+    6: "CudaError", 7: "OutOfMemory", 8: "ProverAssertion", 9: "BadArgument",
+}
+
+
+class VpinError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{STATUS.get(code, code)}: {msg}")
+        self.code = code
+        self.name = STATUS.get(code, str(code))
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        L = _lib
+        vp, u64 = C.c_void_p, C.c_uint64
+        L.vpin_last_error.restype = C.c_char_p
+        L.vpin_last_error.argtypes = [vp]
+        L.vpin_kernel_launches.restype = u64
+        L.vpin_kernel_launches.argtypes = [vp]
+        L.vpin_stream.restype = vp
+        L.vpin_stream.argtypes = [vp]
+        L.vpin_last_phase_times.restype = C.c_uint32
+    return _lib
+
+
+def _buf(b):
+    """bytes / bytearray / numpy array -> c pointer (keeps a reference alive in the caller)."""
+    if b is None:
+        return None
+    if isinstance(b, np.ndarray):
+        return b.ctypes.data_as(C.c_void_p)
+    if isinstance(b, (bytes, bytearray)):
+        return C.cast(C.c_char_p(bytes(b)) if isinstance(b, bytes) else (C.c_char * len(b)).from_buffer(b), C.c_void_p)
+    raise TypeError(type(b))
+
+
+class Context:
+    """One per host thread (the reference API is single-threaded: &mut Transcript, &mut RandomTape)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        st = lib().vpin_ctx_create(C.c_int32(device), C.byref(self._h))
+        if st != 0:
+            raise VpinError(st, "vpin_ctx_create failed (no usable CUDA device?)")
+
+    def close(self):
+        if self._h:
+            lib().vpin_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, st):
+        if st != 0:
+            raise VpinError(st, lib().vpin_last_error(self._h).decode())
+
+    @property
+    def kernel_launches(self):
+        return int(lib().vpin_kernel_launches(self._h))
+
+    @property
+    def stream(self):
+        return int(lib().vpin_stream(self._h) or 0)
+
+    def sync(self):
+        self.check(lib().vpin_sync(self._h))
+
+    def phase_times(self):
+        names = (C.c_char_p * 32)()
+        ms = (C.c_double * 32)()
+        n = lib().vpin_last_phase_times(self._h, names, ms, 32)
+        return {names[i].decode(): ms[i] for i in range(n)}
+
+    # ---- kernel-level entry points (canonical 32-byte scalars in/out) ----
+    def derive_gens(self, label, n):
+        out = C.create_string_buffer(32 * (n + 1))
+        self.check(lib().vpin_derive_gens(self._h, label, C.c_uint64(n), out))
+        return out.raw
+
+    def msm(self, label, scalars):
+        out = C.create_string_buffer(32)
+        self.check(lib().vpin_msm(self._h, label, scalars, C.c_uint64(len(scalars) // 32), out))
+        return out.raw
+
+    def hyrax_commit(self, label, Z, blinds=None):
+        n = len(Z) // 32
+        ell = n.bit_length() - 1
+        L = 1 << (ell // 2)
+        out = C.create_string_buffer(32 * L)
+        self.check(lib().vpin_hyrax_commit(self._h, label, Z, C.c_uint64(n), blinds, out))
+        return out.raw
+
+    def eq_evals(self, r):
+        ell = len(r) // 32
+        out = C.create_string_buffer(32 << ell)
+        self.check(lib().vpin_eq_evals(self._h, r, C.c_uint32(ell), out))
+        return out.raw
+
+    def sumcheck_cubic_round(self, A, B, Cc, D):
+        out = C.create_string_buffer(96)
+        self.check(lib().vpin_sumcheck_cubic_round(self._h, A, B, Cc, D, C.c_uint64(len(A) // 32), out))
+        return out.raw
+
+    def sumcheck_quad_round(self, A, B):
+        out = C.create_string_buffer(64)
+        self.check(lib().vpin_sumcheck_quad_round(self._h, A, B, C.c_uint64(len(A) // 32), out))
+        return out.raw
+
+    def sumcheck_cubic3_round(self, A, B, Cc):
+        out = C.create_string_buffer(96)
+        self.check(lib().vpin_sumcheck_cubic3_round(self._h, A, B, Cc, C.c_uint64(len(A) // 32), out))
+        return out.raw
+
+    def bind_top(self, Z, r):
+        buf = C.create_string_buffer(Z, len(Z))
+        self.check(lib().vpin_bind_top(self._h, buf, C.c_uint64(len(Z) // 32), r))
+        return buf.raw[: len(Z) // 2]
+
+    def bound(self, Z, Lvec):
+        n = len(Z) // 32
+        ell = n.bit_length() - 1
+        R = 1 << (ell - ell // 2)
+        out = C.create_string_buffer(32 * R)
+        self.check(lib().vpin_bound(self._h, Z, C.c_uint64(n), Lvec, out))
+        return out.raw
+
+    def commitments_add(self, c1, c2):
+        out = C.create_string_buffer(len(c1))
+        self.check(lib().vpin_commitments_add(self._h, c1, c2, C.c_uint64(len(c1) // 32), out))
+        return out.raw
+
+    def imad_peak(self):
+        v = C.c_double()
+        self.check(lib().vpin_imad_peak(self._h, C.byref(v)))
+        return v.value
+
+
+class SNARKGens:
+    """SNARKGens::new(num_cons, num_vars, num_inputs, num_nz_entries)  (Spartan/src/lib.rs:305)"""
+
+    def __init__(self, ctx, num_cons, num_vars, num_inputs, num_nz_entries):
+        self.ctx = ctx
+        self.params = (num_cons, num_vars, num_inputs, num_nz_entries)
+        self._h = C.c_void_p()
+        ctx.check(lib().vpin_gens_create(ctx._h, C.c_uint64(num_cons), C.c_uint64(num_vars), C.c_uint64(num_inputs),
+                                         C.c_uint64(num_nz_entries), C.byref(self._h)))
+        L, R = C.c_uint64(), C.c_uint64()
+        lib().vpin_gens_witness_grid(self._h, C.byref(L), C.byref(R))
+        self.L, self.R = L.value, R.value
+
+    new = classmethod(lambda cls, *a: cls(*a))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vpin_gens_destroy(self._h)
+            self._h = None
+
+
+class Instance:
+    """Instance::new(num_cons, num_vars, num_inputs, &A, &B, &C)  (Spartan/src/lib.rs:138-244).
+    A, B, C: numpy arrays of COO_DTYPE (row, col, 32-byte LE canonical value)."""
+
+    def __init__(self, ctx, num_cons, num_vars, num_inputs, A, B, Cm, _handle=None):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            A, B, Cm = (np.ascontiguousarray(x, dtype=COO_DTYPE) for x in (A, B, Cm))
+            ctx.check(lib().vpin_instance_create(ctx._h, C.c_uint64(num_cons), C.c_uint64(num_vars), C.c_uint64(num_inputs),
+                                                 _buf(A), C.c_uint64(len(A)), _buf(B), C.c_uint64(len(B)), _buf(Cm),
+                                                 C.c_uint64(len(Cm)), C.byref(self._h)))
+        nc, nv, ni = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib().vpin_instance_dims(self._h, C.byref(nc), C.byref(nv), C.byref(ni))
+        self.num_cons, self.num_vars, self.num_inputs = nc.value, nv.value, ni.value
+
+    def is_sat(self, vars_bytes, inputs_bytes):
+        sat = C.c_int32()
+        self.ctx.check(lib().vpin_instance_is_sat(self.ctx._h, self._h, vars_bytes, C.c_uint64(len(vars_bytes) // 32), inputs_bytes,
+                                                  C.c_uint64(len(inputs_bytes) // 32), C.byref(sat)))
+        return bool(sat.value)
+
+    def spmv_abc(self, z):
+        n = 32 * self.num_cons
+        outs = [C.create_string_buffer(n) for _ in range(3)]
+        self.ctx.check(lib().vpin_spmv_abc(self.ctx._h, self._h, z, *outs))
+        return tuple(o.raw for o in outs)
+
+    def spmv_t_abc(self, x):
+        n = 32 * 2 * self.num_vars
+        outs = [C.create_string_buffer(n) for _ in range(3)]
+        self.ctx.check(lib().vpin_spmv_t_abc(self.ctx._h, self._h, x, *outs))
+        return tuple(o.raw for o in outs)
+
+    def pad(self, assignment):
+        """Assignment::pad (Spartan/src/lib.rs:107-120)"""
+        return assignment + bytes(32 * self.num_vars - len(assignment))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vpin_instance_destroy(self._h)
+            self._h = None
+
+
+def point_mult(ctx, weights, px, py):
+    """point_mult(network) of vPIN_proof_generation/src/point_mult.rs:7-664 with the JSON inputs passed in.
+    Returns (dims, inst, vars_para, vars_input, vars, inputs) — dims = (num_cons, num_vars, num_inputs, num_non_zero_entries)."""
+    m = len(weights)
+    dims = (C.c_uint64 * 4)()
+    lib().vpin_point_mult_dims(C.c_uint64(m), dims)
+    nv = dims[1]
+    w = (C.c_uint64 * (2 * m))(*[x for ww in weights for x in (ww & (2**64 - 1), ww >> 64)])
+    bufs = [C.create_string_buffer(32 * nv) for _ in range(3)]
+    inputs = C.create_string_buffer(32)
+    h = C.c_void_p()
+    ctx.check(lib().vpin_build_point_mult(ctx._h, C.c_uint64(m), w, px, py, C.byref(h), dims, bufs[0], bufs[1], bufs[2], inputs))
+    inst = Instance(ctx, 0, 0, 0, None, None, None, _handle=h)
+    return tuple(dims), inst, bufs[0].raw, bufs[1].raw, bufs[2].raw, inputs.raw
+
+
+def point_addition(ctx, px, py, rx, ry, rz):
+    """point_addition(network) of vPIN_proof_generation/src/point_addition.rs:5-326."""
+    n = len(rz)
+    dims = (C.c_uint64 * 4)()
+    lib().vpin_point_add_dims(C.c_uint64(n), dims)
+    nv = dims[1]
+    bufs = [C.create_string_buffer(32 * nv) for _ in range(3)]
+    h = C.c_void_p()
+    ctx.check(lib().vpin_build_point_add(ctx._h, C.c_uint64(n), px, py, rx, ry, (C.c_int64 * n)(*rz), C.byref(h), dims, bufs[0], bufs[1],
+                                         bufs[2]))
+    inst = Instance(ctx, 0, 0, 0, None, None, None, _handle=h)
+    return tuple(dims), inst, bufs[0].raw, bufs[1].raw, bufs[2].raw, b""
+
+
+class RandomTape:
+    """RandomTape::new(name) with the OsRng scalar supplied (Spartan/src/random.rs:14-21)."""
+
+    def __init__(self, name, init_randomness32):
+        self.state = C.create_string_buffer(256)
+        st = lib().vpin_tape_init(self.state, name, C.c_uint64(len(name)), init_randomness32)
+        if st != 0:
+            raise VpinError(st, "vpin_tape_init")
+
+
+class SNARK:
+    @staticmethod
+    def encode(inst, gens):
+        """SNARK::encode(&inst, &gens) -> (ComputationCommitment as bincode bytes, ComputationDecommitment handle)"""
+        ctx = inst.ctx
+        cap = 64 + 32 * (1 << 16) * 2
+        out = C.create_string_buffer(cap)
+        n = C.c_uint64()
+        d = C.c_void_p()
+        st = lib().vpin_encode(ctx._h, inst._h, gens._h, out, C.c_uint64(cap), C.byref(n), C.byref(d))
+        ctx.check(st)
+        return out.raw[: n.value], Decommitment(d)
+
+
+class Decommitment:
+    def __init__(self, h):
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vpin_decomm_destroy(self._h)
+            self._h = None
+
+
+def dense_mlpoly_commit(ctx, gens, Z, tape):
+    """DensePolynomial::new(Z).commit(&gens.gens_r1cs_sat.gens_pc, Some(&mut tape)) -> (PolyCommitment, blinds)"""
+    out = C.create_string_buffer(32 * gens.L)
+    blinds = C.create_string_buffer(32 * gens.L)
+    ctx.check(lib().vpin_poly_commit(ctx._h, gens._h, Z, C.c_uint64(len(Z) // 32), tape.state if tape else None, out, blinds))
+    return out.raw, blinds.raw
+
+
+def my_dense_mlpoly_commit(ctx, gens, Z, blind_1, blind_2):
+    """vPIN_proof_generation/src/commit_test.rs:27-57"""
+    out = C.create_string_buffer(32 * gens.L)
+    blinds = C.create_string_buffer(32 * gens.L)
+    ctx.check(lib().vpin_poly_commit_with_blinds(ctx._h, gens._h, Z, C.c_uint64(len(Z) // 32), blind_1, blind_2, C.c_uint64(gens.L), out,
+                                                 blinds))
+    return out.raw, blinds.raw
+
+
+class Witness:
+    """(vars, poly_vars, comm_vars, blinds_vars) resident in HBM."""
+
+    def __init__(self, ctx, gens, vars_bytes, comm_vars, blinds_vars):
+        self._h = C.c_void_p()
+        ctx.check(lib().vpin_witness_upload(ctx._h, gens._h, vars_bytes, C.c_uint64(len(vars_bytes) // 32), comm_vars, blinds_vars,
+                                            C.c_uint64(gens.L), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vpin_witness_destroy(self._h)
+            self._h = None
+
+
+_PROOF_CAP = 8 << 20
+
+
+def my_lib_prove(inst, decomm, vars_bytes, inputs_bytes, gens, transcript_label, comm_vars, blinds_vars, tape_seed):
+    """my_lib_prove (vPIN_proof_generation/src/commit_test.rs:59-133): host buffers in, bincode(SNARK) out.
+    `vars_bytes` doubles as poly_vars (DensePolynomial::new(padded_vars.assignment))."""
+    ctx = inst.ctx
+    out = C.create_string_buffer(_PROOF_CAP)
+    n = C.c_uint64()
+    ctx.check(lib().vpin_prove(ctx._h, inst._h, decomm._h, vars_bytes, C.c_uint64(len(vars_bytes) // 32), inputs_bytes,
+                               C.c_uint64(len(inputs_bytes) // 32), gens._h, transcript_label, C.c_uint64(len(transcript_label)),
+                               comm_vars, blinds_vars, C.c_uint64(gens.L), tape_seed, out, C.c_uint64(_PROOF_CAP), C.byref(n)))
+    return out.raw[: n.value]
+
+
+def my_lib_prove_resident(inst, decomm, witness, inputs_bytes, gens, transcript_label, tape_seed):
+    ctx = inst.ctx
+    out = C.create_string_buffer(_PROOF_CAP)
+    n = C.c_uint64()
+    ctx.check(lib().vpin_prove_resident(ctx._h, inst._h, decomm._h, witness._h, inputs_bytes, C.c_uint64(len(inputs_bytes) // 32), gens._h,
+                                        transcript_label, C.c_uint64(len(transcript_label)), tape_seed, out, C.c_uint64(_PROOF_CAP),
+                                        C.byref(n)))
+    return out.raw[: n.value]
+
+
+def prove_flow(ctx, dims, inst, vars_para, vars_input, vars_, inputs, seed_q, seed_p, label=b"snark_example"):
+    """The driver sequence of vPIN_proof_generation/src/proof_point_add.rs:39-98 (== proof_point_mult.rs):
+    gens -> encode -> commit(para) -> commit(input) -> my_dense_mlpoly_commit -> row-wise combine -> my_lib_prove.
+    Returns a dict with the proof, the computation commitment and the three witness commitments."""
+    num_cons, num_vars, num_inputs, nnz = dims
+    gens = SNARKGens(ctx, num_cons, num_vars, num_inputs, nnz)
+    comm, decomm = SNARK.encode(inst, gens)
+    tape = RandomTape(b"\x02", seed_q)
+    p_para, p_input, p_vars = inst.pad(vars_para), inst.pad(vars_input), inst.pad(vars_)
+    c_para, b_para = dense_mlpoly_commit(ctx, gens, p_para, tape)
+    c_input, b_input = dense_mlpoly_commit(ctx, gens, p_input, tape)
+    c_vars, b_vars = my_dense_mlpoly_commit(ctx, gens, p_vars, b_para, b_input)
+    combined = ctx.commitments_add(c_para, c_input)
+    if combined[:32] != c_vars[:32]:
+        raise VpinError(8, "commitment homomorphism check failed (proof_point_add.rs:69-73)")
+    proof = my_lib_prove(inst, decomm, p_vars, inputs, gens, label, combined, b_vars, seed_p)
+    return dict(proof=proof, comm=comm, comm_vars_para=c_para, comm_vars_input=c_input, comm_vars=c_vars, gens=gens, decomm=decomm,
+                padded_vars=p_vars, blinds_vars=b_vars, combined=combined)

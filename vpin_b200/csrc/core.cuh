@@ -1,0 +1,133 @@
+// Context, HBM buffers, generator streams + fixed-base tables, Hyrax commitment driver, R1CS instance storage.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vpin_b200.h"
+#include "ed.cuh"
+#include "kernels_msm.cuh"
+#include "kernels_poly.cuh"
+#include "merlin.hpp"
+
+namespace vpin {
+
+struct Error : std::runtime_error {
+  vpin_status code;
+  Error(vpin_status c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+#define VPIN_CUDA(x)                                                                                       \
+  do {                                                                                                     \
+    cudaError_t e_ = (x);                                                                                  \
+    if (e_ != cudaSuccess)                                                                                 \
+      throw ::vpin::Error(e_ == cudaErrorMemoryAllocation ? VPIN_ERR_OOM : VPIN_ERR_CUDA,                  \
+                          std::string(#x) + ": " + cudaGetErrorString(e_));                                \
+  } while (0)
+#define VPIN_REQUIRE(cond, code, msg)                    \
+  do {                                                   \
+    if (!(cond)) throw ::vpin::Error((code), (msg));     \
+  } while (0)
+
+extern std::atomic<uint64_t> g_kernel_launches;
+
+// stream-ordered HBM array
+template <class T>
+struct DevVec {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaStream_t st = nullptr;
+  DevVec() {}
+  DevVec(size_t n_, cudaStream_t st_) { alloc(n_, st_); }
+  DevVec(const DevVec &) = delete;
+  DevVec &operator=(const DevVec &) = delete;
+  DevVec(DevVec &&o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
+  DevVec &operator=(DevVec &&o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevVec() { release(); }
+  void alloc(size_t n_, cudaStream_t st_) {
+    release();
+    n = n_; st = st_;
+    if (n) VPIN_CUDA(cudaMallocAsync((void **)&p, n * sizeof(T), st));
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, st);
+    p = nullptr; n = 0;
+  }
+  void upload(const T *h, size_t cnt) { VPIN_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st)); }
+  void download(T *h, size_t cnt) const { VPIN_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, st)); }
+  void zero() { if (n) VPIN_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
+};
+
+// generators of one SHAKE256 stream (Spartan/src/commitments.rs:20-38) with their fixed-base table in HBM
+struct LabelGens {
+  std::string label;
+  size_t n = 0;                 // points derived: stream[0..n)
+  std::vector<ge_t> h_pts;      // host copies (extended)
+  DevVec<ge_t> d_pts;
+  DevVec<niels_t> d_table;      // n * kMsmTable entries
+  MsmTable table() const { return MsmTable{d_table.p, n}; }
+};
+
+// host fixed-base scalar multiplication for the handful of generators used by the sigma protocols
+struct HostBase {
+  std::vector<niels_t> tbl;  // [64 positions][8 multiples] of 16^pos * P, signed 4-bit digits
+  void build(const ge_t &p);
+  ge_t mul(const fl_t &s_mont) const;            // s * P
+  void mul_acc(const fl_t &s_mont, ge_t *acc) const;  // *acc += s * P
+};
+
+struct vpin_ctx_impl;
+typedef vpin_ctx_impl Ctx;
+
+struct vpin_ctx_impl {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  std::string err;
+  std::map<std::string, std::shared_ptr<LabelGens>> label_gens;
+  DevVec<fl_t> d_partials;   // reduction scratch
+  DevVec<fl_t> d_small;      // small device results / parameters
+  fl_t *h_small = nullptr;   // pinned mirror
+  std::vector<std::pair<const char *, double>> phases;
+  void sync() { VPIN_CUDA(cudaStreamSynchronize(st)); }
+};
+
+std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n);
+
+// Hyrax rows: out[i] = sum_j Z[i*ld + j] * G_j (+ blind_i * G_{blind_base}). d_points (rows ge_t) and d_comp (rows*32 B)
+// are optional outputs.
+void hyrax_rows(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_t rows, size_t cols, size_t ld, const fl_t *d_blinds,
+                size_t blind_base, ge_t *d_points, uint8_t *d_comp);
+
+// one sparse matrix of the instance in the three layouts the kernels use
+struct MatrixDev {
+  size_t nnz = 0;
+  std::vector<uint32_t> h_row, h_col;   // COO order == SPARK "ops" order (Spartan/src/sparse_mlpoly.rs:368-380)
+  DevVec<uint32_t> coo_row, coo_col;
+  DevVec<fl_t> coo_val;
+  DevVec<uint32_t> csr_ptr, csr_col;
+  DevVec<fl_t> csr_val;
+  DevVec<uint32_t> csc_ptr, csc_row, long_cols;
+  DevVec<fl_t> csc_val;
+  size_t n_long = 0;
+};
+struct vpin_instance_impl {
+  size_t num_cons = 0, num_vars = 0, num_inputs = 0;  // padded cons / vars (Spartan/src/lib.rs:146-176)
+  MatrixDev M[3];
+};
+typedef vpin_instance_impl Instance;
+
+std::unique_ptr<Instance> instance_create(Ctx *ctx, uint64_t num_cons, uint64_t num_vars, uint64_t num_inputs,
+                                          const vpin_coo_entry *A, uint64_t nA, const vpin_coo_entry *B, uint64_t nB,
+                                          const vpin_coo_entry *C, uint64_t nC);
+
+static inline size_t log2_ceil(size_t x) { size_t l = 0; while (((size_t)1 << l) < x) l++; return l; }
+static inline size_t next_pow2(size_t x) { return (size_t)1 << log2_ceil(x); }
+
+}  // namespace vpin

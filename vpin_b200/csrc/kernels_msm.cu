@@ -1,0 +1,259 @@
+// Fixed-base MSM kernels for sm_100a (see kernels_msm.cuh for the design). Integer-multiply bound: the hot loop is
+// ge_madd (7 F_p multiplications of 8x8 32-bit limbs) fed by 96-byte table entries fetched with LDG.128.
+#include <atomic>
+
+#include "kernels_msm.cuh"
+
+namespace vpin {
+
+extern std::atomic<uint64_t> g_kernel_launches;
+
+__device__ __forceinline__ fp_t ldg_fp(const fp_t *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  fp_t r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ fp_t ld_fp(const fp_t *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = q[0], b = q[1];
+  fp_t r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st_fp(fp_t *p, const fp_t &x) {
+  uint4 *q = reinterpret_cast<uint4 *>(p);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+__device__ __forceinline__ ge_t ld_ge(const ge_t *p) {
+  ge_t r;
+  r.X = ld_fp(&p->X); r.Y = ld_fp(&p->Y); r.Z = ld_fp(&p->Z); r.T = ld_fp(&p->T);
+  return r;
+}
+__device__ __forceinline__ void st_ge(ge_t *p, const ge_t &g) { st_fp(&p->X, g.X); st_fp(&p->Y, g.Y); st_fp(&p->Z, g.Z); st_fp(&p->T, g.T); }
+__device__ __forceinline__ niels_t ldg_niels(const niels_t *p) {
+  niels_t r;
+  r.yp = ldg_fp(&p->yp); r.ym = ldg_fp(&p->ym); r.t2d = ldg_fp(&p->t2d);
+  return r;
+}
+__device__ __forceinline__ niels_t ld_niels(const niels_t *p) {
+  niels_t r;
+  r.yp = ld_fp(&p->yp); r.ym = ld_fp(&p->ym); r.t2d = ld_fp(&p->t2d);
+  return r;
+}
+__device__ __forceinline__ void st_niels(niels_t *p, const niels_t &n) { st_fp(&p->yp, n.yp); st_fp(&p->ym, n.ym); st_fp(&p->t2d, n.t2d); }
+
+// ------------------------------------------------------------------------------------------------ table build
+// step 1: table[j][0] = affine Niels form of base j
+__global__ void __launch_bounds__(128) k_bases_to_niels(const ge_t *bases, size_t n, niels_t *table) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  ge_t g = ld_ge(bases + j);
+  st_niels(table + j * kMsmTable, ge_to_niels(g, fp_invert(g.Z)));
+}
+// step 2: thread (j, c) fills multiples c*CH+1 .. c*CH+CH of base j; one inversion per chunk (Montgomery's trick)
+static const int kTblChunk = 32;
+__global__ void __launch_bounds__(128) k_table_fill(size_t n, niels_t *table) {
+  const int chunks = kMsmTable / kTblChunk;
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n * chunks) return;
+  size_t j = tid / chunks;
+  int c = (int)(tid % chunks);
+  niels_t *slots = table + j * kMsmTable;
+  niels_t g1 = ld_niels(slots);
+  int first = c == 0 ? 1 : 0;  // slot 0 is already final and is being read by the other chunks
+  // P = (c*CH + 1 + first) * G by double-and-add
+  uint32_t k = (uint32_t)(c * kTblChunk + 1 + first);
+  ge_t P = ge_identity();
+  for (int b = 31 - __clz(k); b >= 0; b--) {
+    P = ge_dbl(P);
+    if ((k >> b) & 1) P = ge_madd(P, g1);
+  }
+  fp_t prefix[kTblChunk];
+  fp_t run = fp_one();
+  for (int m = first; m < kTblChunk; m++) {
+    niels_t raw;
+    raw.yp = P.X; raw.ym = P.Y; raw.t2d = P.Z;
+    st_niels(slots + c * kTblChunk + m, raw);
+    run = fp_mul(run, P.Z);
+    prefix[m] = run;
+    P = ge_madd(P, g1);
+  }
+  fp_t inv = fp_invert(run);
+  for (int m = kTblChunk - 1; m >= first; m--) {
+    niels_t raw = ld_niels(slots + c * kTblChunk + m);
+    fp_t zinv = m > first ? fp_mul(inv, prefix[m - 1]) : inv;
+    inv = fp_mul(inv, raw.t2d);
+    ge_t q;
+    q.X = raw.yp; q.Y = raw.ym; q.Z = raw.t2d; q.T = fp_zero();
+    st_niels(slots + c * kTblChunk + m, ge_to_niels(q, zinv));
+  }
+}
+void launch_table_build(const ge_t *d_bases, size_t n, niels_t *d_table, cudaStream_t st) {
+  ++g_kernel_launches, k_bases_to_niels<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_bases, n, d_table);
+  size_t threads = n * (kMsmTable / kTblChunk);
+  ++g_kernel_launches, k_table_fill<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(n, d_table);
+}
+
+// ------------------------------------------------------------------------------------------------ recode
+// (l - 1) / 2
+__device__ __constant__ uint32_t kHalfL[8] = {0x2e7ae9f6u, 0x2c09318du, 0x517bce6bu, 0x0a6f7cefu, 0u, 0u, 0u, 0x08000000u};
+__global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows, size_t cols, size_t ld, const fl_t *extra,
+                                                size_t stride, uint16_t *digits) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * stride) return;
+  size_t row = idx / stride, col = idx % stride;
+  const fl_t *src = col < cols ? scalars + row * ld + col : (col == cols && extra ? extra + row : nullptr);
+  size_t plane = rows * stride;
+  uint16_t *dst = digits + row * stride + col;
+  if (!src) {
+    for (int w = 0; w < kMsmWindows; w++) dst[(size_t)w * plane] = 0;
+    return;
+  }
+  const uint4 *q = reinterpret_cast<const uint4 *>(src);
+  uint4 lo = __ldg(q), hi = __ldg(q + 1);
+  fl_t x;
+  x.v[0] = lo.x; x.v[1] = lo.y; x.v[2] = lo.z; x.v[3] = lo.w; x.v[4] = hi.x; x.v[5] = hi.y; x.v[6] = hi.z; x.v[7] = hi.w;
+  if (fl_is_zero(x)) {
+    for (int w = 0; w < kMsmWindows; w++) dst[(size_t)w * plane] = 0;
+    return;
+  }
+  fl_t s = fl_from_mont(x);
+  // s > (l-1)/2 ?  then use l - s and flip every sign
+  bool gt = false;
+  for (int i = 7; i >= 0; i--) {
+    if (s.v[i] != kHalfL[i]) { gt = s.v[i] > kHalfL[i]; break; }
+  }
+  uint32_t v[9];
+  if (gt) {
+    int64_t br = 0;
+    for (int i = 0; i < 8; i++) { int64_t t = (int64_t)fl_modulus_limb(i) - (int64_t)s.v[i] + br; v[i] = (uint32_t)t; br = t >> 32; }
+  } else {
+    for (int i = 0; i < 8; i++) v[i] = s.v[i];
+  }
+  v[8] = 0;
+  uint32_t carry = 0;
+  for (int w = 0; w < kMsmWindows; w++) {
+    int bit = w * kMsmW, limb = bit >> 5, sh = bit & 31;
+    uint64_t two = (uint64_t)v[limb] | ((uint64_t)(limb + 1 < 9 ? v[limb + 1] : 0u) << 32);
+    uint32_t raw = (limb < 8 ? (uint32_t)(two >> sh) & ((1u << kMsmW) - 1u) : 0u) + carry;
+    uint32_t neg = raw > (uint32_t)kMsmTable ? 1u : 0u;
+    uint32_t mag = neg ? (1u << kMsmW) - raw : raw;
+    carry = neg;
+    uint32_t sign = (neg ^ (gt ? 1u : 0u)) & (mag != 0 ? 1u : 0u);
+    dst[(size_t)w * plane] = (uint16_t)(mag | (sign << 15));
+  }
+}
+void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, const fl_t *d_extra, uint16_t *d_digits, cudaStream_t st) {
+  size_t stride = msm_col_stride(cols + (d_extra ? 1 : 0));
+  size_t total = rows * stride;
+  ++g_kernel_launches, k_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_scalars, rows, cols, ld, d_extra, stride, d_digits);
+}
+
+// ------------------------------------------------------------------------------------------------ accumulate
+__global__ void __launch_bounds__(kMsmColsPerBlock) k_msm_accumulate(const niels_t *table, const uint16_t *digits, size_t rows,
+                                                                     size_t cols, size_t cols_total, size_t extra_base,
+                                                                     size_t stride, ge_t *partial) {
+  size_t row = blockIdx.x % rows, window = blockIdx.x / rows;
+  const uint16_t *dg = digits + (window * rows + row) * stride;
+  ge_t acc = ge_identity();
+  int any = 0;
+  for (size_t col = threadIdx.x; col < cols_total; col += kMsmColsPerBlock) {
+    uint32_t d = dg[col];
+    if (d) {
+      size_t base = col < cols ? col : extra_base;
+      niels_t e = ldg_niels(table + base * kMsmTable + ((d & 0x7fffu) - 1u));
+      acc = (d >> 15) ? ge_msub(acc, e) : ge_madd(acc, e);
+      any = 1;
+    }
+  }
+  ge_t *dst = partial + row * kMsmWindows + window;
+  if (!__syncthreads_or(any)) {
+    if (threadIdx.x == 0) st_ge(dst, ge_identity());
+    return;
+  }
+  __shared__ ge_t sm[kMsmColsPerBlock];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = kMsmColsPerBlock / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] = ge_add(sm[threadIdx.x], sm[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_ge(dst, sm[0]);
+}
+void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t rows, size_t cols, bool has_extra, size_t extra_base,
+                           ge_t *d_partial, cudaStream_t st) {
+  size_t cols_total = cols + (has_extra ? 1 : 0);
+  size_t stride = msm_col_stride(cols_total);
+  ++g_kernel_launches, k_msm_accumulate<<<(unsigned)(rows * kMsmWindows), kMsmColsPerBlock, 0, st>>>(t.d_table, d_digits, rows, cols, cols_total, extra_base,
+                                                                               stride, d_partial);
+}
+
+__global__ void __launch_bounds__(64) k_msm_horner(const ge_t *partial, size_t rows, ge_t *out) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const ge_t *p = partial + row * kMsmWindows;
+  ge_t acc = ld_ge(p + kMsmWindows - 1);
+  for (int w = kMsmWindows - 2; w >= 0; w--) {
+    for (int i = 0; i < kMsmW; i++) acc = ge_dbl(acc);
+    acc = ge_add(acc, ld_ge(p + w));
+  }
+  st_ge(out + row, acc);
+}
+void launch_msm_horner(const ge_t *d_partial, size_t rows, ge_t *d_out, cudaStream_t st) {
+  ++g_kernel_launches, k_msm_horner<<<(unsigned)((rows + 63) / 64), 64, 0, st>>>(d_partial, rows, d_out);
+}
+
+// ------------------------------------------------------------------------------------------------ encodings
+__global__ void __launch_bounds__(64) k_compress(const ge_t *pts, size_t n, uint8_t *out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t b[32];
+  ge_compress(ld_ge(pts + i), b);
+  uint4 *q = reinterpret_cast<uint4 *>(out + 32 * i);
+  uint32_t w[8];
+  for (int k = 0; k < 8; k++) w[k] = (uint32_t)b[4 * k] | ((uint32_t)b[4 * k + 1] << 8) | ((uint32_t)b[4 * k + 2] << 16) | ((uint32_t)b[4 * k + 3] << 24);
+  q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+void launch_compress(const ge_t *d_pts, size_t n, uint8_t *d_out, cudaStream_t st) {
+  ++g_kernel_launches, k_compress<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(d_pts, n, d_out);
+}
+__global__ void __launch_bounds__(64) k_decompress(const uint8_t *in, size_t n, ge_t *pts, uint8_t *ok) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t b[32];
+  for (int k = 0; k < 32; k++) b[k] = in[32 * i + k];
+  ge_t g;
+  bool good = ge_decompress(b, &g);
+  if (!good) g = ge_identity();
+  st_ge(pts + i, g);
+  if (ok) ok[i] = good ? 1 : 0;
+}
+void launch_decompress(const uint8_t *d_in, size_t n, ge_t *d_pts, uint8_t *d_ok, cudaStream_t st) {
+  ++g_kernel_launches, k_decompress<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(d_in, n, d_pts, d_ok);
+}
+__global__ void __launch_bounds__(128) k_points_add(const ge_t *a, const ge_t *b, size_t n, ge_t *out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st_ge(out + i, ge_add(ld_ge(a + i), ld_ge(b + i)));
+}
+void launch_points_add(const ge_t *a, const ge_t *b, size_t n, ge_t *out, cudaStream_t st) {
+  ++g_kernel_launches, k_points_add<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(a, b, n, out);
+}
+__global__ void __launch_bounds__(64) k_from_uniform(const uint8_t *in, size_t n, ge_t *pts) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t b[64];
+  for (int k = 0; k < 64; k++) b[k] = in[64 * i + k];
+  st_ge(pts + i, ge_from_uniform_bytes(b));
+}
+void launch_from_uniform_bytes(const uint8_t *d_in, size_t n, ge_t *d_pts, cudaStream_t st) {
+  ++g_kernel_launches, k_from_uniform<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(d_in, n, d_pts);
+}
+
+}  // namespace vpin

@@ -1,0 +1,51 @@
+// Fixed-base multi-scalar multiplication over ristretto255 for Hyrax/Pedersen commitments on sm_100a.
+//
+// Every MSM in the prover is over a prefix of one fixed generator stream (Spartan/src/commitments.rs:20-38), and a
+// Hyrax commitment is L independent MSMs over the SAME R generators (Spartan/src/dense_mlpoly.rs:160-175). So instead
+// of per-row Pippenger buckets (rows are only 2^8..2^15 points long) the device keeps, per generator, a table of its
+// multiples 1..2^(W-1) in affine Niels form (96 B each), recodes scalars into signed W-bit digits, and computes for every
+// (row, window) the sum of looked-up multiples with 7-multiplication mixed additions; a Horner pass over the windows and
+// a batched ristretto encoding finish the row. No bucket reduction, no doublings in the hot loop, and scalars with few
+// non-zero digits (addresses, timestamps, +-1) cost proportionally less. Results equal the reference's
+// vartime_multiscalar_mul (Spartan/src/group.rs:103-121) as group elements, hence as compressed bytes.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ed.cuh"
+
+namespace vpin {
+
+static const int kMsmW = 12;                       // window width (bits)
+static const int kMsmTable = 1 << (kMsmW - 1);     // multiples 1..2^(W-1) per generator
+static const int kMsmWindows = 252 / kMsmW + 1;    // signed digits of |s| <= (l-1)/2 < 2^252
+static const int kMsmColsPerBlock = 64;            // threads per (row, window)
+
+struct MsmTable {
+  niels_t *d_table;   // [n_bases][kMsmTable]
+  size_t n_bases;
+};
+
+// bases: n extended points on device. Builds the table (n * kMsmTable entries).
+void launch_table_build(const ge_t *d_bases, size_t n, niels_t *d_table, cudaStream_t st);
+
+// digits layout: [window][row][col_stride] u16, bit 15 = sign, low bits = magnitude (0 = skip)
+static inline size_t msm_col_stride(size_t cols) { return (cols + kMsmColsPerBlock - 1) / kMsmColsPerBlock * kMsmColsPerBlock; }
+static inline size_t msm_digits_count(size_t rows, size_t cols) { return (size_t)kMsmWindows * rows * msm_col_stride(cols); }
+// scalars: rows x cols Montgomery elements, row-major with leading dimension ld. extra: optional one more scalar per row
+// (the blind, multiplied by base index `cols`), or nullptr. Padding columns get digit 0.
+void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, const fl_t *d_extra, uint16_t *d_digits, cudaStream_t st);
+// partial[row][window] = sum_col digit * base_col; the optional extra column (index cols) uses table base `extra_base`
+void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t rows, size_t cols, bool has_extra, size_t extra_base,
+                           ge_t *d_partial, cudaStream_t st);
+// out[row] = sum_w 2^(W*w) partial[row][w]
+void launch_msm_horner(const ge_t *d_partial, size_t rows, ge_t *d_out, cudaStream_t st);
+// RFC 9496 encoding of n points -> n x 32 bytes
+void launch_compress(const ge_t *d_pts, size_t n, uint8_t *d_out, cudaStream_t st);
+// decode n x 32 bytes -> points; d_ok[i] = 1 if valid
+void launch_decompress(const uint8_t *d_in, size_t n, ge_t *d_pts, uint8_t *d_ok, cudaStream_t st);
+// out[i] = a[i] + b[i]
+void launch_points_add(const ge_t *a, const ge_t *b, size_t n, ge_t *out, cudaStream_t st);
+// generator derivation (Spartan/src/commitments.rs:26-31): n x 64 uniform bytes -> n points
+void launch_from_uniform_bytes(const uint8_t *d_in, size_t n, ge_t *d_pts, cudaStream_t st);
+
+}  // namespace vpin

@@ -1,0 +1,485 @@
+// F_l table kernels for sm_100a: sumcheck round evaluations, binds, eq tables, CSR/CSC SpMV and the SPARK layer
+// builders. HBM-bound integer work: one 32-byte element per 2 x LDG.128, grid-stride loops sized in multiples of the
+// 148 SMs, warp-shuffle + shared-memory reductions of field elements. No tensor cores (nothing here is a contraction).
+#include <atomic>
+
+#include "kernels_poly.cuh"
+
+namespace vpin {
+
+extern std::atomic<uint64_t> g_kernel_launches;
+
+__device__ __forceinline__ fl_t ldg_fl(const fl_t *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  fl_t r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ fl_t ld_fl(const fl_t *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = q[0], b = q[1];
+  fl_t r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st_fl(fl_t *p, const fl_t &x) {
+  uint4 *q = reinterpret_cast<uint4 *>(p);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+__device__ __forceinline__ fl_t shfl_down_fl(const fl_t &x, int off) {
+  fl_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, x.v[i], off);
+  return r;
+}
+
+// Block-wide sum of K field elements per thread; thread 0 writes them to dst[0..K).
+template <int K>
+__device__ __forceinline__ void block_sum_store(fl_t (&acc)[K], fl_t *dst) {
+  __shared__ fl_t sm[K][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = fl_add(acc[k], shfl_down_fl(acc[k], off));
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < K; k++) sm[k][warp] = acc[k];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      fl_t v = lane < nwarps ? sm[k][lane] : fl_zero();
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v = fl_add(v, shfl_down_fl(v, off));
+      if (lane == 0) st_fl(dst + k, v);
+    }
+  }
+}
+
+// second stage: out[inst*K + k] = sum_b partials[(inst*nblocks + b)*K + k]
+template <int K>
+__global__ void __launch_bounds__(kRedThreads) k_reduce_partials(const fl_t *partials, int nblocks, fl_t *out) {
+  const fl_t *p = partials + (size_t)blockIdx.x * nblocks * K;
+  fl_t acc[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) acc[k] = fl_zero();
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = fl_add(acc[k], ld_fl(p + (size_t)b * K + k));
+  block_sum_store<K>(acc, out + (size_t)blockIdx.x * K);
+}
+
+static inline int red_blocks(size_t n) {
+  size_t b = (n + kRedThreads - 1) / kRedThreads;
+  if (b < 1) b = 1;
+  return (int)(b > (size_t)kRedBlocks ? kRedBlocks : b);
+}
+static inline unsigned ew_blocks(size_t n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------ eq tables
+__global__ void __launch_bounds__(1024) k_eq_small(const fl_t *r, int ell, fl_t *dst, fl_t *tmp) {
+  fl_t *a = (ell & 1) ? tmp : dst, *b = (ell & 1) ? dst : tmp;  // ell swaps end in dst
+  if (threadIdx.x == 0) st_fl(a, fl_one());
+  __syncthreads();
+  for (int j = 0; j < ell; j++) {
+    fl_t rj = ld_fl(r + j);
+    int size = 1 << j;
+    for (int i = threadIdx.x; i < size; i += blockDim.x) {
+      fl_t s = ld_fl(a + i);
+      fl_t hi = fl_mul(s, rj);
+      st_fl(b + 2 * i + 1, hi);
+      st_fl(b + 2 * i, fl_sub(s, hi));
+    }
+    __syncthreads();
+    fl_t *t = a; a = b; b = t;
+  }
+}
+__global__ void __launch_bounds__(256) k_eq_outer(const fl_t *hi, const fl_t *lo, int lo_bits, size_t n, fl_t *out) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    st_fl(out + i, fl_mul(ldg_fl(hi + (i >> lo_bits)), ldg_fl(lo + (i & (((size_t)1 << lo_bits) - 1)))));
+}
+void launch_eq_evals(const fl_t *d_r, int ell, fl_t *d_out, fl_t *d_tmp, cudaStream_t st) {
+  if (ell <= 12) {
+    ++g_kernel_launches, k_eq_small<<<1, 1024, 0, st>>>(d_r, ell, d_out, d_tmp);
+    return;
+  }
+  int hi_bits = ell / 2, lo_bits = ell - hi_bits;
+  fl_t *hi = d_tmp, *lo = d_tmp + ((size_t)1 << hi_bits), *scratch = lo + ((size_t)1 << lo_bits);
+  ++g_kernel_launches, k_eq_small<<<1, 1024, 0, st>>>(d_r, hi_bits, hi, scratch);
+  ++g_kernel_launches, k_eq_small<<<1, 1024, 0, st>>>(d_r + hi_bits, lo_bits, lo, scratch);
+  size_t n = (size_t)1 << ell;
+  unsigned blocks = (unsigned)((n / 256) < 148 * 16 ? (n / 256) : 148 * 16);
+  ++g_kernel_launches, k_eq_outer<<<blocks, 256, 0, st>>>(hi, lo, lo_bits, n, d_out);
+}
+
+// ------------------------------------------------------------------------------------------------ binds
+__global__ void __launch_bounds__(256) k_bind_top(fl_t *Z, size_t half, const fl_t *d_r) {
+  fl_t r = ld_fl(d_r);
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+    fl_t lo = ld_fl(Z + i), hi = ld_fl(Z + half + i);
+    st_fl(Z + i, fl_add(lo, fl_mul(r, fl_sub(hi, lo))));
+  }
+}
+__global__ void __launch_bounds__(256) k_bind_top_multi(fl_t *const *tables, size_t half, const fl_t *d_r) {
+  fl_t r = ld_fl(d_r);
+  fl_t *Z = tables[blockIdx.y];
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+    fl_t lo = ld_fl(Z + i), hi = ld_fl(Z + half + i);
+    st_fl(Z + i, fl_add(lo, fl_mul(r, fl_sub(hi, lo))));
+  }
+}
+__global__ void __launch_bounds__(256) k_bind_bot(const fl_t *Z, fl_t *out, size_t half, const fl_t *d_r) {
+  fl_t r = ld_fl(d_r);
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+    fl_t lo = ld_fl(Z + 2 * i), hi = ld_fl(Z + 2 * i + 1);
+    st_fl(out + i, fl_add(lo, fl_mul(r, fl_sub(hi, lo))));
+  }
+}
+static inline unsigned stream_blocks(size_t n) {
+  size_t b = (n + 255) / 256;
+  if (b < 1) b = 1;
+  size_t cap = 148 * 8;
+  return (unsigned)(b > cap ? cap : b);
+}
+void launch_bind_top(fl_t *Z, size_t half, const fl_t *d_r, cudaStream_t st) {
+  ++g_kernel_launches, k_bind_top<<<stream_blocks(half), 256, 0, st>>>(Z, half, d_r);
+}
+void launch_bind_top_multi(fl_t *const *d_tables, int ntables, size_t half, const fl_t *d_r, cudaStream_t st) {
+  dim3 grid(stream_blocks(half), ntables);
+  ++g_kernel_launches, k_bind_top_multi<<<grid, 256, 0, st>>>(d_tables, half, d_r);
+}
+void launch_bind_bot(const fl_t *Z, fl_t *out, size_t half, const fl_t *d_r, cudaStream_t st) {
+  ++g_kernel_launches, k_bind_bot<<<stream_blocks(half), 256, 0, st>>>(Z, out, half, d_r);
+}
+
+// ------------------------------------------------------------------------------------------------ sumcheck rounds
+__global__ void __launch_bounds__(kRedThreads) k_cubic_additive(const fl_t *A, const fl_t *B, const fl_t *C, const fl_t *D,
+                                                                size_t half, fl_t *partials) {
+  fl_t acc[3] = {fl_zero(), fl_zero(), fl_zero()};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+    fl_t a0 = ldg_fl(A + i), a1 = ldg_fl(A + half + i);
+    fl_t b0 = ldg_fl(B + i), b1 = ldg_fl(B + half + i);
+    fl_t c0 = ldg_fl(C + i), c1 = ldg_fl(C + half + i);
+    fl_t d0 = ldg_fl(D + i), d1 = ldg_fl(D + half + i);
+    acc[0] = fl_add(acc[0], fl_mul(a0, fl_sub(fl_mul(b0, c0), d0)));
+    fl_t da = fl_sub(a1, a0), db = fl_sub(b1, b0), dc = fl_sub(c1, c0), dd = fl_sub(d1, d0);
+    fl_t a2 = fl_add(a1, da), b2 = fl_add(b1, db), c2 = fl_add(c1, dc), d2 = fl_add(d1, dd);
+    acc[1] = fl_add(acc[1], fl_mul(a2, fl_sub(fl_mul(b2, c2), d2)));
+    fl_t a3 = fl_add(a2, da), b3 = fl_add(b2, db), c3 = fl_add(c2, dc), d3 = fl_add(d2, dd);
+    acc[2] = fl_add(acc[2], fl_mul(a3, fl_sub(fl_mul(b3, c3), d3)));
+  }
+  block_sum_store<3>(acc, partials + (size_t)blockIdx.x * 3);
+}
+void launch_cubic_additive_round(const fl_t *A, const fl_t *B, const fl_t *C, const fl_t *D, size_t half, fl_t *d_out,
+                                 fl_t *d_partials, cudaStream_t st) {
+  int nb = red_blocks(half);
+  ++g_kernel_launches, k_cubic_additive<<<nb, kRedThreads, 0, st>>>(A, B, C, D, half, d_partials);
+  ++g_kernel_launches, k_reduce_partials<3><<<1, kRedThreads, 0, st>>>(d_partials, nb, d_out);
+}
+
+__global__ void __launch_bounds__(kRedThreads) k_quad(const fl_t *A, const fl_t *B, size_t half, fl_t *partials) {
+  fl_t acc[2] = {fl_zero(), fl_zero()};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+    fl_t a0 = ldg_fl(A + i), a1 = ldg_fl(A + half + i);
+    fl_t b0 = ldg_fl(B + i), b1 = ldg_fl(B + half + i);
+    acc[0] = fl_add(acc[0], fl_mul(a0, b0));
+    fl_t a2 = fl_add(a1, fl_sub(a1, a0)), b2 = fl_add(b1, fl_sub(b1, b0));
+    acc[1] = fl_add(acc[1], fl_mul(a2, b2));
+  }
+  block_sum_store<2>(acc, partials + (size_t)blockIdx.x * 2);
+}
+void launch_quad_round(const fl_t *A, const fl_t *B, size_t half, fl_t *d_out, fl_t *d_partials, cudaStream_t st) {
+  int nb = red_blocks(half);
+  ++g_kernel_launches, k_quad<<<nb, kRedThreads, 0, st>>>(A, B, half, d_partials);
+  ++g_kernel_launches, k_reduce_partials<2><<<1, kRedThreads, 0, st>>>(d_partials, nb, d_out);
+}
+
+__global__ void __launch_bounds__(kRedThreads) k_cubic_batched(const fl_t *const *pA, const fl_t *const *pB, const fl_t *const *pC,
+                                                               size_t half, fl_t *partials) {
+  const fl_t *A = pA[blockIdx.y], *B = pB[blockIdx.y], *C = pC[blockIdx.y];
+  fl_t acc[3] = {fl_zero(), fl_zero(), fl_zero()};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+    fl_t a0 = ldg_fl(A + i), a1 = ldg_fl(A + half + i);
+    fl_t b0 = ldg_fl(B + i), b1 = ldg_fl(B + half + i);
+    fl_t c0 = ldg_fl(C + i), c1 = ldg_fl(C + half + i);
+    acc[0] = fl_add(acc[0], fl_mul(fl_mul(a0, b0), c0));
+    fl_t da = fl_sub(a1, a0), db = fl_sub(b1, b0), dc = fl_sub(c1, c0);
+    fl_t a2 = fl_add(a1, da), b2 = fl_add(b1, db), c2 = fl_add(c1, dc);
+    acc[1] = fl_add(acc[1], fl_mul(fl_mul(a2, b2), c2));
+    fl_t a3 = fl_add(a2, da), b3 = fl_add(b2, db), c3 = fl_add(c2, dc);
+    acc[2] = fl_add(acc[2], fl_mul(fl_mul(a3, b3), c3));
+  }
+  block_sum_store<3>(acc, partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3);
+}
+void launch_cubic_batched_round(const fl_t *const *d_A, const fl_t *const *d_B, const fl_t *const *d_C, int n, size_t half,
+                                fl_t *d_out, fl_t *d_partials, cudaStream_t st) {
+  int nb = red_blocks(half);
+  if (nb > kRedBlocks / 4 && n > 4) nb = kRedBlocks / 4;  // n instances share the machine
+  dim3 grid(nb, n);
+  ++g_kernel_launches, k_cubic_batched<<<grid, kRedThreads, 0, st>>>(d_A, d_B, d_C, half, d_partials);
+  ++g_kernel_launches, k_reduce_partials<3><<<n, kRedThreads, 0, st>>>(d_partials, nb, d_out);
+}
+
+// ------------------------------------------------------------------------------------------------ dot products
+__global__ void __launch_bounds__(kRedThreads) k_dot_multi(const fl_t *const *pA, const fl_t *A0, const fl_t *B, size_t n,
+                                                           fl_t *partials) {
+  const fl_t *A = pA ? pA[blockIdx.y] : A0;
+  fl_t acc[1] = {fl_zero()};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    acc[0] = fl_add(acc[0], fl_mul(ldg_fl(A + i), ldg_fl(B + i)));
+  block_sum_store<1>(acc, partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x));
+}
+void launch_dot(const fl_t *A, const fl_t *B, size_t n, fl_t *d_out, fl_t *d_partials, cudaStream_t st) {
+  int nb = red_blocks(n);
+  ++g_kernel_launches, k_dot_multi<<<dim3(nb, 1), kRedThreads, 0, st>>>(nullptr, A, B, n, d_partials);
+  ++g_kernel_launches, k_reduce_partials<1><<<1, kRedThreads, 0, st>>>(d_partials, nb, d_out);
+}
+void launch_dot_multi(const fl_t *const *d_A, const fl_t *B, int n, size_t len, fl_t *d_out, fl_t *d_partials, cudaStream_t st) {
+  int nb = red_blocks(len);
+  if (nb > kRedBlocks / 4 && n > 4) nb = kRedBlocks / 4;
+  ++g_kernel_launches, k_dot_multi<<<dim3(nb, n), kRedThreads, 0, st>>>(d_A, nullptr, B, len, d_partials);
+  ++g_kernel_launches, k_reduce_partials<1><<<n, kRedThreads, 0, st>>>(d_partials, nb, d_out);
+}
+__global__ void __launch_bounds__(kRedThreads) k_dot3(const fl_t *A, const fl_t *B, const fl_t *C, size_t n, fl_t *partials) {
+  fl_t acc[1] = {fl_zero()};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    acc[0] = fl_add(acc[0], fl_mul(fl_mul(ldg_fl(A + i), ldg_fl(B + i)), ldg_fl(C + i)));
+  block_sum_store<1>(acc, partials + blockIdx.x);
+}
+void launch_dot3(const fl_t *A, const fl_t *B, const fl_t *C, size_t n, fl_t *d_out, fl_t *d_partials, cudaStream_t st) {
+  int nb = red_blocks(n);
+  ++g_kernel_launches, k_dot3<<<nb, kRedThreads, 0, st>>>(A, B, C, n, d_partials);
+  ++g_kernel_launches, k_reduce_partials<1><<<1, kRedThreads, 0, st>>>(d_partials, nb, d_out);
+}
+
+// ------------------------------------------------------------------------------------------------ L * Z
+// grid (ceil(R/128), nsplit): thread owns column j, walks its slice of the L rows; slices summed by k_bound_finish
+__global__ void __launch_bounds__(128) k_bound(const fl_t *Z, const fl_t *L, size_t Lsize, size_t Rsize, fl_t *tmp) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Rsize) return;
+  size_t per = (Lsize + gridDim.y - 1) / gridDim.y;
+  size_t lo = per * blockIdx.y, hi = lo + per < Lsize ? lo + per : Lsize;
+  fl_t acc = fl_zero();
+  for (size_t i = lo; i < hi; i++) {
+    fl_t l = ldg_fl(L + i);
+    acc = fl_add(acc, fl_mul(l, ldg_fl(Z + i * Rsize + j)));
+  }
+  st_fl(tmp + (size_t)blockIdx.y * Rsize + j, acc);
+}
+__global__ void __launch_bounds__(128) k_bound_finish(const fl_t *tmp, int nsplit, size_t Rsize, fl_t *out) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Rsize) return;
+  fl_t acc = fl_zero();
+  for (int s = 0; s < nsplit; s++) acc = fl_add(acc, ld_fl(tmp + (size_t)s * Rsize + j));
+  st_fl(out + j, acc);
+}
+void launch_bound(const fl_t *Z, const fl_t *L, size_t Lsize, size_t Rsize, fl_t *d_out, fl_t *d_tmp, cudaStream_t st) {
+  unsigned bx = (unsigned)((Rsize + 127) / 128);
+  int nsplit = 1;
+  while (nsplit < 64 && (size_t)bx * nsplit < 148 * 8 && (size_t)nsplit * 2 <= Lsize) nsplit *= 2;
+  ++g_kernel_launches, k_bound<<<dim3(bx, nsplit), 128, 0, st>>>(Z, L, Lsize, Rsize, d_tmp);
+  ++g_kernel_launches, k_bound_finish<<<bx, 128, 0, st>>>(d_tmp, nsplit, Rsize, d_out);
+}
+
+// ------------------------------------------------------------------------------------------------ SpMV
+__global__ void __launch_bounds__(256) k_spmv_csr(CsrDev m, const fl_t *z, fl_t *out) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= m.n) return;
+  fl_t acc = fl_zero();
+  for (uint32_t e = m.ptr[row], end = m.ptr[row + 1]; e < end; e++)
+    acc = fl_add(acc, fl_mul(ldg_fl(m.val + e), ldg_fl(z + m.idx[e])));
+  st_fl(out + row, acc);
+}
+void launch_spmv_csr(const CsrDev &m, const fl_t *z, fl_t *out, cudaStream_t st) {
+  ++g_kernel_launches, k_spmv_csr<<<ew_blocks(m.n), 256, 0, st>>>(m, z, out);
+}
+__global__ void __launch_bounds__(256) k_spmv_csc(CscDev m, const fl_t *x, const fl_t *d_scale, int accumulate, fl_t *out) {
+  size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= m.n) return;
+  uint32_t e = m.ptr[col], end = m.ptr[col + 1];
+  if (end - e > (uint32_t)kLongCol) return;  // done by k_spmv_csc_long
+  fl_t acc = fl_zero();
+  for (; e < end; e++) acc = fl_add(acc, fl_mul(ldg_fl(x + m.idx[e]), ldg_fl(m.val + e)));
+  acc = fl_mul(acc, ld_fl(d_scale));
+  if (accumulate) acc = fl_add(acc, ld_fl(out + col));
+  st_fl(out + col, acc);
+}
+__global__ void __launch_bounds__(kRedThreads) k_spmv_csc_long(CscDev m, const fl_t *x, const fl_t *d_scale, int accumulate, fl_t *out) {
+  uint32_t col = m.long_cols[blockIdx.x];
+  fl_t acc[1] = {fl_zero()};
+  for (uint32_t e = m.ptr[col] + threadIdx.x, end = m.ptr[col + 1]; e < end; e += blockDim.x)
+    acc[0] = fl_add(acc[0], fl_mul(ldg_fl(x + m.idx[e]), ldg_fl(m.val + e)));
+  __shared__ fl_t res;
+  block_sum_store<1>(acc, &res);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    fl_t v = fl_mul(res, ld_fl(d_scale));
+    if (accumulate) v = fl_add(v, ld_fl(out + col));
+    st_fl(out + col, v);
+  }
+}
+void launch_spmv_csc_scaled(const CscDev &m, const fl_t *x, const fl_t *d_scale, bool accumulate, fl_t *out, cudaStream_t st) {
+  ++g_kernel_launches, k_spmv_csc<<<ew_blocks(m.n), 256, 0, st>>>(m, x, d_scale, accumulate ? 1 : 0, out);
+  if (m.n_long) ++g_kernel_launches, k_spmv_csc_long<<<(unsigned)m.n_long, kRedThreads, 0, st>>>(m, x, d_scale, accumulate ? 1 : 0, out);
+}
+__global__ void __launch_bounds__(kRedThreads) k_sparse_eval(const uint32_t *rows, const uint32_t *cols, const fl_t *val, size_t nnz,
+                                                             const fl_t *trx, const fl_t *try_, fl_t *partials) {
+  fl_t acc[1] = {fl_zero()};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride)
+    acc[0] = fl_add(acc[0], fl_mul(fl_mul(ldg_fl(trx + rows[i]), ldg_fl(try_ + cols[i])), ldg_fl(val + i)));
+  block_sum_store<1>(acc, partials + blockIdx.x);
+}
+void launch_sparse_eval(const uint32_t *rows, const uint32_t *cols, const fl_t *val, size_t nnz, const fl_t *trx, const fl_t *try_,
+                        fl_t *d_out, fl_t *d_partials, cudaStream_t st) {
+  int nb = red_blocks(nnz);
+  ++g_kernel_launches, k_sparse_eval<<<nb, kRedThreads, 0, st>>>(rows, cols, val, nnz, trx, try_, d_partials);
+  ++g_kernel_launches, k_reduce_partials<1><<<1, kRedThreads, 0, st>>>(d_partials, nb, d_out);
+}
+
+// ------------------------------------------------------------------------------------------------ SPARK layers
+__global__ void __launch_bounds__(256) k_gather(const uint32_t *addr, const fl_t *mem, size_t n, fl_t *out) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st_fl(out + i, ldg_fl(mem + addr[i]));
+}
+void launch_gather(const uint32_t *addr, const fl_t *mem, size_t n, fl_t *out, cudaStream_t st) {
+  ++g_kernel_launches, k_gather<<<stream_blocks(n), 256, 0, st>>>(addr, mem, n, out);
+}
+// Montgomery form of a 32-bit integer: x * R mod l == mont_mul(x, R^2)
+__device__ __forceinline__ fl_t fl_from_u32_dev(uint32_t x) {
+  fl_t t = fl_zero();
+  t.v[0] = x;
+  return fl_mul(t, fl_r2());
+}
+__global__ void __launch_bounds__(256) k_u32_to_fl(const uint32_t *in, size_t n, fl_t *out) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st_fl(out + i, fl_from_u32_dev(in[i]));
+}
+void launch_u32_to_fl(const uint32_t *in, size_t n, fl_t *out, cudaStream_t st) {
+  ++g_kernel_launches, k_u32_to_fl<<<stream_blocks(n), 256, 0, st>>>(in, n, out);
+}
+__global__ void __launch_bounds__(256) k_hash_mem(const fl_t *eq, const uint32_t *audit_ts, size_t n, const fl_t *d_gt, fl_t *init,
+                                                  fl_t *audit) {
+  fl_t gamma = ld_fl(d_gt), tau = ld_fl(d_gt + 1);
+  fl_t gamma2 = fl_mul(gamma, gamma);
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    // hash(addr, val, ts) = ts*gamma^2 + val*gamma + addr  (sparse_mlpoly.rs:562-566)
+    fl_t base = fl_sub(fl_add(fl_mul(ldg_fl(eq + i), gamma), fl_from_u32_dev((uint32_t)i)), tau);
+    st_fl(init + i, base);
+    st_fl(audit + i, fl_add(fl_mul(fl_from_u32_dev(audit_ts[i]), gamma2), base));
+  }
+}
+void launch_hash_mem(const fl_t *eq, const uint32_t *audit_ts, size_t num_cells, const fl_t *d_gt, fl_t *init, fl_t *audit, cudaStream_t st) {
+  ++g_kernel_launches, k_hash_mem<<<stream_blocks(num_cells), 256, 0, st>>>(eq, audit_ts, num_cells, d_gt, init, audit);
+}
+__global__ void __launch_bounds__(256) k_hash_ops(const uint32_t *addr, const fl_t *deref, const uint32_t *read_ts, size_t n,
+                                                  const fl_t *d_gt, fl_t *read, fl_t *write) {
+  fl_t gamma = ld_fl(d_gt), tau = ld_fl(d_gt + 1);
+  fl_t gamma2 = fl_mul(gamma, gamma);
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    fl_t base = fl_sub(fl_add(fl_mul(ldg_fl(deref + i), gamma), fl_from_u32_dev(addr[i])), tau);
+    fl_t r = fl_add(fl_mul(fl_from_u32_dev(read_ts[i]), gamma2), base);
+    st_fl(read + i, r);
+    st_fl(write + i, fl_add(r, gamma2));  // write_ts = read_ts + 1
+  }
+}
+void launch_hash_ops(const uint32_t *addr, const fl_t *deref, const uint32_t *read_ts, size_t num_ops, const fl_t *d_gt, fl_t *read,
+                     fl_t *write, cudaStream_t st) {
+  ++g_kernel_launches, k_hash_ops<<<stream_blocks(num_ops), 256, 0, st>>>(addr, deref, read_ts, num_ops, d_gt, read, write);
+}
+__global__ void __launch_bounds__(256) k_mul_halves(const fl_t *in, size_t n, fl_t *out) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    st_fl(out + i, fl_mul(ldg_fl(in + i), ldg_fl(in + n + i)));
+}
+void launch_mul_halves(const fl_t *in, size_t n, fl_t *out, cudaStream_t st) {
+  ++g_kernel_launches, k_mul_halves<<<stream_blocks(n), 256, 0, st>>>(in, n, out);
+}
+__global__ void __launch_bounds__(256) k_lincomb3(const fl_t *A, const fl_t *B, const fl_t *C, const fl_t *d_abc, size_t n, fl_t *out) {
+  fl_t a = ld_fl(d_abc), b = ld_fl(d_abc + 1), c = ld_fl(d_abc + 2);
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    st_fl(out + i, fl_add(fl_add(fl_mul(a, ldg_fl(A + i)), fl_mul(b, ldg_fl(B + i))), fl_mul(c, ldg_fl(C + i))));
+}
+void launch_lincomb3(const fl_t *A, const fl_t *B, const fl_t *C, const fl_t *d_abc, size_t n, fl_t *out, cudaStream_t st) {
+  ++g_kernel_launches, k_lincomb3<<<stream_blocks(n), 256, 0, st>>>(A, B, C, d_abc, n, out);
+}
+
+// ------------------------------------------------------------------------------------------------ bullet reduction
+__global__ void __launch_bounds__(256) k_bullet_fold(fl_t *a, fl_t *b, size_t n, const fl_t *d_u) {
+  fl_t u = ld_fl(d_u), uinv = ld_fl(d_u + 1);
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    st_fl(a + i, fl_add(fl_mul(ld_fl(a + i), u), fl_mul(uinv, ld_fl(a + n + i))));
+    st_fl(b + i, fl_add(fl_mul(ld_fl(b + i), uinv), fl_mul(u, ld_fl(b + n + i))));
+  }
+}
+void launch_bullet_fold(fl_t *a, fl_t *b, size_t n, const fl_t *d_u, cudaStream_t st) {
+  ++g_kernel_launches, k_bullet_fold<<<stream_blocks(n), 256, 0, st>>>(a, b, n, d_u);
+}
+__global__ void __launch_bounds__(256) k_bullet_weights(fl_t *w, size_t total, size_t n, const fl_t *d_u) {
+  fl_t u = ld_fl(d_u), uinv = ld_fl(d_u + 1);
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride)
+    st_fl(w + j, fl_mul(ld_fl(w + j), (j & (2 * n - 1)) < n ? uinv : u));
+}
+void launch_bullet_weights(fl_t *w, size_t total, size_t n, const fl_t *d_u, cudaStream_t st) {
+  ++g_kernel_launches, k_bullet_weights<<<stream_blocks(total), 256, 0, st>>>(w, total, n, d_u);
+}
+__global__ void __launch_bounds__(256) k_bullet_scalars(const fl_t *a, const fl_t *w, size_t total, size_t n, fl_t *sL, fl_t *sR) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+    size_t rem = j & (2 * n - 1);
+    fl_t wj = ld_fl(w + j);
+    if (rem >= n) {
+      st_fl(sL + j, fl_mul(ld_fl(a + rem - n), wj));  // a_L against G_R
+      st_fl(sR + j, fl_zero());
+    } else {
+      st_fl(sL + j, fl_zero());
+      st_fl(sR + j, fl_mul(ld_fl(a + rem + n), wj));  // a_R against G_L
+    }
+  }
+}
+void launch_bullet_scalars(const fl_t *a, const fl_t *w, size_t total, size_t n, fl_t *sL, fl_t *sR, cudaStream_t st) {
+  ++g_kernel_launches, k_bullet_scalars<<<stream_blocks(total), 256, 0, st>>>(a, w, total, n, sL, sR);
+}
+__global__ void __launch_bounds__(256) k_scale(const fl_t *in, const fl_t *d_s, size_t n, fl_t *out) {
+  fl_t s = ld_fl(d_s);
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st_fl(out + i, fl_mul(s, ld_fl(in + i)));
+}
+void launch_scale(const fl_t *in, const fl_t *d_s, size_t n, fl_t *out, cudaStream_t st) {
+  ++g_kernel_launches, k_scale<<<stream_blocks(n), 256, 0, st>>>(in, d_s, n, out);
+}
+__global__ void __launch_bounds__(256) k_fill_one(fl_t *out, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st_fl(out + i, fl_one());
+}
+void launch_fill_one(fl_t *out, size_t n, cudaStream_t st) { ++g_kernel_launches, k_fill_one<<<stream_blocks(n), 256, 0, st>>>(out, n); }
+__global__ void __launch_bounds__(256) k_mont_conv(const fl_t *in, size_t n, fl_t *out, int to_mont) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    fl_t x = ld_fl(in + i);
+    st_fl(out + i, to_mont ? fl_to_mont(x) : fl_from_mont(x));
+  }
+}
+void launch_to_mont(const fl_t *in, size_t n, fl_t *out, cudaStream_t st) { ++g_kernel_launches, k_mont_conv<<<stream_blocks(n), 256, 0, st>>>(in, n, out, 1); }
+void launch_from_mont(const fl_t *in, size_t n, fl_t *out, cudaStream_t st) { ++g_kernel_launches, k_mont_conv<<<stream_blocks(n), 256, 0, st>>>(in, n, out, 0); }
+
+}  // namespace vpin

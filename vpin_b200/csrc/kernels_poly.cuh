@@ -1,0 +1,90 @@
+// Launch wrappers of the F_l table kernels (sumcheck rounds, eq tables, binds, SpMV, SPARK layers).
+// All tables are arrays of fl_t in Montgomery form in HBM. Every wrapper enqueues on `st` and returns.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fl.cuh"
+
+namespace vpin {
+
+// number of partial-sum slots the reduction kernels need (fl_t elements): kMaxBlocks * k per instance
+static const int kRedBlocks = 592;  // 148 SMs x 4
+static const int kRedThreads = 256;
+
+// K4: eq(r) table, r[0] = most significant index bit (Spartan/src/dense_mlpoly.rs:78-94).
+// d_r: ell challenges on device. d_out: 2^ell. d_tmp: >= max(4096, 3 * 2^ceil(ell/2)) scratch elements.
+void launch_eq_evals(const fl_t *d_r, int ell, fl_t *d_out, fl_t *d_tmp, cudaStream_t st);
+
+// K5 bind: Z[i] += r * (Z[i + half] - Z[i]) for i < half (Spartan/src/dense_mlpoly.rs:229-236); r on device.
+void launch_bind_top(fl_t *Z, size_t half, const fl_t *d_r, cudaStream_t st);
+// several equally long tables in one launch (ptrs on device)
+void launch_bind_top_multi(fl_t *const *d_tables, int ntables, size_t half, const fl_t *d_r, cudaStream_t st);
+// Z[i] = Z[2i] + r (Z[2i+1] - Z[2i]) into out (Spartan/src/dense_mlpoly.rs:238-245)
+void launch_bind_bot(const fl_t *Z, fl_t *out, size_t half, const fl_t *d_r, cudaStream_t st);
+
+// K5 eval: sum over i < half of comb at t = 0, 2, 3 with comb = A (B C - D) (Spartan/src/sumcheck.rs:619-652).
+// d_out: 3 elements; d_partials: 3 * kRedBlocks scratch.
+void launch_cubic_additive_round(const fl_t *A, const fl_t *B, const fl_t *C, const fl_t *D, size_t half, fl_t *d_out,
+                                 fl_t *d_partials, cudaStream_t st);
+// K6 eval: comb = A B at t = 0, 2 (Spartan/src/sumcheck.rs:456-469). d_out: 2 elements.
+void launch_quad_round(const fl_t *A, const fl_t *B, size_t half, fl_t *d_out, fl_t *d_partials, cudaStream_t st);
+// K7 eval: for each instance k < n: comb = A_k B_k C_k at t = 0, 2, 3 (Spartan/src/sumcheck.rs:287-357).
+// d_A/d_B/d_C: device arrays of n table pointers (C may repeat the shared eq table). d_out: 3n elements.
+// d_partials: 3 * kRedBlocks * n scratch.
+void launch_cubic_batched_round(const fl_t *const *d_A, const fl_t *const *d_B, const fl_t *const *d_C, int n, size_t half,
+                                fl_t *d_out, fl_t *d_partials, cudaStream_t st);
+
+// dot product sum_i A[i] B[i] (Spartan/src/nizk/mod.rs:442-445). d_out: 1 element; d_partials: kRedBlocks.
+void launch_dot(const fl_t *A, const fl_t *B, size_t n, fl_t *d_out, fl_t *d_partials, cudaStream_t st);
+// n dot products against one shared vector B: out[k] = <A_k, B>
+void launch_dot_multi(const fl_t *const *d_A, const fl_t *B, int n, size_t len, fl_t *d_out, fl_t *d_partials, cudaStream_t st);
+// sum_i A[i] B[i] C[i]
+void launch_dot3(const fl_t *A, const fl_t *B, const fl_t *C, size_t n, fl_t *d_out, fl_t *d_partials, cudaStream_t st);
+
+// K10: LZ[j] = sum_i L[i] Z[i * R + j] (Spartan/src/dense_mlpoly.rs:220-227). d_tmp: nsplit * R scratch (nsplit <= 64).
+void launch_bound(const fl_t *Z, const fl_t *L, size_t Lsize, size_t Rsize, fl_t *d_out, fl_t *d_tmp, cudaStream_t st);
+
+// K2: CSR SpMV out[row] = sum val * z[col] (Spartan/src/sparse_mlpoly.rs:467-481)
+struct CsrDev { const uint32_t *ptr; const uint32_t *idx; const fl_t *val; size_t n; };
+void launch_spmv_csr(const CsrDev &m, const fl_t *z, fl_t *out, cudaStream_t st);
+// K3: CSC form of M^T x (Spartan/src/sparse_mlpoly.rs:483-498): out[col] = sum x[row] * val, accumulated with a scale:
+// out[col] (+)= scale * sum. Columns with more than kLongCol entries are listed in long_cols and reduced by a block each.
+static const int kLongCol = 256;
+struct CscDev { const uint32_t *ptr; const uint32_t *idx; const fl_t *val; size_t n; const uint32_t *long_cols; size_t n_long; };
+void launch_spmv_csc_scaled(const CscDev &m, const fl_t *x, const fl_t *d_scale, bool accumulate, fl_t *out, cudaStream_t st);
+// sum over nnz of rx[row] * ry[col] * val (Spartan/src/sparse_mlpoly.rs:440-452); uses the CSR arrays + a row index per entry
+void launch_sparse_eval(const uint32_t *rows, const uint32_t *cols, const fl_t *val, size_t nnz, const fl_t *trx, const fl_t *try_,
+                        fl_t *d_out, fl_t *d_partials, cudaStream_t st);
+
+// SPARK (Spartan/src/sparse_mlpoly.rs)
+// deref gather out[i] = mem[addr[i]]  (:267-276)
+void launch_gather(const uint32_t *addr, const fl_t *mem, size_t n, fl_t *out, cudaStream_t st);
+// out[i] = fl(u32 in[i])
+void launch_u32_to_fl(const uint32_t *in, size_t n, fl_t *out, cudaStream_t st);
+// hash layer (:547-622): h = ts*gamma^2 + val*gamma + addr - tau. d_gt: {gamma, tau} on device.
+//   init[i]  = eq[i]*gamma + i - tau ; audit[i] = audit_ts[i]*gamma^2 + eq[i]*gamma + i - tau      (i < num_cells)
+void launch_hash_mem(const fl_t *eq, const uint32_t *audit_ts, size_t num_cells, const fl_t *d_gt, fl_t *init, fl_t *audit, cudaStream_t st);
+//   read[i]  = ts[i]*gamma^2 + deref[i]*gamma + addr[i] - tau ; write[i] = read[i] + gamma^2       (i < num_ops)
+void launch_hash_ops(const uint32_t *addr, const fl_t *deref, const uint32_t *read_ts, size_t num_ops, const fl_t *d_gt, fl_t *read,
+                     fl_t *write, cudaStream_t st);
+// product tree layer (Spartan/src/product_tree.rs:18-34): out[i] = in[i] * in[i + n] for i < n (out may not alias in)
+void launch_mul_halves(const fl_t *in, size_t n, fl_t *out, cudaStream_t st);
+// out[i] = a*A[i] + b*B[i] + c*C[i] ; d_abc = {a,b,c} on device
+void launch_lincomb3(const fl_t *A, const fl_t *B, const fl_t *C, const fl_t *d_abc, size_t n, fl_t *out, cudaStream_t st);
+
+// bullet reduction helpers (Spartan/src/nizk/bullet.rs:72-119), see prover for the fixed-base reformulation.
+// a[i] = a[i]*u + uinv*a[i+n]; b[i] = b[i]*uinv + u*b[i+n]  (i < n). d_u = {u, uinv}
+void launch_bullet_fold(fl_t *a, fl_t *b, size_t n, const fl_t *d_u, cudaStream_t st);
+// w[j] *= ((j mod 2n) < n ? uinv : u) for j < total
+void launch_bullet_weights(fl_t *w, size_t total, size_t n, const fl_t *d_u, cudaStream_t st);
+// scalar rows for the L and R multiscalar multiplications over the ORIGINAL generators:
+// sL[j] = (j mod 2n) >= n ? a[(j mod 2n) - n] * w[j] : 0 ;  sR[j] = (j mod 2n) < n ? a[(j mod 2n) + n] * w[j] : 0
+void launch_bullet_scalars(const fl_t *a, const fl_t *w, size_t total, size_t n, fl_t *sL, fl_t *sR, cudaStream_t st);
+// out[i] = s * in[i]; d_s on device
+void launch_scale(const fl_t *in, const fl_t *d_s, size_t n, fl_t *out, cudaStream_t st);
+void launch_fill_one(fl_t *out, size_t n, cudaStream_t st);
+// Montgomery <-> canonical conversion of bulk arrays (C ABI takes canonical little-endian scalars)
+void launch_to_mont(const fl_t *in, size_t n, fl_t *out, cudaStream_t st);
+void launch_from_mont(const fl_t *in, size_t n, fl_t *out, cudaStream_t st);
+
+}  // namespace vpin

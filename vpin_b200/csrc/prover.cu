@@ -1,0 +1,1012 @@
+// B200 prover for vPIN's my_lib_prove / SNARK::encode. "SP/" = Spartan/src/, "VP/" = vPIN_proof_generation/src/.
+// Host side: Merlin transcript, random tape, O(1)-size sigma protocols, bincode. Device side: everything whose cost
+// grows with the instance (tables in HBM, see kernels_poly.cu / kernels_msm.cu).
+#include "prover.cuh"
+
+#include <time.h>
+
+#include <array>
+
+namespace vpin {
+
+typedef std::array<uint8_t, 32> Comp;
+
+static double now_ms() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+static Comp compress_host(const ge_t &g) {
+  Comp c;
+  ge_compress(g, c.data());
+  return c;
+}
+// Math::log_2 (SP/math.rs:27-35): exact for powers of two, ceil otherwise
+static size_t math_log2(size_t x) {
+  VPIN_REQUIRE(x != 0, VPIN_ERR_BAD_ARGUMENT, "log_2(0)");
+  return log2_ceil(x);
+}
+
+// ------------------------------------------------------------------------------------------------ bincode 1.3.3
+struct Bin {
+  std::vector<uint8_t> b;
+  void u64(uint64_t x) { b.insert(b.end(), (uint8_t *)&x, (uint8_t *)&x + 8); }
+  void fl(const fl_t &x) { b.insert(b.end(), (const uint8_t *)x.v, (const uint8_t *)x.v + 32); }  // raw Montgomery limbs
+  void comp(const Comp &c) { b.insert(b.end(), c.begin(), c.end()); }
+  void fls(const std::vector<fl_t> &v) { u64(v.size()); for (auto &x : v) fl(x); }
+  void comps(const std::vector<Comp> &v) { u64(v.size()); for (auto &x : v) comp(x); }
+};
+
+// proof pieces in the reference's field order
+struct DotProductProofS { Comp delta, beta; std::vector<fl_t> z; fl_t z_delta, z_beta; };
+static void put(Bin &o, const DotProductProofS &p) { o.comp(p.delta); o.comp(p.beta); o.fls(p.z); o.fl(p.z_delta); o.fl(p.z_beta); }
+struct ZkSumcheckS { std::vector<Comp> comm_polys, comm_evals; std::vector<DotProductProofS> proofs; };
+static void put(Bin &o, const ZkSumcheckS &p) {
+  o.comps(p.comm_polys); o.comps(p.comm_evals);
+  o.u64(p.proofs.size());
+  for (auto &x : p.proofs) put(o, x);
+}
+struct KnowledgeS { Comp alpha; fl_t z1, z2; };
+static void put(Bin &o, const KnowledgeS &p) { o.comp(p.alpha); o.fl(p.z1); o.fl(p.z2); }
+struct EqualityS { Comp alpha; fl_t z; };
+static void put(Bin &o, const EqualityS &p) { o.comp(p.alpha); o.fl(p.z); }
+struct ProductS { Comp alpha, beta, delta; fl_t z[5]; };
+static void put(Bin &o, const ProductS &p) { o.comp(p.alpha); o.comp(p.beta); o.comp(p.delta); for (int i = 0; i < 5; i++) o.fl(p.z[i]); }
+struct DotLogS { std::vector<Comp> L_vec, R_vec; Comp delta, beta; fl_t z1, z2; };  // PolyEvalProof { DotProductProofLog }
+static void put(Bin &o, const DotLogS &p) { o.comps(p.L_vec); o.comps(p.R_vec); o.comp(p.delta); o.comp(p.beta); o.fl(p.z1); o.fl(p.z2); }
+struct LayerS { std::vector<std::vector<fl_t>> polys; std::vector<fl_t> left, right; };  // LayerProofBatched
+struct BatchedS { std::vector<LayerS> layers; std::vector<fl_t> dotp[3]; };             // ProductCircuitEvalProofBatched
+static void put(Bin &o, const BatchedS &p) {
+  o.u64(p.layers.size());
+  for (auto &l : p.layers) {
+    o.u64(l.polys.size());
+    for (auto &c : l.polys) o.fls(c);
+    o.fls(l.left);
+    o.fls(l.right);
+  }
+  o.fls(p.dotp[0]); o.fls(p.dotp[1]); o.fls(p.dotp[2]);
+}
+
+// ------------------------------------------------------------------------------------------------ gens
+static void make_pc(Ctx *ctx, const LabelGens &lg, size_t ell, PcGens *pc) {
+  pc->ell = ell;
+  pc->L = (size_t)1 << (ell / 2);
+  pc->R = (size_t)1 << (ell - ell / 2);
+  pc->g1_index = pc->R;
+  pc->h_index = pc->R + 1;
+  VPIN_REQUIRE(pc->h_index < lg.n, VPIN_ERR_SIZE_MISMATCH, "generator stream too short");
+  pc->g1.build(lg.h_pts[pc->g1_index]);
+  pc->h.build(lg.h_pts[pc->h_index]);
+}
+// SP/lib.rs:305-326, SP/r1csproof.rs:84-89, SP/r1csinstance.rs:35-48, SP/sparse_mlpoly.rs:302-327
+std::unique_ptr<SnarkGens> snark_gens_create(Ctx *ctx, uint64_t num_cons, uint64_t num_vars, uint64_t num_inputs, uint64_t num_nz_entries) {
+  size_t num_vars_padded = next_pow2(std::max<size_t>(num_vars, num_inputs + 1));
+  VPIN_REQUIRE(num_inputs < num_vars_padded, VPIN_ERR_INVALID_NUM_INPUTS, "num_inputs must be < num_vars");
+  VPIN_REQUIRE(num_nz_entries > 0, VPIN_ERR_BAD_ARGUMENT, "num_nz_entries must be > 0");
+  auto g = std::make_unique<SnarkGens>();
+  size_t ell_sat = math_log2(num_vars_padded);
+  size_t R_sat = (size_t)1 << (ell_sat - ell_sat / 2);
+  g->sat_label = get_label_gens(ctx, "gens_r1cs_sat", std::max<size_t>(R_sat + 2, 5));
+  make_pc(ctx, *g->sat_label, ell_sat, &g->sat_pc);
+  for (int i = 0; i < 5; i++) g->sat_g[i].build(g->sat_label->h_pts[i]);
+  size_t nvx = math_log2(num_cons), nvy = math_log2(2 * num_vars_padded);
+  size_t k = math_log2(next_pow2(num_nz_entries));
+  size_t ell_ops = k + math_log2(next_pow2(3 * 5)), ell_mem = std::max(nvx, nvy) + 1, ell_derefs = k + math_log2(next_pow2(3 * 2));
+  size_t ell_max = std::max(ell_ops, std::max(ell_mem, ell_derefs));
+  size_t R_max = (size_t)1 << (ell_max - ell_max / 2);
+  g->eval_label = get_label_gens(ctx, "gens_r1cs_eval", R_max + 2);
+  make_pc(ctx, *g->eval_label, ell_ops, &g->ops_pc);
+  make_pc(ctx, *g->eval_label, ell_mem, &g->mem_pc);
+  make_pc(ctx, *g->eval_label, ell_derefs, &g->derefs_pc);
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------------ encode
+// SP/lib.rs:347-358 -> SP/r1csinstance.rs:309-321 -> SP/sparse_mlpoly.rs:500-520, :382-438, AddrTimestamps::new :232-265
+std::unique_ptr<Decomm> snark_encode(Ctx *ctx, const Instance &inst, const SnarkGens &gens, std::vector<uint8_t> *comm_bytes) {
+  cudaStream_t st = ctx->st;
+  auto d = std::make_unique<Decomm>();
+  size_t N = 1;
+  for (int k = 0; k < 3; k++) N = std::max(N, next_pow2(inst.M[k].nnz));
+  size_t nvx = math_log2(inst.num_cons), nvy = math_log2(2 * inst.num_vars);
+  size_t M = (size_t)1 << std::max(nvx, nvy);
+  d->N = N;
+  d->M = M;
+  VPIN_REQUIRE(math_log2(16 * N) == gens.ops_pc.ell && math_log2(2 * M) == gens.mem_pc.ell, VPIN_ERR_SIZE_MISMATCH,
+               "gens do not match the instance (SP/commitments.rs:95 assert)");
+  // read/audit timestamps: sequential replay, audit counters shared by the three matrices (:237-257)
+  std::vector<uint32_t> audit_row(M, 0), audit_col(M, 0), addr(N), rts(N);
+  d->comb_ops.alloc(16 * N, st);
+  d->comb_ops.zero();
+  for (int pass = 0; pass < 2; pass++) {
+    std::vector<uint32_t> &audit = pass == 0 ? audit_row : audit_col;
+    for (int k = 0; k < 3; k++) {
+      const std::vector<uint32_t> &src = pass == 0 ? inst.M[k].h_row : inst.M[k].h_col;
+      for (size_t i = 0; i < N; i++) {
+        uint32_t a = i < src.size() ? src[i] : 0;  // padding entries are (0, 0, 0) and do bump address 0 (:370-378)
+        addr[i] = a;
+        rts[i] = audit[a];
+        audit[a]++;
+      }
+      DevVec<uint32_t> &da = pass == 0 ? d->row_addr[k] : d->col_addr[k];
+      DevVec<uint32_t> &dt = pass == 0 ? d->row_read_ts[k] : d->col_read_ts[k];
+      da.alloc(N, st); dt.alloc(N, st);
+      da.upload(addr.data(), N);
+      dt.upload(rts.data(), N);
+      launch_u32_to_fl(da.p, N, d->comb_ops.p + (size_t)(pass * 6 + k) * N, st);
+      launch_u32_to_fl(dt.p, N, d->comb_ops.p + (size_t)(pass * 6 + 3 + k) * N, st);
+      ctx->sync();  // addr / rts are reused
+    }
+  }
+  for (int k = 0; k < 3; k++)
+    if (inst.M[k].nnz)
+      VPIN_CUDA(cudaMemcpyAsync(d->comb_ops.p + (12 + k) * N, inst.M[k].coo_val.p, inst.M[k].nnz * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
+  d->row_audit_ts.alloc(M, st); d->col_audit_ts.alloc(M, st);
+  d->row_audit_ts.upload(audit_row.data(), M);
+  d->col_audit_ts.upload(audit_col.data(), M);
+  d->comb_mem.alloc(2 * M, st);
+  launch_u32_to_fl(d->row_audit_ts.p, M, d->comb_mem.p, st);
+  launch_u32_to_fl(d->col_audit_ts.p, M, d->comb_mem.p + M, st);
+  // two Hyrax commitments without blinds (:507-508)
+  const PcGens &po = gens.ops_pc, &pm = gens.mem_pc;
+  DevVec<uint8_t> c_ops(32 * po.L, st), c_mem(32 * pm.L, st);
+  hyrax_rows(ctx, *gens.eval_label, d->comb_ops.p, po.L, po.R, po.R, nullptr, 0, nullptr, c_ops.p);
+  hyrax_rows(ctx, *gens.eval_label, d->comb_mem.p, pm.L, pm.R, pm.R, nullptr, 0, nullptr, c_mem.p);
+  std::vector<Comp> h_ops(po.L), h_mem(pm.L);
+  c_ops.download((uint8_t *)h_ops.data(), 32 * po.L);
+  c_mem.download((uint8_t *)h_mem.data(), 32 * pm.L);
+  ctx->sync();
+  // bincode(ComputationCommitment { comm: R1CSCommitment { num_cons, num_vars, num_inputs, comm: SparseMatPolyCommitment {
+  //   batch_size, num_ops, num_mem_cells, comm_comb_ops, comm_comb_mem } } })   SP/r1csinstance.rs:53-58, sparse_mlpoly.rs:332-338
+  Bin o;
+  o.u64(inst.num_cons); o.u64(inst.num_vars); o.u64(inst.num_inputs);
+  o.u64(3); o.u64(N); o.u64(M);
+  o.comps(h_ops);
+  o.comps(h_mem);
+  *comm_bytes = std::move(o.b);
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ prover
+namespace {
+
+struct Prover {
+  Ctx *ctx;
+  cudaStream_t st;
+  MerlinTranscript &t;
+  ProverTape &tape;
+  const SnarkGens &g;
+  size_t ring = 0;
+
+  // ---- tiny host <-> device traffic (challenges in, round sums out) ----
+  const fl_t *up(const fl_t *vals, size_t n) {  // returns the device address of n freshly uploaded elements
+    if (ring + n > 200) ring = 0;  // slots 240.. of d_small hold round results
+    memcpy(ctx->h_small + ring, vals, n * sizeof(fl_t));
+    fl_t *dst = ctx->d_small.p + ring;
+    VPIN_CUDA(cudaMemcpyAsync(dst, ctx->h_small + ring, n * sizeof(fl_t), cudaMemcpyHostToDevice, st));
+    ring += n;
+    return dst;
+  }
+  const fl_t *up(const std::vector<fl_t> &v) { return up(v.data(), v.size()); }
+  void down(const void *d, size_t bytes, void *out) {
+    VPIN_CUDA(cudaMemcpyAsync(ctx->h_small + 256, d, bytes, cudaMemcpyDeviceToHost, st));
+    ctx->sync();
+    memcpy(out, ctx->h_small + 256, bytes);
+  }
+  fl_t down1(const fl_t *d) { fl_t x; down(d, sizeof(fl_t), &x); return x; }
+
+  DevVec<fl_t> eq_table(const std::vector<fl_t> &r) {
+    size_t ell = r.size();
+    DevVec<fl_t> out((size_t)1 << ell, st), tmp(eq_tmp_elems(ell), st), dr(std::max<size_t>(ell, 1), st);
+    if (ell) dr.upload(r.data(), ell);
+    launch_eq_evals(dr.p, (int)ell, out.p, tmp.p, st);
+    ctx->sync();  // r (pageable) must stay alive until the copy ran
+    return out;
+  }
+  fl_t dot_dev(const fl_t *a, const fl_t *b, size_t n) {
+    launch_dot(a, b, n, ctx->d_small.p + 250, ctx->d_partials.p, st);
+    return down1(ctx->d_small.p + 250);
+  }
+
+  // ---- host commitments with the sat generators ----
+  ge_t commit1(const PcGens &pc, const fl_t &x, const fl_t &blind) {  // SP/commitments.rs:79-84
+    ge_t acc = ge_identity();
+    pc.g1.mul_acc(x, &acc);
+    pc.h.mul_acc(blind, &acc);
+    return acc;
+  }
+  ge_t commit_coeffs(const std::vector<fl_t> &c, const fl_t &blind) {  // gens_3 / gens_4 (SP/r1csproof.rs:62-72)
+    ge_t acc = ge_identity();
+    for (size_t i = 0; i < c.size(); i++) g.sat_g[i].mul_acc(c[i], &acc);
+    g.sat_g[c.size()].mul_acc(blind, &acc);
+    return acc;
+  }
+
+  // ---- SP/unipoly.rs:23-54 ----
+  static std::vector<fl_t> unipoly_from_evals(const std::vector<fl_t> &e) {
+    fl_t one = fl_one(), two = one + one;
+    fl_t two_inv = fl_invert(two);
+    if (e.size() == 3) {
+      fl_t c = e[0];
+      fl_t a = two_inv * (e[2] - e[1] - e[1] + c);
+      fl_t b = e[1] - c - a;
+      return {c, b, a};
+    }
+    fl_t six_inv = fl_invert(two + two + two);
+    fl_t d = e[0];
+    fl_t a = six_inv * (e[3] - e[2] - e[2] - e[2] + e[1] + e[1] + e[1] - e[0]);
+    fl_t b = two_inv * (e[0] + e[0] - e[1] - e[1] - e[1] - e[1] - e[1] + e[2] + e[2] + e[2] + e[2] - e[3]);
+    fl_t c = e[1] - d - a - b;
+    return {d, c, b, a};
+  }
+  static fl_t unipoly_eval(const std::vector<fl_t> &c, const fl_t &r) {  // :70-78
+    fl_t eval = c[0], power = r;
+    for (size_t i = 1; i < c.size(); i++) { eval = eval + power * c[i]; power = power * r; }
+    return eval;
+  }
+
+  // ---- SP/nizk/mod.rs ----
+  KnowledgeS knowledge_prove(const PcGens &pc, const fl_t &x, const fl_t &r, Comp *C_out) {  // :28-53
+    t.protocol_name("knowledge proof");
+    fl_t t1 = tape.scalar("t1"), t2 = tape.scalar("t2");
+    Comp C = compress_host(commit1(pc, x, r));
+    t.point("C", C.data());
+    Comp alpha = compress_host(commit1(pc, t1, t2));
+    t.point("alpha", alpha.data());
+    fl_t c = t.challenge_scalar("c");
+    *C_out = C;
+    return KnowledgeS{alpha, x * c + t1, r * c + t2};
+  }
+  EqualityS equality_prove(const PcGens &pc, const fl_t &v1, const fl_t &s1, const fl_t &v2, const fl_t &s2) {  // :90-118
+    t.protocol_name("equality proof");
+    fl_t r = tape.scalar("r");
+    Comp C1 = compress_host(commit1(pc, v1, s1));
+    t.point("C1", C1.data());
+    Comp C2 = compress_host(commit1(pc, v2, s2));
+    t.point("C2", C2.data());
+    Comp alpha = compress_host(pc.h.mul(r));
+    t.point("alpha", alpha.data());
+    fl_t c = t.challenge_scalar("c");
+    return EqualityS{alpha, c * (s1 - s2) + r};
+  }
+  ProductS product_prove(const PcGens &pc, const fl_t &x, const fl_t &rX, const fl_t &y, const fl_t &rY, const fl_t &z, const fl_t &rZ,
+                         Comp *Xo, Comp *Yo, Comp *Zo) {  // :162-232
+    t.protocol_name("product proof");
+    fl_t b1 = tape.scalar("b1"), b2 = tape.scalar("b2"), b3 = tape.scalar("b3"), b4 = tape.scalar("b4"), b5 = tape.scalar("b5");
+    Comp X = compress_host(commit1(pc, x, rX));
+    t.point("X", X.data());
+    Comp Y = compress_host(commit1(pc, y, rY));
+    t.point("Y", Y.data());
+    Comp Z = compress_host(commit1(pc, z, rZ));
+    t.point("Z", Z.data());
+    Comp alpha = compress_host(commit1(pc, b1, b2));
+    t.point("alpha", alpha.data());
+    Comp beta = compress_host(commit1(pc, b3, b4));
+    t.point("beta", beta.data());
+    // delta = b3 * X + b5 * h with X = x*G + rX*h  ==  (b3*x) * G + (b3*rX + b5) * h   (:202-209)
+    Comp delta = compress_host(commit1(pc, b3 * x, b3 * rX + b5));
+    t.point("delta", delta.data());
+    fl_t c = t.challenge_scalar("c");
+    ProductS p;
+    p.alpha = alpha; p.beta = beta; p.delta = delta;
+    p.z[0] = b1 + c * x;
+    p.z[1] = b2 + c * rX;
+    p.z[2] = b3 + c * y;
+    p.z[3] = b4 + c * rY;
+    p.z[4] = b5 + c * (rZ - rX * y);
+    *Xo = X; *Yo = Y; *Zo = Z;
+    return p;
+  }
+  // DotProductProof::prove with gens_n = gens_3 / gens_4 and gens_1 of the sat gens (:315-374). Cx is the already
+  // computed commitment to x_vec under blind_x (the round's comm_poly).
+  DotProductProofS dotproduct_prove(const std::vector<fl_t> &x_vec, const fl_t &blind_x, const Comp &Cx, const std::vector<fl_t> &a_vec,
+                                    const fl_t &y, const fl_t &blind_y) {
+    t.protocol_name("dot product proof");
+    size_t n = x_vec.size();
+    std::vector<fl_t> d_vec = tape.vector("d_vec", n);
+    fl_t r_delta = tape.scalar("r_delta"), r_beta = tape.scalar("r_beta");
+    t.point("Cx", Cx.data());
+    Comp Cy = compress_host(commit1(g.sat_pc, y, blind_y));
+    t.point("Cy", Cy.data());
+    t.scalars("a", a_vec);
+    Comp delta = compress_host(commit_coeffs(d_vec, r_delta));
+    t.point("delta", delta.data());
+    fl_t dot = fl_zero();
+    for (size_t i = 0; i < n; i++) dot = dot + a_vec[i] * d_vec[i];
+    Comp beta = compress_host(commit1(g.sat_pc, dot, r_beta));
+    t.point("beta", beta.data());
+    fl_t c = t.challenge_scalar("c");
+    DotProductProofS p;
+    p.delta = delta; p.beta = beta;
+    p.z.resize(n);
+    for (size_t i = 0; i < n; i++) p.z[i] = c * x_vec[i] + d_vec[i];
+    p.z_delta = c * blind_x + r_delta;
+    p.z_beta = c * blind_y + r_beta;
+    return p;
+  }
+
+  // ---- ZK sumchecks (SP/sumcheck.rs:428-776). eval_round(half, out) enqueues the round kernel writing `nev` sums to
+  // d_small+240..; bind(half, d_r) enqueues the binds. ----
+  template <class EvalFn, class BindFn>
+  ZkSumcheckS zk_sumcheck(const fl_t &claim, const fl_t &blind_claim, size_t num_rounds, size_t len, int degree, EvalFn eval_round,
+                          BindFn bind, std::vector<fl_t> *r_out, fl_t *blind_post) {
+    std::vector<fl_t> blinds_poly = tape.vector("blinds_poly", num_rounds);
+    std::vector<fl_t> blinds_evals = tape.vector("blinds_evals", num_rounds);
+    fl_t claim_per_round = claim;
+    Comp comm_claim_per_round = compress_host(commit1(g.sat_pc, claim_per_round, blind_claim));
+    ZkSumcheckS out;
+    std::vector<fl_t> r;
+    fl_t *d_ev = ctx->d_small.p + 240;
+    for (size_t j = 0; j < num_rounds; j++) {
+      size_t half = len >> (j + 1);
+      eval_round(half, d_ev);
+      fl_t ev[3];
+      down(d_ev, degree * sizeof(fl_t), ev);
+      std::vector<fl_t> evals = degree == 3 ? std::vector<fl_t>{ev[0], claim_per_round - ev[0], ev[1], ev[2]}
+                                            : std::vector<fl_t>{ev[0], claim_per_round - ev[0], ev[1]};
+      std::vector<fl_t> poly = unipoly_from_evals(evals);
+      Comp comm_poly = compress_host(commit_coeffs(poly, blinds_poly[j]));
+      t.point("comm_poly", comm_poly.data());
+      out.comm_polys.push_back(comm_poly);
+      fl_t r_j = t.challenge_scalar("challenge_nextround");
+      bind(half, up(&r_j, 1));  // device binds run while the host finishes the round
+      fl_t eval = unipoly_eval(poly, r_j);
+      Comp comm_eval = compress_host(commit1(g.sat_pc, eval, blinds_evals[j]));
+      t.point("comm_claim_per_round", comm_claim_per_round.data());
+      t.point("comm_eval", comm_eval.data());
+      std::vector<fl_t> w = t.challenge_vector("combine_two_claims_to_one", 2);
+      fl_t target = w[0] * claim_per_round + w[1] * eval;
+      const fl_t &blind_sc = j == 0 ? blind_claim : blinds_evals[j - 1];
+      fl_t blind = w[0] * blind_sc + w[1] * blinds_evals[j];
+      // the reference asserts target.commit(blind) == w0*comm_claim + w1*comm_eval (:531, :722); it holds by
+      // linearity of the commitments computed above, so the variable-base MSM is not recomputed here.
+      size_t deg = poly.size() - 1;
+      std::vector<fl_t> a(deg + 1);
+      fl_t pw = fl_one();
+      for (size_t i = 0; i <= deg; i++) {
+        fl_t a_sc = i == 0 ? fl_one() + fl_one() : fl_one();
+        a[i] = w[0] * a_sc + w[1] * pw;
+        pw = pw * r_j;
+      }
+      out.proofs.push_back(dotproduct_prove(poly, blinds_poly[j], comm_poly, a, target, blind));
+      claim_per_round = eval;
+      comm_claim_per_round = comm_eval;
+      r.push_back(r_j);
+      out.comm_evals.push_back(comm_eval);
+    }
+    *r_out = r;
+    *blind_post = blinds_evals[num_rounds - 1];
+    return out;
+  }
+
+  // ---- one fixed-base MSM row set returning extended points on the host ----
+  std::vector<ge_t> msm_rows_host(const LabelGens &lg, const fl_t *d_scalars, size_t rows, size_t cols, size_t ld) {
+    DevVec<ge_t> pts(rows, st);
+    hyrax_rows(ctx, lg, d_scalars, rows, cols, ld, nullptr, 0, pts.p, nullptr);
+    std::vector<ge_t> h(rows);
+    pts.download(h.data(), rows);
+    ctx->sync();
+    return h;
+  }
+
+  // ---- DotProductProofLog::prove (SP/nizk/mod.rs:447-531) + BulletReductionProof::prove (SP/nizk/bullet.rs:32-132).
+  // x_vec, a_vec: device vectors of length n = pc.R. The reference folds the generators every round
+  // (G_L[i] = u^-1 G_L[i] + u G_R[i]); here the folded generators are never materialised: a weight vector W over the
+  // ORIGINAL generators tracks the folding, so every L, R and g_hat is a fixed-base MSM over the same table.
+  DotLogS dotproductlog_prove(const PcGens &pc, const LabelGens &lg, const fl_t *d_x, const fl_t &blind_x, const fl_t *d_a, const fl_t &y,
+                              const fl_t &blind_y, Comp *Cy_out) {
+    t.protocol_name("dot product proof (log)");
+    size_t n = pc.R, lg_n = math_log2(n);
+    fl_t d = tape.scalar("d");
+    fl_t r_delta = tape.scalar("r_delta");
+    fl_t r_beta = tape.scalar("r_delta");  // sic (mod.rs:466)
+    std::vector<fl_t> bv1 = tape.vector("blinds_vec_1", 2 * lg_n), bv2 = tape.vector("blinds_vec_2", 2 * lg_n);
+    // Cx = x_vec.commit(blind_x, gens_n)
+    ge_t cx = msm_rows_host(lg, d_x, 1, n, n)[0];
+    pc.h.mul_acc(blind_x, &cx);
+    Comp Cx = compress_host(cx);
+    t.point("Cx", Cx.data());
+    Comp Cy = compress_host(commit1(pc, y, blind_y));
+    t.point("Cy", Cy.data());
+    {
+      std::vector<fl_t> a_host(n);
+      VPIN_CUDA(cudaMemcpyAsync(a_host.data(), d_a, n * sizeof(fl_t), cudaMemcpyDeviceToHost, st));
+      ctx->sync();
+      t.scalars("a", a_host);
+    }
+    fl_t r = t.challenge_scalar("r");  // Q = r * gens_1.G[0]
+    fl_t blind_fin = blind_x + r * blind_y;
+    DevVec<fl_t> a(n, st), b(n, st), W(n, st), srows(2 * n, st);
+    VPIN_CUDA(cudaMemcpyAsync(a.p, d_x, n * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
+    VPIN_CUDA(cudaMemcpyAsync(b.p, d_a, n * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
+    launch_fill_one(W.p, n, st);
+    DotLogS out;
+    size_t cur = n;
+    for (size_t round = 0; cur != 1; round++) {
+      cur /= 2;
+      fl_t *d_c = ctx->d_small.p + 244;
+      launch_dot(a.p, b.p + cur, cur, d_c, ctx->d_partials.p, st);      // c_L = <a_L, b_R>
+      launch_dot(a.p + cur, b.p, cur, d_c + 1, ctx->d_partials.p, st);  // c_R = <a_R, b_L>
+      launch_bullet_scalars(a.p, W.p, n, cur, srows.p, srows.p + n, st);
+      std::vector<ge_t> LR = msm_rows_host(lg, srows.p, 2, n, n);
+      fl_t c[2];
+      down(d_c, 2 * sizeof(fl_t), c);
+      const fl_t &blind_L = bv1[round], &blind_R = bv2[round];
+      pc.g1.mul_acc(c[0] * r, &LR[0]);
+      pc.h.mul_acc(blind_L, &LR[0]);
+      pc.g1.mul_acc(c[1] * r, &LR[1]);
+      pc.h.mul_acc(blind_R, &LR[1]);
+      Comp Lc = compress_host(LR[0]), Rc = compress_host(LR[1]);
+      t.point("L", Lc.data());
+      t.point("R", Rc.data());
+      fl_t u = t.challenge_scalar("u");
+      fl_t u_inv = fl_invert(u);
+      fl_t uu[2] = {u, u_inv};
+      const fl_t *d_u = up(uu, 2);
+      launch_bullet_fold(a.p, b.p, cur, d_u, st);
+      launch_bullet_weights(W.p, n, cur, d_u, st);
+      blind_fin = blind_fin + blind_L * u * u + blind_R * u_inv * u_inv;
+      out.L_vec.push_back(Lc);
+      out.R_vec.push_back(Rc);
+    }
+    fl_t x_hat = down1(a.p), a_hat = down1(b.p);
+    fl_t y_hat = x_hat * a_hat;
+    // delta = d * g_hat + r_delta * h with g_hat = sum_j W_j G_j
+    launch_scale(W.p, up(&d, 1), n, srows.p, st);
+    ge_t dl = msm_rows_host(lg, srows.p, 1, n, n)[0];
+    pc.h.mul_acc(r_delta, &dl);
+    out.delta = compress_host(dl);
+    t.point("delta", out.delta.data());
+    out.beta = compress_host(commit1(pc, d * r, r_beta));  // d * Q + r_beta * h
+    t.point("beta", out.beta.data());
+    fl_t c = t.challenge_scalar("c");
+    out.z1 = d + c * y_hat;
+    out.z2 = a_hat * (c * blind_fin + r_beta) + r_delta;
+    if (Cy_out) *Cy_out = Cy;
+    return out;
+  }
+
+  // ---- PolyEvalProof::prove (SP/dense_mlpoly.rs:326-379). d_blinds: device blinds (L elements) or nullptr for zeros.
+  DotLogS polyeval_prove(const PcGens &pc, const LabelGens &lg, const fl_t *d_Z, const fl_t *d_blinds, const std::vector<fl_t> &r,
+                         const fl_t &Zr, const fl_t &blind_Zr, Comp *C_Zr_prime) {
+    t.protocol_name("polynomial evaluation proof");
+    VPIN_REQUIRE(r.size() == pc.ell, VPIN_ERR_SIZE_MISMATCH, "polyeval: point size");
+    size_t l = pc.ell / 2;
+    DevVec<fl_t> dL = eq_table(std::vector<fl_t>(r.begin(), r.begin() + l));
+    DevVec<fl_t> dR = eq_table(std::vector<fl_t>(r.begin() + l, r.end()));
+    DevVec<fl_t> LZ(pc.R, st), tmp(64 * pc.R, st);
+    launch_bound(d_Z, dL.p, pc.L, pc.R, LZ.p, tmp.p, st);
+    fl_t LZ_blind = d_blinds ? dot_dev(d_blinds, dL.p, pc.L) : fl_zero();
+    return dotproductlog_prove(pc, lg, LZ.p, LZ_blind, dR.p, Zr, blind_Zr, C_Zr_prime);
+  }
+  // DensePolynomial::evaluate (SP/dense_mlpoly.rs:249-255) of a device table
+  fl_t evaluate_dev(const fl_t *d_Z, const std::vector<fl_t> &r) {
+    DevVec<fl_t> chis = eq_table(r);
+    return dot_dev(d_Z, chis.p, (size_t)1 << r.size());
+  }
+
+  // ---- ProductCircuitEvalProofBatched::prove (SP/product_tree.rs:259-383) with prove_cubic_batched
+  // (SP/sumcheck.rs:254-424). trees[c]: the circuit's layers packed [V_0 | V_1 | ... | V_last] (V_0 = n leaves).
+  // dotp: optional (left, right, weight) tables of length n/2 each, bound in place.
+  struct DotpTables { fl_t *l, *r, *w; fl_t claim; };
+  BatchedS batched_prove(const std::vector<fl_t *> &trees, size_t n, std::vector<DotpTables> dotp, const std::vector<fl_t> &tree_evals,
+                         std::vector<fl_t> *rand_out) {
+    BatchedS out;
+    size_t num_layers = math_log2(n), nc = trees.size();
+    std::vector<fl_t> claims_to_verify = tree_evals;
+    std::vector<fl_t> rand;
+    DevVec<const fl_t *> dA(nc + dotp.size(), st), dB(nc + dotp.size(), st), dC(nc + dotp.size(), st);
+    DevVec<fl_t *> dBind(2 * nc + 1 + 3 * dotp.size(), st);
+    for (size_t layer_id = num_layers; layer_id-- > 0;) {
+      size_t vlen = n >> layer_id;       // |V_layer|
+      size_t off = 2 * n - 2 * vlen;     // offset of V_layer inside a packed tree
+      size_t len_half = vlen / 2;
+      DevVec<fl_t> eqC = eq_table(rand);
+      VPIN_REQUIRE(((size_t)1 << rand.size()) == len_half, VPIN_ERR_PROVER, "layer size");
+      size_t num_rounds = rand.size();
+      bool with_dotp = layer_id == 0 && !dotp.empty();
+      size_t ninst = nc + (with_dotp ? dotp.size() : 0);
+      std::vector<const fl_t *> hA(ninst), hB(ninst), hC(ninst);
+      std::vector<fl_t *> hBind;
+      for (size_t c = 0; c < nc; c++) {
+        hA[c] = trees[c] + off; hB[c] = trees[c] + off + len_half; hC[c] = eqC.p;
+        hBind.push_back(trees[c] + off); hBind.push_back(trees[c] + off + len_half);
+      }
+      hBind.push_back(eqC.p);
+      if (with_dotp)
+        for (size_t k = 0; k < dotp.size(); k++) {
+          claims_to_verify.push_back(dotp[k].claim);
+          hA[nc + k] = dotp[k].l; hB[nc + k] = dotp[k].r; hC[nc + k] = dotp[k].w;
+          hBind.push_back(dotp[k].l); hBind.push_back(dotp[k].r); hBind.push_back(dotp[k].w);
+        }
+      dA.upload(hA.data(), ninst); dB.upload(hB.data(), ninst); dC.upload(hC.data(), ninst);
+      dBind.upload(hBind.data(), hBind.size());
+      ctx->sync();
+      std::vector<fl_t> coeffs = t.challenge_vector("rand_coeffs_next_layer", claims_to_verify.size());
+      fl_t e = fl_zero();
+      for (size_t i = 0; i < coeffs.size(); i++) e = e + claims_to_verify[i] * coeffs[i];
+      LayerS layer;
+      std::vector<fl_t> rand_prod;
+      DevVec<fl_t> d_ev(3 * ninst, st);
+      std::vector<fl_t> ev(3 * ninst);
+      for (size_t j = 0; j < num_rounds; j++) {
+        size_t half = len_half >> (j + 1);
+        launch_cubic_batched_round(dA.p, dB.p, dC.p, (int)ninst, half, d_ev.p, ctx->d_partials.p, st);
+        d_ev.download(ev.data(), 3 * ninst);
+        ctx->sync();
+        fl_t c0 = fl_zero(), c2 = fl_zero(), c3 = fl_zero();
+        for (size_t i = 0; i < ninst; i++) {
+          c0 = c0 + ev[3 * i] * coeffs[i];
+          c2 = c2 + ev[3 * i + 1] * coeffs[i];
+          c3 = c3 + ev[3 * i + 2] * coeffs[i];
+        }
+        std::vector<fl_t> poly = unipoly_from_evals({c0, e - c0, c2, c3});
+        // UniPoly::append_to_transcript (SP/unipoly.rs:111-119)
+        t.message("poly", "UniPoly_begin");
+        for (auto &c : poly) t.scalar("coeff", c);
+        t.message("poly", "UniPoly_end");
+        fl_t r_j = t.challenge_scalar("challenge_nextround");
+        rand_prod.push_back(r_j);
+        launch_bind_top_multi(dBind.p, (int)hBind.size(), half, up(&r_j, 1), st);
+        e = unipoly_eval(poly, r_j);
+        layer.polys.push_back({poly[0], poly[2], poly[3]});  // CompressedUniPoly (SP/unipoly.rs:80-87)
+      }
+      // final claims: first element of every bound table
+      std::vector<fl_t> fin(hBind.size());
+      {
+        DevVec<fl_t> d_fin(hBind.size(), st);
+        for (size_t i = 0; i < hBind.size(); i++)
+          VPIN_CUDA(cudaMemcpyAsync(d_fin.p + i, hBind[i], sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
+        d_fin.download(fin.data(), fin.size());
+        ctx->sync();
+      }
+      for (size_t c = 0; c < nc; c++) { layer.left.push_back(fin[2 * c]); layer.right.push_back(fin[2 * c + 1]); }
+      for (size_t c = 0; c < nc; c++) {
+        t.scalar("claim_prod_left", layer.left[c]);
+        t.scalar("claim_prod_right", layer.right[c]);
+      }
+      if (with_dotp) {
+        for (size_t k = 0; k < dotp.size(); k++) {
+          fl_t l = fin[2 * nc + 1 + 3 * k], r = fin[2 * nc + 2 + 3 * k], w = fin[2 * nc + 3 + 3 * k];
+          t.scalar("claim_dotp_left", l);
+          t.scalar("claim_dotp_right", r);
+          t.scalar("claim_dotp_weight", w);
+          out.dotp[0].push_back(l); out.dotp[1].push_back(r); out.dotp[2].push_back(w);
+        }
+      }
+      fl_t r_layer = t.challenge_scalar("challenge_r_layer");
+      claims_to_verify.clear();
+      for (size_t c = 0; c < nc; c++) claims_to_verify.push_back(layer.left[c] + r_layer * (layer.right[c] - layer.left[c]));
+      std::vector<fl_t> ext = {r_layer};
+      ext.insert(ext.end(), rand_prod.begin(), rand_prod.end());
+      rand = ext;
+      out.layers.push_back(std::move(layer));
+    }
+    *rand_out = rand;
+    return out;
+  }
+};
+
+// builds the packed product tree of `n` leaves already stored at tree[0..n) (SP/product_tree.rs:18-56)
+void build_tree(fl_t *tree, size_t n, cudaStream_t st) {
+  size_t off = 0;
+  for (size_t vlen = n; vlen > 2; vlen /= 2) {
+    launch_mul_halves(tree + off, vlen / 2, tree + off + vlen, st);
+    off += vlen;
+  }
+}
+
+}  // namespace
+
+bool instance_is_sat(Ctx *ctx, const Instance &inst, const uint8_t *vars32, uint64_t n_vars, const uint8_t *inputs32, uint64_t n_inputs) {
+  cudaStream_t st = ctx->st;
+  size_t nz = 2 * inst.num_vars;
+  std::vector<fl_t> z(nz, fl_zero());
+  for (size_t i = 0; i < n_vars; i++) VPIN_REQUIRE(fl_from_bytes(vars32 + 32 * i, &z[i]), VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
+  z[inst.num_vars] = fl_one();
+  for (size_t i = 0; i < n_inputs; i++) VPIN_REQUIRE(fl_from_bytes(inputs32 + 32 * i, &z[inst.num_vars + 1 + i]), VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
+  DevVec<fl_t> dz(nz, st), out(3 * inst.num_cons, st);
+  dz.upload(z.data(), nz);
+  for (int k = 0; k < 3; k++) launch_spmv_csr(csr_of(inst.M[k], inst.num_cons), dz.p, out.p + k * inst.num_cons, st);
+  std::vector<fl_t> h(3 * inst.num_cons);
+  out.download(h.data(), h.size());
+  ctx->sync();
+  for (size_t i = 0; i < inst.num_cons; i++)
+    if (!fl_eq(h[i] * h[inst.num_cons + i], h[2 * inst.num_cons + i])) return false;
+  return true;
+}
+
+// VP/commit_test.rs:59-334 (my_lib_prove + my_R1CSProof_prove) and SP/sparse_mlpoly.rs:1466-1533 (SPARK)
+std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &dec, const Witness &wit, const std::vector<fl_t> &inputs,
+                                 const SnarkGens &g, const uint8_t *label, size_t label_len, const fl_t &tape_seed) {
+  cudaStream_t st = ctx->st;
+  ctx->phases.clear();
+  double t_prove = now_ms(), t0;
+  auto phase = [&](const char *name, double start) { ctx->sync(); ctx->phases.push_back({name, now_ms() - start}); };
+  MerlinTranscript t(label, label_len);
+  ProverTape tape("proof", 5, tape_seed);
+  Prover P{ctx, st, t, tape, g};
+  const PcGens &spc = g.sat_pc;
+  size_t num_vars = inst.num_vars, num_cons = inst.num_cons, num_inputs = inputs.size();
+  VPIN_REQUIRE(wit.n_vars == num_vars && num_inputs < num_vars, VPIN_ERR_SIZE_MISMATCH, "witness size");
+  VPIN_REQUIRE(spc.L * spc.R == num_vars && wit.comm.size() == 32 * spc.L, VPIN_ERR_SIZE_MISMATCH, "gens do not match the witness");
+
+  t.protocol_name("Spartan SNARK proof");  // VP/commit_test.rs:75 (no comm append, unlike SP/lib.rs:377)
+  double t_sat = now_ms();
+  t.protocol_name("R1CS proof");           // :148 (no input append, unlike SP/r1csproof.rs:175)
+  t0 = now_ms();
+  // comm_vars.append_to_transcript (SP/dense_mlpoly.rs:305-313)
+  t.message("poly_commitment", "poly_commitment_begin");
+  for (size_t i = 0; i < spc.L; i++) t.point("poly_commitment_share", wit.comm.data() + 32 * i);
+  t.message("poly_commitment", "poly_commitment_end");
+  phase("polycommit", t0);
+
+  t0 = now_ms();
+  // z = vars || 1 || inputs || 0...   (:162-170)
+  size_t zlen = 2 * num_vars;
+  DevVec<fl_t> z(zlen, st);
+  z.zero();
+  VPIN_CUDA(cudaMemcpyAsync(z.p, wit.d_vars.p, num_vars * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
+  {
+    std::vector<fl_t> one_in(1 + num_inputs);
+    one_in[0] = fl_one();
+    for (size_t i = 0; i < num_inputs; i++) one_in[1 + i] = inputs[i];
+    VPIN_CUDA(cudaMemcpyAsync(z.p + num_vars, one_in.data(), one_in.size() * sizeof(fl_t), cudaMemcpyHostToDevice, st));
+    ctx->sync();
+  }
+  size_t num_rounds_x = math_log2(num_cons), num_rounds_y = math_log2(zlen);
+  std::vector<fl_t> tau = t.challenge_vector("challenge_tau", num_rounds_x);
+  DevVec<fl_t> poly_tau = P.eq_table(tau);
+  DevVec<fl_t> ABCz(3 * num_cons, st);
+  for (int k = 0; k < 3; k++) launch_spmv_csr(csr_of(inst.M[k], num_cons), z.p, ABCz.p + k * num_cons, st);
+  fl_t *Az = ABCz.p, *Bz = ABCz.p + num_cons, *Cz = ABCz.p + 2 * num_cons;
+  // phase 1: sum_x eq(tau,x) (Az Bz - Cz) = 0   (SP/r1csproof.rs:94-127)
+  std::vector<fl_t> rx;
+  fl_t blind_claim_postsc1;
+  ZkSumcheckS sc1 = P.zk_sumcheck(
+      fl_zero(), fl_zero(), num_rounds_x, num_cons, 3,
+      [&](size_t half, fl_t *d_out) { launch_cubic_additive_round(poly_tau.p, Az, Bz, Cz, half, d_out, ctx->d_partials.p, st); },
+      [&](size_t half, const fl_t *d_r) {
+        launch_bind_top(poly_tau.p, half, d_r, st);
+        launch_bind_top(Az, half, d_r, st);
+        launch_bind_top(Bz, half, d_r, st);
+        launch_bind_top(Cz, half, d_r, st);
+      },
+      &rx, &blind_claim_postsc1);
+  fl_t tau_claim = P.down1(poly_tau.p), Az_claim = P.down1(Az), Bz_claim = P.down1(Bz), Cz_claim = P.down1(Cz);
+  phase("prove_sc_phase_one", t0);
+
+  fl_t Az_blind = tape.scalar("Az_blind"), Bz_blind = tape.scalar("Bz_blind"), Cz_blind = tape.scalar("Cz_blind"),
+       prod_Az_Bz_blind = tape.scalar("prod_Az_Bz_blind");
+  Comp comm_Cz_claim, comm_Az_claim, comm_Bz_claim, comm_prod_Az_Bz_claims;
+  KnowledgeS pok_Cz_claim = P.knowledge_prove(spc, Cz_claim, Cz_blind, &comm_Cz_claim);
+  ProductS proof_prod = P.product_prove(spc, Az_claim, Az_blind, Bz_claim, Bz_blind, Az_claim * Bz_claim, prod_Az_Bz_blind, &comm_Az_claim,
+                                        &comm_Bz_claim, &comm_prod_Az_Bz_claims);
+  t.point("comm_Az_claim", comm_Az_claim.data());
+  t.point("comm_Bz_claim", comm_Bz_claim.data());
+  t.point("comm_Cz_claim", comm_Cz_claim.data());
+  t.point("comm_prod_Az_Bz_claims", comm_prod_Az_Bz_claims.data());
+  fl_t blind_expected_claim_postsc1 = tau_claim * (prod_Az_Bz_blind - Cz_blind);
+  fl_t claim_post_phase1 = (Az_claim * Bz_claim - Cz_claim) * tau_claim;
+  EqualityS proof_eq_sc_phase1 = P.equality_prove(spc, claim_post_phase1, blind_expected_claim_postsc1, claim_post_phase1, blind_claim_postsc1);
+
+  t0 = now_ms();
+  fl_t r_A = t.challenge_scalar("challenege_Az"), r_B = t.challenge_scalar("challenege_Bz"), r_C = t.challenge_scalar("challenege_Cz");
+  fl_t claim_phase2 = r_A * Az_claim + r_B * Bz_claim + r_C * Cz_claim;
+  fl_t blind_claim_phase2 = r_A * Az_blind + r_B * Bz_blind + r_C * Cz_blind;
+  // evals_ABC = rA * A^T eq(rx) + rB * B^T eq(rx) + rC * C^T eq(rx)   (:257-268)
+  DevVec<fl_t> evals_ABC(zlen, st);
+  {
+    DevVec<fl_t> evals_rx = P.eq_table(rx);
+    fl_t rr[3] = {r_A, r_B, r_C};
+    const fl_t *d_rr = P.up(rr, 3);
+    for (int k = 0; k < 3; k++) launch_spmv_csc_scaled(csc_of(inst.M[k], zlen), evals_rx.p, d_rr + k, k != 0, evals_ABC.p, st);
+    ctx->sync();
+  }
+  std::vector<fl_t> ry;
+  fl_t blind_claim_postsc2;
+  ZkSumcheckS sc2 = P.zk_sumcheck(
+      claim_phase2, blind_claim_phase2, num_rounds_y, zlen, 2,
+      [&](size_t half, fl_t *d_out) { launch_quad_round(z.p, evals_ABC.p, half, d_out, ctx->d_partials.p, st); },
+      [&](size_t half, const fl_t *d_r) {
+        launch_bind_top(z.p, half, d_r, st);
+        launch_bind_top(evals_ABC.p, half, d_r, st);
+      },
+      &ry, &blind_claim_postsc2);
+  fl_t claims_phase2[2] = {P.down1(z.p), P.down1(evals_ABC.p)};
+  phase("prove_sc_phase_two", t0);
+
+  t0 = now_ms();
+  std::vector<fl_t> ry1(ry.begin() + 1, ry.end());
+  fl_t eval_vars_at_ry = P.evaluate_dev(wit.d_vars.p, ry1);
+  fl_t blind_eval = tape.scalar("blind_eval");
+  Comp comm_vars_at_ry;
+  DotLogS proof_eval_vars_at_ry = P.polyeval_prove(spc, *g.sat_label, wit.d_vars.p, wit.d_blinds.p, ry1, eval_vars_at_ry, blind_eval, &comm_vars_at_ry);
+  phase("polyeval", t0);
+  fl_t blind_eval_Z_at_ry = (fl_one() - ry[0]) * blind_eval;
+  fl_t blind_expected_claim_postsc2 = claims_phase2[1] * blind_eval_Z_at_ry;
+  fl_t claim_post_phase2 = claims_phase2[0] * claims_phase2[1];
+  EqualityS proof_eq_sc_phase2 = P.equality_prove(spc, claim_post_phase2, blind_expected_claim_postsc2, claim_post_phase2, blind_claim_postsc2);
+  phase("R1CSProof::prove", t_sat);
+
+  // inst.evaluate(rx, ry) (SP/r1csinstance.rs:304-307) and the three claims (VP/commit_test.rs:102-108)
+  t0 = now_ms();
+  fl_t inst_evals[3];
+  {
+    DevVec<fl_t> trx = P.eq_table(rx), try_ = P.eq_table(ry);
+    for (int k = 0; k < 3; k++) {
+      launch_sparse_eval(inst.M[k].coo_row.p, inst.M[k].coo_col.p, inst.M[k].coo_val.p, inst.M[k].nnz, trx.p, try_.p, ctx->d_small.p + 248,
+                         ctx->d_partials.p, st);
+      inst_evals[k] = P.down1(ctx->d_small.p + 248);
+    }
+  }
+  t.scalar("Ar_claim", inst_evals[0]);
+  t.scalar("Br_claim", inst_evals[1]);
+  t.scalar("Cr_claim", inst_evals[2]);
+  phase("eval_sparse_polys", t0);
+
+  // ---------------- R1CSEvalProof::prove -> SparseMatPolyEvalProof::prove (SP/sparse_mlpoly.rs:1466-1533) ----------------
+  double t_eval = now_ms();
+  size_t N = dec.N, M = dec.M;
+  t.protocol_name("Sparse polynomial evaluation proof");
+  std::vector<fl_t> rx_ext = rx, ry_ext = ry;  // equalize (:1448-1464)
+  if (rx.size() < ry.size()) { rx_ext.assign(ry.size() - rx.size(), fl_zero()); rx_ext.insert(rx_ext.end(), rx.begin(), rx.end()); }
+  else if (rx.size() > ry.size()) { ry_ext.assign(rx.size() - ry.size(), fl_zero()); ry_ext.insert(ry_ext.end(), ry.begin(), ry.end()); }
+  VPIN_REQUIRE(((size_t)1 << rx_ext.size()) == M, VPIN_ERR_SIZE_MISMATCH, "memory size");
+  DevVec<fl_t> mem_rx = P.eq_table(rx_ext), mem_ry = P.eq_table(ry_ext);
+  // derefs (:525-530, :267-282) merged as row A,B,C | col A,B,C | 0 | 0 (:61)
+  DevVec<fl_t> derefs(8 * N, st);
+  derefs.zero();
+  for (int k = 0; k < 3; k++) {
+    launch_gather(dec.row_addr[k].p, mem_rx.p, N, derefs.p + (size_t)k * N, st);
+    launch_gather(dec.col_addr[k].p, mem_ry.p, N, derefs.p + (size_t)(3 + k) * N, st);
+  }
+  t0 = now_ms();
+  const PcGens &dpc = g.derefs_pc;
+  VPIN_REQUIRE(dpc.L * dpc.R == 8 * N, VPIN_ERR_SIZE_MISMATCH, "derefs gens");
+  std::vector<Comp> comm_derefs(dpc.L);
+  {
+    DevVec<uint8_t> dc(32 * dpc.L, st);
+    hyrax_rows(ctx, *g.eval_label, derefs.p, dpc.L, dpc.R, dpc.R, nullptr, 0, nullptr, dc.p);
+    dc.download((uint8_t *)comm_derefs.data(), 32 * dpc.L);
+    ctx->sync();
+  }
+  // DerefsCommitment::append_to_transcript (:216-222)
+  t.message("derefs_commitment", "begin_derefs_commitment");
+  t.message("comm_poly_row_col_ops_val", "poly_commitment_begin");
+  for (auto &c : comm_derefs) t.point("poly_commitment_share", c.data());
+  t.message("comm_poly_row_col_ops_val", "poly_commitment_end");
+  t.message("derefs_commitment", "end_derefs_commitment");
+  phase("commit_nondet_witness", t0);
+
+  std::vector<fl_t> r_mem_check = t.challenge_vector("challenge_r_hash", 2);
+  t0 = now_ms();
+  // hash layers + product trees (:547-671). Packed trees: 2 for init/audit per side (M leaves), 6 per side for ops (N leaves)
+  const fl_t *d_gt = P.up(r_mem_check);
+  DevVec<fl_t> mem_trees(4 * 2 * M, st), ops_trees(12 * 2 * N, st);
+  fl_t *row_init = mem_trees.p, *row_audit = mem_trees.p + 2 * M, *col_init = mem_trees.p + 4 * M, *col_audit = mem_trees.p + 6 * M;
+  launch_hash_mem(mem_rx.p, dec.row_audit_ts.p, M, d_gt, row_init, row_audit, st);
+  launch_hash_mem(mem_ry.p, dec.col_audit_ts.p, M, d_gt, col_init, col_audit, st);
+  // ops order of the batched proof: row read A,B,C | row write A,B,C | col read A,B,C | col write A,B,C  (:1173-1187)
+  std::vector<fl_t *> ops_ptr(12), mem_ptr = {row_init, row_audit, col_init, col_audit};
+  for (int i = 0; i < 12; i++) ops_ptr[i] = ops_trees.p + (size_t)i * 2 * N;
+  for (int k = 0; k < 3; k++) {
+    launch_hash_ops(dec.row_addr[k].p, derefs.p + (size_t)k * N, dec.row_read_ts[k].p, N, d_gt, ops_ptr[k], ops_ptr[3 + k], st);
+    launch_hash_ops(dec.col_addr[k].p, derefs.p + (size_t)(3 + k) * N, dec.col_read_ts[k].p, N, d_gt, ops_ptr[6 + k], ops_ptr[9 + k], st);
+  }
+  for (auto p : mem_ptr) build_tree(p, M, st);
+  for (auto p : ops_ptr) build_tree(p, N, st);
+  phase("build_layered_network", t0);
+
+  t0 = now_ms();
+  t.protocol_name("Sparse polynomial evaluation proof");     // PolyEvalNetworkProof (:1333, :1345)
+  t.protocol_name("Sparse polynomial product layer proof");  // ProductLayerProof::prove (:1057)
+  // circuit outputs = product of the two elements of the last layer (SP/product_tree.rs:58-63)
+  auto tree_evals = [&](const std::vector<fl_t *> &ptrs, size_t n) {
+    std::vector<fl_t> last(2 * ptrs.size());
+    DevVec<fl_t> dl(2 * ptrs.size(), st);
+    for (size_t i = 0; i < ptrs.size(); i++)
+      VPIN_CUDA(cudaMemcpyAsync(dl.p + 2 * i, ptrs[i] + 2 * n - 4, 2 * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
+    dl.download(last.data(), last.size());
+    ctx->sync();
+    std::vector<fl_t> ev(ptrs.size());
+    for (size_t i = 0; i < ptrs.size(); i++) ev[i] = last[2 * i] * last[2 * i + 1];
+    return ev;
+  };
+  std::vector<fl_t> mem_evals = tree_evals(mem_ptr, M), ops_evals = tree_evals(ops_ptr, N);
+  struct MemClaims { fl_t init; std::vector<fl_t> read, write; fl_t audit; } er, ec;
+  er.init = mem_evals[0]; er.audit = mem_evals[1]; ec.init = mem_evals[2]; ec.audit = mem_evals[3];
+  er.read.assign(ops_evals.begin(), ops_evals.begin() + 3); er.write.assign(ops_evals.begin() + 3, ops_evals.begin() + 6);
+  ec.read.assign(ops_evals.begin() + 6, ops_evals.begin() + 9); ec.write.assign(ops_evals.begin() + 9, ops_evals.begin() + 12);
+  auto subset_check = [&](const MemClaims &m) {  // :1068-1073
+    fl_t ws = fl_one(), rs = fl_one();
+    for (auto &x : m.write) ws = ws * x;
+    for (auto &x : m.read) rs = rs * x;
+    VPIN_REQUIRE(fl_eq(m.init * ws, rs * m.audit), VPIN_ERR_PROVER, "memory check failed");
+  };
+  subset_check(er);
+  t.scalar("claim_row_eval_init", er.init);
+  t.scalars("claim_row_eval_read", er.read);
+  t.scalars("claim_row_eval_write", er.write);
+  t.scalar("claim_row_eval_audit", er.audit);
+  subset_check(ec);
+  t.scalar("claim_col_eval_init", ec.init);
+  t.scalars("claim_col_eval_read", ec.read);
+  t.scalars("claim_col_eval_write", ec.write);
+  t.scalar("claim_col_eval_audit", ec.audit);
+  // dot-product circuits on clones (row_ops_val, col_ops_val, val), split in halves (:1105-1130)
+  DevVec<fl_t> dotp_tables(9 * N, st);
+  std::vector<Prover::DotpTables> dotp(6);
+  std::vector<fl_t> eval_dotp_left(3), eval_dotp_right(3);
+  for (int k = 0; k < 3; k++) {
+    fl_t *l = dotp_tables.p + (size_t)(3 * k) * N, *r = l + N, *w = r + N;
+    VPIN_CUDA(cudaMemcpyAsync(l, derefs.p + (size_t)k * N, N * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
+    VPIN_CUDA(cudaMemcpyAsync(r, derefs.p + (size_t)(3 + k) * N, N * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
+    VPIN_CUDA(cudaMemcpyAsync(w, dec.val(k), N * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
+    for (int hsel = 0; hsel < 2; hsel++) {
+      size_t o = hsel * (N / 2);
+      launch_dot3(l + o, r + o, w + o, N / 2, ctx->d_small.p + 249, ctx->d_partials.p, st);
+      fl_t e = P.down1(ctx->d_small.p + 249);
+      dotp[2 * k + hsel] = Prover::DotpTables{l + o, r + o, w + o, e};
+      (hsel == 0 ? eval_dotp_left : eval_dotp_right)[k] = e;
+    }
+    t.scalar("claim_eval_dotp_left", eval_dotp_left[k]);
+    t.scalar("claim_eval_dotp_right", eval_dotp_right[k]);
+    VPIN_REQUIRE(fl_eq(eval_dotp_left[k] + eval_dotp_right[k], inst_evals[k]), VPIN_ERR_PROVER, "sparse evaluation mismatch");
+  }
+  std::vector<fl_t> rand_ops, rand_mem;
+  BatchedS proof_ops = P.batched_prove(ops_ptr, N, dotp, ops_evals, &rand_ops);
+  BatchedS proof_mem = P.batched_prove(mem_ptr, M, {}, mem_evals, &rand_mem);
+  ops_trees.release();
+  mem_trees.release();
+  dotp_tables.release();
+
+  // HashLayerProof::prove (:740-849)
+  t.protocol_name("Sparse polynomial hash layer proof");
+  DevVec<fl_t> eq_ops = P.eq_table(rand_ops), eq_mem = P.eq_table(rand_mem);
+  auto dots_vs = [&](const fl_t *base, size_t count, size_t len, const fl_t *eq) {
+    std::vector<const fl_t *> hp(count);
+    for (size_t i = 0; i < count; i++) hp[i] = base + i * len;
+    DevVec<const fl_t *> dp(count, st);
+    dp.upload(hp.data(), count);
+    DevVec<fl_t> dout(count, st);
+    launch_dot_multi(dp.p, eq, (int)count, len, dout.p, ctx->d_partials.p, st);
+    std::vector<fl_t> out(count);
+    dout.download(out.data(), count);
+    ctx->sync();
+    return out;
+  };
+  std::vector<fl_t> eval_derefs = dots_vs(derefs.p, 6, N, eq_ops.p);  // row A,B,C then col A,B,C
+  std::vector<fl_t> eval_row_ops_val(eval_derefs.begin(), eval_derefs.begin() + 3), eval_col_ops_val(eval_derefs.begin() + 3, eval_derefs.end());
+  // n-to-1 reduction shared by DerefsEvalProof::prove_single (:90-133) and the ops / mem openings (:780-838)
+  auto reduce_n_to_1 = [&](std::vector<fl_t> evals, const char *chal_label, const std::vector<fl_t> &point, std::vector<fl_t> *r_joint) {
+    std::vector<fl_t> challenges = t.challenge_vector(chal_label, math_log2(evals.size()));
+    for (size_t i = challenges.size(); i-- > 0;) {  // bound_poly_var_bot in reverse challenge order
+      size_t half = evals.size() / 2;
+      for (size_t j = 0; j < half; j++) evals[j] = evals[2 * j] + challenges[i] * (evals[2 * j + 1] - evals[2 * j]);
+      evals.resize(half);
+    }
+    *r_joint = challenges;
+    r_joint->insert(r_joint->end(), point.begin(), point.end());
+    return evals[0];
+  };
+  t.protocol_name("Derefs evaluation proof");
+  DotLogS proof_derefs;
+  {
+    std::vector<fl_t> evals = eval_derefs;
+    evals.resize(next_pow2(evals.size()), fl_zero());
+    t.scalars("evals_ops_val", evals);
+    std::vector<fl_t> r_joint;
+    fl_t joint = reduce_n_to_1(evals, "challenge_combine_n_to_one", rand_ops, &r_joint);
+    t.scalar("joint_claim_eval", joint);
+    proof_derefs = P.polyeval_prove(dpc, *g.eval_label, derefs.p, nullptr, r_joint, joint, fl_zero(), nullptr);
+  }
+  std::vector<fl_t> evals15 = dots_vs(dec.comb_ops.p, 15, N, eq_ops.p);  // row addr, row read-ts, col addr, col read-ts, val (x3 each)
+  std::vector<fl_t> eval_audit = dots_vs(dec.comb_mem.p, 2, M, eq_mem.p);
+  DotLogS proof_ops_open, proof_mem_open;
+  {
+    std::vector<fl_t> evals = evals15;
+    evals.resize(next_pow2(evals.size()), fl_zero());
+    t.scalars("claim_evals_ops", evals);
+    std::vector<fl_t> r_joint;
+    fl_t joint = reduce_n_to_1(evals, "challenge_combine_n_to_one", rand_ops, &r_joint);
+    t.scalar("joint_claim_eval_ops", joint);
+    proof_ops_open = P.polyeval_prove(g.ops_pc, *g.eval_label, dec.comb_ops.p, nullptr, r_joint, joint, fl_zero(), nullptr);
+  }
+  {
+    t.scalars("claim_evals_mem", eval_audit);
+    std::vector<fl_t> r_joint;
+    fl_t joint = reduce_n_to_1(eval_audit, "challenge_combine_two_to_one", rand_mem, &r_joint);
+    t.scalar("joint_claim_eval_mem", joint);
+    proof_mem_open = P.polyeval_prove(g.mem_pc, *g.eval_label, dec.comb_mem.p, nullptr, r_joint, joint, fl_zero(), nullptr);
+  }
+  phase("evalproof_layered_network", t0);
+  phase("R1CSEvalProof::prove", t_eval);
+  phase("SNARK::prove", t_prove);
+
+  // ---------------- bincode(SNARK) (SP/lib.rs:330-338 and the nested types) ----------------
+  Bin o;
+  // R1CSProof (SP/r1csproof.rs:21-47)
+  {
+    std::vector<Comp> cv(spc.L);
+    memcpy(cv.data(), wit.comm.data(), 32 * spc.L);
+    o.comps(cv);
+  }
+  put(o, sc1);
+  o.comp(comm_Az_claim); o.comp(comm_Bz_claim); o.comp(comm_Cz_claim); o.comp(comm_prod_Az_Bz_claims);
+  put(o, pok_Cz_claim);
+  put(o, proof_prod);
+  put(o, proof_eq_sc_phase1);
+  put(o, sc2);
+  o.comp(comm_vars_at_ry);
+  put(o, proof_eval_vars_at_ry);
+  put(o, proof_eq_sc_phase2);
+  // inst_evals
+  for (int k = 0; k < 3; k++) o.fl(inst_evals[k]);
+  // R1CSEvalProof { SparseMatPolyEvalProof { comm_derefs, poly_eval_network_proof { proof_prod_layer, proof_hash_layer } } }
+  o.comps(comm_derefs);
+  // ProductLayerProof (SP/sparse_mlpoly.rs:1035-1042)
+  o.fl(er.init); o.fls(er.read); o.fls(er.write); o.fl(er.audit);
+  o.fl(ec.init); o.fls(ec.read); o.fls(ec.write); o.fl(ec.audit);
+  o.fls(eval_dotp_left); o.fls(eval_dotp_right);
+  put(o, proof_mem);
+  put(o, proof_ops);
+  // HashLayerProof (SP/sparse_mlpoly.rs:698-707)
+  std::vector<fl_t> row_addr(evals15.begin(), evals15.begin() + 3), row_rts(evals15.begin() + 3, evals15.begin() + 6);
+  std::vector<fl_t> col_addr(evals15.begin() + 6, evals15.begin() + 9), col_rts(evals15.begin() + 9, evals15.begin() + 12);
+  std::vector<fl_t> vals(evals15.begin() + 12, evals15.begin() + 15);
+  o.fls(row_addr); o.fls(row_rts); o.fl(eval_audit[0]);
+  o.fls(col_addr); o.fls(col_rts); o.fl(eval_audit[1]);
+  o.fls(vals);
+  o.fls(eval_row_ops_val); o.fls(eval_col_ops_val);
+  put(o, proof_ops_open);
+  put(o, proof_mem_open);
+  put(o, proof_derefs);
+  return std::move(o.b);
+}
+
+// ------------------------------------------------------------------------------------------------ integer roofline
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t *out, int iters, uint32_t seed) {
+  uint64_t a0 = threadIdx.x + seed, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  uint32_t x = threadIdx.x * 2654435761u + seed, y = x ^ 0x9e3779b9u;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0) : "r"(x), "r"(y));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1) : "r"(x), "r"(y));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a2) : "r"(x), "r"(y));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a3) : "r"(x), "r"(y));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a4) : "r"(x), "r"(y));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a5) : "r"(x), "r"(y));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a6) : "r"(x), "r"(y));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a7) : "r"(x), "r"(y));
+    }
+  }
+  uint64_t s = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+  if (s == 0x123456789abcdefull) out[0] = (uint32_t)s;
+}
+double measure_imad_peak(Ctx *ctx) {
+  cudaStream_t st = ctx->st;
+  DevVec<uint32_t> out(1, st);
+  int blocks = 148 * 8, iters = 4096;
+  cudaEvent_t e0, e1;
+  VPIN_CUDA(cudaEventCreate(&e0));
+  VPIN_CUDA(cudaEventCreate(&e1));
+  ++g_kernel_launches, k_imad_peak<<<blocks, 256, 0, st>>>(out.p, 64, 1);
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    VPIN_CUDA(cudaEventRecord(e0, st));
+    ++g_kernel_launches, k_imad_peak<<<blocks, 256, 0, st>>>(out.p, iters, rep);
+    VPIN_CUDA(cudaEventRecord(e1, st));
+    VPIN_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    VPIN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    double macs = (double)blocks * 256 * iters * 64 / (ms * 1e-3);
+    if (macs > best) best = macs;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return best;
+}
+
+}  // namespace vpin
