@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""bench.py — Spartan prove time of one vPIN workload on N B200s (default: CNN network A, BASELINE.json configs[1]).
+
+A "step" is what vPIN's Rust driver does per network after the R1CS is built
+(vPIN_proof_generation/src/main.rs:14-46 -> proof_point_add.rs:39-98 and proof_point_mult.rs:39-98), for BOTH instances
+of the network (point additions, point multiplications):
+    SNARK::encode -> commit(vars_para) -> commit(vars_input) -> my_dense_mlpoly_commit(vars) -> row-wise combine -> my_lib_prove
+
+  value : seconds per step with the instance, the public parameters (generator tables) and the three assignments already
+          resident in HBM (Montgomery form); device-timed with CUDA events on the library's stream, max over ranks.
+  e2e   : the same step through the host-buffer C ABI the reference's Rust driver would bind: Instance::new from host COO
+          triples, SNARKGens::new (generator tables cached in the context after warm-up), encode, the three commitments
+          from host assignments, my_lib_prove with host buffers, proof bytes back on the host.
+  --impl reference : the CPU restatement of the reference prover (oracle/, kind "port": the Rust reference cannot be built
+          here — no cargo, no crates) on the host cores, on a bounded sample of the same workload (see REF_SAMPLE below).
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "spartan_prove_time_s"
+UNIT = "s"
+TRANSCRIPT_LABEL = b"snark_example"  # vPIN_proof_generation/src/proof_point_add.rs:83
+
+# Reference-arm / cpu_baseline sample. The CPU port needs ~60 s for CNN A's point-mult instance (8 cores), too long to
+# repeat K times, so each reference step proves (i) the point-addition instance of the workload at FULL size and (ii) a
+# point-mult instance of m = 18 multiplications (the `-d 3 32` shape, 2^16 constraints) and scales (ii) to the workload's m.
+# Scale: measured once with this same port in the build container (8 cores): m=178 takes 59.1 s, m=18 takes 8.87 s
+# -> 6.67 (smaller, i.e. more favourable to the CPU, than the ratio of padded sizes 2^20/2^16 = 16 or 2^20/2^17 = 8).
+REF_SAMPLE_M = 18
+REF_SCALE = {"A": 6.67}
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def rank_world():
+    return env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx = max(mx, float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------ workload
+def make_workload(tag):
+    from vpin_b200 import workloads as W
+    m, n_add = W.SHAPES[tag]
+    return dict(tag=tag, m=m, n_add=n_add, mult=W.synth_point_mult(m), add=W.synth_point_add(n_add) if n_add else None,
+                seeds=W.tape_seeds())
+
+
+class InstanceState:
+    """One R1CS instance of the workload with everything the two timed legs need, host and device side."""
+
+    def __init__(self, ctx, kind, built, torch):
+        from vpin_b200 import api
+        self.kind = kind
+        self.dims, self.inst, vp, vi, v, self.inputs = built
+        self.gens = api.SNARKGens(ctx, *self.dims)
+        self.p_para, self.p_input, self.p_vars = self.inst.pad(vp), self.inst.pad(vi), self.inst.pad(v)
+        self.n = len(self.p_vars) // 32
+        self.coo = self.inst.export_coo(self.dims[1])
+        # pinned host copies (e2e leg reads its inputs from pinned memory)
+        self.h_coo = []
+        for a in self.coo:
+            t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8).pin_memory()
+            t[: a.nbytes] = torch.from_numpy(a.view("u1").reshape(-1))
+            self.h_coo.append((t, len(a)))
+        self.h_assign = []
+        for b in (self.p_para, self.p_input, self.p_vars):
+            t = torch.empty(len(b), dtype=torch.uint8).pin_memory()
+            t[:] = torch.frombuffer(bytearray(b), dtype=torch.uint8)
+            self.h_assign.append(t)
+        # HBM-resident Montgomery copies (value leg)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.d_assign = []
+        for t in self.h_assign:
+            d = t.to(dev)
+            torch.cuda.synchronize()
+            api.dev_to_mont(ctx, d, self.n, d)
+            self.d_assign.append(d)
+        L = self.gens.L
+        self.d_pts = [torch.empty(32 * L, dtype=torch.uint8, device=dev) for _ in range(4)]
+        self.d_blinds = [torch.empty(32 * L, dtype=torch.uint8, device=dev) for _ in range(3)]
+        ctx.sync()
+
+    def h2d_bytes(self):
+        # COO triples + three assignments for the commitments + the assignment, commitment and blinds again for my_lib_prove
+        L = self.gens.L
+        return sum(a.nbytes for a in self.coo) + 4 * 32 * self.n + 2 * 32 * L * 2 + 64 * L + len(self.inputs)
+
+    def step_resident(self, ctx, seeds):
+        from vpin_b200 import api
+        sq, sp = seeds
+        comm, decomm = api.SNARK.encode(self.inst, self.gens)
+        tape = api.RandomTape(b"\x02", sq)
+        api.dev_poly_commit(ctx, self.gens, self.d_assign[0], self.n, tape, self.d_pts[0], self.d_blinds[0])
+        api.dev_poly_commit(ctx, self.gens, self.d_assign[1], self.n, tape, self.d_pts[1], self.d_blinds[1])
+        api.dev_poly_commit_with_blinds(ctx, self.gens, self.d_assign[2], self.n, self.d_blinds[0], self.d_blinds[1], self.d_pts[2],
+                                        self.d_blinds[2])
+        api.dev_commitments_add(ctx, self.d_pts[0], self.d_pts[1], self.gens.L, self.d_pts[3])
+        wit = api.DeviceWitness(ctx, self.gens, self.d_assign[2], self.n, self.d_pts[3], self.d_blinds[2])
+        proof = api.my_lib_prove_resident(self.inst, decomm, wit, self.inputs, self.gens, TRANSCRIPT_LABEL, sp)
+        return comm, proof
+
+    def step_e2e(self, ctx, seeds):
+        """host buffers in, host bytes out — every call a Rust shim of the reference driver would make"""
+        from vpin_b200 import api
+        import numpy as np
+        A, B, Cm = (np.frombuffer(t.numpy()[: n * api.COO_DTYPE.itemsize], dtype=api.COO_DTYPE) for t, n in self.h_coo)
+        inst = api.Instance(ctx, self.dims[0], self.dims[1], self.dims[2], A, B, Cm)
+        vp, vi, v = (t.numpy() for t in self.h_assign)
+        sq, sp = seeds
+        gens = api.SNARKGens(ctx, *self.dims)
+        comm, decomm = api.SNARK.encode(inst, gens)
+        tape = api.RandomTape(b"\x02", sq)
+        c_para, b_para = api.dense_mlpoly_commit(ctx, gens, api._buf(vp), tape, n=self.n)
+        c_input, b_input = api.dense_mlpoly_commit(ctx, gens, api._buf(vi), tape, n=self.n)
+        c_vars, b_vars = api.my_dense_mlpoly_commit(ctx, gens, api._buf(v), b_para, b_input, n=self.n)
+        combined = ctx.commitments_add(c_para, c_input)
+        proof = api.my_lib_prove(inst, decomm, api._buf(v), self.inputs, gens, TRANSCRIPT_LABEL, combined, b_vars, sp, n=self.n)
+        return comm, proof, (c_para, c_input, c_vars)
+
+
+# ------------------------------------------------------------------------------------------------------------ reference arm
+def reference_step(wl, threads):
+    """one bounded sample of the workload on the CPU port; returns (seconds scaled to the workload, raw seconds, phase ms)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from vpin_b200 import workloads as W
+    sq, sp = wl["seeds"]
+    raw = 0.0
+    scaled = 0.0
+    phases = {}
+    keys = ("gens", "SNARK::encode", "witness_commits", "SNARK::prove")
+    if wl["add"] is not None:
+        f = O.Flow(O.build_point_add(*wl["add"]), sq, sp, verify=False, threads=threads)
+        t = sum(f.times[k] for k in keys) / 1e3
+        raw += t
+        scaled += t
+        phases["point_add_full"] = t
+    m = min(REF_SAMPLE_M, wl["m"])
+    f = O.Flow(O.build_point_mult(*W.synth_point_mult(m)), sq, sp, verify=False, threads=threads)
+    t = sum(f.times[k] for k in keys) / 1e3
+    scale = 1.0 if m == wl["m"] else REF_SCALE.get(wl["tag"], wl["m"] / m)
+    raw += t
+    scaled += t * scale
+    phases["point_mult_sample"] = t
+    phases["point_mult_scale"] = scale
+    return scaled, raw, phases
+
+
+def run_reference(args):
+    rank, local_rank, world = rank_world()
+    if rank != 0:
+        return
+    wl = make_workload(args.workload)
+    threads = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    O.lib()
+    for _ in range(args.warmup):
+        reference_step(wl, threads)
+    t0 = time.time()
+    vals, raws = [], []
+    for _ in range(args.steps):
+        s, r, ph = reference_step(wl, threads)
+        vals.append(s)
+        raws.append(r)
+    wall = time.time() - t0
+    value = sum(vals) / len(vals)
+    sample = (f"point-add instance n={wl['n_add']} at full size + point-mult instance m={min(REF_SAMPLE_M, wl['m'])} "
+              f"x{ph['point_mult_scale']} (calibrated, see bench.py REF_SCALE); {sum(raws) / len(raws):.2f} s of CPU work per step")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64 (4x64 Montgomery F_l, 5x51 F_p)", "data": "synthetic",
+        "config": {"workload": f"cnn{wl['tag']}" if len(wl['tag']) == 1 else wl["tag"], "point_mults": wl["m"], "point_adds": wl["n_add"],
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from vpin_b200 import api
+
+    rank, local_rank, world = rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 prover has no CPU path (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    hbm_peak, peak_src = load_peaks()
+    ctx = api.Context(local_rank)
+    imad_peak = ctx.imad_peak()
+    wl = make_workload(args.workload)
+    seeds = wl["seeds"]
+
+    states = []
+    if wl["add"] is not None:
+        states.append(InstanceState(ctx, "point_add", api.point_addition(ctx, *wl["add"]), torch))
+    states.append(InstanceState(ctx, "point_mult", api.point_mult(ctx, *wl["mult"]), torch))
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def one_step_resident():
+        flush.zero_()  # L2 flush between steps (and the working set, ~2 GB, is far larger than L2 anyway)
+        torch.cuda.synchronize()
+        out = []
+        for s in states:
+            out.append(s.step_resident(ctx, seeds))
+        return out
+
+    # ---- value: HBM-resident -------------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        first = one_step_resident()
+    barrier()
+    ctx.profile_enable(True, 32768.0)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    l0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        last = one_step_resident()
+    e1.record(stream)
+    barrier()
+    wall = time.time() - t0
+    dev_ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - l0
+    prof, madds = ctx.profile_read()
+    ctx.profile_enable(False)
+    phase_pm = ctx.phase_times()
+    clk = clocks.stop() if clocks else None
+    step_s = max_over_ranks(dev_ms / 1e3 / args.steps)
+    wall_step_s = max_over_ranks(wall / args.steps)
+    assert [p for _, p in last] == [p for _, p in first], "proof bytes changed between steps (must be deterministic)"
+
+    # ---- e2e: host buffers through the C ABI ---------------------------------------------------------------------
+    def one_step_e2e():
+        flush.zero_()
+        torch.cuda.synchronize()
+        return [s.step_e2e(ctx, seeds) for s in states]
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_out = one_step_e2e()
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        e2e_out = one_step_e2e()
+    barrier()
+    e2e_s = max_over_ranks((time.time() - t0) / args.steps)
+    for (c1, p1), (c2, p2, _) in zip(last, e2e_out):
+        assert c1 == c2 and p1 == p2, "resident and host-buffer legs disagree"
+    h2d = sum(s.h2d_bytes() for s in states)
+    d2h = sum(len(c) + len(p) + 3 * 32 * s.gens.L + 3 * 32 * s.gens.L for (c, p, _), s in zip(e2e_out, states))
+
+    # ---- MSM microbench: uniform full-width scalars, 2^22 points as a 2048 x 2048 Hyrax grid ----------------------------
+    msm = msm_uniform_bench(ctx, torch, dev, stream, imad_peak)
+
+    # ---- roofline of the dominant kernel class -----------------------------------------------------------------------
+    rooflines = []
+    for name, p in prof.items():
+        if p["ms"] <= 0:
+            continue
+        ent = {"kernel": name, "launches": p["launches"] // args.steps, "ms_per_step": p["ms"] / args.steps,
+               "share_of_step": p["ms"] / dev_ms}
+        if name == "msm_accumulate":
+            macs = madds * 504.0  # 7 F_p multiplications of 72 multiply-accumulates per mixed addition
+            ent.update(bound="imad", achieved=macs / (p["ms"] * 1e-3) / 1e12, peak=imad_peak / 1e12, unit="TMAC/s",
+                       madds_per_step=madds // args.steps, points_per_step=p["units"] / args.steps)
+        elif p["bytes"] > 0:
+            ent.update(bound="hbm", achieved=p["bytes"] / (p["ms"] * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s")
+        else:
+            continue
+        ent["frac"] = ent["achieved"] / ent["peak"]
+        ent["traffic"] = None
+        rooflines.append(ent)
+    rooflines.sort(key=lambda e: -e["ms_per_step"])
+    top = dict(rooflines[0]) if rooflines else None
+    if top:
+        top["peak_source"] = peak_src if top["bound"] == "hbm" else "measured live: dependency-free mad.wide.u32 loop (vpin_imad_peak)"
+
+    line = {
+        "metric": METRIC, "value": step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * step_s, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32 limbs (8x32 Montgomery F_l, 8x32 F_p; IMAD.WIDE)", "data": "synthetic",
+        "config": {"workload": f"cnn{wl['tag']}" if len(wl['tag']) == 1 else wl["tag"], "point_mults": wl["m"], "point_adds": wl["n_add"],
+                   "instances": [{"kind": s.kind, "num_cons": s.dims[0], "num_vars": s.dims[1], "nnz_param": s.dims[3],
+                                  "hyrax_grid": [s.gens.L, s.gens.R]} for s in states],
+                   "l2": "256 MB buffer written between steps; working set ~2 GB >> 126 MB L2",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: Hyrax rows sharded, rest replicated"},
+        "wall_s_per_step": wall_step_s,
+        "gpu_launches": launches,
+        "clocks": clk,
+        "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "roofline": top,
+        "rooflines": rooflines[:8],
+        "msm": msm,
+        "phases_ms_point_mult": phase_pm,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        s, r, ph = reference_step(wl, threads)
+        line["cpu_baseline"] = {"value": s, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"point-add n={wl['n_add']} full + point-mult m={min(REF_SAMPLE_M, wl['m'])} x{ph['point_mult_scale']} "
+                                          f"(calibrated); {r:.2f} s of CPU work, MSM rows on all cores, the rest on one (as the reference)"}
+    else:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    # handles (gens, instances, decommitments) must go before the context that owns their stream
+    import gc
+    del states, last, first, e2e_out
+    gc.collect()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def msm_uniform_bench(ctx, torch, dev, stream, imad_peak):
+    """Hyrax commitment of 2^22 uniform full-width scalars (2048 rows x 2048 generators), device resident."""
+    from vpin_b200 import api
+    ell = 22
+    n = 1 << ell
+    g = torch.Generator(device="cpu").manual_seed(0x7650494E)
+    z = torch.randint(0, 256, (n, 32), dtype=torch.uint8, generator=g)
+    z[:, 31] &= 0x0F  # < 2^252 < l: canonical
+    d = z.to(dev)
+    torch.cuda.synchronize()
+    api.dev_to_mont(ctx, d, n, d)
+    out = torch.empty(32 * (1 << (ell // 2)), dtype=torch.uint8, device=dev)
+    label = b"gens_r1cs_eval"
+    lib = api.lib()
+    for _ in range(2):
+        ctx.check(lib.vpin_dev_hyrax_commit(ctx._h, label, C.c_void_p(d.data_ptr()), C.c_uint64(n), None, C.c_void_p(out.data_ptr())))
+    ctx.sync()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        ctx.check(lib.vpin_dev_hyrax_commit(ctx._h, label, C.c_void_p(d.data_ptr()), C.c_uint64(n), None, C.c_void_p(out.data_ptr())))
+    e1.record(stream)
+    ctx.sync()
+    sec = e0.elapsed_time(e1) / 1e3 / reps
+    return {"workload": "Hyrax commit, 2^22 uniform full-width scalars, 2048x2048", "mpoints_per_s": n / sec / 1e6,
+            "algorithmic_macs_per_point": 8064, "algorithmic_frac_of_imad_peak": n * 8064 / sec / imad_peak,
+            "imad_peak_tmacs": imad_peak / 1e12}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="A")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,11 @@ vpin_status vpin_instance_dims(const vpin_instance *inst, uint64_t *num_cons_pad
 vpin_status vpin_instance_is_sat(vpin_ctx *ctx, const vpin_instance *inst, const uint8_t *vars32, uint64_t n_vars,
                                  const uint8_t *inputs32, uint64_t n_inputs, int32_t *sat);
 
+/* the instance's COO triples back in Instance::new's format (unpadded column indices, canonical values) */
+vpin_status vpin_instance_nnz(const vpin_instance *inst, uint64_t nnz_out[3]);
+vpin_status vpin_instance_export_coo(vpin_ctx *ctx, const vpin_instance *inst, uint64_t num_vars_unpadded, int32_t which,
+                                     vpin_coo_entry *out);
+
 /* ---- SNARK::encode(&inst, &gens)   SP/lib.rs:347-358 -------------------------------------------------------------
  * comm_out receives bincode(ComputationCommitment); *decomm keeps the dense representation in HBM. */
 vpin_status vpin_encode(vpin_ctx *ctx, const vpin_instance *inst, const vpin_gens *gens, uint8_t *comm_out,
@@ -195,6 +200,21 @@ vpin_status vpin_dev_quad_round(vpin_ctx *ctx, const void *dA, const void *dB, u
 vpin_status vpin_dev_bind_top(vpin_ctx *ctx, void *dZ, uint64_t len, const void *d_r);
 vpin_status vpin_dev_eq_evals(vpin_ctx *ctx, const void *d_r, uint32_t ell, void *d_out);
 vpin_status vpin_dev_spmv_abc(vpin_ctx *ctx, const vpin_instance *inst, const void *d_z, void *dAz, void *dBz, void *dCz);
+/* HBM-resident forms of the three witness commitments of VP/proof_point_add.rs:44-80 (what bench.py times as `value`):
+ * d_Z: n Montgomery scalars; outputs stay on the device (L x 32 B compressed points, L Montgomery blinds). */
+vpin_status vpin_dev_poly_commit(vpin_ctx *ctx, const vpin_gens *gens, const void *d_Z, uint64_t n, uint8_t *tape_state,
+                                 void *d_points_out, void *d_blinds_out);
+vpin_status vpin_dev_poly_commit_with_blinds(vpin_ctx *ctx, const vpin_gens *gens, const void *d_Z, uint64_t n, const void *d_blind1,
+                                             const void *d_blind2, void *d_points_out, void *d_blinds_out);
+vpin_status vpin_dev_commitments_add(vpin_ctx *ctx, const void *d_c1, const void *d_c2, uint64_t L, void *d_out);
+vpin_status vpin_witness_from_device(vpin_ctx *ctx, const vpin_gens *gens, const void *d_vars, uint64_t n_vars,
+                                     const void *d_comm_points, const void *d_blinds, uint64_t L, vpin_witness **out);
+/* Per-kernel-class device timing with CUDA events on the context stream (bench.py's roofline lines). Scopes that
+ * process fewer than min_units elements are not timed. vpin_profile_read drains the events and returns the number of
+ * classes written; *msm_madds_out = mixed additions executed by the MSM kernels since vpin_profile_enable. */
+vpin_status vpin_profile_enable(vpin_ctx *ctx, int32_t on, double min_units);
+uint32_t vpin_profile_read(vpin_ctx *ctx, const char **names_out, double *ms_out, uint64_t *launches_out, double *units_out,
+                           double *bytes_out, uint32_t cap, uint64_t *msm_madds_out);
 /* dependency-free mad.wide.u32 microbenchmark: returns multiply-accumulates per second (the integer roofline) */
 vpin_status vpin_imad_peak(vpin_ctx *ctx, double *macs_per_second);
 

@@ -48,6 +48,7 @@ def lib():
         L.vpin_stream.restype = vp
         L.vpin_stream.argtypes = [vp]
         L.vpin_last_phase_times.restype = C.c_uint32
+        L.vpin_profile_read.restype = C.c_uint32
     return _lib
 
 
@@ -161,6 +162,23 @@ class Context:
         self.check(lib().vpin_commitments_add(self._h, c1, c2, C.c_uint64(len(c1) // 32), out))
         return out.raw
 
+    def profile_enable(self, on=True, min_units=-1.0):
+        """per-kernel-class CUDA-event timing on the context stream (see vpin_profile_enable in the header)"""
+        self.check(lib().vpin_profile_enable(self._h, C.c_int32(1 if on else 0), C.c_double(min_units)))
+
+    def profile_read(self):
+        """-> ({class: dict(ms, launches, units, bytes)}, msm_madds)"""
+        cap = 32
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        launches = (C.c_uint64 * cap)()
+        units = (C.c_double * cap)()
+        nbytes = (C.c_double * cap)()
+        madds = C.c_uint64()
+        n = lib().vpin_profile_read(self._h, names, ms, launches, units, nbytes, C.c_uint32(cap), C.byref(madds))
+        out = {names[i].decode(): dict(ms=ms[i], launches=int(launches[i]), units=units[i], bytes=nbytes[i]) for i in range(n)}
+        return out, int(madds.value)
+
     def imad_peak(self):
         v = C.c_double()
         self.check(lib().vpin_imad_peak(self._h, C.byref(v)))
@@ -223,6 +241,17 @@ class Instance:
         outs = [C.create_string_buffer(n) for _ in range(3)]
         self.ctx.check(lib().vpin_spmv_t_abc(self.ctx._h, self._h, x, *outs))
         return tuple(o.raw for o in outs)
+
+    def export_coo(self, num_vars_unpadded):
+        """(A, B, C) as numpy COO_DTYPE arrays in Instance::new's input format"""
+        nnz = (C.c_uint64 * 3)()
+        lib().vpin_instance_nnz(self._h, nnz)
+        out = []
+        for k in range(3):
+            a = np.zeros(nnz[k], COO_DTYPE)
+            self.ctx.check(lib().vpin_instance_export_coo(self.ctx._h, self._h, C.c_uint64(num_vars_unpadded), C.c_int32(k), _buf(a)))
+            out.append(a)
+        return tuple(out)
 
     def pad(self, assignment):
         """Assignment::pad (Spartan/src/lib.rs:107-120)"""
@@ -298,20 +327,22 @@ class Decommitment:
             self._h = None
 
 
-def dense_mlpoly_commit(ctx, gens, Z, tape):
-    """DensePolynomial::new(Z).commit(&gens.gens_r1cs_sat.gens_pc, Some(&mut tape)) -> (PolyCommitment, blinds)"""
+def dense_mlpoly_commit(ctx, gens, Z, tape, n=None):
+    """DensePolynomial::new(Z).commit(&gens.gens_r1cs_sat.gens_pc, Some(&mut tape)) -> (PolyCommitment, blinds).
+    Z: bytes, or a host pointer (c_void_p) together with n."""
     out = C.create_string_buffer(32 * gens.L)
     blinds = C.create_string_buffer(32 * gens.L)
-    ctx.check(lib().vpin_poly_commit(ctx._h, gens._h, Z, C.c_uint64(len(Z) // 32), tape.state if tape else None, out, blinds))
+    n = len(Z) // 32 if n is None else n
+    ctx.check(lib().vpin_poly_commit(ctx._h, gens._h, Z, C.c_uint64(n), tape.state if tape else None, out, blinds))
     return out.raw, blinds.raw
 
 
-def my_dense_mlpoly_commit(ctx, gens, Z, blind_1, blind_2):
+def my_dense_mlpoly_commit(ctx, gens, Z, blind_1, blind_2, n=None):
     """vPIN_proof_generation/src/commit_test.rs:27-57"""
     out = C.create_string_buffer(32 * gens.L)
     blinds = C.create_string_buffer(32 * gens.L)
-    ctx.check(lib().vpin_poly_commit_with_blinds(ctx._h, gens._h, Z, C.c_uint64(len(Z) // 32), blind_1, blind_2, C.c_uint64(gens.L), out,
-                                                 blinds))
+    n = len(Z) // 32 if n is None else n
+    ctx.check(lib().vpin_poly_commit_with_blinds(ctx._h, gens._h, Z, C.c_uint64(n), blind_1, blind_2, C.c_uint64(gens.L), out, blinds))
     return out.raw, blinds.raw
 
 
@@ -332,13 +363,14 @@ class Witness:
 _PROOF_CAP = 8 << 20
 
 
-def my_lib_prove(inst, decomm, vars_bytes, inputs_bytes, gens, transcript_label, comm_vars, blinds_vars, tape_seed):
+def my_lib_prove(inst, decomm, vars_bytes, inputs_bytes, gens, transcript_label, comm_vars, blinds_vars, tape_seed, n=None):
     """my_lib_prove (vPIN_proof_generation/src/commit_test.rs:59-133): host buffers in, bincode(SNARK) out.
     `vars_bytes` doubles as poly_vars (DensePolynomial::new(padded_vars.assignment))."""
     ctx = inst.ctx
     out = C.create_string_buffer(_PROOF_CAP)
+    n_vars = len(vars_bytes) // 32 if n is None else n
     n = C.c_uint64()
-    ctx.check(lib().vpin_prove(ctx._h, inst._h, decomm._h, vars_bytes, C.c_uint64(len(vars_bytes) // 32), inputs_bytes,
+    ctx.check(lib().vpin_prove(ctx._h, inst._h, decomm._h, vars_bytes, C.c_uint64(n_vars), inputs_bytes,
                                C.c_uint64(len(inputs_bytes) // 32), gens._h, transcript_label, C.c_uint64(len(transcript_label)),
                                comm_vars, blinds_vars, C.c_uint64(gens.L), tape_seed, out, C.c_uint64(_PROOF_CAP), C.byref(n)))
     return out.raw[: n.value]
@@ -372,3 +404,36 @@ def prove_flow(ctx, dims, inst, vars_para, vars_input, vars_, inputs, seed_q, se
     proof = my_lib_prove(inst, decomm, p_vars, inputs, gens, label, combined, b_vars, seed_p)
     return dict(proof=proof, comm=comm, comm_vars_para=c_para, comm_vars_input=c_input, comm_vars=c_vars, gens=gens, decomm=decomm,
                 padded_vars=p_vars, blinds_vars=b_vars, combined=combined)
+
+
+# ---- HBM-resident forms (device pointers, Montgomery scalars): what bench.py times as `value` ----
+def _dp(x):
+    """torch tensor or int -> device pointer"""
+    return C.c_void_p(x if isinstance(x, int) else x.data_ptr())
+
+
+def dev_to_mont(ctx, d_in, n, d_out):
+    ctx.check(lib().vpin_dev_to_mont(ctx._h, _dp(d_in), C.c_uint64(n), _dp(d_out)))
+
+
+def dev_poly_commit(ctx, gens, d_Z, n, tape, d_points_out, d_blinds_out):
+    ctx.check(lib().vpin_dev_poly_commit(ctx._h, gens._h, _dp(d_Z), C.c_uint64(n), tape.state if tape else None, _dp(d_points_out),
+                                         _dp(d_blinds_out)))
+
+
+def dev_poly_commit_with_blinds(ctx, gens, d_Z, n, d_b1, d_b2, d_points_out, d_blinds_out):
+    ctx.check(lib().vpin_dev_poly_commit_with_blinds(ctx._h, gens._h, _dp(d_Z), C.c_uint64(n), _dp(d_b1), _dp(d_b2), _dp(d_points_out),
+                                                     _dp(d_blinds_out)))
+
+
+def dev_commitments_add(ctx, d_c1, d_c2, L, d_out):
+    ctx.check(lib().vpin_dev_commitments_add(ctx._h, _dp(d_c1), _dp(d_c2), C.c_uint64(L), _dp(d_out)))
+
+
+class DeviceWitness(Witness):
+    """Witness built from device-resident (vars, comm_vars, blinds_vars)"""
+
+    def __init__(self, ctx, gens, d_vars, n_vars, d_comm, d_blinds):
+        self._h = C.c_void_p()
+        ctx.check(lib().vpin_witness_from_device(ctx._h, gens._h, _dp(d_vars), C.c_uint64(n_vars), _dp(d_comm), _dp(d_blinds),
+                                                 C.c_uint64(gens.L), C.byref(self._h)))

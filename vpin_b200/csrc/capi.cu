@@ -26,18 +26,25 @@ using namespace vpin;
 namespace {
 // canonical LE bytes -> Montgomery table in HBM (rejects values >= l like Scalar::from_bytes)
 DevVec<fl_t> upload_scalars(Ctx *ctx, const uint8_t *b, size_t n) {
-  std::vector<fl_t> h(n);
-  for (size_t i = 0; i < n; i++) VPIN_REQUIRE(fl_from_bytes(b + 32 * i, &h[i]), VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
   DevVec<fl_t> d(n, ctx->st);
-  if (n) d.upload(h.data(), n);
-  ctx->sync();  // h goes out of scope
+  if (!n) return d;
+  // raw canonical bytes go up as they are; the Montgomery conversion and the `>= l` check run on the device
+  VPIN_CUDA(cudaMemcpyAsync(d.p, b, n * sizeof(fl_t), cudaMemcpyHostToDevice, ctx->st));
+  uint32_t *d_bad = reinterpret_cast<uint32_t *>(ctx->d_counters.p + 1);
+  VPIN_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), ctx->st));
+  launch_from_bytes_checked(d.p, n, d.p, d_bad, ctx->st);
+  uint32_t bad = 0;
+  VPIN_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
+  ctx->sync();
+  VPIN_REQUIRE(bad == 0, VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
   return d;
 }
 void download_scalars(Ctx *ctx, const fl_t *d, size_t n, uint8_t *out) {
-  std::vector<fl_t> h(n);
-  VPIN_CUDA(cudaMemcpyAsync(h.data(), d, n * sizeof(fl_t), cudaMemcpyDeviceToHost, ctx->st));
+  if (!n) return;
+  DevVec<fl_t> tmp(n, ctx->st);
+  launch_from_mont(d, n, tmp.p, ctx->st);
+  VPIN_CUDA(cudaMemcpyAsync(out, tmp.p, n * sizeof(fl_t), cudaMemcpyDeviceToHost, ctx->st));
   ctx->sync();
-  for (size_t i = 0; i < n; i++) fl_to_bytes(h[i], out + 32 * i);
 }
 bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
 }  // namespace
@@ -60,6 +67,8 @@ vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out) {
     VPIN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     ctx->d_partials.alloc((size_t)3 * kRedBlocks * 32, ctx->st);
     ctx->d_small.alloc(256, ctx->st);
+    ctx->d_counters.alloc(4, ctx->st);
+    ctx->d_counters.zero();
     VPIN_CUDA(cudaMallocHost((void **)&ctx->h_small, 512 * sizeof(fl_t)));
     ctx->sync();
   } catch (const std::exception &) {
@@ -77,6 +86,9 @@ void vpin_ctx_destroy(vpin_ctx *ctx_) {
   ctx->label_gens.clear();
   ctx->d_partials.release();
   ctx->d_small.release();
+  ctx->d_counters.release();
+  for (auto &p : ctx->prof.pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+  for (auto e : ctx->prof.pool) cudaEventDestroy(e);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   cudaStreamSynchronize(ctx->st);
   cudaStreamDestroy(ctx->st);
@@ -131,6 +143,36 @@ vpin_status vpin_instance_is_sat(vpin_ctx *ctx, const vpin_instance *inst, const
   VPIN_REQUIRE(I && sat, VPIN_ERR_BAD_ARGUMENT, "null argument");
   VPIN_REQUIRE(n_vars <= I->num_vars && n_inputs == I->num_inputs, VPIN_ERR_INVALID_NUM_INPUTS, "InvalidNumberOfInputs");
   *sat = instance_is_sat(c_, *I, vars32, n_vars, inputs32, n_inputs) ? 1 : 0;
+  VPIN_CATCH
+}
+
+// COO triples of the instance in Instance::new's format (unpadded column indices, canonical values): lets a caller that
+// built the instance with vpin_build_point_* replay Instance::new from host buffers (bench.py's e2e leg).
+vpin_status vpin_instance_nnz(const vpin_instance *inst, uint64_t nnz_out[3]) {
+  if (!inst || !nnz_out) return VPIN_ERR_BAD_ARGUMENT;
+  const Instance *I = reinterpret_cast<const Instance *>(inst);
+  for (int k = 0; k < 3; k++) nnz_out[k] = I->M[k].nnz;
+  return VPIN_OK;
+}
+vpin_status vpin_instance_export_coo(vpin_ctx *ctx, const vpin_instance *inst, uint64_t num_vars_unpadded, int32_t which,
+                                     vpin_coo_entry *out) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  const Instance *I = reinterpret_cast<const Instance *>(inst);
+  VPIN_REQUIRE(I && out && which >= 0 && which < 3 && num_vars_unpadded <= I->num_vars, VPIN_ERR_BAD_ARGUMENT, "bad argument");
+  const MatrixDev &m = I->M[which];
+  std::vector<fl_t> v(m.nnz);
+  if (m.nnz) {
+    DevVec<fl_t> tmp(m.nnz, c_->st);
+    launch_from_mont(m.coo_val.p, m.nnz, tmp.p, c_->st);
+    tmp.download(v.data(), m.nnz);
+    c_->sync();
+  }
+  for (size_t i = 0; i < m.nnz; i++) {
+    out[i].row = m.h_row[i];
+    uint64_t col = m.h_col[i];
+    out[i].col = col >= I->num_vars ? col - (I->num_vars - num_vars_unpadded) : col;  // undo the shift of Spartan/src/lib.rs:196-200
+    memcpy(out[i].val, v[i].v, 32);
+  }
   VPIN_CATCH
 }
 
@@ -280,6 +322,110 @@ uint32_t vpin_last_phase_times(const vpin_ctx *ctx, const char **names_out, doub
     if (n >= cap) break;
     names_out[n] = p.first;
     ms_out[n] = p.second;
+    n++;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------- device-resident flow
+static std::vector<fl_t> draw_blinds(uint8_t *tape_state, size_t L) {
+  ProverTape t(nullptr, 0, fl_zero());
+  memcpy(&t, tape_state, sizeof(t));
+  std::vector<fl_t> blinds = t.vector("poly_blinds", L);  // Spartan/src/dense_mlpoly.rs:207-210
+  memcpy(tape_state, &t, sizeof(t));
+  return blinds;
+}
+vpin_status vpin_dev_poly_commit(vpin_ctx *ctx, const vpin_gens *gens, const void *d_Z, uint64_t n, uint8_t *tape_state,
+                                 void *d_points_out, void *d_blinds_out) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  const SnarkGens *sg = reinterpret_cast<const SnarkGens *>(gens);
+  VPIN_REQUIRE(sg && d_Z && d_points_out && d_blinds_out, VPIN_ERR_BAD_ARGUMENT, "null argument");
+  VPIN_REQUIRE(n == sg->sat_pc.L * sg->sat_pc.R, VPIN_ERR_SIZE_MISMATCH, "polynomial size does not match gens");
+  size_t L = sg->sat_pc.L;
+  std::vector<fl_t> blinds = tape_state ? draw_blinds(tape_state, L) : std::vector<fl_t>(L, fl_zero());
+  VPIN_CUDA(cudaMemcpyAsync(d_blinds_out, blinds.data(), L * sizeof(fl_t), cudaMemcpyHostToDevice, c_->st));
+  hyrax_rows(c_, *sg->sat_label, (const fl_t *)d_Z, L, sg->sat_pc.R, sg->sat_pc.R, tape_state ? (const fl_t *)d_blinds_out : nullptr,
+             sg->sat_pc.h_index, nullptr, (uint8_t *)d_points_out);
+  c_->sync();  // `blinds` (pageable) must outlive the copy
+  VPIN_CATCH
+}
+vpin_status vpin_dev_poly_commit_with_blinds(vpin_ctx *ctx, const vpin_gens *gens, const void *d_Z, uint64_t n, const void *d_blind1,
+                                             const void *d_blind2, void *d_points_out, void *d_blinds_out) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  const SnarkGens *sg = reinterpret_cast<const SnarkGens *>(gens);
+  VPIN_REQUIRE(sg && d_Z && d_blind1 && d_blind2 && d_points_out && d_blinds_out, VPIN_ERR_BAD_ARGUMENT, "null argument");
+  VPIN_REQUIRE(n == sg->sat_pc.L * sg->sat_pc.R, VPIN_ERR_SIZE_MISMATCH, "polynomial size does not match gens");
+  size_t L = sg->sat_pc.L;
+  launch_add_vec((const fl_t *)d_blind1, (const fl_t *)d_blind2, L, (fl_t *)d_blinds_out, c_->st);  // commit_test.rs:44-47
+  hyrax_rows(c_, *sg->sat_label, (const fl_t *)d_Z, L, sg->sat_pc.R, sg->sat_pc.R, (const fl_t *)d_blinds_out, sg->sat_pc.h_index, nullptr,
+             (uint8_t *)d_points_out);
+  VPIN_CATCH
+}
+vpin_status vpin_dev_commitments_add(vpin_ctx *ctx, const void *d_c1, const void *d_c2, uint64_t L, void *d_out) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE(d_c1 && d_c2 && d_out, VPIN_ERR_BAD_ARGUMENT, "null argument");
+  DevVec<uint8_t> ok(2 * L, c_->st);
+  DevVec<ge_t> p1(L, c_->st), p2(L, c_->st);
+  launch_decompress((const uint8_t *)d_c1, L, p1.p, ok.p, c_->st);
+  launch_decompress((const uint8_t *)d_c2, L, p2.p, ok.p + L, c_->st);
+  launch_points_add(p1.p, p2.p, L, p1.p, c_->st);
+  launch_compress(p1.p, L, (uint8_t *)d_out, c_->st);
+  std::vector<uint8_t> hok(2 * L);
+  ok.download(hok.data(), 2 * L);
+  c_->sync();
+  for (uint8_t v : hok) VPIN_REQUIRE(v == 1, VPIN_ERR_BAD_ARGUMENT, "point does not decompress");
+  VPIN_CATCH
+}
+vpin_status vpin_witness_from_device(vpin_ctx *ctx, const vpin_gens *gens, const void *d_vars, uint64_t n_vars, const void *d_comm_points,
+                                     const void *d_blinds, uint64_t L, vpin_witness **out) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  const SnarkGens *sg = reinterpret_cast<const SnarkGens *>(gens);
+  VPIN_REQUIRE(sg && d_vars && d_comm_points && d_blinds && out, VPIN_ERR_BAD_ARGUMENT, "null argument");
+  VPIN_REQUIRE(n_vars == sg->sat_pc.L * sg->sat_pc.R && L == sg->sat_pc.L, VPIN_ERR_SIZE_MISMATCH, "witness size does not match gens");
+  auto w = std::make_unique<Witness>();
+  w->n_vars = n_vars;
+  w->d_vars.alloc(n_vars, c_->st);
+  w->d_blinds.alloc(L, c_->st);
+  VPIN_CUDA(cudaMemcpyAsync(w->d_vars.p, d_vars, n_vars * sizeof(fl_t), cudaMemcpyDeviceToDevice, c_->st));
+  VPIN_CUDA(cudaMemcpyAsync(w->d_blinds.p, d_blinds, L * sizeof(fl_t), cudaMemcpyDeviceToDevice, c_->st));
+  w->comm.resize(32 * L);
+  VPIN_CUDA(cudaMemcpyAsync(w->comm.data(), d_comm_points, 32 * L, cudaMemcpyDeviceToHost, c_->st));
+  c_->sync();
+  *out = reinterpret_cast<vpin_witness *>(w.release());
+  VPIN_CATCH
+}
+
+// ---------------------------------------------------------------------------------------------- kernel-class timing
+vpin_status vpin_profile_enable(vpin_ctx *ctx, int32_t on, double min_units) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  prof_drain(c_);
+  for (int i = 0; i < PROF_COUNT; i++) c_->prof.acc[i] = Prof::Acc();
+  c_->prof.on = on != 0;
+  if (min_units >= 0) c_->prof.min_units = min_units;
+  c_->d_counters.zero();
+  VPIN_CATCH
+}
+uint32_t vpin_profile_read(vpin_ctx *ctx, const char **names_out, double *ms_out, uint64_t *launches_out, double *units_out,
+                           double *bytes_out, uint32_t cap, uint64_t *msm_madds_out) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  uint32_t n = 0;
+  try {
+    prof_drain(c);
+    unsigned long long madds = 0;
+    VPIN_CUDA(cudaMemcpyAsync(&madds, c->d_counters.p, sizeof(madds), cudaMemcpyDeviceToHost, c->st));
+    c->sync();
+    if (msm_madds_out) *msm_madds_out = madds;
+  } catch (const std::exception &e) {
+    c->err = e.what();
+    return 0;
+  }
+  for (int i = 0; i < PROF_COUNT && n < cap; i++) {
+    if (!c->prof.acc[i].launches) continue;
+    names_out[n] = prof_class_name(i);
+    ms_out[n] = c->prof.acc[i].ms;
+    launches_out[n] = c->prof.acc[i].launches;
+    units_out[n] = c->prof.acc[i].units;
+    bytes_out[n] = c->prof.acc[i].bytes;
     n++;
   }
   return n;

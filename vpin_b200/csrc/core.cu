@@ -6,6 +6,44 @@ namespace vpin {
 
 std::atomic<uint64_t> g_kernel_launches{0};
 
+// ------------------------------------------------------------------------------------------------ profiling
+const char *prof_class_name(int cls) {
+  static const char *names[PROF_COUNT] = {"msm_recode", "msm_accumulate", "msm_finish", "sumcheck_cubic_round", "sumcheck_quad_round",
+                                          "sumcheck_batched_round", "bind_top", "spmv_csr", "spmv_csc", "eq_evals", "product_tree",
+                                          "hash_layer", "deref_gather", "bound_LZ", "dot"};
+  return cls >= 0 && cls < PROF_COUNT ? names[cls] : "?";
+}
+static cudaEvent_t prof_event(Ctx *c) {
+  if (!c->prof.pool.empty()) { cudaEvent_t e = c->prof.pool.back(); c->prof.pool.pop_back(); return e; }
+  cudaEvent_t e;
+  VPIN_CUDA(cudaEventCreate(&e));
+  return e;
+}
+ProfScope::ProfScope(Ctx *ctx, int cls_, double units, double bytes, int launches) : c(ctx), cls(cls_) {
+  if (!c->prof.on || units < c->prof.min_units) return;
+  Prof::Acc &a = c->prof.acc[cls];
+  a.launches += launches; a.units += units; a.bytes += bytes;
+  e0 = prof_event(c);
+  cudaEventRecord(e0, c->st);
+}
+ProfScope::~ProfScope() {
+  if (!e0) return;
+  cudaEvent_t e1 = prof_event(c);
+  cudaEventRecord(e1, c->st);
+  c->prof.pending.push_back({cls, e0, e1});
+}
+void prof_drain(Ctx *c) {
+  c->sync();
+  for (auto &p : c->prof.pending) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p.e0, p.e1);
+    c->prof.acc[p.cls].ms += ms;
+    c->prof.pool.push_back(p.e0);
+    c->prof.pool.push_back(p.e1);
+  }
+  c->prof.pending.clear();
+}
+
 // ------------------------------------------------------------------------------------------------ host fixed base
 void HostBase::build(const ge_t &p) {
   const int P = 64, M = 8;
@@ -93,9 +131,17 @@ void hyrax_rows(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_t rows, size_
   if (!d_points) pts_tmp.alloc(chunk, ctx->st);
   for (size_t r0 = 0; r0 < rows; r0 += chunk) {
     size_t nr = rows - r0 < chunk ? rows - r0 : chunk;
-    launch_recode(dZ + r0 * ld, nr, cols, ld, d_blinds ? d_blinds + r0 : nullptr, digits.p, ctx->st);
-    launch_msm_accumulate(g.table(), digits.p, nr, cols, d_blinds != nullptr, blind_base, partial.p, ctx->st);
+    double pts = (double)nr * cols_total;
+    {
+      ProfScope ps(ctx, PROF_MSM_RECODE, pts, pts * (32 + 2 * kMsmWindows));
+      launch_recode(dZ + r0 * ld, nr, cols, ld, d_blinds ? d_blinds + r0 : nullptr, digits.p, ctx->d_counters.p, ctx->st);
+    }
+    {
+      ProfScope ps(ctx, PROF_MSM_ACCUMULATE, pts, 0);
+      launch_msm_accumulate(g.table(), digits.p, nr, cols, d_blinds != nullptr, blind_base, partial.p, ctx->st);
+    }
     ge_t *out = d_points ? d_points + r0 : pts_tmp.p;
+    ProfScope ps(ctx, PROF_MSM_FINISH, pts, 0, 2);
     launch_msm_horner(partial.p, nr, out, ctx->st);
     if (d_comp) launch_compress(out, nr, d_comp + 32 * r0, ctx->st);
   }

@@ -86,6 +86,31 @@ struct HostBase {
 struct vpin_ctx_impl;
 typedef vpin_ctx_impl Ctx;
 
+// Per-kernel-class device timing (CUDA events on the context stream) for bench.py's roofline lines.
+// Off by default; when on, scopes whose work is below `min_units` are not timed (keeps the event overhead out of the
+// latency-bound tail rounds).
+enum ProfClass {
+  PROF_MSM_RECODE, PROF_MSM_ACCUMULATE, PROF_MSM_FINISH, PROF_SC_CUBIC, PROF_SC_QUAD, PROF_SC_BATCHED, PROF_BIND, PROF_SPMV,
+  PROF_SPMV_T, PROF_EQ, PROF_TREE, PROF_HASH, PROF_GATHER, PROF_BOUND, PROF_DOT, PROF_COUNT
+};
+const char *prof_class_name(int cls);
+struct Prof {
+  bool on = false;
+  double min_units = 32768;
+  struct Acc { double ms = 0; uint64_t launches = 0; double units = 0; double bytes = 0; } acc[PROF_COUNT];
+  struct Pending { int cls; cudaEvent_t e0, e1; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+};
+struct ProfScope {
+  Ctx *c;
+  int cls;
+  cudaEvent_t e0 = nullptr;
+  ProfScope(Ctx *ctx, int cls, double units, double bytes, int launches = 1);
+  ~ProfScope();
+};
+void prof_drain(Ctx *ctx);
+
 struct vpin_ctx_impl {
   int device = 0;
   cudaStream_t st = nullptr;
@@ -95,6 +120,8 @@ struct vpin_ctx_impl {
   DevVec<fl_t> d_small;      // small device results / parameters
   fl_t *h_small = nullptr;   // pinned mirror
   std::vector<std::pair<const char *, double>> phases;
+  Prof prof;
+  DevVec<unsigned long long> d_counters;  // [0] = non-zero MSM digits recoded (= mixed additions executed)
   void sync() { VPIN_CUDA(cudaStreamSynchronize(st)); }
 };
 

@@ -102,17 +102,10 @@ void launch_table_build(const ge_t *d_bases, size_t n, niels_t *d_table, cudaStr
 // ------------------------------------------------------------------------------------------------ recode
 // (l - 1) / 2
 __device__ __constant__ uint32_t kHalfL[8] = {0x2e7ae9f6u, 0x2c09318du, 0x517bce6bu, 0x0a6f7cefu, 0u, 0u, 0u, 0x08000000u};
-__global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows, size_t cols, size_t ld, const fl_t *extra,
-                                                size_t stride, uint16_t *digits) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * stride) return;
-  size_t row = idx / stride, col = idx % stride;
-  const fl_t *src = col < cols ? scalars + row * ld + col : (col == cols && extra ? extra + row : nullptr);
-  size_t plane = rows * stride;
-  uint16_t *dst = digits + row * stride + col;
+__device__ __forceinline__ uint32_t recode_one(const fl_t *src, uint16_t *dst, size_t plane) {
   if (!src) {
     for (int w = 0; w < kMsmWindows; w++) dst[(size_t)w * plane] = 0;
-    return;
+    return 0;
   }
   const uint4 *q = reinterpret_cast<const uint4 *>(src);
   uint4 lo = __ldg(q), hi = __ldg(q + 1);
@@ -120,7 +113,7 @@ __global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows
   x.v[0] = lo.x; x.v[1] = lo.y; x.v[2] = lo.z; x.v[3] = lo.w; x.v[4] = hi.x; x.v[5] = hi.y; x.v[6] = hi.z; x.v[7] = hi.w;
   if (fl_is_zero(x)) {
     for (int w = 0; w < kMsmWindows; w++) dst[(size_t)w * plane] = 0;
-    return;
+    return 0;
   }
   fl_t s = fl_from_mont(x);
   // s > (l-1)/2 ?  then use l - s and flip every sign
@@ -136,7 +129,7 @@ __global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows
     for (int i = 0; i < 8; i++) v[i] = s.v[i];
   }
   v[8] = 0;
-  uint32_t carry = 0;
+  uint32_t carry = 0, nz = 0;
   for (int w = 0; w < kMsmWindows; w++) {
     int bit = w * kMsmW, limb = bit >> 5, sh = bit & 31;
     uint64_t two = (uint64_t)v[limb] | ((uint64_t)(limb + 1 < 9 ? v[limb + 1] : 0u) << 32);
@@ -145,13 +138,30 @@ __global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows
     uint32_t mag = neg ? (1u << kMsmW) - raw : raw;
     carry = neg;
     uint32_t sign = (neg ^ (gt ? 1u : 0u)) & (mag != 0 ? 1u : 0u);
+    nz += mag != 0 ? 1u : 0u;
     dst[(size_t)w * plane] = (uint16_t)(mag | (sign << 15));
   }
+  return nz;
 }
-void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, const fl_t *d_extra, uint16_t *d_digits, cudaStream_t st) {
+__global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows, size_t cols, size_t ld, const fl_t *extra,
+                                                size_t stride, uint16_t *digits, unsigned long long *nonzero) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nz = 0;
+  if (idx < rows * stride) {
+    size_t row = idx / stride, col = idx % stride;
+    const fl_t *src = col < cols ? scalars + row * ld + col : (col == cols && extra ? extra + row : nullptr);
+    nz = recode_one(src, digits + row * stride + col, rows * stride);
+  }
+  if (nonzero) {
+    nz = __reduce_add_sync(0xffffffffu, nz);
+    if ((threadIdx.x & 31) == 0 && nz) atomicAdd(nonzero, (unsigned long long)nz);
+  }
+}
+void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, const fl_t *d_extra, uint16_t *d_digits,
+                   unsigned long long *d_nonzero, cudaStream_t st) {
   size_t stride = msm_col_stride(cols + (d_extra ? 1 : 0));
   size_t total = rows * stride;
-  ++g_kernel_launches, k_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_scalars, rows, cols, ld, d_extra, stride, d_digits);
+  ++g_kernel_launches, k_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_scalars, rows, cols, ld, d_extra, stride, d_digits, d_nonzero);
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate

@@ -33,7 +33,10 @@ static inline size_t msm_col_stride(size_t cols) { return (cols + kMsmColsPerBlo
 static inline size_t msm_digits_count(size_t rows, size_t cols) { return (size_t)kMsmWindows * rows * msm_col_stride(cols); }
 // scalars: rows x cols Montgomery elements, row-major with leading dimension ld. extra: optional one more scalar per row
 // (the blind, multiplied by base index `cols`), or nullptr. Padding columns get digit 0.
-void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, const fl_t *d_extra, uint16_t *d_digits, cudaStream_t st);
+// d_nonzero (optional): device counter incremented by the number of non-zero digits written (= mixed additions the
+// accumulate kernel will execute)
+void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, const fl_t *d_extra, uint16_t *d_digits,
+                   unsigned long long *d_nonzero, cudaStream_t st);
 // partial[row][window] = sum_col digit * base_col; the optional extra column (index cols) uses table base `extra_base`
 void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t rows, size_t cols, bool has_extra, size_t extra_base,
                            ge_t *d_partial, cudaStream_t st);

@@ -467,6 +467,13 @@ __global__ void __launch_bounds__(256) k_scale(const fl_t *in, const fl_t *d_s, 
 void launch_scale(const fl_t *in, const fl_t *d_s, size_t n, fl_t *out, cudaStream_t st) {
   ++g_kernel_launches, k_scale<<<stream_blocks(n), 256, 0, st>>>(in, d_s, n, out);
 }
+__global__ void __launch_bounds__(256) k_add_vec(const fl_t *a, const fl_t *b, size_t n, fl_t *out) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st_fl(out + i, fl_add(ld_fl(a + i), ld_fl(b + i)));
+}
+void launch_add_vec(const fl_t *a, const fl_t *b, size_t n, fl_t *out, cudaStream_t st) {
+  ++g_kernel_launches, k_add_vec<<<stream_blocks(n), 256, 0, st>>>(a, b, n, out);
+}
 __global__ void __launch_bounds__(256) k_fill_one(fl_t *out, size_t n) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st_fl(out + i, fl_one());
@@ -478,6 +485,24 @@ __global__ void __launch_bounds__(256) k_mont_conv(const fl_t *in, size_t n, fl_
     fl_t x = ld_fl(in + i);
     st_fl(out + i, to_mont ? fl_to_mont(x) : fl_from_mont(x));
   }
+}
+// Scalar::from_bytes on the device (Spartan/src/scalar/ristretto255.rs:398-424): canonical limbs -> Montgomery; any value >= l
+// raises *bad (the C ABI then reports InvalidScalar)
+__global__ void __launch_bounds__(256) k_from_bytes_checked(const fl_t *in, size_t n, fl_t *out, uint32_t *bad) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  uint32_t any_bad = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    fl_t x = ld_fl(in + i);
+    int64_t br = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { int64_t d = (int64_t)x.v[k] - (int64_t)fl_modulus_limb(k) + br; br = d >> 32; }
+    any_bad |= br == 0 ? 1u : 0u;  // no borrow -> x >= l
+    st_fl(out + i, fl_to_mont(x));
+  }
+  if (any_bad) atomicOr(bad, 1u);
+}
+void launch_from_bytes_checked(const fl_t *in, size_t n, fl_t *out, uint32_t *d_bad, cudaStream_t st) {
+  ++g_kernel_launches, k_from_bytes_checked<<<stream_blocks(n), 256, 0, st>>>(in, n, out, d_bad);
 }
 void launch_to_mont(const fl_t *in, size_t n, fl_t *out, cudaStream_t st) { ++g_kernel_launches, k_mont_conv<<<stream_blocks(n), 256, 0, st>>>(in, n, out, 1); }
 void launch_from_mont(const fl_t *in, size_t n, fl_t *out, cudaStream_t st) { ++g_kernel_launches, k_mont_conv<<<stream_blocks(n), 256, 0, st>>>(in, n, out, 0); }

@@ -82,8 +82,12 @@ void launch_bullet_weights(fl_t *w, size_t total, size_t n, const fl_t *d_u, cud
 void launch_bullet_scalars(const fl_t *a, const fl_t *w, size_t total, size_t n, fl_t *sL, fl_t *sR, cudaStream_t st);
 // out[i] = s * in[i]; d_s on device
 void launch_scale(const fl_t *in, const fl_t *d_s, size_t n, fl_t *out, cudaStream_t st);
+// out[i] = a[i] + b[i]
+void launch_add_vec(const fl_t *a, const fl_t *b, size_t n, fl_t *out, cudaStream_t st);
 void launch_fill_one(fl_t *out, size_t n, cudaStream_t st);
 // Montgomery <-> canonical conversion of bulk arrays (C ABI takes canonical little-endian scalars)
+// canonical -> Montgomery with the range check of Scalar::from_bytes; *d_bad |= 1 if any input >= l (in == out allowed)
+void launch_from_bytes_checked(const fl_t *in, size_t n, fl_t *out, uint32_t *d_bad, cudaStream_t st);
 void launch_to_mont(const fl_t *in, size_t n, fl_t *out, cudaStream_t st);
 void launch_from_mont(const fl_t *in, size_t n, fl_t *out, cudaStream_t st);
 

@@ -199,12 +199,18 @@ struct Prover {
     size_t ell = r.size();
     DevVec<fl_t> out((size_t)1 << ell, st), tmp(eq_tmp_elems(ell), st), dr(std::max<size_t>(ell, 1), st);
     if (ell) dr.upload(r.data(), ell);
-    launch_eq_evals(dr.p, (int)ell, out.p, tmp.p, st);
+    {
+      ProfScope ps(ctx, PROF_EQ, (double)((size_t)1 << ell), 32.0 * (double)((size_t)1 << ell), ell <= 12 ? 1 : 3);
+      launch_eq_evals(dr.p, (int)ell, out.p, tmp.p, st);
+    }
     ctx->sync();  // r (pageable) must stay alive until the copy ran
     return out;
   }
   fl_t dot_dev(const fl_t *a, const fl_t *b, size_t n) {
-    launch_dot(a, b, n, ctx->d_small.p + 250, ctx->d_partials.p, st);
+    {
+      ProfScope ps(ctx, PROF_DOT, (double)n, 64.0 * n, 2);
+      launch_dot(a, b, n, ctx->d_small.p + 250, ctx->d_partials.p, st);
+    }
     return down1(ctx->d_small.p + 250);
   }
 
@@ -475,7 +481,10 @@ struct Prover {
     DevVec<fl_t> dL = eq_table(std::vector<fl_t>(r.begin(), r.begin() + l));
     DevVec<fl_t> dR = eq_table(std::vector<fl_t>(r.begin() + l, r.end()));
     DevVec<fl_t> LZ(pc.R, st), tmp(64 * pc.R, st);
-    launch_bound(d_Z, dL.p, pc.L, pc.R, LZ.p, tmp.p, st);
+    {
+      ProfScope ps(ctx, PROF_BOUND, (double)pc.L * pc.R, 32.0 * pc.L * pc.R, 2);
+      launch_bound(d_Z, dL.p, pc.L, pc.R, LZ.p, tmp.p, st);
+    }
     fl_t LZ_blind = d_blinds ? dot_dev(d_blinds, dL.p, pc.L) : fl_zero();
     return dotproductlog_prove(pc, lg, LZ.p, LZ_blind, dR.p, Zr, blind_Zr, C_Zr_prime);
   }
@@ -531,7 +540,11 @@ struct Prover {
       std::vector<fl_t> ev(3 * ninst);
       for (size_t j = 0; j < num_rounds; j++) {
         size_t half = len_half >> (j + 1);
-        launch_cubic_batched_round(dA.p, dB.p, dC.p, (int)ninst, half, d_ev.p, ctx->d_partials.p, st);
+        {
+          double tables = 2.0 * nc + 1 + (with_dotp ? 3.0 * dotp.size() : 0);
+          ProfScope ps(ctx, PROF_SC_BATCHED, (double)ninst * half, tables * 2 * half * 32, 2);
+          launch_cubic_batched_round(dA.p, dB.p, dC.p, (int)ninst, half, d_ev.p, ctx->d_partials.p, st);
+        }
         d_ev.download(ev.data(), 3 * ninst);
         ctx->sync();
         fl_t c0 = fl_zero(), c2 = fl_zero(), c3 = fl_zero();
@@ -547,7 +560,11 @@ struct Prover {
         t.message("poly", "UniPoly_end");
         fl_t r_j = t.challenge_scalar("challenge_nextround");
         rand_prod.push_back(r_j);
-        launch_bind_top_multi(dBind.p, (int)hBind.size(), half, up(&r_j, 1), st);
+        {
+          const fl_t *d_rj = up(&r_j, 1);
+          ProfScope ps(ctx, PROF_BIND, (double)hBind.size() * half, 96.0 * hBind.size() * half);
+          launch_bind_top_multi(dBind.p, (int)hBind.size(), half, d_rj, st);
+        }
         e = unipoly_eval(poly, r_j);
         layer.polys.push_back({poly[0], poly[2], poly[3]});  // CompressedUniPoly (SP/unipoly.rs:80-87)
       }
@@ -588,9 +605,10 @@ struct Prover {
 };
 
 // builds the packed product tree of `n` leaves already stored at tree[0..n) (SP/product_tree.rs:18-56)
-void build_tree(fl_t *tree, size_t n, cudaStream_t st) {
+void build_tree(Ctx *ctx, fl_t *tree, size_t n, cudaStream_t st) {
   size_t off = 0;
   for (size_t vlen = n; vlen > 2; vlen /= 2) {
+    ProfScope ps(ctx, PROF_TREE, (double)vlen / 2, 48.0 * vlen);
     launch_mul_halves(tree + off, vlen / 2, tree + off + vlen, st);
     off += vlen;
   }
@@ -658,15 +676,22 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   std::vector<fl_t> tau = t.challenge_vector("challenge_tau", num_rounds_x);
   DevVec<fl_t> poly_tau = P.eq_table(tau);
   DevVec<fl_t> ABCz(3 * num_cons, st);
-  for (int k = 0; k < 3; k++) launch_spmv_csr(csr_of(inst.M[k], num_cons), z.p, ABCz.p + k * num_cons, st);
+  for (int k = 0; k < 3; k++) {
+    ProfScope ps(ctx, PROF_SPMV, (double)inst.M[k].nnz, 68.0 * inst.M[k].nnz + 36.0 * num_cons);
+    launch_spmv_csr(csr_of(inst.M[k], num_cons), z.p, ABCz.p + k * num_cons, st);
+  }
   fl_t *Az = ABCz.p, *Bz = ABCz.p + num_cons, *Cz = ABCz.p + 2 * num_cons;
   // phase 1: sum_x eq(tau,x) (Az Bz - Cz) = 0   (SP/r1csproof.rs:94-127)
   std::vector<fl_t> rx;
   fl_t blind_claim_postsc1;
   ZkSumcheckS sc1 = P.zk_sumcheck(
       fl_zero(), fl_zero(), num_rounds_x, num_cons, 3,
-      [&](size_t half, fl_t *d_out) { launch_cubic_additive_round(poly_tau.p, Az, Bz, Cz, half, d_out, ctx->d_partials.p, st); },
+      [&](size_t half, fl_t *d_out) {
+        ProfScope ps(ctx, PROF_SC_CUBIC, (double)half, 256.0 * half, 2);
+        launch_cubic_additive_round(poly_tau.p, Az, Bz, Cz, half, d_out, ctx->d_partials.p, st);
+      },
       [&](size_t half, const fl_t *d_r) {
+        ProfScope ps(ctx, PROF_BIND, 4.0 * half, 4 * 96.0 * half, 4);
         launch_bind_top(poly_tau.p, half, d_r, st);
         launch_bind_top(Az, half, d_r, st);
         launch_bind_top(Bz, half, d_r, st);
@@ -700,15 +725,22 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
     DevVec<fl_t> evals_rx = P.eq_table(rx);
     fl_t rr[3] = {r_A, r_B, r_C};
     const fl_t *d_rr = P.up(rr, 3);
-    for (int k = 0; k < 3; k++) launch_spmv_csc_scaled(csc_of(inst.M[k], zlen), evals_rx.p, d_rr + k, k != 0, evals_ABC.p, st);
+    for (int k = 0; k < 3; k++) {
+      ProfScope ps(ctx, PROF_SPMV_T, (double)inst.M[k].nnz, 68.0 * inst.M[k].nnz + 36.0 * zlen, 2);
+      launch_spmv_csc_scaled(csc_of(inst.M[k], zlen), evals_rx.p, d_rr + k, k != 0, evals_ABC.p, st);
+    }
     ctx->sync();
   }
   std::vector<fl_t> ry;
   fl_t blind_claim_postsc2;
   ZkSumcheckS sc2 = P.zk_sumcheck(
       claim_phase2, blind_claim_phase2, num_rounds_y, zlen, 2,
-      [&](size_t half, fl_t *d_out) { launch_quad_round(z.p, evals_ABC.p, half, d_out, ctx->d_partials.p, st); },
+      [&](size_t half, fl_t *d_out) {
+        ProfScope ps(ctx, PROF_SC_QUAD, (double)half, 128.0 * half, 2);
+        launch_quad_round(z.p, evals_ABC.p, half, d_out, ctx->d_partials.p, st);
+      },
       [&](size_t half, const fl_t *d_r) {
+        ProfScope ps(ctx, PROF_BIND, 2.0 * half, 2 * 96.0 * half, 2);
         launch_bind_top(z.p, half, d_r, st);
         launch_bind_top(evals_ABC.p, half, d_r, st);
       },
@@ -758,6 +790,7 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   DevVec<fl_t> derefs(8 * N, st);
   derefs.zero();
   for (int k = 0; k < 3; k++) {
+    ProfScope ps(ctx, PROF_GATHER, 2.0 * N, 2.0 * N * 68, 2);
     launch_gather(dec.row_addr[k].p, mem_rx.p, N, derefs.p + (size_t)k * N, st);
     launch_gather(dec.col_addr[k].p, mem_ry.p, N, derefs.p + (size_t)(3 + k) * N, st);
   }
@@ -785,17 +818,21 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   const fl_t *d_gt = P.up(r_mem_check);
   DevVec<fl_t> mem_trees(4 * 2 * M, st), ops_trees(12 * 2 * N, st);
   fl_t *row_init = mem_trees.p, *row_audit = mem_trees.p + 2 * M, *col_init = mem_trees.p + 4 * M, *col_audit = mem_trees.p + 6 * M;
-  launch_hash_mem(mem_rx.p, dec.row_audit_ts.p, M, d_gt, row_init, row_audit, st);
-  launch_hash_mem(mem_ry.p, dec.col_audit_ts.p, M, d_gt, col_init, col_audit, st);
+  {
+    ProfScope ps(ctx, PROF_HASH, 2.0 * M, 2.0 * M * 100, 2);
+    launch_hash_mem(mem_rx.p, dec.row_audit_ts.p, M, d_gt, row_init, row_audit, st);
+    launch_hash_mem(mem_ry.p, dec.col_audit_ts.p, M, d_gt, col_init, col_audit, st);
+  }
   // ops order of the batched proof: row read A,B,C | row write A,B,C | col read A,B,C | col write A,B,C  (:1173-1187)
   std::vector<fl_t *> ops_ptr(12), mem_ptr = {row_init, row_audit, col_init, col_audit};
   for (int i = 0; i < 12; i++) ops_ptr[i] = ops_trees.p + (size_t)i * 2 * N;
   for (int k = 0; k < 3; k++) {
+    ProfScope ps(ctx, PROF_HASH, 2.0 * N, 2.0 * N * 104, 2);
     launch_hash_ops(dec.row_addr[k].p, derefs.p + (size_t)k * N, dec.row_read_ts[k].p, N, d_gt, ops_ptr[k], ops_ptr[3 + k], st);
     launch_hash_ops(dec.col_addr[k].p, derefs.p + (size_t)(3 + k) * N, dec.col_read_ts[k].p, N, d_gt, ops_ptr[6 + k], ops_ptr[9 + k], st);
   }
-  for (auto p : mem_ptr) build_tree(p, M, st);
-  for (auto p : ops_ptr) build_tree(p, N, st);
+  for (auto p : mem_ptr) build_tree(ctx, p, M, st);
+  for (auto p : ops_ptr) build_tree(ctx, p, N, st);
   phase("build_layered_network", t0);
 
   t0 = now_ms();
@@ -870,7 +907,10 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
     DevVec<const fl_t *> dp(count, st);
     dp.upload(hp.data(), count);
     DevVec<fl_t> dout(count, st);
-    launch_dot_multi(dp.p, eq, (int)count, len, dout.p, ctx->d_partials.p, st);
+    {
+      ProfScope ps(ctx, PROF_DOT, (double)count * len, 32.0 * (count + 1) * len, 2);
+      launch_dot_multi(dp.p, eq, (int)count, len, dout.p, ctx->d_partials.p, st);
+    }
     std::vector<fl_t> out(count);
     dout.download(out.data(), count);
     ctx->sync();
