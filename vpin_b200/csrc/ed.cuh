@@ -32,53 +32,87 @@ VPIN_HD fp_t fp_one() { fp_t r = fp_zero(); r.v[0] = 1; return r; }
 
 VPIN_HD fp_t fp_add(const fp_t &a, const fp_t &b) {
   fp_t r;
-  uint64_t c = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + b.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
+#if defined(__CUDA_ARCH__)
+  uint32_t c;
+  asm("add.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20;"
+      "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.cc.u32 %7, %16, %24; addc.u32 %8, 0, 0;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(c)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
   // fold the carry twice (2^256 == 38)
+  asm("mad.lo.cc.u32 %0, %8, 38, %0; addc.cc.u32 %1, %1, 0; addc.cc.u32 %2, %2, 0; addc.cc.u32 %3, %3, 0;"
+      "addc.cc.u32 %4, %4, 0; addc.cc.u32 %5, %5, 0; addc.cc.u32 %6, %6, 0; addc.cc.u32 %7, %7, 0; addc.u32 %8, 0, 0;"
+      "mad.lo.u32 %0, %8, 38, %0;"
+      : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "+r"(c));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + b.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
   c *= 38;
-#pragma unroll
   for (int i = 0; i < 8; i++) { c += r.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
   r.v[0] += 38u * (uint32_t)c;
+#endif
   return r;
 }
 VPIN_HD fp_t fp_sub(const fp_t &a, const fp_t &b) {
   fp_t r;
+#if defined(__CUDA_ARCH__)
+  uint32_t br;
+  asm("sub.cc.u32 %0, %9, %17; subc.cc.u32 %1, %10, %18; subc.cc.u32 %2, %11, %19; subc.cc.u32 %3, %12, %20;"
+      "subc.cc.u32 %4, %13, %21; subc.cc.u32 %5, %14, %22; subc.cc.u32 %6, %15, %23; subc.cc.u32 %7, %16, %24; subc.u32 %8, 0, 0;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(br)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  // br = 0xffffffff when the difference wrapped by 2^256: subtract 38, possibly twice
+  br &= 38u;
+  asm("sub.cc.u32 %0, %0, %8; subc.cc.u32 %1, %1, 0; subc.cc.u32 %2, %2, 0; subc.cc.u32 %3, %3, 0;"
+      "subc.cc.u32 %4, %4, 0; subc.cc.u32 %5, %5, 0; subc.cc.u32 %6, %6, 0; subc.cc.u32 %7, %7, 0; subc.u32 %8, 0, 0;"
+      : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "+r"(br));
+  r.v[0] -= br & 38u;
+#else
   int64_t br = 0;
-#pragma unroll
   for (int i = 0; i < 8; i++) { int64_t t = (int64_t)a.v[i] - (int64_t)b.v[i] + br; r.v[i] = (uint32_t)t; br = t >> 32; }
   // wrapped by 2^256 -> subtract 38, possibly twice
   int64_t k = br ? 38 : 0;
   br = 0;
-#pragma unroll
   for (int i = 0; i < 8; i++) { int64_t t = (int64_t)r.v[i] - (i == 0 ? k : 0) + br; r.v[i] = (uint32_t)t; br = t >> 32; }
   r.v[0] -= br ? 38u : 0u;
+#endif
   return r;
 }
 VPIN_HD fp_t fp_neg(const fp_t &a) { return fp_sub(fp_zero(), a); }
 
+// t (16 limbs) -> t mod 2^256-38, lazily reduced into [0, 2^256)
 VPIN_HD fp_t fp_reduce_wide(const uint32_t t[16]) {
   fp_t r;
-  uint64_t c = 0;
+#if defined(__CUDA_ARCH__)
+  uint32_t lo[8], tmp[8], w8 = 0;
 #pragma unroll
+  for (int i = 0; i < 8; i++) lo[i] = t[i];
+  limb::mad_row(lo, t + 8, 38u, w8);   // 38 * (t8, t10, t12, t14) at limbs 0, 2, 4, 6
+  limb::mul_row(tmp, t + 9, 38u);      // 38 * (t9, t11, t13, t15) at limbs 1, 3, 5, 7
+  asm("add.cc.u32 %0, %0, %8; addc.cc.u32 %1, %1, %9; addc.cc.u32 %2, %2, %10; addc.cc.u32 %3, %3, %11;"
+      "addc.cc.u32 %4, %4, %12; addc.cc.u32 %5, %5, %13; addc.cc.u32 %6, %6, %14; addc.u32 %7, %7, %15;"
+      : "+r"(lo[1]), "+r"(lo[2]), "+r"(lo[3]), "+r"(lo[4]), "+r"(lo[5]), "+r"(lo[6]), "+r"(lo[7]), "+r"(w8)
+      : "r"(tmp[0]), "r"(tmp[1]), "r"(tmp[2]), "r"(tmp[3]), "r"(tmp[4]), "r"(tmp[5]), "r"(tmp[6]), "r"(tmp[7]));
+  // w8 <= 39: fold it, and the (rare) carry of that fold
+  asm("mad.lo.cc.u32 %0, %8, 38, %0; addc.cc.u32 %1, %1, 0; addc.cc.u32 %2, %2, 0; addc.cc.u32 %3, %3, 0;"
+      "addc.cc.u32 %4, %4, 0; addc.cc.u32 %5, %5, 0; addc.cc.u32 %6, %6, 0; addc.cc.u32 %7, %7, 0; addc.u32 %8, 0, 0;"
+      "mad.lo.u32 %0, %8, 38, %0;"
+      : "+r"(lo[0]), "+r"(lo[1]), "+r"(lo[2]), "+r"(lo[3]), "+r"(lo[4]), "+r"(lo[5]), "+r"(lo[6]), "+r"(lo[7]), "+r"(w8));
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = lo[i];
+#else
+  uint64_t c = 0;
   for (int i = 0; i < 8; i++) { c += (uint64_t)t[8 + i] * 38u + t[i]; r.v[i] = (uint32_t)c; c >>= 32; }
   c *= 38;
-#pragma unroll
   for (int i = 0; i < 8; i++) { c += r.v[i]; r.v[i] = (uint32_t)c; c >>= 32; }
   r.v[0] += 38u * (uint32_t)c;
+#endif
   return r;
 }
 VPIN_HD fp_t fp_mul(const fp_t &a, const fp_t &b) {
   uint32_t t[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) t[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    uint64_t c = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) { c += (uint64_t)a.v[j] * b.v[i] + t[i + j]; t[i + j] = (uint32_t)c; c >>= 32; }
-    t[i + 8] = (uint32_t)c;
-  }
+  limb::mul_8x8(t, a.v, b.v);
   return fp_reduce_wide(t);
 }
 VPIN_HD fp_t fp_sqr(const fp_t &a) { return fp_mul(a, a); }

@@ -7,11 +7,7 @@
 #include <cstdint>
 #include <cstring>
 
-#if defined(__CUDACC__)
-#define VPIN_HD __host__ __device__ __forceinline__
-#else
-#define VPIN_HD inline
-#endif
+#include "limbs.cuh"
 
 namespace vpin {
 
@@ -66,34 +62,62 @@ VPIN_HD bool fl_eq(const fl_t &a, const fl_t &b) {
 // r = a - l if a >= l else a   (a < 2l)
 VPIN_HD fl_t fl_cond_sub(const fl_t &a) {
   fl_t d;
+#if defined(__CUDA_ARCH__)
+  uint32_t br;
+  asm("sub.cc.u32 %0, %9, %17; subc.cc.u32 %1, %10, %18; subc.cc.u32 %2, %11, %19; subc.cc.u32 %3, %12, %20;"
+      "subc.cc.u32 %4, %13, 0; subc.cc.u32 %5, %14, 0; subc.cc.u32 %6, %15, 0; subc.cc.u32 %7, %16, %21; subc.u32 %8, 0, 0;"
+      : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]), "=r"(d.v[7]), "=r"(br)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "n"(VPIN_FL_P0), "n"(VPIN_FL_P1), "n"(VPIN_FL_P2), "n"(VPIN_FL_P3), "n"(VPIN_FL_P7));
+  bool keep = br != 0;  // borrow -> a < l
+#else
   int64_t br = 0;
-#pragma unroll
   for (int i = 0; i < 8; i++) {
     int64_t t = (int64_t)a.v[i] - (int64_t)fl_modulus_limb(i) + br;
     d.v[i] = (uint32_t)t;
     br = t >> 32;
   }
+  bool keep = br != 0;
+#endif
   fl_t r;
-  bool keep = br != 0;  // borrow -> a < l
 #pragma unroll
   for (int i = 0; i < 8; i++) r.v[i] = keep ? a.v[i] : d.v[i];
   return r;
 }
 VPIN_HD fl_t fl_add(const fl_t &a, const fl_t &b) {
   fl_t s;
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, %17; addc.cc.u32 %2, %10, %18; addc.cc.u32 %3, %11, %19;"
+      "addc.cc.u32 %4, %12, %20; addc.cc.u32 %5, %13, %21; addc.cc.u32 %6, %14, %22; addc.u32 %7, %15, %23;"
+      : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+#else
   uint64_t c = 0;
-#pragma unroll
   for (int i = 0; i < 8; i++) {
     c += (uint64_t)a.v[i] + b.v[i];
     s.v[i] = (uint32_t)c;
     c >>= 32;
   }
+#endif
   return fl_cond_sub(s);  // a + b < 2l < 2^254, no carry out
 }
 VPIN_HD fl_t fl_sub(const fl_t &a, const fl_t &b) {
   fl_t d;
+#if defined(__CUDA_ARCH__)
+  uint32_t mask;
+  asm("sub.cc.u32 %0, %9, %17; subc.cc.u32 %1, %10, %18; subc.cc.u32 %2, %11, %19; subc.cc.u32 %3, %12, %20;"
+      "subc.cc.u32 %4, %13, %21; subc.cc.u32 %5, %14, %22; subc.cc.u32 %6, %15, %23; subc.cc.u32 %7, %16, %24; subc.u32 %8, 0, 0;"
+      : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]), "=r"(d.v[7]), "=r"(mask)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+  // mask = 0xffffffff on borrow: add l back
+  asm("add.cc.u32 %0, %0, %8; addc.cc.u32 %1, %1, %9; addc.cc.u32 %2, %2, %10; addc.cc.u32 %3, %3, %11;"
+      "addc.cc.u32 %4, %4, 0; addc.cc.u32 %5, %5, 0; addc.cc.u32 %6, %6, 0; addc.u32 %7, %7, %12;"
+      : "+r"(d.v[0]), "+r"(d.v[1]), "+r"(d.v[2]), "+r"(d.v[3]), "+r"(d.v[4]), "+r"(d.v[5]), "+r"(d.v[6]), "+r"(d.v[7])
+      : "r"(mask & VPIN_FL_P0), "r"(mask & VPIN_FL_P1), "r"(mask & VPIN_FL_P2), "r"(mask & VPIN_FL_P3), "r"(mask & VPIN_FL_P7));
+#else
   int64_t br = 0;
-#pragma unroll
   for (int i = 0; i < 8; i++) {
     int64_t t = (int64_t)a.v[i] - (int64_t)b.v[i] + br;
     d.v[i] = (uint32_t)t;
@@ -101,51 +125,22 @@ VPIN_HD fl_t fl_sub(const fl_t &a, const fl_t &b) {
   }
   uint32_t mask = br ? 0xffffffffu : 0u;
   uint64_t c = 0;
-#pragma unroll
   for (int i = 0; i < 8; i++) {
     c += (uint64_t)d.v[i] + (fl_modulus_limb(i) & mask);
     d.v[i] = (uint32_t)c;
     c >>= 32;
   }
+#endif
   return d;
 }
 VPIN_HD fl_t fl_neg(const fl_t &a) { return fl_sub(fl_zero(), a); }
 VPIN_HD fl_t fl_dbl(const fl_t &a) { return fl_add(a, a); }
 
-// Montgomery product a*b/R mod l. CIOS over 32-bit limbs; the modulus has limbs 4..6 == 0 so the reduction
-// step costs 5 multiplies instead of 8.
+// Montgomery product a*b/R mod l: interleaved product / reduction rows of limbs.cuh (the modulus has limbs 4..6 == 0 and
+// limb 7 == 2^28, so a reduction row costs 5 multiplies), then one conditional subtraction.
 VPIN_HD fl_t fl_mul(const fl_t &a, const fl_t &b) {
-  uint32_t t[9];
-#pragma unroll
-  for (int i = 0; i < 9; i++) t[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    uint64_t c = 0;
-    uint32_t bi = b.v[i];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      c += (uint64_t)a.v[j] * bi + t[j];
-      t[j] = (uint32_t)c;
-      c >>= 32;
-    }
-    c += t[8];
-    t[8] = (uint32_t)c;
-    uint32_t t9 = (uint32_t)(c >> 32);
-    uint32_t m = t[0] * VPIN_FL_INV32;
-    c = ((uint64_t)m * VPIN_FL_P0 + t[0]) >> 32;
-    c += (uint64_t)m * VPIN_FL_P1 + t[1]; t[0] = (uint32_t)c; c >>= 32;
-    c += (uint64_t)m * VPIN_FL_P2 + t[2]; t[1] = (uint32_t)c; c >>= 32;
-    c += (uint64_t)m * VPIN_FL_P3 + t[3]; t[2] = (uint32_t)c; c >>= 32;
-    c += t[4]; t[3] = (uint32_t)c; c >>= 32;
-    c += t[5]; t[4] = (uint32_t)c; c >>= 32;
-    c += t[6]; t[5] = (uint32_t)c; c >>= 32;
-    c += (uint64_t)m * VPIN_FL_P7 + t[7]; t[6] = (uint32_t)c; c >>= 32;
-    c += t[8]; t[7] = (uint32_t)c; c >>= 32;
-    t[8] = t9 + (uint32_t)c;
-  }
   fl_t r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.v[i] = t[i];
+  limb::mont_mul_l(r.v, a.v, b.v);
   return fl_cond_sub(r);
 }
 VPIN_HD fl_t fl_sqr(const fl_t &a) { return fl_mul(a, a); }

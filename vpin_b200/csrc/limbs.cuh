@@ -1,0 +1,242 @@
+// Multi-limb building blocks shared by F_p (ed.cuh) and F_l (fl.cuh): 256 x 256 -> 512-bit products in 32-bit limbs.
+//
+// Device path: every 32 x 32 -> 64 partial product is ONE IMAD.WIDE.U32 with carry-in/carry-out (ptxas fuses the
+// mad.lo.cc / madc.hi.cc pairs below into IMAD.WIDE.U32[.X] Rd, P, Ra, Rb, Rc, P), using the even/odd column split:
+// the products a[j] * b of one row with j even occupy disjoint 64-bit slots and are chained by the carry flag, the
+// ones with j odd go to a second accumulator that is offset by one limb. 64 IMAD.WIDE per 8 x 8 product instead of
+// the ~190 IMAD/IADD3 the compiler emits for the portable `c += (uint64_t)a * b + t` loop.
+// Host path: the same functions in portable 64-bit arithmetic (used by the host-side sigma protocols and by the
+// CPU-side unit tests of the index logic).
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define VPIN_HD __host__ __device__ __forceinline__
+#else
+#define VPIN_HD inline
+#endif
+
+namespace vpin {
+namespace limb {
+
+// r[0..8) = (a[0], a[2], a[4], a[6]) * b as four 64-bit products (a is addressed with stride 2)
+VPIN_HD void mul_row(uint32_t *r, const uint32_t *a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(r[0]), "=r"(r[1]) : "r"(a[0]), "r"(b));
+  asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(r[2]), "=r"(r[3]) : "r"(a[2]), "r"(b));
+  asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(r[4]), "=r"(r[5]) : "r"(a[4]), "r"(b));
+  asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(r[6]), "=r"(r[7]) : "r"(a[6]), "r"(b));
+#else
+  for (int k = 0; k < 4; k++) {
+    uint64_t p = (uint64_t)a[2 * k] * b;
+    r[2 * k] = (uint32_t)p;
+    r[2 * k + 1] = (uint32_t)(p >> 32);
+  }
+#endif
+}
+// r[0..8) += (a[0], a[2], a[4], a[6]) * b with one carry chain; cw += carry out
+VPIN_HD void mad_row(uint32_t *r, const uint32_t *a, uint32_t b, uint32_t &cw) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %9, %13, %0; madc.hi.cc.u32 %1, %9, %13, %1;"
+      "madc.lo.cc.u32 %2, %10, %13, %2; madc.hi.cc.u32 %3, %10, %13, %3;"
+      "madc.lo.cc.u32 %4, %11, %13, %4; madc.hi.cc.u32 %5, %11, %13, %5;"
+      "madc.lo.cc.u32 %6, %12, %13, %6; madc.hi.cc.u32 %7, %12, %13, %7;"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(cw)
+      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(b));
+#else
+  uint64_t c = 0;
+  for (int k = 0; k < 4; k++) {
+    uint64_t p = (uint64_t)a[2 * k] * b;
+    uint64_t lo = (uint64_t)r[2 * k] + (uint32_t)p + c;
+    r[2 * k] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)r[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+    r[2 * k + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+  cw += (uint32_t)c;
+#endif
+}
+// same without a carry word (the caller knows the chain cannot overflow)
+VPIN_HD void mad_row_nc(uint32_t *r, const uint32_t *a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %8, %12, %0; madc.hi.cc.u32 %1, %8, %12, %1;"
+      "madc.lo.cc.u32 %2, %9, %12, %2; madc.hi.cc.u32 %3, %9, %12, %3;"
+      "madc.lo.cc.u32 %4, %10, %12, %4; madc.hi.cc.u32 %5, %10, %12, %5;"
+      "madc.lo.cc.u32 %6, %11, %12, %6; madc.hi.u32 %7, %11, %12, %7;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(b));
+#else
+  uint32_t dummy = 0;
+  mad_row(r, a, b, dummy);
+#endif
+}
+
+// t[0..16) = a * b (8 x 8 limbs). 64 IMAD.WIDE + 14 carry words + one 15-limb add chain.
+VPIN_HD void mul_8x8(uint32_t *t, const uint32_t *a, const uint32_t *b) {
+  uint32_t ev[16], od[16];  // od[k] has weight 2^(32 (k + 1))
+#pragma unroll
+  for (int k = 8; k < 16; k++) ev[k] = od[k] = 0;
+  mul_row(ev, a, b[0]);
+  mul_row(od, a + 1, b[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    if (i & 1) {
+      mad_row(od + i - 1, a, b[i], od[i + 7]);
+      if (i + 9 < 16) mad_row(ev + i + 1, a + 1, b[i], ev[i + 9]);
+      else mad_row_nc(ev + i + 1, a + 1, b[i]);
+    } else {
+      mad_row(ev + i, a, b[i], ev[i + 8]);
+      mad_row(od + i, a + 1, b[i], od[i + 8]);
+    }
+  }
+  // t = ev + (od << 32)
+  t[0] = ev[0];
+#if defined(__CUDA_ARCH__)
+  uint32_t cy;
+  asm("add.cc.u32 %0, %8, %15; addc.cc.u32 %1, %9, %16; addc.cc.u32 %2, %10, %17; addc.cc.u32 %3, %11, %18;"
+      "addc.cc.u32 %4, %12, %19; addc.cc.u32 %5, %13, %20; addc.cc.u32 %6, %14, %21; addc.u32 %7, 0, 0;"
+      : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(cy)
+      : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+        "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]));
+  asm("add.cc.u32 %8, %8, 0xffffffff;"
+      "addc.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20;"
+      "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.u32 %7, %16, %24;"
+      : "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]), "+r"(cy)
+      : "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
+        "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+#else
+  uint64_t c = 0;
+  for (int k = 1; k < 16; k++) {
+    c += (uint64_t)ev[k] + od[k - 1];
+    t[k] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+}
+
+// ---- Montgomery reduction rows for l = 2^252 + 27742317777372353535851937790883648493 (limbs P0..P3, 0, 0, 0, 2^28) ----
+#define VPIN_L_P0 0x5cf5d3edu
+#define VPIN_L_P1 0x5812631au
+#define VPIN_L_P2 0xa2f79cd6u
+#define VPIN_L_P3 0x14def9deu
+#define VPIN_L_P7 0x10000000u
+#define VPIN_L_INV32 0x12547e1bu  // -(l^-1) mod 2^32
+
+// w += mergeval (if do_merge); m = w * INV; then, continuing the carry of that addition, the limbs of m * l that sit one
+// limb above w: o[0..1] += m P1, o[2..3] += m P3, o[4], o[5] ripple, o[6..7] += m 2^28, cw += carry out.
+template <bool kMerge>
+VPIN_HD void redc_other(uint32_t &w, uint32_t mergeval, uint32_t &m, uint32_t *o, uint32_t &cw) {
+#if defined(__CUDA_ARCH__)
+  if (kMerge) {
+    asm("add.cc.u32 %0, %0, %11; mul.lo.u32 %1, %0, %12;"
+        "madc.lo.cc.u32 %2, %1, %13, %2; madc.hi.cc.u32 %3, %1, %13, %3;"
+        "madc.lo.cc.u32 %4, %1, %14, %4; madc.hi.cc.u32 %5, %1, %14, %5;"
+        "addc.cc.u32 %6, %6, 0; addc.cc.u32 %7, %7, 0;"
+        "madc.lo.cc.u32 %8, %1, %15, %8; madc.hi.cc.u32 %9, %1, %15, %9;"
+        "addc.u32 %10, %10, 0;"
+        : "+r"(w), "=&r"(m), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(cw)
+        : "r"(mergeval), "n"(VPIN_L_INV32), "n"(VPIN_L_P1), "n"(VPIN_L_P3), "n"(VPIN_L_P7));
+  } else {
+    asm("mul.lo.u32 %1, %0, %11;"
+        "mad.lo.cc.u32 %2, %1, %12, %2; madc.hi.cc.u32 %3, %1, %12, %3;"
+        "madc.lo.cc.u32 %4, %1, %13, %4; madc.hi.cc.u32 %5, %1, %13, %5;"
+        "addc.cc.u32 %6, %6, 0; addc.cc.u32 %7, %7, 0;"
+        "madc.lo.cc.u32 %8, %1, %14, %8; madc.hi.cc.u32 %9, %1, %14, %9;"
+        "addc.u32 %10, %10, 0;"
+        : "+r"(w), "=&r"(m), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(cw)
+        : "n"(VPIN_L_INV32), "n"(VPIN_L_P1), "n"(VPIN_L_P3), "n"(VPIN_L_P7));
+  }
+#else
+  uint64_t c = 0;
+  if (kMerge) {
+    c = (uint64_t)w + mergeval;
+    w = (uint32_t)c;
+    c >>= 32;
+  }
+  m = w * VPIN_L_INV32;
+  const uint32_t mul[4] = {VPIN_L_P1, VPIN_L_P3, 0u, VPIN_L_P7};
+  for (int k = 0; k < 4; k++) {
+    uint64_t p = (uint64_t)m * mul[k];
+    uint64_t lo = (uint64_t)o[2 * k] + (uint32_t)p + c;
+    o[2 * k] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)o[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+    o[2 * k + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+  cw += (uint32_t)c;
+#endif
+}
+// s[0..1] += m P0 (s[0] becomes 0), s[2..3] += m P2, s[4..7] ripple, cw += carry out
+VPIN_HD void redc_own(uint32_t *s, uint32_t m, uint32_t &cw) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %9, %10, %0; madc.hi.cc.u32 %1, %9, %10, %1;"
+      "madc.lo.cc.u32 %2, %9, %11, %2; madc.hi.cc.u32 %3, %9, %11, %3;"
+      "addc.cc.u32 %4, %4, 0; addc.cc.u32 %5, %5, 0; addc.cc.u32 %6, %6, 0; addc.cc.u32 %7, %7, 0;"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]), "+r"(s[4]), "+r"(s[5]), "+r"(s[6]), "+r"(s[7]), "+r"(cw)
+      : "r"(m), "n"(VPIN_L_P0), "n"(VPIN_L_P2));
+#else
+  uint64_t c = 0;
+  const uint32_t mul[4] = {VPIN_L_P0, VPIN_L_P2, 0u, 0u};
+  for (int k = 0; k < 4; k++) {
+    uint64_t p = (uint64_t)m * mul[k];
+    uint64_t lo = (uint64_t)s[2 * k] + (uint32_t)p + c;
+    s[2 * k] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)s[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+    s[2 * k + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+  cw += (uint32_t)c;
+#endif
+}
+
+// r[0..8) = a * b / 2^256 mod l, in [0, 2l): product rows interleaved with reduction rows (word-serial Montgomery),
+// all carries confined to 8-limb windows plus one small carry word. 112 IMAD(.WIDE) in total.
+VPIN_HD void mont_mul_l(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+  uint32_t ev[18], od[18];  // od[k] has weight 2^(32 (k + 1))
+#pragma unroll
+  for (int k = 8; k < 18; k++) ev[k] = od[k] = 0;
+  uint32_t m;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if (i == 0) {
+      mul_row(ev, a, b[0]);
+      mul_row(od, a + 1, b[0]);
+    } else if (i & 1) {
+      mad_row(od + i - 1, a, b[i], od[i + 7]);
+      mad_row(ev + i + 1, a + 1, b[i], ev[i + 9]);
+    } else {
+      mad_row(ev + i, a, b[i], ev[i + 8]);
+      mad_row(od + i, a + 1, b[i], od[i + 8]);
+    }
+    if (i == 0) {
+      redc_other<false>(ev[0], 0u, m, od, od[8]);
+      redc_own(ev, m, ev[8]);
+    } else if (i & 1) {
+      redc_other<true>(od[i - 1], ev[i], m, ev + i + 1, ev[i + 9]);
+      redc_own(od + i - 1, m, od[i + 7]);
+    } else {
+      redc_other<true>(ev[i], od[i - 1], m, od + i, od[i + 8]);
+      redc_own(ev + i, m, ev[i + 8]);
+    }
+  }
+  // r = ev[8..16) + od[7..15)
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, %17; addc.cc.u32 %2, %10, %18; addc.cc.u32 %3, %11, %19;"
+      "addc.cc.u32 %4, %12, %20; addc.cc.u32 %5, %13, %21; addc.cc.u32 %6, %14, %22; addc.u32 %7, %15, %23;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
+        "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+#else
+  uint64_t c = 0;
+  for (int k = 0; k < 8; k++) {
+    c += (uint64_t)ev[8 + k] + od[7 + k];
+    r[k] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+}
+
+}  // namespace limb
+}  // namespace vpin
