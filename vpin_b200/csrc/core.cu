@@ -108,8 +108,11 @@ std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, si
   launch_from_uniform_bytes(d_stream.p, n, g->d_pts.p, ctx->st);
   g->h_pts.resize(n);
   g->d_pts.download(g->h_pts.data(), n);
-  g->d_table.alloc(n * (size_t)kMsmTable, ctx->st);
-  launch_table_build(g->d_pts.p, n, g->d_table.p, ctx->st);
+  g->d_table.alloc(msm_table_entries(n), ctx->st);
+  {
+    DevVec<ge_t> scratch(n, ctx->st);
+    launch_table_build(g->d_pts.p, n, g->d_table.p, scratch.p, ctx->st);
+  }
   ctx->sync();
   ctx->label_gens[label] = g;
   return g;
@@ -125,10 +128,9 @@ void hyrax_rows(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_t rows, size_
   size_t max_rows = ((size_t)1 << 30) / (stride * kMsmWindows * sizeof(uint16_t));
   if (max_rows < 1) max_rows = 1;
   size_t chunk = rows < max_rows ? rows : max_rows;
+  size_t segs = msm_num_segments(chunk, cols_total);
   DevVec<uint16_t> digits(msm_digits_count(chunk, cols_total), ctx->st);
-  DevVec<ge_t> partial(chunk * kMsmWindows, ctx->st);
-  DevVec<ge_t> pts_tmp;
-  if (!d_points) pts_tmp.alloc(chunk, ctx->st);
+  DevVec<ge_t> partial(chunk * kMsmGroup * segs, ctx->st), sums(segs > 1 ? chunk * kMsmGroup : 0, ctx->st);
   for (size_t r0 = 0; r0 < rows; r0 += chunk) {
     size_t nr = rows - r0 < chunk ? rows - r0 : chunk;
     double pts = (double)nr * cols_total;
@@ -138,12 +140,10 @@ void hyrax_rows(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_t rows, size_
     }
     {
       ProfScope ps(ctx, PROF_MSM_ACCUMULATE, pts, 0);
-      launch_msm_accumulate(g.table(), digits.p, nr, cols, d_blinds != nullptr, blind_base, partial.p, ctx->st);
+      launch_msm_accumulate(g.table(), digits.p, nr, cols, d_blinds != nullptr, blind_base, segs, partial.p, ctx->st);
     }
-    ge_t *out = d_points ? d_points + r0 : pts_tmp.p;
-    ProfScope ps(ctx, PROF_MSM_FINISH, pts, 0, 2);
-    launch_msm_horner(partial.p, nr, out, ctx->st);
-    if (d_comp) launch_compress(out, nr, d_comp + 32 * r0, ctx->st);
+    ProfScope ps(ctx, PROF_MSM_FINISH, pts, 0);
+    launch_msm_finish(partial.p, nr, segs, sums.p, d_points ? d_points + r0 : nullptr, d_comp ? d_comp + 32 * r0 : nullptr, ctx->st);
   }
 }
 

@@ -93,10 +93,26 @@ __global__ void __launch_bounds__(128) k_table_fill(size_t n, niels_t *table) {
     st_niels(slots + c * kTblChunk + m, ge_to_niels(q, zinv));
   }
 }
-void launch_table_build(const ge_t *d_bases, size_t n, niels_t *d_table, cudaStream_t st) {
-  ++g_kernel_launches, k_bases_to_niels<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_bases, n, d_table);
+// bases_out[j] = 2^ndbl * bases_in[j]
+__global__ void __launch_bounds__(128) k_points_dbl_n(const ge_t *in, size_t n, int ndbl, ge_t *out) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  ge_t g = ld_ge(in + j);
+  for (int i = 0; i < ndbl; i++) g = ge_dbl(g);
+  st_ge(out + j, g);
+}
+void launch_table_build(const ge_t *d_bases, size_t n, niels_t *d_table, ge_t *d_scratch, cudaStream_t st) {
+  const ge_t *cur = d_bases;
   size_t threads = n * (kMsmTable / kTblChunk);
-  ++g_kernel_launches, k_table_fill<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(n, d_table);
+  for (int t = 0; t < kMsmSub; t++) {
+    if (t > 0) {
+      ++g_kernel_launches, k_points_dbl_n<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cur, n, kMsmW * kMsmGroup, d_scratch);
+      cur = d_scratch;
+    }
+    niels_t *tbl = d_table + (size_t)t * n * kMsmTable;
+    ++g_kernel_launches, k_bases_to_niels<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cur, n, tbl);
+    ++g_kernel_launches, k_table_fill<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(n, tbl);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ recode
@@ -165,57 +181,128 @@ void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, c
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate
-__global__ void __launch_bounds__(kMsmColsPerBlock) k_msm_accumulate(const niels_t *table, const uint16_t *digits, size_t rows,
-                                                                     size_t cols, size_t cols_total, size_t extra_base,
-                                                                     size_t stride, ge_t *partial) {
-  size_t row = blockIdx.x % rows, window = blockIdx.x / rows;
-  const uint16_t *dg = digits + (window * rows + row) * stride;
+// acc += (neg ? -e : e) without a divergent branch: the sign swaps the two multiplicands (by address) and F with G.
+__device__ __forceinline__ void madd_signed(ge_t &p, const niels_t *e, uint32_t neg) {
+  const fp_t *p_yp = neg ? &e->ym : &e->yp, *p_ym = neg ? &e->yp : &e->ym;
+  fp_t yp = ldg_fp(p_yp), ym = ldg_fp(p_ym), t2d = ldg_fp(&e->t2d);
+  fp_t a = fp_mul(fp_sub(p.Y, p.X), ym);
+  fp_t b = fp_mul(fp_add(p.Y, p.X), yp);
+  fp_t c = fp_mul(p.T, t2d);
+  fp_t d = fp_add(p.Z, p.Z);
+  fp_t s1 = fp_sub(d, c), s2 = fp_add(d, c);
+  fp_t f, g;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { f.v[i] = neg ? s2.v[i] : s1.v[i]; g.v[i] = neg ? s1.v[i] : s2.v[i]; }
+  fp_t e_ = fp_sub(b, a), h = fp_add(b, a);
+  p.X = fp_mul(e_, f); p.Y = fp_mul(g, h); p.Z = fp_mul(f, g); p.T = fp_mul(e_, h);
+}
+// grid (ceil(rows / 128), kMsmGroup, segs), block 128: thread = (row, local window w', column segment)
+__global__ void __launch_bounds__(kMsmRowsPerBlock) k_msm_accumulate(const niels_t *table, const uint16_t *digits, size_t rows, size_t cols,
+                                                                     size_t cols_total, size_t extra_base, size_t stride, size_t n_bases,
+                                                                     size_t seg_len, ge_t *partial) {
+  size_t row = (size_t)blockIdx.x * kMsmRowsPerBlock + threadIdx.x;
+  if (row >= rows) return;
+  const int wl = blockIdx.y;
+  const size_t seg = blockIdx.z, segs = gridDim.z;
+  size_t c0 = seg * seg_len, c1 = c0 + seg_len < cols_total ? c0 + seg_len : cols_total;
+  const size_t plane = rows * stride;
+  const uint16_t *dg = digits + row * stride;
   ge_t acc = ge_identity();
-  int any = 0;
-  for (size_t col = threadIdx.x; col < cols_total; col += kMsmColsPerBlock) {
-    uint32_t d = dg[col];
-    if (d) {
-      size_t base = col < cols ? col : extra_base;
-      niels_t e = ldg_niels(table + base * kMsmTable + ((d & 0x7fffu) - 1u));
-      acc = (d >> 15) ? ge_msub(acc, e) : ge_madd(acc, e);
-      any = 1;
+  for (size_t col = c0; col < c1; col++) {
+    size_t base = col < cols ? col : extra_base;
+#pragma unroll 1
+    for (int t = 0; t < kMsmSub; t++) {  // not unrolled: one copy of the 7-multiplication body keeps the loop inside the I-cache
+      int w = t * kMsmGroup + wl;
+      if (w >= kMsmWindows) break;
+      uint32_t d = dg[(size_t)w * plane + col];
+      if (d) madd_signed(acc, table + ((size_t)t * n_bases + base) * kMsmTable + ((d & 0x7fffu) - 1u), d >> 15);
     }
   }
-  ge_t *dst = partial + row * kMsmWindows + window;
-  if (!__syncthreads_or(any)) {
-    if (threadIdx.x == 0) st_ge(dst, ge_identity());
-    return;
-  }
-  __shared__ ge_t sm[kMsmColsPerBlock];
-  sm[threadIdx.x] = acc;
-  __syncthreads();
-  for (int s = kMsmColsPerBlock / 2; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) sm[threadIdx.x] = ge_add(sm[threadIdx.x], sm[threadIdx.x + s]);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) st_ge(dst, sm[0]);
+  st_ge(partial + (row * kMsmGroup + wl) * segs + seg, acc);
+}
+size_t msm_num_segments(size_t rows, size_t cols_total) {
+  const size_t want_threads = (size_t)148 * 1024;
+  size_t per = rows * kMsmGroup;
+  size_t segs = (want_threads + per - 1) / per;
+  size_t max_segs = (cols_total + 7) / 8;  // at least 8 columns per thread
+  if (segs > max_segs) segs = max_segs;
+  if (segs < 1) segs = 1;
+  if (segs > 65535) segs = 65535;
+  return segs;
 }
 void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t rows, size_t cols, bool has_extra, size_t extra_base,
-                           ge_t *d_partial, cudaStream_t st) {
+                           size_t segs, ge_t *d_partial, cudaStream_t st) {
   size_t cols_total = cols + (has_extra ? 1 : 0);
   size_t stride = msm_col_stride(cols_total);
-  ++g_kernel_launches, k_msm_accumulate<<<(unsigned)(rows * kMsmWindows), kMsmColsPerBlock, 0, st>>>(t.d_table, d_digits, rows, cols, cols_total, extra_base,
-                                                                               stride, d_partial);
+  size_t seg_len = (cols_total + segs - 1) / segs;
+  dim3 grid((unsigned)((rows + kMsmRowsPerBlock - 1) / kMsmRowsPerBlock), kMsmGroup, (unsigned)segs);
+  ++g_kernel_launches, k_msm_accumulate<<<grid, kMsmRowsPerBlock, 0, st>>>(t.d_table, d_digits, rows, cols, cols_total, extra_base, stride,
+                                                                           t.n_bases, seg_len, d_partial);
 }
 
-__global__ void __launch_bounds__(64) k_msm_horner(const ge_t *partial, size_t rows, ge_t *out) {
+// finish, step 1 (only when a row was split into segments): one warp per (row, local window) adds the segment partials
+// (lane-strided, then a shuffle tree) -> sums[row][w'].
+__device__ __forceinline__ ge_t shfl_down_ge(const ge_t &g, int off) {
+  ge_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.X.v[i] = __shfl_down_sync(0xffffffffu, g.X.v[i], off);
+    r.Y.v[i] = __shfl_down_sync(0xffffffffu, g.Y.v[i], off);
+    r.Z.v[i] = __shfl_down_sync(0xffffffffu, g.Z.v[i], off);
+    r.T.v[i] = __shfl_down_sync(0xffffffffu, g.T.v[i], off);
+  }
+  return r;
+}
+__global__ void __launch_bounds__(128) k_msm_segsum(const ge_t *partial, size_t pairs, size_t segs, ge_t *sums) {
+  size_t pair = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);  // (row, w') flattened
+  if (pair >= pairs) return;
+  const int lane = threadIdx.x & 31;
+  const ge_t *p = partial + pair * segs;
+  ge_t acc = ge_identity();
+  bool first = true;
+  for (size_t s = lane; s < segs; s += 32) {
+    ge_t q = ld_ge(p + s);
+    acc = first ? q : ge_add(acc, q);
+    first = false;
+  }
+  int width = segs >= 32 ? 32 : (int)segs;
+  for (int off = 16; off > 0; off >>= 1) {
+    if (off < width) {  // warp-uniform; lanes beyond the data hold the identity
+      ge_t o = shfl_down_ge(acc, off);
+      acc = ge_add(acc, o);
+    }
+  }
+  if (lane == 0) st_ge(sums + pair, acc);
+}
+// finish, step 2: one thread per row runs the Horner pass over the kMsmGroup window sums and encodes the point
+__global__ void __launch_bounds__(32) k_msm_horner(const ge_t *sums, size_t rows, ge_t *out, uint8_t *comp) {
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
-  const ge_t *p = partial + row * kMsmWindows;
-  ge_t acc = ld_ge(p + kMsmWindows - 1);
-  for (int w = kMsmWindows - 2; w >= 0; w--) {
-    for (int i = 0; i < kMsmW; i++) acc = ge_dbl(acc);
-    acc = ge_add(acc, ld_ge(p + w));
+  const ge_t *p = sums + row * kMsmGroup;
+  ge_t h = ld_ge(p + kMsmGroup - 1);
+  for (int w = kMsmGroup - 2; w >= 0; w--) {
+    for (int i = 0; i < kMsmW; i++) h = ge_dbl(h);
+    h = ge_add(h, ld_ge(p + w));
   }
-  st_ge(out + row, acc);
+  if (out) st_ge(out + row, h);
+  if (comp) {
+    uint8_t b[32];
+    ge_compress(h, b);
+    uint4 *q = reinterpret_cast<uint4 *>(comp + 32 * row);
+    uint32_t w[8];
+    for (int k = 0; k < 8; k++) w[k] = (uint32_t)b[4 * k] | ((uint32_t)b[4 * k + 1] << 8) | ((uint32_t)b[4 * k + 2] << 16) | ((uint32_t)b[4 * k + 3] << 24);
+    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
 }
-void launch_msm_horner(const ge_t *d_partial, size_t rows, ge_t *d_out, cudaStream_t st) {
-  ++g_kernel_launches, k_msm_horner<<<(unsigned)((rows + 63) / 64), 64, 0, st>>>(d_partial, rows, d_out);
+void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, ge_t *d_sums, ge_t *d_out, uint8_t *d_comp, cudaStream_t st) {
+  const ge_t *sums = d_partial;
+  if (segs > 1) {
+    size_t pairs = rows * kMsmGroup;
+    ++g_kernel_launches, k_msm_segsum<<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(d_partial, pairs, segs, d_sums);
+    sums = d_sums;
+  }
+  ++g_kernel_launches, k_msm_horner<<<(unsigned)((rows + 31) / 32), 32, 0, st>>>(sums, rows, d_out, d_comp);
 }
 
 // ------------------------------------------------------------------------------------------------ encodings
