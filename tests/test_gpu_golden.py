@@ -1,0 +1,41 @@
+"""GPU: the CUDA prover against the COMMITTED golden digests (tests/golden/golden_flows.json), through the C ABI."""
+import hashlib
+import json
+import os
+
+import pytest
+
+import helpers as H
+from vpin_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_flows.json")))
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: f"{c['kind']}-{'-'.join(str(v) for v in c['args'].values())}")
+def test_cuda_flow_matches_golden(ctx, case):
+    from vpin_b200 import api
+    kw = case["args"]
+    if case["kind"] == "point_add":
+        dims, inst, vp, vi, v, inputs = api.point_addition(ctx, *W.synth_point_add(kw["n"], infinity_every=kw["infinity_every"]))
+    elif case["kind"] == "point_mult":
+        dims, inst, vp, vi, v, inputs = api.point_mult(ctx, *W.synth_point_mult(kw["m"]))
+    else:
+        A, B, Cm, vp, vi, v, inputs = H.synthetic_r1cs(kw["num_cons"], kw["num_vars"], kw["num_inputs"], seed=kw["num_cons"])
+        nnz = max(len(A), 2) if kw["num_cons"] > 1 else 2
+        dims = (kw["num_cons"], kw["num_vars"], kw["num_inputs"], nnz)
+        inst = api.Instance(ctx, kw["num_cons"], kw["num_vars"], kw["num_inputs"], A, B, Cm)
+    assert list(dims) == case["dims"]
+    sq, sp = (bytes.fromhex(s) for s in GOLD["tape_seeds"])
+    got = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp, label=GOLD["transcript_label"].encode())
+    assert len(got["proof"]) == case["proof_len"]
+    assert got["proof"][:64].hex() == case["proof_head"]
+    assert sha(got["proof"]) == case["proof_sha256"]
+    assert sha(got["comm"]) == case["comm_sha256"]
+    assert sha(got["comm_vars_para"]) == case["comm_vars_para_sha256"]
+    assert sha(got["comm_vars_input"]) == case["comm_vars_input_sha256"]
+    assert sha(got["comm_vars"]) == case["comm_vars_sha256"]
