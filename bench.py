@@ -260,6 +260,7 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     hbm_peak, peak_src = load_peaks()
     ctx = api.Context(local_rank)
+    ctx.init_distributed(rank, world, dist)
     imad_peak = ctx.imad_peak()
     wl = make_workload(args.workload)
     seeds = wl["seeds"]
@@ -371,7 +372,8 @@ def run_b200(args):
                    "instances": [{"kind": s.kind, "num_cons": s.dims[0], "num_vars": s.dims[1], "nnz_param": s.dims[3],
                                   "hyrax_grid": [s.gens.L, s.gens.R]} for s in states],
                    "l2": "256 MB buffer written between steps; working set ~2 GB >> 126 MB L2",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: Hyrax rows sharded, rest replicated"},
+                   "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one proof: Hyrax commitment rows sharded + NCCL all-gather, "
+                                  "transcript and sumchecks replicated"},
         "wall_s_per_step": wall_step_s,
         "gpu_launches": launches,
         "clocks": clk,

@@ -59,6 +59,15 @@ typedef struct vpin_coo_entry {
 /* ---- context ---------------------------------------------------------------------------------------------- */
 vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out);
 void vpin_ctx_destroy(vpin_ctx *ctx);
+/* Multi-GPU, one process (and one context) per GPU. Rank 0 calls vpin_nccl_unique_id and ships the 128 bytes to the other
+ * ranks by any means (bench.py: a torch.distributed broadcast); every rank then calls vpin_ctx_init_distributed. After
+ * that every rank runs the SAME calls with the SAME inputs (the Fiat-Shamir transcript is replayed identically on every
+ * rank, so no challenge is ever broadcast); the L independent rows of every Hyrax commitment (SP/dense_mlpoly.rs:160-175,
+ * the reference's one rayon par_iter) are split across ranks and exchanged with one in-place NCCL all-gather of 32 B
+ * per row. vpin_shard_rows tells which rows a rank owns (whole range when the grid is too small to shard). */
+vpin_status vpin_nccl_unique_id(uint8_t id_out[128]);
+vpin_status vpin_ctx_init_distributed(vpin_ctx *ctx, int32_t rank, int32_t world, const uint8_t nccl_id[128]);
+void vpin_shard_rows(uint64_t rows, int32_t rank, int32_t world, uint64_t *r0, uint64_t *r1, int32_t *sharded);
 /* message of the last failure on this context (never NULL) */
 const char *vpin_last_error(const vpin_ctx *ctx);
 /* number of this library's kernels launched on the context so far (bench.py's gpu_launches) */

@@ -72,6 +72,15 @@ class Context:
         if st != 0:
             raise VpinError(st, "vpin_ctx_create failed (no usable CUDA device?)")
 
+    def init_distributed(self, rank, world, dist):
+        """One process per GPU: rank 0 creates the NCCL id, `dist` (torch.distributed, any backend) ships it, every rank
+        joins the communicator. Afterwards every rank must issue the same calls with the same inputs."""
+        self.rank, self.world = rank, world
+        if world == 1:
+            return
+        uid = exchange_unique_id(dist, rank)
+        self.check(lib().vpin_ctx_init_distributed(self._h, C.c_int32(rank), C.c_int32(world), uid))
+
     def close(self):
         if self._h:
             lib().vpin_ctx_destroy(self._h)
@@ -183,6 +192,30 @@ class Context:
         v = C.c_double()
         self.check(lib().vpin_imad_peak(self._h, C.byref(v)))
         return v.value
+
+
+def exchange_unique_id(dist, rank, make_id=None):
+    """rank 0 makes the 128-byte NCCL unique id (vpin_nccl_unique_id), everyone receives it through `dist`."""
+    box = [None]
+    if rank == 0:
+        if make_id is None:
+            buf = C.create_string_buffer(128)
+            st = lib().vpin_nccl_unique_id(buf)
+            if st != 0:
+                raise VpinError(st, "vpin_nccl_unique_id failed (libnccl not loadable?)")
+            box[0] = buf.raw
+        else:
+            box[0] = make_id()
+    dist.broadcast_object_list(box, src=0)
+    assert isinstance(box[0], bytes) and len(box[0]) == 128
+    return box[0]
+
+
+def shard_rows(rows, rank, world):
+    """(r0, r1, sharded): the Hyrax rows rank `rank` of `world` commits to (vpin_shard_rows)"""
+    r0, r1, s = C.c_uint64(), C.c_uint64(), C.c_int32()
+    lib().vpin_shard_rows(C.c_uint64(rows), C.c_int32(rank), C.c_int32(world), C.byref(r0), C.byref(r1), C.byref(s))
+    return r0.value, r1.value, bool(s.value)
 
 
 class SNARKGens:

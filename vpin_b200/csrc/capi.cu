@@ -83,6 +83,7 @@ void vpin_ctx_destroy(vpin_ctx *ctx_) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->st);
+  try { dist_destroy(ctx); } catch (...) {}
   ctx->label_gens.clear();
   ctx->d_partials.release();
   ctx->d_small.release();
@@ -93,6 +94,28 @@ void vpin_ctx_destroy(vpin_ctx *ctx_) {
   cudaStreamSynchronize(ctx->st);
   cudaStreamDestroy(ctx->st);
   delete ctx;
+}
+vpin_status vpin_nccl_unique_id(uint8_t id_out[128]) {
+  if (!id_out) return VPIN_ERR_BAD_ARGUMENT;
+  try {
+    dist_get_unique_id(id_out);
+  } catch (const std::exception &) {
+    return VPIN_ERR_CUDA;
+  }
+  return VPIN_OK;
+}
+vpin_status vpin_ctx_init_distributed(vpin_ctx *ctx, int32_t rank, int32_t world, const uint8_t nccl_id[128]) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE(world == 1 || nccl_id, VPIN_ERR_BAD_ARGUMENT, "null id");
+  dist_init(c_, rank, world, nccl_id);
+  VPIN_CATCH
+}
+void vpin_shard_rows(uint64_t rows, int32_t rank, int32_t world, uint64_t *r0, uint64_t *r1, int32_t *sharded) {
+  size_t a, b;
+  bool s = shard_rows(rows, rank, world, &a, &b);
+  if (r0) *r0 = a;
+  if (r1) *r1 = b;
+  if (sharded) *sharded = s ? 1 : 0;
 }
 const char *vpin_last_error(const vpin_ctx *ctx) { return ctx ? reinterpret_cast<const Ctx *>(ctx)->err.c_str() : "null context"; }
 uint64_t vpin_kernel_launches(const vpin_ctx *) { return g_kernel_launches.load(); }

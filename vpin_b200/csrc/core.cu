@@ -1,5 +1,8 @@
 #include "core.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 
 namespace vpin {
@@ -42,6 +45,89 @@ void prof_drain(Ctx *c) {
     c->prof.pool.push_back(p.e1);
   }
   c->prof.pending.clear();
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU plumbing
+// NCCL is resolved at run time (dlopen) so that the library has no link-time dependency on it and a process that has
+// already loaded torch's bundled libnccl.so.2 shares that copy.
+namespace {
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi &nccl() {
+  static NcclApi api;
+  if (api.h) return api;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  VPIN_REQUIRE(h, VPIN_ERR_CUDA, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define VPIN_NCCL_SYM(field, name)                                       \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name));     \
+  VPIN_REQUIRE(api.field, VPIN_ERR_CUDA, "libnccl is missing " name)
+  VPIN_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+  VPIN_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+  VPIN_NCCL_SYM(AllGather, "ncclAllGather");
+  VPIN_NCCL_SYM(AllReduce, "ncclAllReduce");
+  VPIN_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+  VPIN_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef VPIN_NCCL_SYM
+  api.h = h;
+  return api;
+}
+#define VPIN_NCCL(x)                                                                                             \
+  do {                                                                                                           \
+    ncclResult_t r_ = (x);                                                                                       \
+    if (r_ != ncclSuccess) throw ::vpin::Error(VPIN_ERR_CUDA, std::string(#x) + ": " + nccl().GetErrorString(r_)); \
+  } while (0)
+}  // namespace
+
+bool shard_rows(size_t rows, int rank, int world, size_t *r0, size_t *r1) {
+  *r0 = 0;
+  *r1 = rows;
+  if (world <= 1 || rows % (size_t)world != 0 || rows / (size_t)world < kMinShardRows) return false;
+  size_t per = rows / (size_t)world;
+  *r0 = per * (size_t)rank;
+  *r1 = *r0 + per;
+  return true;
+}
+void dist_get_unique_id(uint8_t out[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  VPIN_NCCL(nccl().GetUniqueId(&id));
+  memcpy(out, &id, 128);
+}
+void dist_init(Ctx *ctx, int rank, int world, const uint8_t id_bytes[128]) {
+  VPIN_REQUIRE(world >= 1 && rank >= 0 && rank < world, VPIN_ERR_BAD_ARGUMENT, "bad rank / world");
+  dist_destroy(ctx);
+  ctx->rank = rank;
+  ctx->world = world;
+  if (world == 1) return;
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, 128);
+  ncclComm_t comm;
+  VPIN_CUDA(cudaSetDevice(ctx->device));
+  VPIN_NCCL(nccl().CommInitRank(&comm, world, id, rank));
+  ctx->nccl_comm = comm;
+}
+void dist_destroy(Ctx *ctx) {
+  if (ctx->nccl_comm) {
+    cudaStreamSynchronize(ctx->st);
+    nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+  }
+  ctx->rank = 0;
+  ctx->world = 1;
+}
+void dist_allgather_inplace(Ctx *ctx, void *buf, size_t bytes_per_rank) {
+  VPIN_REQUIRE(ctx->nccl_comm, VPIN_ERR_BAD_ARGUMENT, "context is not distributed");
+  const uint8_t *send = (const uint8_t *)buf + (size_t)ctx->rank * bytes_per_rank;
+  VPIN_NCCL(nccl().AllGather(send, buf, bytes_per_rank, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->st));
 }
 
 // ------------------------------------------------------------------------------------------------ host fixed base
@@ -119,9 +205,8 @@ std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, si
 }
 
 // ------------------------------------------------------------------------------------------------ Hyrax rows
-void hyrax_rows(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_t rows, size_t cols, size_t ld, const fl_t *d_blinds,
-                size_t blind_base, ge_t *d_points, uint8_t *d_comp) {
-  VPIN_REQUIRE(cols <= g.n && (!d_blinds || blind_base < g.n), VPIN_ERR_SIZE_MISMATCH, "hyrax_rows: not enough generators");
+static void hyrax_rows_local(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_t rows, size_t cols, size_t ld, const fl_t *d_blinds,
+                             size_t blind_base, ge_t *d_points, uint8_t *d_comp) {
   size_t cols_total = cols + (d_blinds ? 1 : 0);
   size_t stride = msm_col_stride(cols_total);
   // bound the digit buffer (2 bytes x windows per scalar) to ~1 GiB per pass
@@ -146,48 +231,178 @@ void hyrax_rows(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_t rows, size_
     launch_msm_finish(partial.p, nr, segs, sums.p, d_points ? d_points + r0 : nullptr, d_comp ? d_comp + 32 * r0 : nullptr, ctx->st);
   }
 }
+// Multi-GPU: the L rows of a commitment are independent MSMs over replicated generator tables, so rank r commits to
+// rows [r L/G, (r+1) L/G) and the compressed rows (32 B each) are exchanged with one in-place NCCL all-gather.
+void hyrax_rows(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_t rows, size_t cols, size_t ld, const fl_t *d_blinds,
+                size_t blind_base, ge_t *d_points, uint8_t *d_comp) {
+  VPIN_REQUIRE(cols <= g.n && (!d_blinds || blind_base < g.n), VPIN_ERR_SIZE_MISMATCH, "hyrax_rows: not enough generators");
+  size_t r0, r1;
+  bool sharded = shard_rows(rows, ctx->rank, ctx->world, &r0, &r1) && ctx->nccl_comm;
+  if (!sharded) { r0 = 0; r1 = rows; }
+  hyrax_rows_local(ctx, g, dZ + r0 * ld, r1 - r0, cols, ld, d_blinds ? d_blinds + r0 : nullptr, blind_base,
+                   d_points ? d_points + r0 : nullptr, d_comp ? d_comp + 32 * r0 : nullptr);
+  if (sharded) {
+    if (d_comp) dist_allgather_inplace(ctx, d_comp, 32 * (r1 - r0));
+    if (d_points) dist_allgather_inplace(ctx, d_points, sizeof(ge_t) * (r1 - r0));
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ instance
-static void build_matrix(Ctx *ctx, MatrixDev &m, const std::vector<uint32_t> &row, const std::vector<uint32_t> &col,
-                         const std::vector<fl_t> &val, size_t num_rows, size_t num_cols) {
-  size_t nnz = row.size();
-  m.nnz = nnz;
-  m.h_row = row;
-  m.h_col = col;
-  cudaStream_t st = ctx->st;
-  m.coo_row.alloc(nnz, st); m.coo_col.alloc(nnz, st); m.coo_val.alloc(nnz, st);
-  if (nnz) { m.coo_row.upload(row.data(), nnz); m.coo_col.upload(col.data(), nnz); m.coo_val.upload(val.data(), nnz); }
-  // CSR by counting sort on rows
-  std::vector<uint32_t> ptr(num_rows + 1, 0), idx(nnz);
-  std::vector<fl_t> v(nnz);
-  for (size_t i = 0; i < nnz; i++) ptr[row[i] + 1]++;
-  for (size_t r = 0; r < num_rows; r++) ptr[r + 1] += ptr[r];
-  {
-    std::vector<uint32_t> pos(ptr.begin(), ptr.end() - 1);
-    for (size_t i = 0; i < nnz; i++) { uint32_t p = pos[row[i]]++; idx[p] = col[i]; v[p] = val[i]; }
+// Instance::new on the device: the raw 48-byte COO triples go up as they are; one kernel validates them (first failing
+// entry wins, like the reference's sequential loop), converts the values to Montgomery form, applies the column shift of
+// Spartan/src/lib.rs:196-200 and counts rows / columns; a prefix sum and a scatter kernel then produce the CSR and CSC
+// forms (entry order inside a row or column is irrelevant: field addition is exact and commutative).
+namespace {
+__global__ void __launch_bounds__(256) k_coo_unpack(const vpin_coo_entry *raw, size_t n, uint64_t num_cons, uint64_t num_vars,
+                                                    uint64_t num_cols_in, uint64_t shift, uint32_t *row, uint32_t *col, fl_t *val,
+                                                    uint32_t *row_cnt, uint32_t *col_cnt, unsigned long long *first_err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 *q = reinterpret_cast<const uint4 *>(raw + i);
+  uint4 rc = __ldg(q), v0 = __ldg(q + 1), v1 = __ldg(q + 2);
+  uint64_t r = (uint64_t)rc.x | ((uint64_t)rc.y << 32), c = (uint64_t)rc.z | ((uint64_t)rc.w << 32);
+  fl_t x;
+  x.v[0] = v0.x; x.v[1] = v0.y; x.v[2] = v0.z; x.v[3] = v0.w; x.v[4] = v1.x; x.v[5] = v1.y; x.v[6] = v1.z; x.v[7] = v1.w;
+  int64_t br = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) { int64_t d = (int64_t)x.v[k] - (int64_t)fl_modulus_limb(k) + br; br = d >> 32; }
+  uint32_t kind = (r >= num_cons || c >= num_cols_in) ? 2u : (br == 0 ? 1u : 0u);  // 2 = InvalidIndex, 1 = InvalidScalar
+  if (kind) {
+    atomicMin(first_err, ((unsigned long long)i << 2) | kind);
+    return;
   }
-  m.csr_ptr.alloc(num_rows + 1, st); m.csr_col.alloc(nnz, st); m.csr_val.alloc(nnz, st);
-  m.csr_ptr.upload(ptr.data(), num_rows + 1);
-  if (nnz) { m.csr_col.upload(idx.data(), nnz); m.csr_val.upload(v.data(), nnz); }
-  ctx->sync();
-  // CSC by counting sort on columns
-  std::vector<uint32_t> cptr(num_cols + 1, 0);
-  for (size_t i = 0; i < nnz; i++) cptr[col[i] + 1]++;
-  for (size_t c = 0; c < num_cols; c++) cptr[c + 1] += cptr[c];
-  {
-    std::vector<uint32_t> pos(cptr.begin(), cptr.end() - 1);
-    for (size_t i = 0; i < nnz; i++) { uint32_t p = pos[col[i]]++; idx[p] = row[i]; v[p] = val[i]; }
-  }
-  std::vector<uint32_t> longc;
-  for (size_t c = 0; c < num_cols; c++)
-    if (cptr[c + 1] - cptr[c] > (uint32_t)kLongCol) longc.push_back((uint32_t)c);
-  m.n_long = longc.size();
-  m.csc_ptr.alloc(num_cols + 1, st); m.csc_row.alloc(nnz, st); m.csc_val.alloc(nnz, st); m.long_cols.alloc(longc.size(), st);
-  m.csc_ptr.upload(cptr.data(), num_cols + 1);
-  if (nnz) { m.csc_row.upload(idx.data(), nnz); m.csc_val.upload(v.data(), nnz); }
-  if (!longc.empty()) m.long_cols.upload(longc.data(), longc.size());
-  ctx->sync();
+  uint32_t cc = (uint32_t)(c >= num_vars ? c + shift : c);
+  row[i] = (uint32_t)r;
+  col[i] = cc;
+  fl_t m = fl_to_mont(x);
+  uint4 *o = reinterpret_cast<uint4 *>(val + i);
+  o[0] = make_uint4(m.v[0], m.v[1], m.v[2], m.v[3]);
+  o[1] = make_uint4(m.v[4], m.v[5], m.v[6], m.v[7]);
+  atomicAdd(row_cnt + r, 1u);
+  atomicAdd(col_cnt + cc, 1u);
 }
+// exclusive prefix sum of n + 1 counters (cnt[n] == 0 on entry) by one block; n is at most 2^27 here
+__global__ void __launch_bounds__(1024) k_exclusive_scan(uint32_t *cnt, size_t n_plus_1) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (size_t base = 0; base < n_plus_1; base += 1024 * 4) {
+    size_t i = base + (size_t)threadIdx.x * 4;
+    uint32_t v[4], t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = i + k < n_plus_1 ? cnt[i + k] : 0u; t += v[k]; }
+    uint32_t incl = t;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += o; }
+      warp_sums[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    uint32_t excl = carry + warp_sums[warp] + incl - t;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (i + k < n_plus_1) cnt[i + k] = excl; excl += v[k]; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_coo_scatter(const uint32_t *row, const uint32_t *col, const fl_t *val, size_t n, uint32_t *row_cur,
+                                                     uint32_t *col_cur, uint32_t *csr_col, fl_t *csr_val, uint32_t *csc_row, fl_t *csc_val) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t r = row[i], c = col[i];
+  const uint4 *q = reinterpret_cast<const uint4 *>(val + i);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  uint32_t p = atomicAdd(row_cur + r, 1u);
+  csr_col[p] = c;
+  reinterpret_cast<uint4 *>(csr_val + p)[0] = a;
+  reinterpret_cast<uint4 *>(csr_val + p)[1] = b;
+  uint32_t p2 = atomicAdd(col_cur + c, 1u);
+  csc_row[p2] = r;
+  reinterpret_cast<uint4 *>(csc_val + p2)[0] = a;
+  reinterpret_cast<uint4 *>(csc_val + p2)[1] = b;
+}
+__global__ void __launch_bounds__(256) k_find_long_cols(const uint32_t *cptr, size_t ncols, uint32_t *long_cols, uint32_t *n_long, uint32_t cap) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  if (cptr[c + 1] - cptr[c] > (uint32_t)kLongCol) {
+    uint32_t k = atomicAdd(n_long, 1u);
+    if (k < cap) long_cols[k] = (uint32_t)c;
+  }
+}
+
+// returns 0, or the error kind of the first invalid entry
+uint32_t build_matrix(Ctx *ctx, MatrixDev &m, const vpin_coo_entry *entries, size_t n, size_t n_pad, uint64_t num_cons, uint64_t num_vars,
+                      uint64_t num_inputs, size_t num_rows, size_t num_vars_padded) {
+  cudaStream_t st = ctx->st;
+  size_t num_cols = 2 * num_vars_padded, nnz = n + n_pad;
+  m.nnz = nnz;
+  // host copies of the (shifted) indices: SNARK::encode replays them sequentially for the memory-check timestamps
+  m.h_row.resize(nnz);
+  m.h_col.resize(nnz);
+  uint64_t shift = num_vars_padded - num_vars, ncols_in = num_vars + 1 + num_inputs;
+  for (size_t i = 0; i < n; i++) {
+    m.h_row[i] = (uint32_t)entries[i].row;
+    uint64_t c = entries[i].col;
+    m.h_col[i] = (uint32_t)(c >= num_vars ? c + shift : c);
+  }
+  std::vector<vpin_coo_entry> pad(n_pad);
+  for (size_t i = 0; i < n_pad; i++) {  // Spartan/src/lib.rs:207-211: (i, num_vars, 0), column NOT shifted
+    memset(&pad[i], 0, sizeof(vpin_coo_entry));
+    pad[i].row = n + i;
+    pad[i].col = num_vars;
+    m.h_row[n + i] = (uint32_t)(n + i);
+    m.h_col[n + i] = (uint32_t)num_vars;
+  }
+  DevVec<vpin_coo_entry> raw(nnz, st);
+  if (n) VPIN_CUDA(cudaMemcpyAsync(raw.p, entries, n * sizeof(vpin_coo_entry), cudaMemcpyHostToDevice, st));
+  m.coo_row.alloc(nnz, st); m.coo_col.alloc(nnz, st); m.coo_val.alloc(nnz, st);
+  m.csr_ptr.alloc(num_rows + 1, st); m.csc_ptr.alloc(num_cols + 1, st);
+  m.csr_col.alloc(nnz, st); m.csr_val.alloc(nnz, st); m.csc_row.alloc(nnz, st); m.csc_val.alloc(nnz, st);
+  m.csr_ptr.zero(); m.csc_ptr.zero();
+  DevVec<unsigned long long> d_err(1, st);
+  VPIN_CUDA(cudaMemsetAsync(d_err.p, 0xff, sizeof(unsigned long long), st));
+  if (n)
+    ++g_kernel_launches, k_coo_unpack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw.p, n, num_cons, num_vars, ncols_in, shift, m.coo_row.p, m.coo_col.p,
+                                                                                 m.coo_val.p, m.csr_ptr.p, m.csc_ptr.p, d_err.p);
+  if (n_pad) {  // padding rows carry the unshifted column num_vars and are exempt from the index checks
+    DevVec<vpin_coo_entry> dpad(n_pad, st);
+    dpad.upload(pad.data(), n_pad);
+    ++g_kernel_launches, k_coo_unpack<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(dpad.p, n_pad, num_rows, num_cols, num_cols, 0, m.coo_row.p + n,
+                                                                                     m.coo_col.p + n, m.coo_val.p + n, m.csr_ptr.p, m.csc_ptr.p, d_err.p);
+    ctx->sync();
+  }
+  unsigned long long err = 0;
+  VPIN_CUDA(cudaMemcpyAsync(&err, d_err.p, sizeof(err), cudaMemcpyDeviceToHost, st));
+  ctx->sync();
+  if (err != ~0ull) return (uint32_t)(err & 3);
+  ++g_kernel_launches, k_exclusive_scan<<<1, 1024, 0, st>>>(m.csr_ptr.p, num_rows + 1);
+  ++g_kernel_launches, k_exclusive_scan<<<1, 1024, 0, st>>>(m.csc_ptr.p, num_cols + 1);
+  DevVec<uint32_t> row_cur(num_rows + 1, st), col_cur(num_cols + 1, st), n_long(1, st);
+  VPIN_CUDA(cudaMemcpyAsync(row_cur.p, m.csr_ptr.p, (num_rows + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  VPIN_CUDA(cudaMemcpyAsync(col_cur.p, m.csc_ptr.p, (num_cols + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  if (nnz)
+    ++g_kernel_launches, k_coo_scatter<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(m.coo_row.p, m.coo_col.p, m.coo_val.p, nnz, row_cur.p, col_cur.p,
+                                                                                    m.csr_col.p, m.csr_val.p, m.csc_row.p, m.csc_val.p);
+  const uint32_t cap = 4096;
+  m.long_cols.alloc(cap, st);
+  n_long.zero();
+  ++g_kernel_launches, k_find_long_cols<<<(unsigned)((num_cols + 255) / 256), 256, 0, st>>>(m.csc_ptr.p, num_cols, m.long_cols.p, n_long.p, cap);
+  uint32_t h_long = 0;
+  VPIN_CUDA(cudaMemcpyAsync(&h_long, n_long.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  ctx->sync();
+  VPIN_REQUIRE(h_long <= cap, VPIN_ERR_BAD_ARGUMENT, "too many dense columns");
+  m.n_long = h_long;
+  return 0;
+}
+}  // namespace
 
 // Spartan/src/lib.rs:138-244 (Instance::new): padding rules and error behaviour; the zlib digest (:241) is unused on
 // the SNARK path and is not computed.
@@ -207,22 +422,10 @@ std::unique_ptr<Instance> instance_create(Ctx *ctx, uint64_t num_cons, uint64_t 
   const vpin_coo_entry *src[3] = {A, B, C};
   uint64_t cnt[3] = {nA, nB, nC};
   for (int k = 0; k < 3; k++) {
-    std::vector<uint32_t> row, col;
-    std::vector<fl_t> val;
-    row.reserve(cnt[k]); col.reserve(cnt[k]); val.reserve(cnt[k]);
-    for (uint64_t i = 0; i < cnt[k]; i++) {
-      const vpin_coo_entry &e = src[k][i];
-      VPIN_REQUIRE(e.row < num_cons, VPIN_ERR_INVALID_INDEX, "InvalidIndex: row");
-      VPIN_REQUIRE(e.col < num_vars + 1 + num_inputs, VPIN_ERR_INVALID_INDEX, "InvalidIndex: col");
-      fl_t v;
-      VPIN_REQUIRE(fl_from_bytes(e.val, &v), VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
-      row.push_back((uint32_t)e.row);
-      col.push_back((uint32_t)(e.col >= num_vars ? e.col + num_vars_padded - num_vars : e.col));
-      val.push_back(v);
-    }
-    if (num_cons == 0 || num_cons == 1)
-      for (size_t i = cnt[k]; i < num_cons_padded; i++) { row.push_back((uint32_t)i); col.push_back((uint32_t)num_vars); val.push_back(fl_zero()); }
-    build_matrix(ctx, inst->M[k], row, col, val, num_cons_padded, 2 * num_vars_padded);
+    size_t n_pad = (num_cons == 0 || num_cons == 1) && cnt[k] < num_cons_padded ? num_cons_padded - cnt[k] : 0;
+    uint32_t err = build_matrix(ctx, inst->M[k], src[k], cnt[k], n_pad, num_cons, num_vars, num_inputs, num_cons_padded, num_vars_padded);
+    VPIN_REQUIRE(err != 2, VPIN_ERR_INVALID_INDEX, "InvalidIndex");
+    VPIN_REQUIRE(err != 1, VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
   }
   return inst;
 }

@@ -121,9 +121,22 @@ struct vpin_ctx_impl {
   fl_t *h_small = nullptr;   // pinned mirror
   std::vector<std::pair<const char *, double>> phases;
   Prof prof;
+  // multi-GPU (one process per GPU): NCCL communicator over NVLink/NVSwitch, created by vpin_ctx_init_distributed
+  int rank = 0, world = 1;
+  void *nccl_comm = nullptr;
   DevVec<unsigned long long> d_counters;  // [0] = non-zero MSM digits recoded (= mixed additions executed)
   void sync() { VPIN_CUDA(cudaStreamSynchronize(st)); }
 };
+
+// rows [*r0, *r1) of an L-row Hyrax grid that rank `rank` of `world` commits to; the whole range when the grid is too
+// small to shard (fewer than kMinShardRows rows per rank) or not divisible. Returns true when the grid is sharded.
+static const size_t kMinShardRows = 32;
+bool shard_rows(size_t rows, int rank, int world, size_t *r0, size_t *r1);
+// in-place all-gather of `bytes_per_rank` bytes per rank inside buf (rank r's slice at offset r * bytes_per_rank)
+void dist_allgather_inplace(Ctx *ctx, void *buf, size_t bytes_per_rank);
+void dist_get_unique_id(uint8_t out[128]);
+void dist_init(Ctx *ctx, int rank, int world, const uint8_t id[128]);
+void dist_destroy(Ctx *ctx);
 
 std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n);
 
