@@ -241,7 +241,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------ B200 arm
@@ -392,7 +392,7 @@ def run_b200(args):
     else:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     # handles (gens, instances, decommitments) must go before the context that owns their stream
     import gc
     del states, last, first, e2e_out
@@ -432,7 +432,20 @@ def msm_uniform_bench(ctx, torch, dev, stream, imad_peak):
             "imad_peak_tmacs": imad_peak / 1e12}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line, on the real stdout (fd 1 is pointed at stderr while the run is in progress so that library
+    banners — e.g. NCCL's version line — cannot get in front of it)"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
