@@ -70,6 +70,11 @@ vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out) {
     ctx->d_counters.alloc(4, ctx->st);
     ctx->d_counters.zero();
     VPIN_CUDA(cudaMallocHost((void **)&ctx->h_small, 512 * sizeof(fl_t)));
+    VPIN_CUDA(cudaHostAlloc((void **)&ctx->h_slots, 2 * sizeof(RoundSlot), cudaHostAllocMapped));
+    memset(ctx->h_slots, 0, 2 * sizeof(RoundSlot));
+    VPIN_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_slots, ctx->h_slots, 0));
+    ctx->d_round_counters.alloc(1 + kMaxBatched + 13, ctx->st);
+    ctx->d_round_counters.zero();
     ctx->sync();
   } catch (const std::exception &) {
     delete ctx;
@@ -91,6 +96,8 @@ void vpin_ctx_destroy(vpin_ctx *ctx_) {
   for (auto &p : ctx->prof.pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
+  ctx->d_round_counters.release();
   cudaStreamSynchronize(ctx->st);
   cudaStreamDestroy(ctx->st);
   delete ctx;

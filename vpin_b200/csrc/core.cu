@@ -130,48 +130,6 @@ void dist_allgather_inplace(Ctx *ctx, void *buf, size_t bytes_per_rank) {
   VPIN_NCCL(nccl().AllGather(send, buf, bytes_per_rank, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->st));
 }
 
-// ------------------------------------------------------------------------------------------------ host fixed base
-void HostBase::build(const ge_t &p) {
-  const int P = 64, M = 8;
-  std::vector<ge_t> ext(P * M);
-  ge_t base = p;
-  for (int pos = 0; pos < P; pos++) {
-    ge_t cur = base;
-    for (int m = 0; m < M; m++) {
-      ext[pos * M + m] = cur;
-      if (m + 1 < M) cur = ge_add(cur, base);
-    }
-    for (int k = 0; k < 4; k++) base = ge_dbl(base);
-  }
-  // batch inversion of all Z
-  std::vector<fp_t> prefix(P * M);
-  fp_t run = fp_one();
-  for (int i = 0; i < P * M; i++) { run = fp_mul(run, ext[i].Z); prefix[i] = run; }
-  fp_t inv = fp_invert(run);
-  tbl.resize(P * M);
-  for (int i = P * M - 1; i >= 0; i--) {
-    fp_t zinv = i > 0 ? fp_mul(inv, prefix[i - 1]) : inv;
-    inv = fp_mul(inv, ext[i].Z);
-    tbl[i] = ge_to_niels(ext[i], zinv);
-  }
-}
-void HostBase::mul_acc(const fl_t &s_mont, ge_t *acc) const {
-  fl_t s = fl_from_mont(s_mont);
-  int carry = 0;
-  for (int pos = 0; pos < 64; pos++) {
-    int d = (int)((s.v[pos >> 3] >> ((pos & 7) * 4)) & 15u) + carry;
-    carry = 0;
-    if (d > 8) { d -= 16; carry = 1; }
-    if (d > 0) *acc = ge_madd(*acc, tbl[pos * 8 + d - 1]);
-    else if (d < 0) *acc = ge_msub(*acc, tbl[pos * 8 - d - 1]);
-  }
-}
-ge_t HostBase::mul(const fl_t &s_mont) const {
-  ge_t acc = ge_identity();
-  mul_acc(s_mont, &acc);
-  return acc;
-}
-
 // ------------------------------------------------------------------------------------------------ generators
 std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n) {
   auto it = ctx->label_gens.find(label);

@@ -11,6 +11,7 @@
 
 #include "../../include/vpin_b200.h"
 #include "ed.cuh"
+#include "host_fast.hpp"
 #include "kernels_msm.cuh"
 #include "kernels_poly.cuh"
 #include "merlin.hpp"
@@ -65,6 +66,9 @@ struct DevVec {
   void zero() { if (n) VPIN_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
 };
 
+// host fixed-base scalar multiplication for the handful of generators used by the sigma protocols (host_fast.hpp)
+typedef hf::FixedBase HostBase;
+
 // generators of one SHAKE256 stream (Spartan/src/commitments.rs:20-38) with their fixed-base table in HBM
 struct LabelGens {
   std::string label;
@@ -72,15 +76,15 @@ struct LabelGens {
   std::vector<ge_t> h_pts;      // host copies (extended)
   DevVec<ge_t> d_pts;
   DevVec<niels_t> d_table;      // n * kMsmTable entries
+  std::map<size_t, std::unique_ptr<HostBase>> host_bases;  // built on first use, kept with the stream
   MsmTable table() const { return MsmTable{d_table.p, n}; }
-};
-
-// host fixed-base scalar multiplication for the handful of generators used by the sigma protocols
-struct HostBase {
-  std::vector<niels_t> tbl;  // [64 positions][8 multiples] of 16^pos * P, signed 4-bit digits
-  void build(const ge_t &p);
-  ge_t mul(const fl_t &s_mont) const;            // s * P
-  void mul_acc(const fl_t &s_mont, ge_t *acc) const;  // *acc += s * P
+  const HostBase *host_base(size_t index) {
+    auto it = host_bases.find(index);
+    if (it != host_bases.end()) return it->second.get();
+    auto b = std::make_unique<HostBase>();
+    b->build(hf::ge_from_dev(h_pts.at(index)));
+    return (host_bases[index] = std::move(b)).get();
+  }
 };
 
 struct vpin_ctx_impl;
@@ -119,6 +123,11 @@ struct vpin_ctx_impl {
   DevVec<fl_t> d_partials;   // reduction scratch
   DevVec<fl_t> d_small;      // small device results / parameters
   fl_t *h_small = nullptr;   // pinned mirror
+  // fused sumcheck rounds (kernels_round.cu): two host-mapped result slots used alternately, the counters of the
+  // last-block reductions, and the sequence number of the latest launch
+  RoundSlot *h_slots = nullptr, *d_slots = nullptr;
+  DevVec<unsigned> d_round_counters;
+  uint32_t round_seq = 0;
   std::vector<std::pair<const char *, double>> phases;
   Prof prof;
   // multi-GPU (one process per GPU): NCCL communicator over NVLink/NVSwitch, created by vpin_ctx_init_distributed

@@ -138,10 +138,42 @@ VPIN_HD fl_t fl_dbl(const fl_t &a) { return fl_add(a, a); }
 
 // Montgomery product a*b/R mod l: interleaved product / reduction rows of limbs.cuh (the modulus has limbs 4..6 == 0 and
 // limb 7 == 2^28, so a reduction row costs 5 multiplies), then one conditional subtraction.
+#if !defined(__CUDA_ARCH__)
+// host: 4 x 64-bit CIOS Montgomery multiplication with 128-bit products (the transcript-side arithmetic of the prover)
+inline fl_t fl_mul_host64(const fl_t &a, const fl_t &b) {
+  typedef unsigned __int128 u128;
+  static const uint64_t P[4] = {0x5812631a5cf5d3edull, 0x14def9dea2f79cd6ull, 0ull, 0x1000000000000000ull};
+  static const uint64_t INV = 0xd2b51da312547e1bull;  // reference :305
+  uint64_t x[4], y[4], t[6] = {0, 0, 0, 0, 0, 0};
+  memcpy(x, a.v, 32);
+  memcpy(y, b.v, 32);
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) { c += (u128)x[j] * y[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * INV;
+    c = (u128)m * P[0] + t[0];
+    c >>= 64;
+    for (int j = 1; j < 4; j++) { c += (u128)m * P[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  // t < 2l: one conditional subtraction
+  uint64_t d[4];
+  u128 br = 0;
+  for (int j = 0; j < 4; j++) { u128 s = (u128)t[j] - P[j] - (uint64_t)br; d[j] = (uint64_t)s; br = (s >> 64) & 1; }
+  fl_t r;
+  memcpy(r.v, br ? t : d, 32);
+  return r;
+}
+#endif
 VPIN_HD fl_t fl_mul(const fl_t &a, const fl_t &b) {
+#if defined(__CUDA_ARCH__)
   fl_t r;
   limb::mont_mul_l(r.v, a.v, b.v);
   return fl_cond_sub(r);
+#else
+  return fl_mul_host64(a, b);
+#endif
 }
 VPIN_HD fl_t fl_sqr(const fl_t &a) { return fl_mul(a, a); }
 

@@ -104,6 +104,37 @@ __global__ void __launch_bounds__(256) k_eq_outer(const fl_t *hi, const fl_t *lo
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     st_fl(out + i, fl_mul(ldg_fl(hi + (i >> lo_bits)), ldg_fl(lo + (i & (((size_t)1 << lo_bits) - 1)))));
 }
+// the point in kernel-parameter space (Spartan/src/dense_mlpoly.rs:78-94)
+__global__ void __launch_bounds__(1024) k_eq_small_pt(EqPoint pt, int first, int ell, fl_t *dst, fl_t *tmp) {
+  fl_t *a = (ell & 1) ? tmp : dst, *b = (ell & 1) ? dst : tmp;
+  if (threadIdx.x == 0) st_fl(a, fl_one());
+  __syncthreads();
+  for (int j = 0; j < ell; j++) {
+    fl_t rj = pt.r[first + j];
+    int size = 1 << j;
+    for (int i = threadIdx.x; i < size; i += blockDim.x) {
+      fl_t s = ld_fl(a + i);
+      fl_t hi = fl_mul(s, rj);
+      st_fl(b + 2 * i + 1, hi);
+      st_fl(b + 2 * i, fl_sub(s, hi));
+    }
+    __syncthreads();
+    fl_t *t = a; a = b; b = t;
+  }
+}
+void launch_eq_evals_pt(const EqPoint &pt, int ell, fl_t *d_out, fl_t *d_tmp, cudaStream_t st) {
+  if (ell <= 12) {
+    ++g_kernel_launches, k_eq_small_pt<<<1, ell <= 8 ? 256 : 1024, 0, st>>>(pt, 0, ell, d_out, d_tmp);
+    return;
+  }
+  int hi_bits = ell / 2, lo_bits = ell - hi_bits;
+  fl_t *hi = d_tmp, *lo = d_tmp + ((size_t)1 << hi_bits), *scratch = lo + ((size_t)1 << lo_bits);
+  ++g_kernel_launches, k_eq_small_pt<<<1, 1024, 0, st>>>(pt, 0, hi_bits, hi, scratch);
+  ++g_kernel_launches, k_eq_small_pt<<<1, 1024, 0, st>>>(pt, hi_bits, lo_bits, lo, scratch);
+  size_t n = (size_t)1 << ell;
+  unsigned blocks = (unsigned)((n / 256) < 148 * 16 ? (n / 256) : 148 * 16);
+  ++g_kernel_launches, k_eq_outer<<<blocks, 256, 0, st>>>(hi, lo, lo_bits, n, d_out);
+}
 void launch_eq_evals(const fl_t *d_r, int ell, fl_t *d_out, fl_t *d_tmp, cudaStream_t st) {
   if (ell <= 12) {
     ++g_kernel_launches, k_eq_small<<<1, 1024, 0, st>>>(d_r, ell, d_out, d_tmp);

@@ -34,6 +34,38 @@ void launch_quad_round(const fl_t *A, const fl_t *B, size_t half, fl_t *d_out, f
 void launch_cubic_batched_round(const fl_t *const *d_A, const fl_t *const *d_B, const fl_t *const *d_C, int n, size_t half,
                                 fl_t *d_out, fl_t *d_partials, cudaStream_t st);
 
+// ---- fused rounds (kernels_round.cu): bind with the previous challenge + evaluate the next round in one launch, results
+// delivered to host-mapped pinned memory. ----
+static const int kRoundSlotVals = 64;
+struct RoundSlot {                 // lives in cudaHostAllocMapped memory
+  fl_t vals[kRoundSlotVals];
+  uint32_t seq;                    // written last (after a system-wide fence) with the launch's sequence number
+  uint32_t pad[7];
+};
+struct RoundCtl {
+  fl_t *d_partials;                // >= 3 * kRedBlocks * ninst elements
+  unsigned *d_counters;            // 1 + ninst words, zero between launches
+  RoundSlot *slot;                 // device-visible address of the slot
+  uint32_t seq;
+};
+static const int kMaxBatched = 18;  // 12 product circuits + 6 dot-product halves (Spartan/src/sparse_mlpoly.rs:1173-1197)
+struct BatchedRoundArgs {
+  fl_t *A[kMaxBatched], *B[kMaxBatched];  // bound in place
+  const fl_t *Cin[kMaxBatched];           // third factor; the product circuits share one eq table
+  fl_t *Cout[kMaxBatched];                // where the bound third factor goes (== Cin for an owned table, a ping-pong
+};                                        // buffer for the owner of the shared table, nullptr for its other readers)
+struct FinalArgs { const fl_t *p[kRoundSlotVals]; int n; };
+// q = number of thread items: half the current length without bind, a quarter of it with bind (the tables then shrink
+// to half their length in place). r is ignored without bind.
+void launch_round_cubic_additive(fl_t *A, fl_t *B, fl_t *C, fl_t *D, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
+void launch_round_quad(fl_t *A, fl_t *B, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
+void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
+// vals[k] = p_k[0] + r (p_k[1] - p_k[0]) (bind) or p_k[0]
+void launch_round_final(const FinalArgs &a, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
+// eq table with the point passed by value (no device-side copy of r needed); same output as launch_eq_evals
+struct EqPoint { fl_t r[32]; };
+void launch_eq_evals_pt(const EqPoint &pt, int ell, fl_t *d_out, fl_t *d_tmp, cudaStream_t st);
+
 // dot product sum_i A[i] B[i] (Spartan/src/nizk/mod.rs:442-445). d_out: 1 element; d_partials: kRedBlocks.
 void launch_dot(const fl_t *A, const fl_t *B, size_t n, fl_t *d_out, fl_t *d_partials, cudaStream_t st);
 // n dot products against one shared vector B: out[k] = <A_k, B>

@@ -1,0 +1,254 @@
+// Fused sumcheck round kernels for sm_100a: one launch per round binds every table with the previous challenge
+// (Spartan/src/dense_mlpoly.rs:229-236) and evaluates the next round polynomial (Spartan/src/sumcheck.rs:287-357, :456-469,
+// :619-652) in the same pass — each table element is read once and the half-length table written once per round
+// (48 * k * L bytes for k tables of length L, the algorithmic figure of SURVEY.md 8d). The challenge travels as a kernel
+// parameter; the round sums are reduced by the last block to arrive and stored straight into host-mapped pinned memory
+// followed by a sequence number, so a round costs one launch and no memcpy / stream synchronisation.
+//
+// Layout of a bind+evaluate step on a table of current length 4q: thread i < q owns T[i], T[i+q], T[i+2q], T[i+3q];
+//   lo' = T[i]   + r (T[i+2q] - T[i])      (element i       of the bound table, length 2q)
+//   hi' = T[i+q] + r (T[i+3q] - T[i+q])    (element i + q   of the bound table)
+// are stored in place (no other thread touches these four slots) and (lo', hi') is the pair the evaluation needs.
+#include <atomic>
+
+#include "kernels_poly.cuh"
+
+namespace vpin {
+
+extern std::atomic<uint64_t> g_kernel_launches;
+
+namespace {
+
+__device__ __forceinline__ fl_t ldr(const fl_t *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = q[0], b = q[1];
+  fl_t r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ fl_t ldcg(const fl_t *p) {  // L2 (partials written by other blocks)
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = __ldcg(q), b = __ldcg(q + 1);
+  fl_t r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void str(fl_t *p, const fl_t &x) {
+  uint4 *q = reinterpret_cast<uint4 *>(p);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+__device__ __forceinline__ fl_t shfl_down(const fl_t &x, int off) {
+  fl_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, x.v[i], off);
+  return r;
+}
+// block-wide sums of K accumulators; valid in thread 0
+template <int K>
+__device__ __forceinline__ void block_sum(fl_t (&acc)[K]) {
+  __shared__ fl_t sm[K][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = fl_add(acc[k], shfl_down(acc[k], off));
+  __syncthreads();  // sm may still be read by a previous call
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < K; k++) sm[k][warp] = acc[k];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      fl_t v = lane < nwarps ? sm[k][lane] : fl_zero();
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v = fl_add(v, shfl_down(v, off));
+      acc[k] = v;
+    }
+  }
+}
+// Writes the block's K sums to partials[(inst * gridDim.x + blockIdx.x) * K ..]; the last block of instance `inst` to
+// arrive adds all partials of the instance and stores them to slot->vals[inst * K ..]; the last instance to finish
+// publishes the sequence number. counters[0] counts finished instances, counters[1 + inst] finished blocks of an instance.
+template <int K>
+__device__ __forceinline__ void publish(fl_t (&acc)[K], int inst, int ninst, fl_t *partials, unsigned *counters, RoundSlot *slot,
+                                        uint32_t seq) {
+  __shared__ bool is_last;
+  block_sum<K>(acc);
+  fl_t *mine = partials + ((size_t)inst * gridDim.x + blockIdx.x) * K;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) str(mine + k, acc[k]);
+    __threadfence();
+    is_last = atomicAdd(counters + 1 + inst, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < K; k++) acc[k] = fl_zero();
+  const fl_t *p = partials + (size_t)inst * gridDim.x * K;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = fl_add(acc[k], ldcg(p + (size_t)b * K + k));
+  block_sum<K>(acc);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) str(slot->vals + inst * K + k, acc[k]);
+    counters[1 + inst] = 0;
+    __threadfence_system();
+    if (atomicAdd(counters, 1u) == (unsigned)ninst - 1) {
+      counters[0] = 0;
+      __threadfence_system();
+      *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
+    }
+  }
+}
+
+__device__ __forceinline__ fl_t bind1(const fl_t &lo, const fl_t &hi, const fl_t &r) { return fl_add(lo, fl_mul(r, fl_sub(hi, lo))); }
+
+// loads the evaluation pair (lo, hi) of thread item i; with kBind the table is first bound in place with r
+template <bool kBind>
+__device__ __forceinline__ void load_pair(fl_t *T, size_t i, size_t q, const fl_t &r, fl_t &lo, fl_t &hi) {
+  if (kBind) {
+    fl_t t0 = ldr(T + i), t1 = ldr(T + i + q), t2 = ldr(T + i + 2 * q), t3 = ldr(T + i + 3 * q);
+    lo = bind1(t0, t2, r);
+    hi = bind1(t1, t3, r);
+    str(T + i, lo);
+    str(T + i + q, hi);
+  } else {
+    lo = ldr(T + i);
+    hi = ldr(T + i + q);
+  }
+}
+// same for a table that is read from `in` and (optionally) written to a different buffer `out`
+template <bool kBind>
+__device__ __forceinline__ void load_pair_oop(const fl_t *in, fl_t *out, bool write, size_t i, size_t q, const fl_t &r, fl_t &lo, fl_t &hi) {
+  if (kBind) {
+    fl_t t0 = ldr(in + i), t1 = ldr(in + i + q), t2 = ldr(in + i + 2 * q), t3 = ldr(in + i + 3 * q);
+    lo = bind1(t0, t2, r);
+    hi = bind1(t1, t3, r);
+    if (write) { str(out + i, lo); str(out + i + q, hi); }
+  } else {
+    lo = ldr(in + i);
+    hi = ldr(in + i + q);
+  }
+}
+
+// ---- A (B C - D) at t = 0, 2, 3 ----
+template <bool kBind>
+__global__ void __launch_bounds__(kRedThreads) k_round_cubic_additive(fl_t *A, fl_t *B, fl_t *C, fl_t *D, size_t q, fl_t r, fl_t *partials,
+                                                                      unsigned *counters, RoundSlot *slot, uint32_t seq) {
+  fl_t acc[3] = {fl_zero(), fl_zero(), fl_zero()};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += stride) {
+    fl_t a0, a1, b0, b1, c0, c1, d0, d1;
+    load_pair<kBind>(A, i, q, r, a0, a1);
+    load_pair<kBind>(B, i, q, r, b0, b1);
+    load_pair<kBind>(C, i, q, r, c0, c1);
+    load_pair<kBind>(D, i, q, r, d0, d1);
+    acc[0] = fl_add(acc[0], fl_mul(a0, fl_sub(fl_mul(b0, c0), d0)));
+    fl_t da = fl_sub(a1, a0), db = fl_sub(b1, b0), dc = fl_sub(c1, c0), dd = fl_sub(d1, d0);
+    fl_t a2 = fl_add(a1, da), b2 = fl_add(b1, db), c2 = fl_add(c1, dc), d2 = fl_add(d1, dd);
+    acc[1] = fl_add(acc[1], fl_mul(a2, fl_sub(fl_mul(b2, c2), d2)));
+    fl_t a3 = fl_add(a2, da), b3 = fl_add(b2, db), c3 = fl_add(c2, dc), d3 = fl_add(d2, dd);
+    acc[2] = fl_add(acc[2], fl_mul(a3, fl_sub(fl_mul(b3, c3), d3)));
+  }
+  publish<3>(acc, 0, 1, partials, counters, slot, seq);
+}
+
+// ---- A B at t = 0, 2 ----
+template <bool kBind>
+__global__ void __launch_bounds__(kRedThreads) k_round_quad(fl_t *A, fl_t *B, size_t q, fl_t r, fl_t *partials, unsigned *counters,
+                                                            RoundSlot *slot, uint32_t seq) {
+  fl_t acc[2] = {fl_zero(), fl_zero()};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += stride) {
+    fl_t a0, a1, b0, b1;
+    load_pair<kBind>(A, i, q, r, a0, a1);
+    load_pair<kBind>(B, i, q, r, b0, b1);
+    acc[0] = fl_add(acc[0], fl_mul(a0, b0));
+    fl_t a2 = fl_add(a1, fl_sub(a1, a0)), b2 = fl_add(b1, fl_sub(b1, b0));
+    acc[1] = fl_add(acc[1], fl_mul(a2, b2));
+  }
+  publish<2>(acc, 0, 1, partials, counters, slot, seq);
+}
+
+// ---- batched A_k B_k C_k at t = 0, 2, 3; instance = blockIdx.y ----
+template <bool kBind>
+__global__ void __launch_bounds__(kRedThreads) k_round_cubic_batched(BatchedRoundArgs a, size_t q, fl_t r, fl_t *partials, unsigned *counters,
+                                                                     RoundSlot *slot, uint32_t seq) {
+  const int inst = blockIdx.y;
+  fl_t *A = a.A[inst], *B = a.B[inst];
+  const fl_t *Cin = a.Cin[inst];
+  fl_t *Cout = a.Cout[inst];
+  const bool writeC = Cout != nullptr;
+  fl_t acc[3] = {fl_zero(), fl_zero(), fl_zero()};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += stride) {
+    fl_t a0, a1, b0, b1, c0, c1;
+    load_pair<kBind>(A, i, q, r, a0, a1);
+    load_pair<kBind>(B, i, q, r, b0, b1);
+    load_pair_oop<kBind>(Cin, Cout, writeC, i, q, r, c0, c1);
+    acc[0] = fl_add(acc[0], fl_mul(fl_mul(a0, b0), c0));
+    fl_t da = fl_sub(a1, a0), db = fl_sub(b1, b0), dc = fl_sub(c1, c0);
+    fl_t a2 = fl_add(a1, da), b2 = fl_add(b1, db), c2 = fl_add(c1, dc);
+    acc[1] = fl_add(acc[1], fl_mul(fl_mul(a2, b2), c2));
+    fl_t a3 = fl_add(a2, da), b3 = fl_add(b2, db), c3 = fl_add(c2, dc);
+    acc[2] = fl_add(acc[2], fl_mul(fl_mul(a3, b3), c3));
+  }
+  publish<3>(acc, inst, gridDim.y, partials, counters, slot, seq);
+}
+
+// ---- final claims: vals[k] = p_k[0] + r (p_k[1] - p_k[0])  (or p_k[0] when nothing is left to bind) ----
+__global__ void __launch_bounds__(64) k_round_final(FinalArgs a, fl_t r, int bind, RoundSlot *slot, uint32_t seq) {
+  int k = threadIdx.x;
+  if (k < a.n) {
+    const fl_t *p = a.p[k];
+    fl_t v = ldr(p);
+    if (bind) v = bind1(v, ldr(p + 1), r);
+    str(slot->vals + k, v);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
+  }
+}
+
+inline int round_blocks(size_t q, int cap) {
+  size_t b = (q + kRedThreads - 1) / kRedThreads;
+  if (b < 1) b = 1;
+  return (int)(b > (size_t)cap ? cap : b);
+}
+
+}  // namespace
+
+void launch_round_cubic_additive(fl_t *A, fl_t *B, fl_t *C, fl_t *D, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
+  int nb = round_blocks(q, kRedBlocks);
+  ++g_kernel_launches;
+  if (bind) k_round_cubic_additive<true><<<nb, kRedThreads, 0, st>>>(A, B, C, D, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
+  else k_round_cubic_additive<false><<<nb, kRedThreads, 0, st>>>(A, B, C, D, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
+}
+void launch_round_quad(fl_t *A, fl_t *B, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
+  int nb = round_blocks(q, kRedBlocks);
+  ++g_kernel_launches;
+  if (bind) k_round_quad<true><<<nb, kRedThreads, 0, st>>>(A, B, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
+  else k_round_quad<false><<<nb, kRedThreads, 0, st>>>(A, B, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
+}
+void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
+  int nb = round_blocks(q, ninst > 4 ? kRedBlocks / 4 : kRedBlocks);
+  dim3 grid(nb, ninst);
+  ++g_kernel_launches;
+  if (bind) k_round_cubic_batched<true><<<grid, kRedThreads, 0, st>>>(a, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
+  else k_round_cubic_batched<false><<<grid, kRedThreads, 0, st>>>(a, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
+}
+void launch_round_final(const FinalArgs &a, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
+  ++g_kernel_launches, k_round_final<<<1, 64, 0, st>>>(a, r, bind ? 1 : 0, c.slot, c.seq);
+}
+
+}  // namespace vpin

@@ -16,9 +16,10 @@ static double now_ms() {
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
-static Comp compress_host(const ge_t &g) {
+typedef hf::ge hge_t;  // host-side points (5 x 51-bit limbs, host_fast.hpp)
+static Comp compress_host(const hge_t &g) {
   Comp c;
-  ge_compress(g, c.data());
+  hf::ge_compress(g, c.data());
   return c;
 }
 // Math::log_2 (SP/math.rs:27-35): exact for powers of two, ceil otherwise
@@ -68,15 +69,15 @@ static void put(Bin &o, const BatchedS &p) {
 }
 
 // ------------------------------------------------------------------------------------------------ gens
-static void make_pc(Ctx *ctx, const LabelGens &lg, size_t ell, PcGens *pc) {
+static void make_pc(Ctx *ctx, LabelGens &lg, size_t ell, PcGens *pc) {
   pc->ell = ell;
   pc->L = (size_t)1 << (ell / 2);
   pc->R = (size_t)1 << (ell - ell / 2);
   pc->g1_index = pc->R;
   pc->h_index = pc->R + 1;
   VPIN_REQUIRE(pc->h_index < lg.n, VPIN_ERR_SIZE_MISMATCH, "generator stream too short");
-  pc->g1.build(lg.h_pts[pc->g1_index]);
-  pc->h.build(lg.h_pts[pc->h_index]);
+  pc->g1 = lg.host_base(pc->g1_index);
+  pc->h = lg.host_base(pc->h_index);
 }
 // SP/lib.rs:305-326, SP/r1csproof.rs:84-89, SP/r1csinstance.rs:35-48, SP/sparse_mlpoly.rs:302-327
 std::unique_ptr<SnarkGens> snark_gens_create(Ctx *ctx, uint64_t num_cons, uint64_t num_vars, uint64_t num_inputs, uint64_t num_nz_entries) {
@@ -88,7 +89,7 @@ std::unique_ptr<SnarkGens> snark_gens_create(Ctx *ctx, uint64_t num_cons, uint64
   size_t R_sat = (size_t)1 << (ell_sat - ell_sat / 2);
   g->sat_label = get_label_gens(ctx, "gens_r1cs_sat", std::max<size_t>(R_sat + 2, 5));
   make_pc(ctx, *g->sat_label, ell_sat, &g->sat_pc);
-  for (int i = 0; i < 5; i++) g->sat_g[i].build(g->sat_label->h_pts[i]);
+  for (int i = 0; i < 5; i++) g->sat_g[i] = g->sat_label->host_base(i);
   size_t nvx = math_log2(num_cons), nvy = math_log2(2 * num_vars_padded);
   size_t k = math_log2(next_pow2(num_nz_entries));
   size_t ell_ops = k + math_log2(next_pow2(3 * 5)), ell_mem = std::max(nvx, nvy) + 1, ell_derefs = k + math_log2(next_pow2(3 * 2));
@@ -195,16 +196,38 @@ struct Prover {
   }
   fl_t down1(const fl_t *d) { fl_t x; down(d, sizeof(fl_t), &x); return x; }
 
-  DevVec<fl_t> eq_table(const std::vector<fl_t> &r) {
+  DevVec<fl_t> eq_table(const std::vector<fl_t> &r) {  // the point travels as a kernel parameter: no copy, no sync
     size_t ell = r.size();
-    DevVec<fl_t> out((size_t)1 << ell, st), tmp(eq_tmp_elems(ell), st), dr(std::max<size_t>(ell, 1), st);
-    if (ell) dr.upload(r.data(), ell);
-    {
-      ProfScope ps(ctx, PROF_EQ, (double)((size_t)1 << ell), 32.0 * (double)((size_t)1 << ell), ell <= 12 ? 1 : 3);
-      launch_eq_evals(dr.p, (int)ell, out.p, tmp.p, st);
-    }
-    ctx->sync();  // r (pageable) must stay alive until the copy ran
+    VPIN_REQUIRE(ell <= 32, VPIN_ERR_BAD_ARGUMENT, "eq table: more than 32 variables");
+    DevVec<fl_t> out((size_t)1 << ell, st), tmp(eq_tmp_elems(ell), st);
+    EqPoint pt;
+    for (size_t i = 0; i < ell; i++) pt.r[i] = r[i];
+    ProfScope ps(ctx, PROF_EQ, (double)((size_t)1 << ell), 32.0 * (double)((size_t)1 << ell), ell <= 12 ? 1 : 3);
+    launch_eq_evals_pt(pt, (int)ell, out.p, tmp.p, st);
     return out;
+  }
+  // ---- fused rounds: results arrive in host-mapped slots (kernels_round.cu) ----
+  RoundCtl round_ctl(int slot, uint32_t *seq_out) {
+    uint32_t seq = ++ctx->round_seq;
+    *seq_out = seq;
+    return RoundCtl{ctx->d_partials.p, ctx->d_round_counters.p, ctx->d_slots + slot, seq};
+  }
+  const fl_t *round_wait(int slot, uint32_t seq) {
+    volatile uint32_t *flag = &ctx->h_slots[slot].seq;
+    for (uint64_t spins = 1;; spins++) {
+      if (*flag == seq) break;
+      if ((spins & 0x3ff) == 0) {  // a faulted kernel must not hang the host
+        cudaError_t e = cudaStreamQuery(st);
+        if (e == cudaSuccess) {
+          if (*flag == seq) break;
+          throw Error(VPIN_ERR_CUDA, "round result never arrived");
+        }
+        if (e != cudaErrorNotReady) VPIN_CUDA(e);
+      }
+      __builtin_ia32_pause();
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return ctx->h_slots[slot].vals;
   }
   fl_t dot_dev(const fl_t *a, const fl_t *b, size_t n) {
     {
@@ -215,30 +238,29 @@ struct Prover {
   }
 
   // ---- host commitments with the sat generators ----
-  ge_t commit1(const PcGens &pc, const fl_t &x, const fl_t &blind) {  // SP/commitments.rs:79-84
-    ge_t acc = ge_identity();
-    pc.g1.mul_acc(x, &acc);
-    pc.h.mul_acc(blind, &acc);
+  hge_t commit1(const PcGens &pc, const fl_t &x, const fl_t &blind) {  // SP/commitments.rs:79-84
+    hge_t acc = hf::ge_identity();
+    pc.g1->mul_acc(x, &acc);
+    pc.h->mul_acc(blind, &acc);
     return acc;
   }
-  ge_t commit_coeffs(const std::vector<fl_t> &c, const fl_t &blind) {  // gens_3 / gens_4 (SP/r1csproof.rs:62-72)
-    ge_t acc = ge_identity();
-    for (size_t i = 0; i < c.size(); i++) g.sat_g[i].mul_acc(c[i], &acc);
-    g.sat_g[c.size()].mul_acc(blind, &acc);
+  hge_t commit_coeffs(const std::vector<fl_t> &c, const fl_t &blind) {  // gens_3 / gens_4 (SP/r1csproof.rs:62-72)
+    hge_t acc = hf::ge_identity();
+    for (size_t i = 0; i < c.size(); i++) g.sat_g[i]->mul_acc(c[i], &acc);
+    g.sat_g[c.size()]->mul_acc(blind, &acc);
     return acc;
   }
 
   // ---- SP/unipoly.rs:23-54 ----
   static std::vector<fl_t> unipoly_from_evals(const std::vector<fl_t> &e) {
-    fl_t one = fl_one(), two = one + one;
-    fl_t two_inv = fl_invert(two);
+    static const fl_t one = fl_one(), two = one + one;
+    static const fl_t two_inv = fl_invert(two), six_inv = fl_invert(two + two + two);
     if (e.size() == 3) {
       fl_t c = e[0];
       fl_t a = two_inv * (e[2] - e[1] - e[1] + c);
       fl_t b = e[1] - c - a;
       return {c, b, a};
     }
-    fl_t six_inv = fl_invert(two + two + two);
     fl_t d = e[0];
     fl_t a = six_inv * (e[3] - e[2] - e[2] - e[2] + e[1] + e[1] + e[1] - e[0]);
     fl_t b = two_inv * (e[0] + e[0] - e[1] - e[1] - e[1] - e[1] - e[1] + e[2] + e[2] + e[2] + e[2] - e[3]);
@@ -270,7 +292,7 @@ struct Prover {
     t.point("C1", C1.data());
     Comp C2 = compress_host(commit1(pc, v2, s2));
     t.point("C2", C2.data());
-    Comp alpha = compress_host(pc.h.mul(r));
+    Comp alpha = compress_host(pc.h->mul(r));
     t.point("alpha", alpha.data());
     fl_t c = t.challenge_scalar("c");
     return EqualityS{alpha, c * (s1 - s2) + r};
@@ -331,23 +353,24 @@ struct Prover {
     return p;
   }
 
-  // ---- ZK sumchecks (SP/sumcheck.rs:428-776). eval_round(half, out) enqueues the round kernel writing `nev` sums to
-  // d_small+240..; bind(half, d_r) enqueues the binds. ----
-  template <class EvalFn, class BindFn>
-  ZkSumcheckS zk_sumcheck(const fl_t &claim, const fl_t &blind_claim, size_t num_rounds, size_t len, int degree, EvalFn eval_round,
-                          BindFn bind, std::vector<fl_t> *r_out, fl_t *blind_post) {
+  // ---- ZK sumchecks (SP/sumcheck.rs:428-776). launch_round(q, bind, r, ctl) enqueues the fused kernel of one round
+  // (bind every table with r, then evaluate `degree` sums over q thread items); launch_final(r, ctl) the last bind, which
+  // delivers the final claims (`nfinal` values, returned in *finals). The kernel of round j+1 is launched as soon as
+  // r_j is known, so the device works on it while the host finishes round j's sigma protocol. ----
+  template <class RoundFn, class FinalFn>
+  ZkSumcheckS zk_sumcheck(const fl_t &claim, const fl_t &blind_claim, size_t num_rounds, size_t len, int degree, RoundFn launch_round,
+                          FinalFn launch_final, size_t nfinal, std::vector<fl_t> *r_out, fl_t *blind_post, std::vector<fl_t> *finals) {
     std::vector<fl_t> blinds_poly = tape.vector("blinds_poly", num_rounds);
     std::vector<fl_t> blinds_evals = tape.vector("blinds_evals", num_rounds);
     fl_t claim_per_round = claim;
     Comp comm_claim_per_round = compress_host(commit1(g.sat_pc, claim_per_round, blind_claim));
     ZkSumcheckS out;
     std::vector<fl_t> r;
-    fl_t *d_ev = ctx->d_small.p + 240;
+    uint32_t seq;
+    launch_round(len >> 1, false, fl_zero(), round_ctl(0, &seq));
     for (size_t j = 0; j < num_rounds; j++) {
-      size_t half = len >> (j + 1);
-      eval_round(half, d_ev);
       fl_t ev[3];
-      down(d_ev, degree * sizeof(fl_t), ev);
+      memcpy(ev, round_wait((int)(j & 1), seq), degree * sizeof(fl_t));
       std::vector<fl_t> evals = degree == 3 ? std::vector<fl_t>{ev[0], claim_per_round - ev[0], ev[1], ev[2]}
                                             : std::vector<fl_t>{ev[0], claim_per_round - ev[0], ev[1]};
       std::vector<fl_t> poly = unipoly_from_evals(evals);
@@ -355,7 +378,8 @@ struct Prover {
       t.point("comm_poly", comm_poly.data());
       out.comm_polys.push_back(comm_poly);
       fl_t r_j = t.challenge_scalar("challenge_nextround");
-      bind(half, up(&r_j, 1));  // device binds run while the host finishes the round
+      if (j + 1 < num_rounds) launch_round(len >> (j + 2), true, r_j, round_ctl((int)((j + 1) & 1), &seq));
+      else launch_final(r_j, round_ctl((int)((j + 1) & 1), &seq));
       fl_t eval = unipoly_eval(poly, r_j);
       Comp comm_eval = compress_host(commit1(g.sat_pc, eval, blinds_evals[j]));
       t.point("comm_claim_per_round", comm_claim_per_round.data());
@@ -380,19 +404,23 @@ struct Prover {
       r.push_back(r_j);
       out.comm_evals.push_back(comm_eval);
     }
+    const fl_t *fin = round_wait((int)(num_rounds & 1), seq);
+    finals->assign(fin, fin + nfinal);
     *r_out = r;
     *blind_post = blinds_evals[num_rounds - 1];
     return out;
   }
 
   // ---- one fixed-base MSM row set returning extended points on the host ----
-  std::vector<ge_t> msm_rows_host(const LabelGens &lg, const fl_t *d_scalars, size_t rows, size_t cols, size_t ld) {
+  std::vector<hge_t> msm_rows_host(const LabelGens &lg, const fl_t *d_scalars, size_t rows, size_t cols, size_t ld) {
     DevVec<ge_t> pts(rows, st);
     hyrax_rows(ctx, lg, d_scalars, rows, cols, ld, nullptr, 0, pts.p, nullptr);
     std::vector<ge_t> h(rows);
     pts.download(h.data(), rows);
     ctx->sync();
-    return h;
+    std::vector<hge_t> out(rows);
+    for (size_t i = 0; i < rows; i++) out[i] = hf::ge_from_dev(h[i]);
+    return out;
   }
 
   // ---- DotProductProofLog::prove (SP/nizk/mod.rs:447-531) + BulletReductionProof::prove (SP/nizk/bullet.rs:32-132).
@@ -408,8 +436,8 @@ struct Prover {
     fl_t r_beta = tape.scalar("r_delta");  // sic (mod.rs:466)
     std::vector<fl_t> bv1 = tape.vector("blinds_vec_1", 2 * lg_n), bv2 = tape.vector("blinds_vec_2", 2 * lg_n);
     // Cx = x_vec.commit(blind_x, gens_n)
-    ge_t cx = msm_rows_host(lg, d_x, 1, n, n)[0];
-    pc.h.mul_acc(blind_x, &cx);
+    hge_t cx = msm_rows_host(lg, d_x, 1, n, n)[0];
+    pc.h->mul_acc(blind_x, &cx);
     Comp Cx = compress_host(cx);
     t.point("Cx", Cx.data());
     Comp Cy = compress_host(commit1(pc, y, blind_y));
@@ -434,14 +462,14 @@ struct Prover {
       launch_dot(a.p, b.p + cur, cur, d_c, ctx->d_partials.p, st);      // c_L = <a_L, b_R>
       launch_dot(a.p + cur, b.p, cur, d_c + 1, ctx->d_partials.p, st);  // c_R = <a_R, b_L>
       launch_bullet_scalars(a.p, W.p, n, cur, srows.p, srows.p + n, st);
-      std::vector<ge_t> LR = msm_rows_host(lg, srows.p, 2, n, n);
+      std::vector<hge_t> LR = msm_rows_host(lg, srows.p, 2, n, n);
       fl_t c[2];
       down(d_c, 2 * sizeof(fl_t), c);
       const fl_t &blind_L = bv1[round], &blind_R = bv2[round];
-      pc.g1.mul_acc(c[0] * r, &LR[0]);
-      pc.h.mul_acc(blind_L, &LR[0]);
-      pc.g1.mul_acc(c[1] * r, &LR[1]);
-      pc.h.mul_acc(blind_R, &LR[1]);
+      pc.g1->mul_acc(c[0] * r, &LR[0]);
+      pc.h->mul_acc(blind_L, &LR[0]);
+      pc.g1->mul_acc(c[1] * r, &LR[1]);
+      pc.h->mul_acc(blind_R, &LR[1]);
       Comp Lc = compress_host(LR[0]), Rc = compress_host(LR[1]);
       t.point("L", Lc.data());
       t.point("R", Rc.data());
@@ -459,8 +487,8 @@ struct Prover {
     fl_t y_hat = x_hat * a_hat;
     // delta = d * g_hat + r_delta * h with g_hat = sum_j W_j G_j
     launch_scale(W.p, up(&d, 1), n, srows.p, st);
-    ge_t dl = msm_rows_host(lg, srows.p, 1, n, n)[0];
-    pc.h.mul_acc(r_delta, &dl);
+    hge_t dl = msm_rows_host(lg, srows.p, 1, n, n)[0];
+    pc.h->mul_acc(r_delta, &dl);
     out.delta = compress_host(dl);
     t.point("delta", out.delta.data());
     out.beta = compress_host(commit1(pc, d * r, r_beta));  // d * Q + r_beta * h
@@ -502,10 +530,10 @@ struct Prover {
                          std::vector<fl_t> *rand_out) {
     BatchedS out;
     size_t num_layers = math_log2(n), nc = trees.size();
+    VPIN_REQUIRE(nc + dotp.size() <= (size_t)kMaxBatched, VPIN_ERR_PROVER, "too many batched instances");
     std::vector<fl_t> claims_to_verify = tree_evals;
     std::vector<fl_t> rand;
-    DevVec<const fl_t *> dA(nc + dotp.size(), st), dB(nc + dotp.size(), st), dC(nc + dotp.size(), st);
-    DevVec<fl_t *> dBind(2 * nc + 1 + 3 * dotp.size(), st);
+    DevVec<fl_t> eq_pong(std::max<size_t>(n / 4, 1), st);  // second buffer of the shared eq table (see BatchedRoundArgs)
     for (size_t layer_id = num_layers; layer_id-- > 0;) {
       size_t vlen = n >> layer_id;       // |V_layer|
       size_t off = 2 * n - 2 * vlen;     // offset of V_layer inside a packed tree
@@ -515,38 +543,41 @@ struct Prover {
       size_t num_rounds = rand.size();
       bool with_dotp = layer_id == 0 && !dotp.empty();
       size_t ninst = nc + (with_dotp ? dotp.size() : 0);
-      std::vector<const fl_t *> hA(ninst), hB(ninst), hC(ninst);
-      std::vector<fl_t *> hBind;
+      BatchedRoundArgs args;
+      memset(&args, 0, sizeof(args));
       for (size_t c = 0; c < nc; c++) {
-        hA[c] = trees[c] + off; hB[c] = trees[c] + off + len_half; hC[c] = eqC.p;
-        hBind.push_back(trees[c] + off); hBind.push_back(trees[c] + off + len_half);
+        args.A[c] = trees[c] + off;
+        args.B[c] = trees[c] + off + len_half;
       }
-      hBind.push_back(eqC.p);
       if (with_dotp)
         for (size_t k = 0; k < dotp.size(); k++) {
           claims_to_verify.push_back(dotp[k].claim);
-          hA[nc + k] = dotp[k].l; hB[nc + k] = dotp[k].r; hC[nc + k] = dotp[k].w;
-          hBind.push_back(dotp[k].l); hBind.push_back(dotp[k].r); hBind.push_back(dotp[k].w);
+          args.A[nc + k] = dotp[k].l; args.B[nc + k] = dotp[k].r;
+          args.Cin[nc + k] = dotp[k].w; args.Cout[nc + k] = dotp[k].w;
         }
-      dA.upload(hA.data(), ninst); dB.upload(hB.data(), ninst); dC.upload(hC.data(), ninst);
-      dBind.upload(hBind.data(), hBind.size());
-      ctx->sync();
+      fl_t *eq_cur = eqC.p, *eq_other = eq_pong.p;
       std::vector<fl_t> coeffs = t.challenge_vector("rand_coeffs_next_layer", claims_to_verify.size());
       fl_t e = fl_zero();
       for (size_t i = 0; i < coeffs.size(); i++) e = e + claims_to_verify[i] * coeffs[i];
       LayerS layer;
       std::vector<fl_t> rand_prod;
-      DevVec<fl_t> d_ev(3 * ninst, st);
+      double tables = 2.0 * nc + 1 + (with_dotp ? 3.0 * dotp.size() : 0);
+      uint32_t seq = 0;
+      int slot = 0;
+      // round j: bind with r_{j-1} (j > 0) and evaluate over q = len_half >> (j+1) thread items
+      auto launch = [&](size_t j, const fl_t &r_prev) {
+        size_t q = len_half >> (j + 1);
+        for (size_t c = 0; c < nc; c++) { args.Cin[c] = eq_cur; args.Cout[c] = nullptr; }
+        if (j > 0) { args.Cout[0] = eq_other; }
+        ProfScope ps(ctx, PROF_SC_BATCHED, (double)ninst * q, tables * (j > 0 ? 6 : 2) * q * 32);
+        launch_round_cubic_batched(args, (int)ninst, q, j > 0, r_prev, round_ctl(slot, &seq), st);
+        if (j > 0) std::swap(eq_cur, eq_other);
+      };
+      fl_t r_j = fl_zero();
+      if (num_rounds) launch(0, r_j);
       std::vector<fl_t> ev(3 * ninst);
       for (size_t j = 0; j < num_rounds; j++) {
-        size_t half = len_half >> (j + 1);
-        {
-          double tables = 2.0 * nc + 1 + (with_dotp ? 3.0 * dotp.size() : 0);
-          ProfScope ps(ctx, PROF_SC_BATCHED, (double)ninst * half, tables * 2 * half * 32, 2);
-          launch_cubic_batched_round(dA.p, dB.p, dC.p, (int)ninst, half, d_ev.p, ctx->d_partials.p, st);
-        }
-        d_ev.download(ev.data(), 3 * ninst);
-        ctx->sync();
+        memcpy(ev.data(), round_wait(slot, seq), 3 * ninst * sizeof(fl_t));
         fl_t c0 = fl_zero(), c2 = fl_zero(), c3 = fl_zero();
         for (size_t i = 0; i < ninst; i++) {
           c0 = c0 + ev[3 * i] * coeffs[i];
@@ -558,25 +589,24 @@ struct Prover {
         t.message("poly", "UniPoly_begin");
         for (auto &c : poly) t.scalar("coeff", c);
         t.message("poly", "UniPoly_end");
-        fl_t r_j = t.challenge_scalar("challenge_nextround");
+        r_j = t.challenge_scalar("challenge_nextround");
         rand_prod.push_back(r_j);
-        {
-          const fl_t *d_rj = up(&r_j, 1);
-          ProfScope ps(ctx, PROF_BIND, (double)hBind.size() * half, 96.0 * hBind.size() * half);
-          launch_bind_top_multi(dBind.p, (int)hBind.size(), half, d_rj, st);
-        }
+        slot ^= 1;
+        if (j + 1 < num_rounds) launch(j + 1, r_j);
         e = unipoly_eval(poly, r_j);
         layer.polys.push_back({poly[0], poly[2], poly[3]});  // CompressedUniPoly (SP/unipoly.rs:80-87)
       }
-      // final claims: first element of every bound table
-      std::vector<fl_t> fin(hBind.size());
-      {
-        DevVec<fl_t> d_fin(hBind.size(), st);
-        for (size_t i = 0; i < hBind.size(); i++)
-          VPIN_CUDA(cudaMemcpyAsync(d_fin.p + i, hBind[i], sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
-        d_fin.download(fin.data(), fin.size());
-        ctx->sync();
-      }
+      // final claims: every table bound with the last challenge (in the kernel; the tables themselves are done with)
+      FinalArgs fa;
+      fa.n = 0;
+      for (size_t c = 0; c < nc; c++) { fa.p[fa.n++] = args.A[c]; fa.p[fa.n++] = args.B[c]; }
+      fa.p[fa.n++] = eq_cur;
+      if (with_dotp)
+        for (size_t k = 0; k < dotp.size(); k++) { fa.p[fa.n++] = dotp[k].l; fa.p[fa.n++] = dotp[k].r; fa.p[fa.n++] = dotp[k].w; }
+      VPIN_REQUIRE(fa.n <= kRoundSlotVals, VPIN_ERR_PROVER, "too many final claims");
+      launch_round_final(fa, num_rounds > 0, r_j, round_ctl(slot, &seq), st);
+      std::vector<fl_t> fin(fa.n);
+      memcpy(fin.data(), round_wait(slot, seq), fa.n * sizeof(fl_t));
       for (size_t c = 0; c < nc; c++) { layer.left.push_back(fin[2 * c]); layer.right.push_back(fin[2 * c + 1]); }
       for (size_t c = 0; c < nc; c++) {
         t.scalar("claim_prod_left", layer.left[c]);
@@ -684,21 +714,21 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   // phase 1: sum_x eq(tau,x) (Az Bz - Cz) = 0   (SP/r1csproof.rs:94-127)
   std::vector<fl_t> rx;
   fl_t blind_claim_postsc1;
+  std::vector<fl_t> fin1;
   ZkSumcheckS sc1 = P.zk_sumcheck(
       fl_zero(), fl_zero(), num_rounds_x, num_cons, 3,
-      [&](size_t half, fl_t *d_out) {
-        ProfScope ps(ctx, PROF_SC_CUBIC, (double)half, 256.0 * half, 2);
-        launch_cubic_additive_round(poly_tau.p, Az, Bz, Cz, half, d_out, ctx->d_partials.p, st);
+      [&](size_t q, bool bind, const fl_t &r, const RoundCtl &c) {
+        ProfScope ps(ctx, PROF_SC_CUBIC, (double)q, (bind ? 4 * 192.0 : 4 * 64.0) * q);
+        launch_round_cubic_additive(poly_tau.p, Az, Bz, Cz, q, bind, r, c, st);
       },
-      [&](size_t half, const fl_t *d_r) {
-        ProfScope ps(ctx, PROF_BIND, 4.0 * half, 4 * 96.0 * half, 4);
-        launch_bind_top(poly_tau.p, half, d_r, st);
-        launch_bind_top(Az, half, d_r, st);
-        launch_bind_top(Bz, half, d_r, st);
-        launch_bind_top(Cz, half, d_r, st);
+      [&](const fl_t &r, const RoundCtl &c) {
+        FinalArgs fa;
+        fa.p[0] = poly_tau.p; fa.p[1] = Az; fa.p[2] = Bz; fa.p[3] = Cz;
+        fa.n = 4;
+        launch_round_final(fa, true, r, c, st);
       },
-      &rx, &blind_claim_postsc1);
-  fl_t tau_claim = P.down1(poly_tau.p), Az_claim = P.down1(Az), Bz_claim = P.down1(Bz), Cz_claim = P.down1(Cz);
+      4, &rx, &blind_claim_postsc1, &fin1);
+  fl_t tau_claim = fin1[0], Az_claim = fin1[1], Bz_claim = fin1[2], Cz_claim = fin1[3];
   phase("prove_sc_phase_one", t0);
 
   fl_t Az_blind = tape.scalar("Az_blind"), Bz_blind = tape.scalar("Bz_blind"), Cz_blind = tape.scalar("Cz_blind"),
@@ -733,19 +763,21 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   }
   std::vector<fl_t> ry;
   fl_t blind_claim_postsc2;
+  std::vector<fl_t> fin2;
   ZkSumcheckS sc2 = P.zk_sumcheck(
       claim_phase2, blind_claim_phase2, num_rounds_y, zlen, 2,
-      [&](size_t half, fl_t *d_out) {
-        ProfScope ps(ctx, PROF_SC_QUAD, (double)half, 128.0 * half, 2);
-        launch_quad_round(z.p, evals_ABC.p, half, d_out, ctx->d_partials.p, st);
+      [&](size_t q, bool bind, const fl_t &r, const RoundCtl &c) {
+        ProfScope ps(ctx, PROF_SC_QUAD, (double)q, (bind ? 2 * 192.0 : 2 * 64.0) * q);
+        launch_round_quad(z.p, evals_ABC.p, q, bind, r, c, st);
       },
-      [&](size_t half, const fl_t *d_r) {
-        ProfScope ps(ctx, PROF_BIND, 2.0 * half, 2 * 96.0 * half, 2);
-        launch_bind_top(z.p, half, d_r, st);
-        launch_bind_top(evals_ABC.p, half, d_r, st);
+      [&](const fl_t &r, const RoundCtl &c) {
+        FinalArgs fa;
+        fa.p[0] = z.p; fa.p[1] = evals_ABC.p;
+        fa.n = 2;
+        launch_round_final(fa, true, r, c, st);
       },
-      &ry, &blind_claim_postsc2);
-  fl_t claims_phase2[2] = {P.down1(z.p), P.down1(evals_ABC.p)};
+      2, &ry, &blind_claim_postsc2, &fin2);
+  fl_t claims_phase2[2] = {fin2[0], fin2[1]};
   phase("prove_sc_phase_two", t0);
 
   t0 = now_ms();

@@ -10,14 +10,14 @@ namespace vpin {
 struct PcGens {
   size_t ell = 0, L = 0, R = 0;
   size_t g1_index = 0, h_index = 0;
-  HostBase g1, h;
+  const HostBase *g1 = nullptr, *h = nullptr;  // owned by the LabelGens of the stream
 };
 
 // SNARKGens (Spartan/src/lib.rs:295-327)
 struct vpin_gens_impl {
   std::shared_ptr<LabelGens> sat_label, eval_label;  // streams "gens_r1cs_sat" / "gens_r1cs_eval" + fixed-base tables
   PcGens sat_pc;                                     // gens_r1cs_sat.gens_pc ; gens_sc.gens_1 is its gens_1
-  HostBase sat_g[5];                                 // stream[0..5): gens_3 = (G[0..3), h = G[3]); gens_4 = (G[0..4), h = G[4])
+  const HostBase *sat_g[5];                               // stream[0..5): gens_3 = (G[0..3), h = G[3]); gens_4 = (G[0..4), h = G[4])
   PcGens ops_pc, mem_pc, derefs_pc;                  // gens_r1cs_eval.gens.{gens_ops, gens_mem, gens_derefs}
 };
 typedef vpin_gens_impl SnarkGens;
