@@ -1,0 +1,79 @@
+// Launch -> host-mapped flag round-trip latency of the prover's per-round kernels (not part of the product or the bench):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o roundtrip roundtrip.cu -I../../vpin_b200/csrc -L../../vpin_b200 -lvpin_b200
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "kernels_poly.cuh"
+using namespace vpin;
+
+__global__ void k_empty_flag(RoundSlot *slot, uint32_t seq) {
+  __threadfence_system();
+  *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
+}
+__global__ void k_spin(long long cycles) {
+  long long t0 = clock64();
+  while (clock64() - t0 < cycles) {}
+}
+static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int main() {
+  cudaStream_t st;
+  cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  RoundSlot *h, *d;
+  cudaHostAlloc((void **)&h, 2 * sizeof(RoundSlot), cudaHostAllocMapped);
+  memset(h, 0, 2 * sizeof(RoundSlot));
+  cudaHostGetDevicePointer((void **)&d, h, 0);
+  const size_t n = 1 << 16;
+  fl_t *tab, *partials;
+  unsigned *counters;
+  cudaMalloc(&tab, 64 * n * sizeof(fl_t));
+  cudaMemset(tab, 0, 64 * n * sizeof(fl_t));
+  cudaMalloc(&partials, 3 * kRedBlocks * 32 * sizeof(fl_t));
+  cudaMalloc(&counters, 64 * sizeof(unsigned));
+  cudaMemset(counters, 0, 64 * sizeof(unsigned));
+  cudaDeviceSynchronize();
+  uint32_t seq = 0;
+  auto wait = [&](int slot) { volatile uint32_t *f = &h[slot].seq; while (*f != seq) __builtin_ia32_pause(); };
+  // keep the clocks up
+  k_spin<<<148, 128, 0, st>>>(400000000LL);
+  cudaStreamSynchronize(st);
+  const int reps = 2000;
+  {
+    double t0 = now_us();
+    for (int i = 0; i < reps; i++) { ++seq; k_empty_flag<<<1, 1, 0, st>>>(d, seq); wait(0); }
+    printf("empty kernel -> flag            : %6.2f us\n", (now_us() - t0) / reps);
+  }
+  BatchedRoundArgs a;
+  memset(&a, 0, sizeof(a));
+  int ninst = 18;
+  for (int k = 0; k < ninst; k++) { a.A[k] = tab + (size_t)(3 * k) * n; a.B[k] = tab + (size_t)(3 * k + 1) * n; a.Cin[k] = tab + (size_t)(3 * k + 2) * n; a.Cout[k] = tab + (size_t)(3 * k + 2) * n; }
+  fl_t r = fl_one();
+  for (size_t q : {1, 16, 64, 128, 1024, 16384}) {
+    for (int bind = 0; bind < 2; bind++) {
+      double t0 = now_us();
+      for (int i = 0; i < reps; i++) {
+        ++seq;
+        RoundCtl c{partials, counters, d, seq};
+        launch_round_cubic_batched(a, ninst, q, bind, r, c, st);
+        wait(0);
+      }
+      printf("batched x18 q=%6zu bind=%d       : %6.2f us\n", q, bind, (now_us() - t0) / reps);
+    }
+  }
+  {
+    FinalArgs fa;
+    fa.n = 43;
+    for (int k = 0; k < fa.n; k++) fa.p[k] = tab + (size_t)k * n;
+    double t0 = now_us();
+    for (int i = 0; i < reps; i++) { ++seq; RoundCtl c{partials, counters, d, seq}; launch_round_final(fa, true, r, c, st); wait(0); }
+    printf("final x43                       : %6.2f us\n", (now_us() - t0) / reps);
+  }
+  for (size_t q : {64, 4096, 65536}) {
+    double t0 = now_us();
+    for (int i = 0; i < reps / 4; i++) { ++seq; RoundCtl c{partials, counters, d, seq}; launch_round_cubic_additive(tab, tab + 4 * n, tab + 8 * n, tab + 12 * n, q / 4, true, r, c, st); wait(0); }
+    printf("zk cubic bind q=%6zu           : %6.2f us\n", q / 4, (now_us() - t0) / (reps / 4));
+  }
+  return 0;
+}

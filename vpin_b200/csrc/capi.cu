@@ -562,7 +562,7 @@ vpin_status vpin_spmv_t_abc(vpin_ctx *ctx, const vpin_instance *inst, const uint
   DevVec<fl_t> out(3 * nc, c_->st), one(1, c_->st);
   fl_t h1 = fl_one();
   one.upload(&h1, 1);
-  for (int k = 0; k < 3; k++) launch_spmv_csc_scaled(csc_of(I->M[k], nc), dx.p, one.p, false, out.p + k * nc, c_->st);
+  for (int k = 0; k < 3; k++) launch_spmv_csc_scaled(csc_of(I->M[k], nc), dx.p, one.p, false, out.p + k * nc, c_->d_partials.p, c_->d_partials.n, c_->st);
   uint8_t *dst[3] = {At32, Bt32, Ct32};
   for (int k = 0; k < 3; k++) download_scalars(c_, out.p + k * nc, nc, dst[k]);
   VPIN_CATCH

@@ -13,7 +13,7 @@ std::atomic<uint64_t> g_kernel_launches{0};
 const char *prof_class_name(int cls) {
   static const char *names[PROF_COUNT] = {"msm_recode", "msm_accumulate", "msm_finish", "sumcheck_cubic_round", "sumcheck_quad_round",
                                           "sumcheck_batched_round", "bind_top", "spmv_csr", "spmv_csc", "eq_evals", "product_tree",
-                                          "hash_layer", "deref_gather", "bound_LZ", "dot"};
+                                          "hash_layer", "deref_gather", "bound_LZ", "dot", "bullet_round", "round_final"};
   return cls >= 0 && cls < PROF_COUNT ? names[cls] : "?";
 }
 static cudaEvent_t prof_event(Ctx *c) {

@@ -95,7 +95,7 @@ typedef vpin_ctx_impl Ctx;
 // latency-bound tail rounds).
 enum ProfClass {
   PROF_MSM_RECODE, PROF_MSM_ACCUMULATE, PROF_MSM_FINISH, PROF_SC_CUBIC, PROF_SC_QUAD, PROF_SC_BATCHED, PROF_BIND, PROF_SPMV,
-  PROF_SPMV_T, PROF_EQ, PROF_TREE, PROF_HASH, PROF_GATHER, PROF_BOUND, PROF_DOT, PROF_COUNT
+  PROF_SPMV_T, PROF_EQ, PROF_TREE, PROF_HASH, PROF_GATHER, PROF_BOUND, PROF_DOT, PROF_BULLET, PROF_FINAL, PROF_COUNT
 };
 const char *prof_class_name(int cls);
 struct Prof {

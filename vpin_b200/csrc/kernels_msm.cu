@@ -3,6 +3,7 @@
 #include <atomic>
 
 #include "kernels_msm.cuh"
+#include "msm_recode.cuh"
 
 namespace vpin {
 
@@ -116,8 +117,6 @@ void launch_table_build(const ge_t *d_bases, size_t n, niels_t *d_table, ge_t *d
 }
 
 // ------------------------------------------------------------------------------------------------ recode
-// (l - 1) / 2
-__device__ __constant__ uint32_t kHalfL[8] = {0x2e7ae9f6u, 0x2c09318du, 0x517bce6bu, 0x0a6f7cefu, 0u, 0u, 0u, 0x08000000u};
 __device__ __forceinline__ uint32_t recode_one(const fl_t *src, uint16_t *dst, size_t plane) {
   if (!src) {
     for (int w = 0; w < kMsmWindows; w++) dst[(size_t)w * plane] = 0;
@@ -127,37 +126,7 @@ __device__ __forceinline__ uint32_t recode_one(const fl_t *src, uint16_t *dst, s
   uint4 lo = __ldg(q), hi = __ldg(q + 1);
   fl_t x;
   x.v[0] = lo.x; x.v[1] = lo.y; x.v[2] = lo.z; x.v[3] = lo.w; x.v[4] = hi.x; x.v[5] = hi.y; x.v[6] = hi.z; x.v[7] = hi.w;
-  if (fl_is_zero(x)) {
-    for (int w = 0; w < kMsmWindows; w++) dst[(size_t)w * plane] = 0;
-    return 0;
-  }
-  fl_t s = fl_from_mont(x);
-  // s > (l-1)/2 ?  then use l - s and flip every sign
-  bool gt = false;
-  for (int i = 7; i >= 0; i--) {
-    if (s.v[i] != kHalfL[i]) { gt = s.v[i] > kHalfL[i]; break; }
-  }
-  uint32_t v[9];
-  if (gt) {
-    int64_t br = 0;
-    for (int i = 0; i < 8; i++) { int64_t t = (int64_t)fl_modulus_limb(i) - (int64_t)s.v[i] + br; v[i] = (uint32_t)t; br = t >> 32; }
-  } else {
-    for (int i = 0; i < 8; i++) v[i] = s.v[i];
-  }
-  v[8] = 0;
-  uint32_t carry = 0, nz = 0;
-  for (int w = 0; w < kMsmWindows; w++) {
-    int bit = w * kMsmW, limb = bit >> 5, sh = bit & 31;
-    uint64_t two = (uint64_t)v[limb] | ((uint64_t)(limb + 1 < 9 ? v[limb + 1] : 0u) << 32);
-    uint32_t raw = (limb < 8 ? (uint32_t)(two >> sh) & ((1u << kMsmW) - 1u) : 0u) + carry;
-    uint32_t neg = raw > (uint32_t)kMsmTable ? 1u : 0u;
-    uint32_t mag = neg ? (1u << kMsmW) - raw : raw;
-    carry = neg;
-    uint32_t sign = (neg ^ (gt ? 1u : 0u)) & (mag != 0 ? 1u : 0u);
-    nz += mag != 0 ? 1u : 0u;
-    dst[(size_t)w * plane] = (uint16_t)(mag | (sign << 15));
-  }
-  return nz;
+  return msm_recode_value(x, dst, plane);
 }
 __global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows, size_t cols, size_t ld, const fl_t *extra,
                                                 size_t stride, uint16_t *digits, unsigned long long *nonzero) {
@@ -220,7 +189,56 @@ __global__ void __launch_bounds__(kMsmRowsPerBlock) k_msm_accumulate(const niels
   }
   st_ge(partial + (row * kMsmGroup + wl) * segs + seg, acc);
 }
+__device__ __forceinline__ ge_t shfl_down_ge(const ge_t &g, int off) {
+  ge_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.X.v[i] = __shfl_down_sync(0xffffffffu, g.X.v[i], off);
+    r.Y.v[i] = __shfl_down_sync(0xffffffffu, g.Y.v[i], off);
+    r.Z.v[i] = __shfl_down_sync(0xffffffffu, g.Z.v[i], off);
+    r.T.v[i] = __shfl_down_sync(0xffffffffu, g.T.v[i], off);
+  }
+  return r;
+}
+// Few rows (the bullet-reduction L / R rows, single Pedersen commitments): rows cannot fill a warp, so the lanes of a warp
+// take the COLUMNS of one (row, local window, segment) instead and the 32 partial sums are added by a shuffle tree.
+// grid (segs, kMsmGroup, rows), one warp per block.
+__global__ void __launch_bounds__(32) k_msm_accumulate_small(const niels_t *table, const uint16_t *digits, size_t rows, size_t cols,
+                                                             size_t cols_total, size_t extra_base, size_t stride, size_t n_bases,
+                                                             size_t seg_len, ge_t *partial) {
+  const size_t row = blockIdx.z, seg = blockIdx.x, segs = gridDim.x;
+  const int wl = blockIdx.y, lane = threadIdx.x;
+  size_t c0 = seg * seg_len, c1 = c0 + seg_len < cols_total ? c0 + seg_len : cols_total;
+  const size_t plane = rows * stride;
+  const uint16_t *dg = digits + row * stride;
+  ge_t acc = ge_identity();
+  for (size_t col = c0 + lane; col < c1; col += 32) {
+    size_t base = col < cols ? col : extra_base;
+#pragma unroll 1
+    for (int t = 0; t < kMsmSub; t++) {
+      int w = t * kMsmGroup + wl;
+      if (w >= kMsmWindows) break;
+      uint32_t d = dg[(size_t)w * plane + col];
+      if (d) madd_signed(acc, table + ((size_t)t * n_bases + base) * kMsmTable + ((d & 0x7fffu) - 1u), d >> 15);
+    }
+  }
+#pragma unroll 1
+  for (int off = 16; off > 0; off >>= 1) {
+    ge_t o = shfl_down_ge(acc, off);
+    acc = ge_add(acc, o);
+  }
+  if (lane == 0) st_ge(partial + (row * kMsmGroup + wl) * segs + seg, acc);
+}
+static const size_t kMsmSmallRows = 16;
 size_t msm_num_segments(size_t rows, size_t cols_total) {
+  if (rows <= kMsmSmallRows) {
+    const size_t want_warps = (size_t)148 * 16;
+    size_t per = rows * kMsmGroup;
+    size_t segs = (want_warps + per - 1) / per;
+    size_t max_segs = (cols_total + 63) / 64;  // at least two columns per lane
+    if (segs > max_segs) segs = max_segs;
+    return segs < 1 ? 1 : segs;
+  }
   const size_t want_threads = (size_t)148 * 1024;
   size_t per = rows * kMsmGroup;
   size_t segs = (want_threads + per - 1) / per;
@@ -235,6 +253,12 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
   size_t cols_total = cols + (has_extra ? 1 : 0);
   size_t stride = msm_col_stride(cols_total);
   size_t seg_len = (cols_total + segs - 1) / segs;
+  if (rows <= kMsmSmallRows) {
+    dim3 grid((unsigned)segs, kMsmGroup, (unsigned)rows);
+    ++g_kernel_launches, k_msm_accumulate_small<<<grid, 32, 0, st>>>(t.d_table, d_digits, rows, cols, cols_total, extra_base, stride,
+                                                                      t.n_bases, seg_len, d_partial);
+    return;
+  }
   dim3 grid((unsigned)((rows + kMsmRowsPerBlock - 1) / kMsmRowsPerBlock), kMsmGroup, (unsigned)segs);
   ++g_kernel_launches, k_msm_accumulate<<<grid, kMsmRowsPerBlock, 0, st>>>(t.d_table, d_digits, rows, cols, cols_total, extra_base, stride,
                                                                            t.n_bases, seg_len, d_partial);
@@ -242,17 +266,6 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
 
 // finish, step 1 (only when a row was split into segments): one warp per (row, local window) adds the segment partials
 // (lane-strided, then a shuffle tree) -> sums[row][w'].
-__device__ __forceinline__ ge_t shfl_down_ge(const ge_t &g, int off) {
-  ge_t r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    r.X.v[i] = __shfl_down_sync(0xffffffffu, g.X.v[i], off);
-    r.Y.v[i] = __shfl_down_sync(0xffffffffu, g.Y.v[i], off);
-    r.Z.v[i] = __shfl_down_sync(0xffffffffu, g.Z.v[i], off);
-    r.T.v[i] = __shfl_down_sync(0xffffffffu, g.T.v[i], off);
-  }
-  return r;
-}
 __global__ void __launch_bounds__(128) k_msm_segsum(const ge_t *partial, size_t pairs, size_t segs, ge_t *sums) {
   size_t pair = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);  // (row, w') flattened
   if (pair >= pairs) return;
@@ -294,6 +307,10 @@ __global__ void __launch_bounds__(32) k_msm_horner(const ge_t *sums, size_t rows
     q[0] = make_uint4(w[0], w[1], w[2], w[3]);
     q[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
+}
+void launch_msm_segsum(const ge_t *d_partial, size_t rows, size_t segs, ge_t *d_sums, cudaStream_t st) {
+  size_t pairs = rows * kMsmGroup;
+  ++g_kernel_launches, k_msm_segsum<<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(d_partial, pairs, segs, d_sums);
 }
 void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, ge_t *d_sums, ge_t *d_out, uint8_t *d_comp, cudaStream_t st) {
   const ge_t *sums = d_partial;

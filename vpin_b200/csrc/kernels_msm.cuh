@@ -53,6 +53,10 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
 // out[row] = sum_w' 2^(W*w') sum_seg partial[row][w'][seg]; d_sums: rows * kMsmGroup scratch points (used when segs > 1);
 // d_out (points) and d_comp (32-byte encodings) are optional
 void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, ge_t *d_sums, ge_t *d_out, uint8_t *d_comp, cudaStream_t st);
+// first half of the finish only: d_sums[row * kMsmGroup + w'] = sum_seg partial[row][w'][seg] (the caller runs the Horner
+// pass itself — the prover's bullet-reduction rounds do it on the host, 60 doublings being far cheaper there than in a
+// single GPU thread)
+void launch_msm_segsum(const ge_t *d_partial, size_t rows, size_t segs, ge_t *d_sums, cudaStream_t st);
 // RFC 9496 encoding of n points -> n x 32 bytes
 void launch_compress(const ge_t *d_pts, size_t n, uint8_t *d_out, cudaStream_t st);
 // decode n x 32 bytes -> points; d_ok[i] = 1 if valid

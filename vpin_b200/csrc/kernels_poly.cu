@@ -349,11 +349,23 @@ __global__ void __launch_bounds__(256) k_spmv_csc(CscDev m, const fl_t *x, const
   if (accumulate) acc = fl_add(acc, ld_fl(out + col));
   st_fl(out + col, acc);
 }
-__global__ void __launch_bounds__(kRedThreads) k_spmv_csc_long(CscDev m, const fl_t *x, const fl_t *d_scale, int accumulate, fl_t *out) {
+// long columns (the constant-1 column of vPIN's instances holds ~15 entries per bit-step of every multiplication): block
+// (c, s) adds slice s of column long_cols[c]; k_spmv_csc_long_fin adds the slices, scales and stores
+__global__ void __launch_bounds__(kRedThreads) k_spmv_csc_long(CscDev m, const fl_t *x, fl_t *scratch) {
+  uint32_t col = m.long_cols[blockIdx.x];
+  uint32_t beg = m.ptr[col], end = m.ptr[col + 1];
+  uint32_t per = (end - beg + gridDim.y - 1) / gridDim.y;
+  uint32_t lo = beg + per * blockIdx.y, hi = lo + per < end ? lo + per : end;
+  fl_t acc[1] = {fl_zero()};
+  for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x)
+    acc[0] = fl_add(acc[0], fl_mul(ldg_fl(x + m.idx[e]), ldg_fl(m.val + e)));
+  block_sum_store<1>(acc, scratch + (size_t)blockIdx.x * gridDim.y + blockIdx.y);
+}
+__global__ void __launch_bounds__(64) k_spmv_csc_long_fin(CscDev m, const fl_t *scratch, int nsplit, const fl_t *d_scale, int accumulate,
+                                                          fl_t *out) {
   uint32_t col = m.long_cols[blockIdx.x];
   fl_t acc[1] = {fl_zero()};
-  for (uint32_t e = m.ptr[col] + threadIdx.x, end = m.ptr[col + 1]; e < end; e += blockDim.x)
-    acc[0] = fl_add(acc[0], fl_mul(ldg_fl(x + m.idx[e]), ldg_fl(m.val + e)));
+  for (int s = threadIdx.x; s < nsplit; s += blockDim.x) acc[0] = fl_add(acc[0], ld_fl(scratch + (size_t)blockIdx.x * nsplit + s));
   __shared__ fl_t res;
   block_sum_store<1>(acc, &res);
   __syncthreads();
@@ -363,9 +375,16 @@ __global__ void __launch_bounds__(kRedThreads) k_spmv_csc_long(CscDev m, const f
     st_fl(out + col, v);
   }
 }
-void launch_spmv_csc_scaled(const CscDev &m, const fl_t *x, const fl_t *d_scale, bool accumulate, fl_t *out, cudaStream_t st) {
+void launch_spmv_csc_scaled(const CscDev &m, const fl_t *x, const fl_t *d_scale, bool accumulate, fl_t *out, fl_t *d_scratch,
+                            size_t scratch_elems, cudaStream_t st) {
   ++g_kernel_launches, k_spmv_csc<<<ew_blocks(m.n), 256, 0, st>>>(m, x, d_scale, accumulate ? 1 : 0, out);
-  if (m.n_long) ++g_kernel_launches, k_spmv_csc_long<<<(unsigned)m.n_long, kRedThreads, 0, st>>>(m, x, d_scale, accumulate ? 1 : 0, out);
+  if (m.n_long) {
+    size_t nsplit = scratch_elems / m.n_long;
+    if (nsplit > 64) nsplit = 64;
+    if (nsplit < 1) nsplit = 1;  // the caller sizes the scratch for at least one slot per long column
+    ++g_kernel_launches, k_spmv_csc_long<<<dim3((unsigned)m.n_long, (unsigned)nsplit), kRedThreads, 0, st>>>(m, x, d_scratch);
+    ++g_kernel_launches, k_spmv_csc_long_fin<<<(unsigned)m.n_long, 64, 0, st>>>(m, d_scratch, (int)nsplit, d_scale, accumulate ? 1 : 0, out);
+  }
 }
 __global__ void __launch_bounds__(kRedThreads) k_sparse_eval(const uint32_t *rows, const uint32_t *cols, const fl_t *val, size_t nnz,
                                                              const fl_t *trx, const fl_t *try_, fl_t *partials) {

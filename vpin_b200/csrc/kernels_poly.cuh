@@ -62,6 +62,21 @@ void launch_round_quad(fl_t *A, fl_t *B, size_t q, bool bind, const fl_t &r, con
 void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
 // vals[k] = p_k[0] + r (p_k[1] - p_k[0]) (bind) or p_k[0]
 void launch_round_final(const FinalArgs &a, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
+// One bullet-reduction round (Spartan/src/nizk/bullet.rs:72-119) in the fixed-base formulation, see kernels_round.cu.
+struct BulletRoundArgs {
+  const fl_t *a_old, *b_old;  // vectors before the pending fold (length 2 * len when fold, len otherwise)
+  fl_t *a_new, *b_new;        // folded vectors, length len (written when fold and not final)
+  fl_t *W;                    // n weights over the original generators, updated in place when fold
+  size_t n, len;              // len: vector length after the pending fold
+  fl_t u, uinv, d;            // previous challenge; d: the final blind multiplier (final mode)
+  int fold, final;
+  uint16_t *digits;           // MSM digits [window][row][stride], rows = final ? 1 : 2 (row 0 = L, row 1 = R)
+  size_t stride;
+  unsigned long long *nonzero;
+  RoundCtl ctl;               // vals[0], vals[1] = c_L, c_R (or a'[0], b'[0] in final mode)
+};
+void launch_bullet_round(const BulletRoundArgs &p, cudaStream_t st);
+void launch_publish_seq(RoundSlot *slot, uint32_t seq, cudaStream_t st);
 // eq table with the point passed by value (no device-side copy of r needed); same output as launch_eq_evals
 struct EqPoint { fl_t r[32]; };
 void launch_eq_evals_pt(const EqPoint &pt, int ell, fl_t *d_out, fl_t *d_tmp, cudaStream_t st);
@@ -83,7 +98,9 @@ void launch_spmv_csr(const CsrDev &m, const fl_t *z, fl_t *out, cudaStream_t st)
 // out[col] (+)= scale * sum. Columns with more than kLongCol entries are listed in long_cols and reduced by a block each.
 static const int kLongCol = 256;
 struct CscDev { const uint32_t *ptr; const uint32_t *idx; const fl_t *val; size_t n; const uint32_t *long_cols; size_t n_long; };
-void launch_spmv_csc_scaled(const CscDev &m, const fl_t *x, const fl_t *d_scale, bool accumulate, fl_t *out, cudaStream_t st);
+// d_scratch: scratch_elems >= n_long elements (up to 64 slices per long column are used)
+void launch_spmv_csc_scaled(const CscDev &m, const fl_t *x, const fl_t *d_scale, bool accumulate, fl_t *out, fl_t *d_scratch,
+                            size_t scratch_elems, cudaStream_t st);
 // sum over nnz of rx[row] * ry[col] * val (Spartan/src/sparse_mlpoly.rs:440-452); uses the CSR arrays + a row index per entry
 void launch_sparse_eval(const uint32_t *rows, const uint32_t *cols, const fl_t *val, size_t nnz, const fl_t *trx, const fl_t *try_,
                         fl_t *d_out, fl_t *d_partials, cudaStream_t st);

@@ -12,6 +12,7 @@
 #include <atomic>
 
 #include "kernels_poly.cuh"
+#include "msm_recode.cuh"
 
 namespace vpin {
 
@@ -78,27 +79,29 @@ __device__ __forceinline__ void publish(fl_t (&acc)[K], int inst, int ninst, fl_
                                         uint32_t seq) {
   __shared__ bool is_last;
   block_sum<K>(acc);
-  fl_t *mine = partials + ((size_t)inst * gridDim.x + blockIdx.x) * K;
-  if (threadIdx.x == 0) {
+  if (gridDim.x > 1) {  // (a single block per instance already holds the instance's sums)
+    fl_t *mine = partials + ((size_t)inst * gridDim.x + blockIdx.x) * K;
+    if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < K; k++) str(mine + k, acc[k]);
+      for (int k = 0; k < K; k++) str(mine + k, acc[k]);
+      __threadfence();
+      is_last = atomicAdd(counters + 1 + inst, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
     __threadfence();
-    is_last = atomicAdd(counters + 1 + inst, 1u) == gridDim.x - 1;
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = fl_zero();
+    const fl_t *p = partials + (size_t)inst * gridDim.x * K;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = fl_add(acc[k], ldcg(p + (size_t)b * K + k));
+    block_sum<K>(acc);
+    if (threadIdx.x == 0) counters[1 + inst] = 0;
   }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-#pragma unroll
-  for (int k = 0; k < K; k++) acc[k] = fl_zero();
-  const fl_t *p = partials + (size_t)inst * gridDim.x * K;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
-#pragma unroll
-    for (int k = 0; k < K; k++) acc[k] = fl_add(acc[k], ldcg(p + (size_t)b * K + k));
-  block_sum<K>(acc);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < K; k++) str(slot->vals + inst * K + k, acc[k]);
-    counters[1 + inst] = 0;
     __threadfence_system();
     if (atomicAdd(counters, 1u) == (unsigned)ninst - 1) {
       counters[0] = 0;
@@ -140,7 +143,7 @@ __device__ __forceinline__ void load_pair_oop(const fl_t *in, fl_t *out, bool wr
 
 // ---- A (B C - D) at t = 0, 2, 3 ----
 template <bool kBind>
-__global__ void __launch_bounds__(kRedThreads) k_round_cubic_additive(fl_t *A, fl_t *B, fl_t *C, fl_t *D, size_t q, fl_t r, fl_t *partials,
+__global__ void __launch_bounds__(kRedThreads, 2) k_round_cubic_additive(fl_t *A, fl_t *B, fl_t *C, fl_t *D, size_t q, fl_t r, fl_t *partials,
                                                                       unsigned *counters, RoundSlot *slot, uint32_t seq) {
   fl_t acc[3] = {fl_zero(), fl_zero(), fl_zero()};
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(kRedThreads) k_round_quad(fl_t *A, fl_t *B, si
 
 // ---- batched A_k B_k C_k at t = 0, 2, 3; instance = blockIdx.y ----
 template <bool kBind>
-__global__ void __launch_bounds__(kRedThreads) k_round_cubic_batched(BatchedRoundArgs a, size_t q, fl_t r, fl_t *partials, unsigned *counters,
+__global__ void __launch_bounds__(kRedThreads, 2) k_round_cubic_batched(BatchedRoundArgs a, size_t q, fl_t r, fl_t *partials, unsigned *counters,
                                                                      RoundSlot *slot, uint32_t seq) {
   const int inst = blockIdx.y;
   fl_t *A = a.A[inst], *B = a.B[inst];
@@ -203,6 +206,56 @@ __global__ void __launch_bounds__(kRedThreads) k_round_cubic_batched(BatchedRoun
   publish<3>(acc, inst, gridDim.y, partials, counters, slot, seq);
 }
 
+// ---- the same for tiny rounds (q <= kSmallQ): ONE block, half a warp per instance, no inter-block traffic at all.
+// Roughly 250 of the ~400 rounds of the two product-circuit proofs of a 2^20 instance are of this kind, and their cost
+// is pure latency (launch -> loads -> a handful of multiplications -> shuffle tree -> PCIe store).
+static const size_t kSmallQ = 64;
+template <bool kBind>
+__global__ void __launch_bounds__(16 * kMaxBatched + 16) k_round_cubic_batched_small(BatchedRoundArgs a, int ninst, size_t q, fl_t r,
+                                                                                    RoundSlot *slot, uint32_t seq) {
+  const int inst = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  fl_t acc[3] = {fl_zero(), fl_zero(), fl_zero()};
+  if (inst < ninst) {
+    fl_t *A = a.A[inst], *B = a.B[inst];
+    const fl_t *Cin = a.Cin[inst];
+    fl_t *Cout = a.Cout[inst];
+    const bool writeC = Cout != nullptr;
+    for (size_t i = lane; i < q; i += 16) {
+      fl_t a0, a1, b0, b1, c0, c1;
+      load_pair<kBind>(A, i, q, r, a0, a1);
+      load_pair<kBind>(B, i, q, r, b0, b1);
+      load_pair_oop<kBind>(Cin, Cout, writeC, i, q, r, c0, c1);
+      acc[0] = fl_add(acc[0], fl_mul(fl_mul(a0, b0), c0));
+      fl_t da = fl_sub(a1, a0), db = fl_sub(b1, b0), dc = fl_sub(c1, c0);
+      fl_t a2 = fl_add(a1, da), b2 = fl_add(b1, db), c2 = fl_add(c1, dc);
+      acc[1] = fl_add(acc[1], fl_mul(fl_mul(a2, b2), c2));
+      fl_t a3 = fl_add(a2, da), b3 = fl_add(b2, db), c3 = fl_add(c2, dc);
+      acc[2] = fl_add(acc[2], fl_mul(fl_mul(a3, b3), c3));
+    }
+  }
+  if (q > 1) {  // (q == 1: only lane 0 of each instance holds a term)
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        fl_t o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.v[i] = __shfl_down_sync(0xffffffffu, acc[k].v[i], off, 16);
+        acc[k] = fl_add(acc[k], o);
+      }
+  }
+  if (lane == 0 && inst < ninst) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) str(slot->vals + inst * 3 + k, acc[k]);
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
+  }
+}
+
 // ---- final claims: vals[k] = p_k[0] + r (p_k[1] - p_k[0])  (or p_k[0] when nothing is left to bind) ----
 __global__ void __launch_bounds__(64) k_round_final(FinalArgs a, fl_t r, int bind, RoundSlot *slot, uint32_t seq) {
   int k = threadIdx.x;
@@ -218,6 +271,62 @@ __global__ void __launch_bounds__(64) k_round_final(FinalArgs a, fl_t r, int bin
     __threadfence_system();
     *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
   }
+}
+
+// ---- bullet reduction (Spartan/src/nizk/bullet.rs:72-119), one launch per round ----
+// The folded generators are never materialised: W holds, per ORIGINAL generator, the product of the u / u^-1 factors it
+// has collected, so L and R are fixed-base MSMs over the original table with scalars a'[partner] * W[j]. This kernel
+// (i) applies the previous round's fold to a, b (ping-pong buffers) and W, (ii) accumulates c_L = <a_L, b_R> and
+// c_R = <a_R, b_L>, (iii) writes the signed MSM digits of the L row (columns in the upper half of their 2*cur block)
+// and the R row (lower half). In `final` mode (vectors of length 1) it emits a'[0], b'[0] and the digits of d * W.
+__global__ void __launch_bounds__(kRedThreads) k_bullet_round(BulletRoundArgs p) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t len = p.len, cur = len >> 1;
+  const bool fold = p.fold != 0;
+  auto A = [&](size_t k) { return fold ? fl_add(fl_mul(ldr(p.a_old + k), p.u), fl_mul(p.uinv, ldr(p.a_old + k + len))) : ldr(p.a_old + k); };
+  auto B = [&](size_t k) { return fold ? fl_add(fl_mul(ldr(p.b_old + k), p.uinv), fl_mul(p.u, ldr(p.b_old + k + len))) : ldr(p.b_old + k); };
+  fl_t acc[2] = {fl_zero(), fl_zero()};
+  if (p.final) {
+    if (j == 0) { acc[0] = A(0); acc[1] = B(0); }
+  } else if (j < cur) {
+    fl_t a_lo = A(j), a_hi = A(j + cur), b_lo = B(j), b_hi = B(j + cur);
+    if (fold) { str(p.a_new + j, a_lo); str(p.a_new + j + cur, a_hi); str(p.b_new + j, b_lo); str(p.b_new + j + cur, b_hi); }
+    acc[0] = fl_mul(a_lo, b_hi);
+    acc[1] = fl_mul(a_hi, b_lo);
+  }
+  uint32_t nz = 0;
+  if (j < p.stride) {
+    const size_t plane = (size_t)(p.final ? 1 : 2) * p.stride;
+    if (j < p.n) {
+      fl_t w = ldr(p.W + j);
+      if (fold) {
+        w = fl_mul(w, (j & (2 * len - 1)) < len ? p.uinv : p.u);
+        str(p.W + j, w);
+      }
+      if (p.final) {
+        nz = msm_recode_value(fl_mul(p.d, w), p.digits + j, plane);
+      } else {
+        size_t rem = j & (len - 1);
+        bool upper = rem >= cur;  // a_L against G_R -> row 0 (L); a_R against G_L -> row 1 (R)
+        fl_t s = fl_mul(A(upper ? rem - cur : rem + cur), w);
+        nz = msm_recode_value(s, p.digits + (upper ? 0 : p.stride) + j, plane);
+        uint16_t *other = p.digits + (upper ? p.stride : 0) + j;
+        for (int wdw = 0; wdw < kMsmWindows; wdw++) other[(size_t)wdw * plane] = 0;
+      }
+    } else {
+      for (int row = 0; row < (p.final ? 1 : 2); row++)
+        for (int wdw = 0; wdw < kMsmWindows; wdw++) p.digits[(size_t)wdw * plane + row * p.stride + j] = 0;
+    }
+  }
+  if (p.nonzero) {
+    nz = __reduce_add_sync(0xffffffffu, nz);
+    if ((threadIdx.x & 31) == 0 && nz) atomicAdd(p.nonzero, (unsigned long long)nz);
+  }
+  publish<2>(acc, 0, 1, p.ctl.d_partials, p.ctl.d_counters, p.ctl.slot, p.ctl.seq);
+}
+__global__ void k_publish_seq(RoundSlot *slot, uint32_t seq) {
+  __threadfence_system();
+  *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
 }
 
 inline int round_blocks(size_t q, int cap) {
@@ -241,12 +350,23 @@ void launch_round_quad(fl_t *A, fl_t *B, size_t q, bool bind, const fl_t &r, con
   else k_round_quad<false><<<nb, kRedThreads, 0, st>>>(A, B, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
 }
 void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
+  ++g_kernel_launches;
+  if (q <= kSmallQ) {
+    int threads = (16 * ninst + 31) / 32 * 32;
+    if (bind) k_round_cubic_batched_small<true><<<1, threads, 0, st>>>(a, ninst, q, r, c.slot, c.seq);
+    else k_round_cubic_batched_small<false><<<1, threads, 0, st>>>(a, ninst, q, r, c.slot, c.seq);
+    return;
+  }
   int nb = round_blocks(q, ninst > 4 ? kRedBlocks / 4 : kRedBlocks);
   dim3 grid(nb, ninst);
-  ++g_kernel_launches;
   if (bind) k_round_cubic_batched<true><<<grid, kRedThreads, 0, st>>>(a, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
   else k_round_cubic_batched<false><<<grid, kRedThreads, 0, st>>>(a, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
 }
+void launch_bullet_round(const BulletRoundArgs &p, cudaStream_t st) {
+  unsigned nb = (unsigned)((p.stride + kRedThreads - 1) / kRedThreads);
+  ++g_kernel_launches, k_bullet_round<<<nb, kRedThreads, 0, st>>>(p);
+}
+void launch_publish_seq(RoundSlot *slot, uint32_t seq, cudaStream_t st) { ++g_kernel_launches, k_publish_seq<<<1, 1, 0, st>>>(slot, seq); }
 void launch_round_final(const FinalArgs &a, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
   ++g_kernel_launches, k_round_final<<<1, 64, 0, st>>>(a, r, bind ? 1 : 0, c.slot, c.seq);
 }

@@ -22,19 +22,30 @@ class Keccak {
         0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
         0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
         0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
-    // rho offsets indexed [x + 5*y]
-    static const int kRho[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+    // lanes in locals, theta / rho+pi / chi written out per plane (the transcript absorbs every commitment row and every
+    // opened scalar vector, ~10^4 permutations per proof, so this is on the host critical path)
+    uint64_t a00 = a[0], a01 = a[1], a02 = a[2], a03 = a[3], a04 = a[4], a05 = a[5], a06 = a[6], a07 = a[7], a08 = a[8], a09 = a[9],
+             a10 = a[10], a11 = a[11], a12 = a[12], a13 = a[13], a14 = a[14], a15 = a[15], a16 = a[16], a17 = a[17], a18 = a[18],
+             a19 = a[19], a20 = a[20], a21 = a[21], a22 = a[22], a23 = a[23], a24 = a[24];
     for (int rnd = 0; rnd < 24; rnd++) {
-      uint64_t c[5], d[5], b[25];
-      for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
-      for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl(c[(x + 1) % 5], 1);
-      for (int i = 0; i < 25; i++) a[i] ^= d[i % 5];
-      for (int x = 0; x < 5; x++)
-        for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rotl(a[x + 5 * y], kRho[x + 5 * y]);
-      for (int y = 0; y < 5; y++)
-        for (int x = 0; x < 5; x++) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
-      a[0] ^= kRound[rnd];
+      uint64_t c0 = a00 ^ a05 ^ a10 ^ a15 ^ a20, c1 = a01 ^ a06 ^ a11 ^ a16 ^ a21, c2 = a02 ^ a07 ^ a12 ^ a17 ^ a22,
+               c3 = a03 ^ a08 ^ a13 ^ a18 ^ a23, c4 = a04 ^ a09 ^ a14 ^ a19 ^ a24;
+      uint64_t d0 = c4 ^ rotl(c1, 1), d1 = c0 ^ rotl(c2, 1), d2 = c1 ^ rotl(c3, 1), d3 = c2 ^ rotl(c4, 1), d4 = c3 ^ rotl(c0, 1);
+      // b[y + 5 * ((2x + 3y) % 5)] = rotl(a[x + 5y] ^ d[x], rho[x + 5y])
+      uint64_t b00 = a00 ^ d0, b10 = rotl(a01 ^ d1, 1), b20 = rotl(a02 ^ d2, 62), b05 = rotl(a03 ^ d3, 28), b15 = rotl(a04 ^ d4, 27);
+      uint64_t b16 = rotl(a05 ^ d0, 36), b01 = rotl(a06 ^ d1, 44), b11 = rotl(a07 ^ d2, 6), b21 = rotl(a08 ^ d3, 55), b06 = rotl(a09 ^ d4, 20);
+      uint64_t b07 = rotl(a10 ^ d0, 3), b17 = rotl(a11 ^ d1, 10), b02 = rotl(a12 ^ d2, 43), b12 = rotl(a13 ^ d3, 25), b22 = rotl(a14 ^ d4, 39);
+      uint64_t b23 = rotl(a15 ^ d0, 41), b08 = rotl(a16 ^ d1, 45), b18 = rotl(a17 ^ d2, 15), b03 = rotl(a18 ^ d3, 21), b13 = rotl(a19 ^ d4, 8);
+      uint64_t b14 = rotl(a20 ^ d0, 18), b24 = rotl(a21 ^ d1, 2), b09 = rotl(a22 ^ d2, 61), b19 = rotl(a23 ^ d3, 56), b04 = rotl(a24 ^ d4, 14);
+      a00 = b00 ^ (~b01 & b02) ^ kRound[rnd]; a01 = b01 ^ (~b02 & b03); a02 = b02 ^ (~b03 & b04); a03 = b03 ^ (~b04 & b00); a04 = b04 ^ (~b00 & b01);
+      a05 = b05 ^ (~b06 & b07); a06 = b06 ^ (~b07 & b08); a07 = b07 ^ (~b08 & b09); a08 = b08 ^ (~b09 & b05); a09 = b09 ^ (~b05 & b06);
+      a10 = b10 ^ (~b11 & b12); a11 = b11 ^ (~b12 & b13); a12 = b12 ^ (~b13 & b14); a13 = b13 ^ (~b14 & b10); a14 = b14 ^ (~b10 & b11);
+      a15 = b15 ^ (~b16 & b17); a16 = b16 ^ (~b17 & b18); a17 = b17 ^ (~b18 & b19); a18 = b18 ^ (~b19 & b15); a19 = b19 ^ (~b15 & b16);
+      a20 = b20 ^ (~b21 & b22); a21 = b21 ^ (~b22 & b23); a22 = b22 ^ (~b23 & b24); a23 = b23 ^ (~b24 & b20); a24 = b24 ^ (~b20 & b21);
     }
+    a[0] = a00; a[1] = a01; a[2] = a02; a[3] = a03; a[4] = a04; a[5] = a05; a[6] = a06; a[7] = a07; a[8] = a08; a[9] = a09;
+    a[10] = a10; a[11] = a11; a[12] = a12; a[13] = a13; a[14] = a14; a[15] = a15; a[16] = a16; a[17] = a17; a[18] = a18; a[19] = a19;
+    a[20] = a20; a[21] = a21; a[22] = a22; a[23] = a23; a[24] = a24;
   }
 
  private:

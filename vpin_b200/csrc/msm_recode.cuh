@@ -1,0 +1,55 @@
+// Signed-digit recoding of one scalar for the fixed-base MSM tables (kernels_msm.cuh), shared by the bulk recode kernel
+// and the fused bullet-reduction kernel.
+#pragma once
+#include "kernels_msm.cuh"
+
+namespace vpin {
+
+__device__ __forceinline__ uint32_t msm_half_l_limb(int i) {  // (l - 1) / 2
+  switch (i) {
+    case 0: return 0x2e7ae9f6u; case 1: return 0x2c09318du; case 2: return 0x517bce6bu; case 3: return 0x0a6f7cefu;
+    case 7: return 0x08000000u; default: return 0u;
+  }
+}
+// x: Montgomery form. Writes the kMsmWindows digits of the representative of smallest absolute value (|s| <= (l-1)/2) to
+// dst[w * plane] as magnitude | sign << 15 and returns the number of non-zero digits.
+__device__ __forceinline__ uint32_t msm_recode_value(const fl_t &x, uint16_t *dst, size_t plane) {
+  if (fl_is_zero(x)) {
+    for (int w = 0; w < kMsmWindows; w++) dst[(size_t)w * plane] = 0;
+    return 0;
+  }
+  fl_t s = fl_from_mont(x);
+  // s > (l-1)/2 ?  then use l - s and flip every sign
+  bool gt = false;
+#pragma unroll
+  for (int i = 7; i >= 0; i--) {
+    uint32_t h = msm_half_l_limb(i);
+    if (s.v[i] != h) { gt = s.v[i] > h; break; }
+  }
+  uint32_t v[9];
+  if (gt) {
+    int64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { int64_t t = (int64_t)fl_modulus_limb(i) - (int64_t)s.v[i] + br; v[i] = (uint32_t)t; br = t >> 32; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = s.v[i];
+  }
+  v[8] = 0;
+  uint32_t carry = 0, nz = 0;
+#pragma unroll
+  for (int w = 0; w < kMsmWindows; w++) {
+    int bit = w * kMsmW, limb = bit >> 5, sh = bit & 31;
+    uint64_t two = (uint64_t)v[limb] | ((uint64_t)(limb + 1 < 9 ? v[limb + 1] : 0u) << 32);
+    uint32_t raw = (limb < 8 ? (uint32_t)(two >> sh) & ((1u << kMsmW) - 1u) : 0u) + carry;
+    uint32_t neg = raw > (uint32_t)kMsmTable ? 1u : 0u;
+    uint32_t mag = neg ? (1u << kMsmW) - raw : raw;
+    carry = neg;
+    uint32_t sign = (neg ^ (gt ? 1u : 0u)) & (mag != 0 ? 1u : 0u);
+    nz += mag != 0 ? 1u : 0u;
+    dst[(size_t)w * plane] = (uint16_t)(mag | (sign << 15));
+  }
+  return nz;
+}
+
+}  // namespace vpin

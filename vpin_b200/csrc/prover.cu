@@ -178,6 +178,9 @@ struct Prover {
   ProverTape &tape;
   const SnarkGens &g;
   size_t ring = 0;
+  // accumulating wall-clock timers (reported next to the phases)
+  double t_bullet_gpu = 0, t_bullet_host = 0, t_bullet_pre = 0, t_b_wait = 0, t_b_host = 0, t_b_launch = 0, t_b_small_wait = 0;
+  size_t n_b_small = 0, n_b_rounds = 0;
 
   // ---- tiny host <-> device traffic (challenges in, round sums out) ----
   const fl_t *up(const fl_t *vals, size_t n) {  // returns the device address of n freshly uploaded elements
@@ -430,6 +433,7 @@ struct Prover {
   DotLogS dotproductlog_prove(const PcGens &pc, const LabelGens &lg, const fl_t *d_x, const fl_t &blind_x, const fl_t *d_a, const fl_t &y,
                               const fl_t &blind_y, Comp *Cy_out) {
     t.protocol_name("dot product proof (log)");
+    double tb0 = now_ms();
     size_t n = pc.R, lg_n = math_log2(n);
     fl_t d = tape.scalar("d");
     fl_t r_delta = tape.scalar("r_delta");
@@ -450,21 +454,72 @@ struct Prover {
     }
     fl_t r = t.challenge_scalar("r");  // Q = r * gens_1.G[0]
     fl_t blind_fin = blind_x + r * blind_y;
-    DevVec<fl_t> a(n, st), b(n, st), W(n, st), srows(2 * n, st);
-    VPIN_CUDA(cudaMemcpyAsync(a.p, d_x, n * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
-    VPIN_CUDA(cudaMemcpyAsync(b.p, d_a, n * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
+    // a / b ping-pong buffers, weights over the original generators, MSM scratch for two rows (kernels_round.cu)
+    DevVec<fl_t> abuf(2 * n, st), bbuf(2 * n, st), W(n, st);
+    fl_t *av[2] = {abuf.p, abuf.p + n}, *bv[2] = {bbuf.p, bbuf.p + n};
+    VPIN_CUDA(cudaMemcpyAsync(av[0], d_x, n * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
+    VPIN_CUDA(cudaMemcpyAsync(bv[0], d_a, n * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
     launch_fill_one(W.p, n, st);
+    size_t segs = msm_num_segments(2, n), stride = msm_col_stride(n);
+    DevVec<uint16_t> digits(msm_digits_count(2, n), st);
+    DevVec<ge_t> partial(2 * kMsmGroup * segs, st), sums(2 * kMsmGroup, st);
     DotLogS out;
-    size_t cur = n;
-    for (size_t round = 0; cur != 1; round++) {
-      cur /= 2;
-      fl_t *d_c = ctx->d_small.p + 244;
-      launch_dot(a.p, b.p + cur, cur, d_c, ctx->d_partials.p, st);      // c_L = <a_L, b_R>
-      launch_dot(a.p + cur, b.p, cur, d_c + 1, ctx->d_partials.p, st);  // c_R = <a_R, b_L>
-      launch_bullet_scalars(a.p, W.p, n, cur, srows.p, srows.p + n, st);
-      std::vector<hge_t> LR = msm_rows_host(lg, srows.p, 2, n, n);
-      fl_t c[2];
-      down(d_c, 2 * sizeof(fl_t), c);
+    t_bullet_pre += now_ms() - tb0;
+    int src = 0, slot = 0;
+    bool fold = false;
+    fl_t u = fl_zero(), u_inv = fl_zero();
+    // one round = k_bullet_round (fold with the previous u, c_L / c_R, MSM digits) + the two-row fixed-base MSM whose
+    // Horner kernel stores L', R' straight into the host-mapped slot
+    auto launch = [&](size_t len, bool final, uint32_t *seq_out) {
+      BulletRoundArgs p;
+      p.a_old = av[src]; p.b_old = bv[src]; p.a_new = av[src ^ 1]; p.b_new = bv[src ^ 1];
+      p.W = W.p; p.n = n; p.len = len; p.u = u; p.uinv = u_inv; p.d = d;
+      p.fold = fold ? 1 : 0; p.final = final ? 1 : 0;
+      p.digits = digits.p; p.stride = stride; p.nonzero = ctx->d_counters.p;
+      uint32_t seq0;
+      p.ctl = round_ctl(slot, &seq0);
+      size_t rows = final ? 1 : 2;
+      double pts = (double)rows * n;
+      {
+        ProfScope ps(ctx, PROF_BULLET, pts, 0);
+        launch_bullet_round(p, st);
+      }
+      size_t sg = final ? msm_num_segments(1, n) : segs;
+      if (sg > segs) sg = segs;
+      {
+        ProfScope ps(ctx, PROF_MSM_ACCUMULATE, pts, 0);
+        launch_msm_accumulate(lg.table(), digits.p, rows, n, false, 0, sg, partial.p, st);
+      }
+      {  // window sums straight into the host-mapped slot: vals[8 ..] = rows x kMsmGroup points
+        ProfScope ps(ctx, PROF_MSM_FINISH, pts, 0);
+        launch_msm_segsum(partial.p, rows, sg, reinterpret_cast<ge_t *>(ctx->d_slots[slot].vals + 8), st);
+      }
+      *seq_out = ++ctx->round_seq;
+      launch_publish_seq(ctx->d_slots + slot, *seq_out, st);
+      if (fold && !final) src ^= 1;
+    };
+    static_assert(8 * sizeof(fl_t) + 2 * kMsmGroup * sizeof(ge_t) <= kRoundSlotVals * sizeof(fl_t), "slot too small for two rows");
+    // Horner pass over the kMsmGroup window sums of one row (kernels_msm.cuh), on the host
+    auto horner = [&](const fl_t *vals, size_t row) {
+      ge_t w[kMsmGroup];
+      memcpy(w, reinterpret_cast<const uint8_t *>(vals + 8) + row * sizeof(w), sizeof(w));
+      hge_t h = hf::ge_from_dev(w[kMsmGroup - 1]);
+      for (int k = kMsmGroup - 2; k >= 0; k--) {
+        for (int i = 0; i < kMsmW; i++) h = hf::ge_dbl(h);
+        h = hf::ge_add(h, hf::ge_from_dev(w[k]));
+      }
+      return h;
+    };
+    size_t len = n;
+    for (size_t round = 0; len != 1; round++) {
+      double tr0 = now_ms();
+      uint32_t seq;
+      launch(len, false, &seq);
+      const fl_t *vals = round_wait(slot, seq);
+      fl_t c[2] = {vals[0], vals[1]};
+      double tr1 = now_ms();
+      hge_t LR[2] = {horner(vals, 0), horner(vals, 1)};
+      t_bullet_gpu += tr1 - tr0;
       const fl_t &blind_L = bv1[round], &blind_R = bv2[round];
       pc.g1->mul_acc(c[0] * r, &LR[0]);
       pc.h->mul_acc(blind_L, &LR[0]);
@@ -473,21 +528,23 @@ struct Prover {
       Comp Lc = compress_host(LR[0]), Rc = compress_host(LR[1]);
       t.point("L", Lc.data());
       t.point("R", Rc.data());
-      fl_t u = t.challenge_scalar("u");
-      fl_t u_inv = fl_invert(u);
-      fl_t uu[2] = {u, u_inv};
-      const fl_t *d_u = up(uu, 2);
-      launch_bullet_fold(a.p, b.p, cur, d_u, st);
-      launch_bullet_weights(W.p, n, cur, d_u, st);
+      u = t.challenge_scalar("u");
+      u_inv = fl_invert(u);
       blind_fin = blind_fin + blind_L * u * u + blind_R * u_inv * u_inv;
       out.L_vec.push_back(Lc);
       out.R_vec.push_back(Rc);
+      fold = true;
+      len /= 2;
+      slot ^= 1;
+      t_bullet_host += now_ms() - tr1;
     }
-    fl_t x_hat = down1(a.p), a_hat = down1(b.p);
+    // last fold -> x_hat, a_hat; delta = d * g_hat + r_delta * h with g_hat = sum_j W_j G_j
+    uint32_t seq;
+    launch(1, true, &seq);
+    const fl_t *vals = round_wait(slot, seq);
+    fl_t x_hat = vals[0], a_hat = vals[1];
     fl_t y_hat = x_hat * a_hat;
-    // delta = d * g_hat + r_delta * h with g_hat = sum_j W_j G_j
-    launch_scale(W.p, up(&d, 1), n, srows.p, st);
-    hge_t dl = msm_rows_host(lg, srows.p, 1, n, n)[0];
+    hge_t dl = horner(vals, 0);
     pc.h->mul_acc(r_delta, &dl);
     out.delta = compress_host(dl);
     t.point("delta", out.delta.data());
@@ -577,7 +634,12 @@ struct Prover {
       if (num_rounds) launch(0, r_j);
       std::vector<fl_t> ev(3 * ninst);
       for (size_t j = 0; j < num_rounds; j++) {
+        double tw0 = now_ms();
         memcpy(ev.data(), round_wait(slot, seq), 3 * ninst * sizeof(fl_t));
+        double tw1 = now_ms();
+        t_b_wait += tw1 - tw0;
+        n_b_rounds++;
+        if ((len_half >> (j + 1)) <= 64) { t_b_small_wait += tw1 - tw0; n_b_small++; }
         fl_t c0 = fl_zero(), c2 = fl_zero(), c3 = fl_zero();
         for (size_t i = 0; i < ninst; i++) {
           c0 = c0 + ev[3 * i] * coeffs[i];
@@ -592,7 +654,10 @@ struct Prover {
         r_j = t.challenge_scalar("challenge_nextround");
         rand_prod.push_back(r_j);
         slot ^= 1;
+        double tw2 = now_ms();
+        t_b_host += tw2 - tw1;
         if (j + 1 < num_rounds) launch(j + 1, r_j);
+        t_b_launch += now_ms() - tw2;
         e = unipoly_eval(poly, r_j);
         layer.polys.push_back({poly[0], poly[2], poly[3]});  // CompressedUniPoly (SP/unipoly.rs:80-87)
       }
@@ -604,7 +669,10 @@ struct Prover {
       if (with_dotp)
         for (size_t k = 0; k < dotp.size(); k++) { fa.p[fa.n++] = dotp[k].l; fa.p[fa.n++] = dotp[k].r; fa.p[fa.n++] = dotp[k].w; }
       VPIN_REQUIRE(fa.n <= kRoundSlotVals, VPIN_ERR_PROVER, "too many final claims");
-      launch_round_final(fa, num_rounds > 0, r_j, round_ctl(slot, &seq), st);
+      {
+        ProfScope ps(ctx, PROF_FINAL, (double)fa.n, 0);
+        launch_round_final(fa, num_rounds > 0, r_j, round_ctl(slot, &seq), st);
+      }
       std::vector<fl_t> fin(fa.n);
       memcpy(fin.data(), round_wait(slot, seq), fa.n * sizeof(fl_t));
       for (size_t c = 0; c < nc; c++) { layer.left.push_back(fin[2 * c]); layer.right.push_back(fin[2 * c + 1]); }
@@ -756,8 +824,8 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
     fl_t rr[3] = {r_A, r_B, r_C};
     const fl_t *d_rr = P.up(rr, 3);
     for (int k = 0; k < 3; k++) {
-      ProfScope ps(ctx, PROF_SPMV_T, (double)inst.M[k].nnz, 68.0 * inst.M[k].nnz + 36.0 * zlen, 2);
-      launch_spmv_csc_scaled(csc_of(inst.M[k], zlen), evals_rx.p, d_rr + k, k != 0, evals_ABC.p, st);
+      ProfScope ps(ctx, PROF_SPMV_T, (double)inst.M[k].nnz, 68.0 * inst.M[k].nnz + 36.0 * zlen, 3);
+      launch_spmv_csc_scaled(csc_of(inst.M[k], zlen), evals_rx.p, d_rr + k, k != 0, evals_ABC.p, ctx->d_partials.p, ctx->d_partials.n, st);
     }
     ctx->sync();
   }
@@ -924,8 +992,14 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
     VPIN_REQUIRE(fl_eq(eval_dotp_left[k] + eval_dotp_right[k], inst_evals[k]), VPIN_ERR_PROVER, "sparse evaluation mismatch");
   }
   std::vector<fl_t> rand_ops, rand_mem;
+  phase("product_layer_setup", t0);
+  double t1 = now_ms();
   BatchedS proof_ops = P.batched_prove(ops_ptr, N, dotp, ops_evals, &rand_ops);
+  phase("product_circuits_ops", t1);
+  t1 = now_ms();
   BatchedS proof_mem = P.batched_prove(mem_ptr, M, {}, mem_evals, &rand_mem);
+  phase("product_circuits_mem", t1);
+  t1 = now_ms();
   ops_trees.release();
   mem_trees.release();
   dotp_tables.release();
@@ -992,8 +1066,18 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
     t.scalar("joint_claim_eval_mem", joint);
     proof_mem_open = P.polyeval_prove(g.mem_pc, *g.eval_label, dec.comb_mem.p, nullptr, r_joint, joint, fl_zero(), nullptr);
   }
+  phase("hash_layer_proof", t1);
   phase("evalproof_layered_network", t0);
   phase("R1CSEvalProof::prove", t_eval);
+  ctx->phases.push_back({"batched_wait", P.t_b_wait});
+  ctx->phases.push_back({"batched_small_wait", P.t_b_small_wait});
+  ctx->phases.push_back({"batched_n_small", (double)P.n_b_small});
+  ctx->phases.push_back({"batched_n_rounds", (double)P.n_b_rounds});
+  ctx->phases.push_back({"batched_host", P.t_b_host});
+  ctx->phases.push_back({"batched_launch", P.t_b_launch});
+  ctx->phases.push_back({"bullet_pre(4 proofs)", P.t_bullet_pre});
+  ctx->phases.push_back({"bullet_rounds_gpu(4 proofs)", P.t_bullet_gpu});
+  ctx->phases.push_back({"bullet_rounds_host(4 proofs)", P.t_bullet_host});
   phase("SNARK::prove", t_prove);
 
   // ---------------- bincode(SNARK) (SP/lib.rs:330-338 and the nested types) ----------------
