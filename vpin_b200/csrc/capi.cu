@@ -4,8 +4,9 @@
 
 using namespace vpin;
 
-#define VPIN_TRY(ctx_) \
-  Ctx *c_ = (ctx_);    \
+#define VPIN_TRY(ctx_)                      \
+  Ctx *c_ = (ctx_);                         \
+  if (c_) cudaSetDevice(c_->device); /* contexts may be driven from different host threads */ \
   try {
 #define VPIN_CATCH                                                    \
   }                                                                   \
@@ -191,15 +192,18 @@ vpin_status vpin_instance_export_coo(vpin_ctx *ctx, const vpin_instance *inst, u
   VPIN_REQUIRE(I && out && which >= 0 && which < 3 && num_vars_unpadded <= I->num_vars, VPIN_ERR_BAD_ARGUMENT, "bad argument");
   const MatrixDev &m = I->M[which];
   std::vector<fl_t> v(m.nnz);
+  std::vector<uint32_t> h_row(m.nnz), h_col(m.nnz);
   if (m.nnz) {
     DevVec<fl_t> tmp(m.nnz, c_->st);
     launch_from_mont(m.coo_val.p, m.nnz, tmp.p, c_->st);
     tmp.download(v.data(), m.nnz);
+    m.coo_row.download(h_row.data(), m.nnz);
+    m.coo_col.download(h_col.data(), m.nnz);
     c_->sync();
   }
   for (size_t i = 0; i < m.nnz; i++) {
-    out[i].row = m.h_row[i];
-    uint64_t col = m.h_col[i];
+    out[i].row = h_row[i];
+    uint64_t col = h_col[i];
     out[i].col = col >= I->num_vars ? col - (I->num_vars - num_vars_unpadded) : col;  // undo the shift of Spartan/src/lib.rs:196-200
     memcpy(out[i].val, v[i].v, 32);
   }

@@ -302,22 +302,12 @@ uint32_t build_matrix(Ctx *ctx, MatrixDev &m, const vpin_coo_entry *entries, siz
   cudaStream_t st = ctx->st;
   size_t num_cols = 2 * num_vars_padded, nnz = n + n_pad;
   m.nnz = nnz;
-  // host copies of the (shifted) indices: SNARK::encode replays them sequentially for the memory-check timestamps
-  m.h_row.resize(nnz);
-  m.h_col.resize(nnz);
   uint64_t shift = num_vars_padded - num_vars, ncols_in = num_vars + 1 + num_inputs;
-  for (size_t i = 0; i < n; i++) {
-    m.h_row[i] = (uint32_t)entries[i].row;
-    uint64_t c = entries[i].col;
-    m.h_col[i] = (uint32_t)(c >= num_vars ? c + shift : c);
-  }
   std::vector<vpin_coo_entry> pad(n_pad);
   for (size_t i = 0; i < n_pad; i++) {  // Spartan/src/lib.rs:207-211: (i, num_vars, 0), column NOT shifted
     memset(&pad[i], 0, sizeof(vpin_coo_entry));
     pad[i].row = n + i;
     pad[i].col = num_vars;
-    m.h_row[n + i] = (uint32_t)(n + i);
-    m.h_col[n + i] = (uint32_t)num_vars;
   }
   DevVec<vpin_coo_entry> raw(nnz, st);
   if (n) VPIN_CUDA(cudaMemcpyAsync(raw.p, entries, n * sizeof(vpin_coo_entry), cudaMemcpyHostToDevice, st));

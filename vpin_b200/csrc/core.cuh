@@ -157,8 +157,7 @@ void hyrax_rows(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_t rows, size_
 // one sparse matrix of the instance in the three layouts the kernels use
 struct MatrixDev {
   size_t nnz = 0;
-  std::vector<uint32_t> h_row, h_col;   // COO order == SPARK "ops" order (Spartan/src/sparse_mlpoly.rs:368-380)
-  DevVec<uint32_t> coo_row, coo_col;
+  DevVec<uint32_t> coo_row, coo_col;    // COO order == SPARK "ops" order (Spartan/src/sparse_mlpoly.rs:368-380)
   DevVec<fl_t> coo_val;
   DevVec<uint32_t> csr_ptr, csr_col;
   DevVec<fl_t> csr_val;

@@ -110,6 +110,12 @@ void launch_sparse_eval(const uint32_t *rows, const uint32_t *cols, const fl_t *
 void launch_gather(const uint32_t *addr, const fl_t *mem, size_t n, fl_t *out, cudaStream_t st);
 // out[i] = fl(u32 in[i])
 void launch_u32_to_fl(const uint32_t *in, size_t n, fl_t *out, cudaStream_t st);
+// memory-checking timestamps (:232-265) by a stable radix sort instead of the reference's sequential replay (kernels_sort.cu).
+// addr[k]: nnz[k] addresses of matrix k (row or column indices, COO order), padded with address 0 to N operations each.
+// Outputs: d_addr_out, d_read_ts (3N words, A | B | C) and d_audit_ts (M words). d_scratch: spark_timestamps_scratch_words.
+size_t spark_timestamps_scratch_words(size_t N, size_t M);
+void launch_spark_timestamps(const uint32_t *const addr[3], const size_t nnz[3], size_t N, size_t M, uint32_t *d_addr_out, uint32_t *d_read_ts,
+                             uint32_t *d_audit_ts, uint32_t *d_scratch, cudaStream_t st);
 // hash layer (:547-622): h = ts*gamma^2 + val*gamma + addr - tau. d_gt: {gamma, tau} on device.
 //   init[i]  = eq[i]*gamma + i - tau ; audit[i] = audit_ts[i]*gamma^2 + eq[i]*gamma + i - tau      (i < num_cells)
 void launch_hash_mem(const fl_t *eq, const uint32_t *audit_ts, size_t num_cells, const fl_t *d_gt, fl_t *init, fl_t *audit, cudaStream_t st);

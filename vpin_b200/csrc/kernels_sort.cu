@@ -1,0 +1,171 @@
+// SPARK memory-checking timestamps on the device (Spartan/src/sparse_mlpoly.rs:232-265, AddrTimestamps::new).
+//
+// The reference replays the 3N operations (matrices A, B, C in that order, entries in COO order, padding entries address 0)
+// sequentially against one counter per memory cell: read_ts[g] = counter[addr[g]]++ and audit_ts = the final counters.
+// Equivalently read_ts[g] is the number of EARLIER operations with the same address, i.e. the rank of g inside its address
+// group when the operations are stably sorted by address. That is what runs here: a least-significant-digit radix sort
+// (8 bits per pass, stable) of (address, g), one pass marking where each address group starts, one pass writing
+// rank = position - group start back to slot g; audit_ts is a plain histogram. No host replay, no host<->device copies.
+#include <atomic>
+
+#include "kernels_poly.cuh"
+
+namespace vpin {
+
+extern std::atomic<uint64_t> g_kernel_launches;
+
+namespace {
+
+const int kSortThreads = 256;                          // 8 warps
+const int kSortItems = 16;                             // elements per thread
+const int kSortTile = kSortThreads * kSortItems;       // 4096 elements per block
+const int kSortWarpChunk = 32 * kSortItems;            // a warp owns 512 consecutive elements of the tile
+
+// keys[g] = address of operation g (0 for padding), vals[g] = g; audit[address]++
+__global__ void __launch_bounds__(256) k_ts_init(const uint32_t *a0, const uint32_t *a1, const uint32_t *a2, size_t n0, size_t n1, size_t n2,
+                                                 size_t N, uint32_t *keys, uint32_t *vals, uint32_t *audit) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= 3 * N) return;
+  size_t k = g / N, i = g - k * N;
+  const uint32_t *a = k == 0 ? a0 : (k == 1 ? a1 : a2);
+  size_t n = k == 0 ? n0 : (k == 1 ? n1 : n2);
+  uint32_t key = i < n ? a[i] : 0u;
+  keys[g] = key;
+  vals[g] = (uint32_t)g;
+  atomicAdd(audit + key, 1u);
+}
+// hist[digit * tiles + tile] = number of keys of the tile with that digit
+__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t *keys, size_t n, int shift, uint32_t *hist, size_t tiles) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  size_t base = (size_t)blockIdx.x * kSortTile;
+  for (int it = 0; it < kSortItems; it++) {
+    size_t p = base + (size_t)it * kSortThreads + threadIdx.x;
+    if (p < n) atomicAdd(&h[(keys[p] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
+}
+// in-place exclusive prefix sum by one block (the histogram has 256 * tiles entries)
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *a, size_t n) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (size_t base = 0; base < n; base += 4096) {
+    size_t i = base + (size_t)threadIdx.x * 4;
+    uint32_t v[4], t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = i + k < n ? a[i + k] : 0u; t += v[k]; }
+    uint32_t incl = t;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, wi, off);
+        if (lane >= off) wi += o;
+      }
+      warp_sums[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    uint32_t excl = carry + warp_sums[warp] + incl - t;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (i + k < n) a[i + k] = excl; excl += v[k]; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl;
+    __syncthreads();
+  }
+}
+// stable scatter of one tile: a warp owns 512 consecutive elements and walks them 32 at a time, so the order inside
+// the tile is (warp, iteration, lane) = the original order
+__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t *keys, const uint32_t *vals, size_t n, int shift,
+                                                               const uint32_t *hist, size_t tiles, uint32_t *keys_out, uint32_t *vals_out) {
+  __shared__ uint32_t cnt[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 8 * 256; i += kSortThreads) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+  size_t base = (size_t)blockIdx.x * kSortTile + (size_t)warp * kSortWarpChunk;
+  uint32_t k[kSortItems], v[kSortItems];
+#pragma unroll
+  for (int it = 0; it < kSortItems; it++) {
+    size_t p = base + (size_t)it * 32 + lane;
+    bool ok = p < n;
+    k[it] = ok ? keys[p] : 0xffffffffu;
+    v[it] = ok ? vals[p] : 0u;
+    uint32_t d = (k[it] >> shift) & 255u;
+    uint32_t m = __match_any_sync(0xffffffffu, ok ? d : 256u + 0u);
+    if (ok && lane == __ffs(m) - 1) cnt[warp][d] += __popc(m);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // thread d: turn the per-warp counts of digit d into starting offsets
+    uint32_t d = threadIdx.x, run = hist[(size_t)d * tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < 8; w++) { uint32_t c = cnt[w][d]; cnt[w][d] = run; run += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kSortItems; it++) {
+    size_t p = base + (size_t)it * 32 + lane;
+    bool ok = p < n;
+    uint32_t d = (k[it] >> shift) & 255u;
+    uint32_t m = __match_any_sync(0xffffffffu, ok ? d : 256u);
+    uint32_t pos = 0;
+    if (ok) pos = cnt[warp][d] + __popc(m & ((1u << lane) - 1u));
+    __syncwarp();
+    if (ok && lane == __ffs(m) - 1) cnt[warp][d] += __popc(m);
+    __syncwarp();
+    if (ok) { keys_out[pos] = k[it]; vals_out[pos] = v[it]; }
+  }
+}
+__global__ void __launch_bounds__(256) k_ts_starts(const uint32_t *keys, size_t n, uint32_t *start) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint32_t key = keys[p];
+  if (p == 0 || keys[p - 1] != key) start[key] = (uint32_t)p;
+}
+__global__ void __launch_bounds__(256) k_ts_ranks(const uint32_t *keys, const uint32_t *vals, size_t n, const uint32_t *start, uint32_t *addr_out,
+                                                  uint32_t *read_ts) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint32_t key = keys[p], g = vals[p];
+  addr_out[g] = key;
+  read_ts[g] = (uint32_t)p - start[key];
+}
+
+}  // namespace
+
+size_t spark_timestamps_scratch_words(size_t N, size_t M) {
+  size_t n = 3 * N, tiles = (n + kSortTile - 1) / kSortTile;
+  return 4 * n + 256 * tiles + M;
+}
+void launch_spark_timestamps(const uint32_t *const addr[3], const size_t nnz[3], size_t N, size_t M, uint32_t *d_addr_out, uint32_t *d_read_ts,
+                             uint32_t *d_audit_ts, uint32_t *d_scratch, cudaStream_t st) {
+  const size_t n = 3 * N, tiles = (n + kSortTile - 1) / kSortTile;
+  uint32_t *keys = d_scratch, *vals = keys + n, *keys2 = vals + n, *vals2 = keys2 + n, *hist = vals2 + n, *start = hist + 256 * tiles;
+  cudaMemsetAsync(d_audit_ts, 0, M * sizeof(uint32_t), st);
+  unsigned eb = (unsigned)((n + 255) / 256);
+  ++g_kernel_launches, k_ts_init<<<eb, 256, 0, st>>>(addr[0], addr[1], addr[2], nnz[0], nnz[1], nnz[2], N, keys, vals, d_audit_ts);
+  int bits = 0;
+  while (((size_t)1 << bits) < M) bits++;
+  for (int shift = 0; shift < bits; shift += 8) {
+    ++g_kernel_launches, k_sort_hist<<<(unsigned)tiles, kSortThreads, 0, st>>>(keys, n, shift, hist, tiles);
+    ++g_kernel_launches, k_sort_scan<<<1, 1024, 0, st>>>(hist, 256 * tiles);
+    ++g_kernel_launches, k_sort_scatter<<<(unsigned)tiles, kSortThreads, 0, st>>>(keys, vals, n, shift, hist, tiles, keys2, vals2);
+    uint32_t *t = keys; keys = keys2; keys2 = t;
+    t = vals; vals = vals2; vals2 = t;
+  }
+  ++g_kernel_launches, k_ts_starts<<<eb, 256, 0, st>>>(keys, n, start);
+  ++g_kernel_launches, k_ts_ranks<<<eb, 256, 0, st>>>(keys, vals, n, start, d_addr_out, d_read_ts);
+}
+
+}  // namespace vpin

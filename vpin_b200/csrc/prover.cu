@@ -115,36 +115,32 @@ std::unique_ptr<Decomm> snark_encode(Ctx *ctx, const Instance &inst, const Snark
   d->M = M;
   VPIN_REQUIRE(math_log2(16 * N) == gens.ops_pc.ell && math_log2(2 * M) == gens.mem_pc.ell, VPIN_ERR_SIZE_MISMATCH,
                "gens do not match the instance (SP/commitments.rs:95 assert)");
-  // read/audit timestamps: sequential replay, audit counters shared by the three matrices (:237-257)
-  std::vector<uint32_t> audit_row(M, 0), audit_col(M, 0), addr(N), rts(N);
+  // read / audit timestamps (:237-257; audit counters shared by the three matrices) from the COO index arrays already in
+  // HBM: stable sort by address instead of the reference's sequential replay (kernels_sort.cu)
   d->comb_ops.alloc(16 * N, st);
   d->comb_ops.zero();
-  for (int pass = 0; pass < 2; pass++) {
-    std::vector<uint32_t> &audit = pass == 0 ? audit_row : audit_col;
-    for (int k = 0; k < 3; k++) {
-      const std::vector<uint32_t> &src = pass == 0 ? inst.M[k].h_row : inst.M[k].h_col;
-      for (size_t i = 0; i < N; i++) {
-        uint32_t a = i < src.size() ? src[i] : 0;  // padding entries are (0, 0, 0) and do bump address 0 (:370-378)
-        addr[i] = a;
-        rts[i] = audit[a];
-        audit[a]++;
+  d->row_audit_ts.alloc(M, st); d->col_audit_ts.alloc(M, st);
+  {
+    DevVec<uint32_t> scratch(spark_timestamps_scratch_words(N, M), st);
+    size_t nnz[3] = {inst.M[0].nnz, inst.M[1].nnz, inst.M[2].nnz};
+    for (int pass = 0; pass < 2; pass++) {
+      DevVec<uint32_t> &da = pass == 0 ? d->row_addr_all : d->col_addr_all;
+      DevVec<uint32_t> &dt = pass == 0 ? d->row_read_ts_all : d->col_read_ts_all;
+      da.alloc(3 * N, st); dt.alloc(3 * N, st);
+      const uint32_t *addr[3];
+      for (int k = 0; k < 3; k++) addr[k] = pass == 0 ? inst.M[k].coo_row.p : inst.M[k].coo_col.p;
+      launch_spark_timestamps(addr, nnz, N, M, da.p, dt.p, pass == 0 ? d->row_audit_ts.p : d->col_audit_ts.p, scratch.p, st);
+      for (int k = 0; k < 3; k++) {
+        (pass == 0 ? d->row_addr : d->col_addr)[k].p = da.p + (size_t)k * N;
+        (pass == 0 ? d->row_read_ts : d->col_read_ts)[k].p = dt.p + (size_t)k * N;
       }
-      DevVec<uint32_t> &da = pass == 0 ? d->row_addr[k] : d->col_addr[k];
-      DevVec<uint32_t> &dt = pass == 0 ? d->row_read_ts[k] : d->col_read_ts[k];
-      da.alloc(N, st); dt.alloc(N, st);
-      da.upload(addr.data(), N);
-      dt.upload(rts.data(), N);
-      launch_u32_to_fl(da.p, N, d->comb_ops.p + (size_t)(pass * 6 + k) * N, st);
-      launch_u32_to_fl(dt.p, N, d->comb_ops.p + (size_t)(pass * 6 + 3 + k) * N, st);
-      ctx->sync();  // addr / rts are reused
+      launch_u32_to_fl(da.p, 3 * N, d->comb_ops.p + (size_t)(pass * 6) * N, st);
+      launch_u32_to_fl(dt.p, 3 * N, d->comb_ops.p + (size_t)(pass * 6 + 3) * N, st);
     }
   }
   for (int k = 0; k < 3; k++)
     if (inst.M[k].nnz)
       VPIN_CUDA(cudaMemcpyAsync(d->comb_ops.p + (12 + k) * N, inst.M[k].coo_val.p, inst.M[k].nnz * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
-  d->row_audit_ts.alloc(M, st); d->col_audit_ts.alloc(M, st);
-  d->row_audit_ts.upload(audit_row.data(), M);
-  d->col_audit_ts.upload(audit_col.data(), M);
   d->comb_mem.alloc(2 * M, st);
   launch_u32_to_fl(d->row_audit_ts.p, M, d->comb_mem.p, st);
   launch_u32_to_fl(d->col_audit_ts.p, M, d->comb_mem.p + M, st);

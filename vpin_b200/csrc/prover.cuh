@@ -25,7 +25,9 @@ typedef vpin_gens_impl SnarkGens;
 // MultiSparseMatPolynomialAsDense (Spartan/src/sparse_mlpoly.rs:285-292) resident in HBM
 struct vpin_decomm_impl {
   size_t N = 0, M = 0;  // ops per matrix (padded nnz), memory cells
-  DevVec<uint32_t> row_addr[3], col_addr[3], row_read_ts[3], col_read_ts[3];
+  struct U32View { uint32_t *p = nullptr; };
+  DevVec<uint32_t> row_addr_all, col_addr_all, row_read_ts_all, col_read_ts_all;  // 3N each: matrices A | B | C
+  U32View row_addr[3], col_addr[3], row_read_ts[3], col_read_ts[3];                // views into the arrays above
   DevVec<uint32_t> row_audit_ts, col_audit_ts;
   DevVec<fl_t> comb_ops;  // 16 N: row-addr A,B,C | row-read-ts A,B,C | col-addr A,B,C | col-read-ts A,B,C | val A,B,C | 0
   DevVec<fl_t> comb_mem;  // 2 M: row audit-ts | col audit-ts
