@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvpin_b200.so")
+LIB_PATH = os.environ.get("VPIN_B200_LIB", os.path.join(_HERE, "libvpin_b200.so"))
 
 COO_DTYPE = np.dtype([("row", "<u8"), ("col", "<u8"), ("val", "u1", (32,))])
 

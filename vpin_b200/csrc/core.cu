@@ -152,10 +152,23 @@ std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, si
   launch_from_uniform_bytes(d_stream.p, n, g->d_pts.p, ctx->st);
   g->h_pts.resize(n);
   g->d_pts.download(g->h_pts.data(), n);
-  g->d_table.alloc(msm_table_entries(n), ctx->st);
+  // window width: the widest whose table takes at most a quarter of the free HBM (and at most 48 GiB); VPIN_MSM_W pins it
+  {
+    size_t free_b = 0, total_b = 0;
+    VPIN_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>(free_b / 4, (size_t)48 << 30);
+    int W = kMsmMinW;
+    while (W < kMsmMaxW && msm_table_bytes_per_base(W + 1) * n <= budget) W++;
+    if (const char *e = getenv("VPIN_MSM_W")) {
+      int w = atoi(e);
+      if (w >= kMsmMinW && w <= kMsmMaxW) W = w;
+    }
+    g->geom = msm_geom(W);
+  }
+  g->d_table.alloc(msm_table_entries(n, g->geom), ctx->st);
   {
     DevVec<ge_t> scratch(n, ctx->st);
-    launch_table_build(g->d_pts.p, n, g->d_table.p, scratch.p, ctx->st);
+    launch_table_build(g->d_pts.p, n, g->geom, g->d_table.p, scratch.p, ctx->st);
   }
   ctx->sync();
   ctx->label_gens[label] = g;
@@ -168,25 +181,26 @@ static void hyrax_rows_local(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_
   size_t cols_total = cols + (d_blinds ? 1 : 0);
   size_t stride = msm_col_stride(cols_total);
   // bound the digit buffer (2 bytes x windows per scalar) to ~1 GiB per pass
-  size_t max_rows = ((size_t)1 << 30) / (stride * kMsmWindows * sizeof(uint16_t));
+  const MsmGeom &geom = g.geom;
+  size_t max_rows = ((size_t)1 << 30) / (stride * geom.windows * sizeof(uint16_t));
   if (max_rows < 1) max_rows = 1;
   size_t chunk = rows < max_rows ? rows : max_rows;
-  size_t segs = msm_num_segments(chunk, cols_total);
-  DevVec<uint16_t> digits(msm_digits_count(chunk, cols_total), ctx->st);
-  DevVec<ge_t> partial(chunk * kMsmGroup * segs, ctx->st), sums(segs > 1 ? chunk * kMsmGroup : 0, ctx->st);
+  size_t segs = msm_num_segments(chunk, cols_total, geom);
+  DevVec<uint16_t> digits(msm_digits_count(chunk, cols_total, geom), ctx->st);
+  DevVec<ge_t> partial(chunk * geom.group * segs, ctx->st), sums(segs > 1 ? chunk * geom.group : 0, ctx->st);
   for (size_t r0 = 0; r0 < rows; r0 += chunk) {
     size_t nr = rows - r0 < chunk ? rows - r0 : chunk;
     double pts = (double)nr * cols_total;
     {
-      ProfScope ps(ctx, PROF_MSM_RECODE, pts, pts * (32 + 2 * kMsmWindows));
-      launch_recode(dZ + r0 * ld, nr, cols, ld, d_blinds ? d_blinds + r0 : nullptr, digits.p, ctx->d_counters.p, ctx->st);
+      ProfScope ps(ctx, PROF_MSM_RECODE, pts, pts * (32 + 2 * geom.windows));
+      launch_recode(dZ + r0 * ld, nr, cols, ld, d_blinds ? d_blinds + r0 : nullptr, geom, digits.p, ctx->d_counters.p, ctx->st);
     }
     {
       ProfScope ps(ctx, PROF_MSM_ACCUMULATE, pts, 0);
       launch_msm_accumulate(g.table(), digits.p, nr, cols, d_blinds != nullptr, blind_base, segs, partial.p, ctx->st);
     }
     ProfScope ps(ctx, PROF_MSM_FINISH, pts, 0);
-    launch_msm_finish(partial.p, nr, segs, sums.p, d_points ? d_points + r0 : nullptr, d_comp ? d_comp + 32 * r0 : nullptr, ctx->st);
+    launch_msm_finish(partial.p, nr, segs, geom, sums.p, d_points ? d_points + r0 : nullptr, d_comp ? d_comp + 32 * r0 : nullptr, ctx->st);
   }
 }
 // Multi-GPU: the L rows of a commitment are independent MSMs over replicated generator tables, so rank r commits to

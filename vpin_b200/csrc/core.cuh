@@ -75,9 +75,10 @@ struct LabelGens {
   size_t n = 0;                 // points derived: stream[0..n)
   std::vector<ge_t> h_pts;      // host copies (extended)
   DevVec<ge_t> d_pts;
-  DevVec<niels_t> d_table;      // n * kMsmTable entries
+  MsmGeom geom = msm_geom(kMsmMinW);  // window width of this stream's table (chosen when the table is built)
+  DevVec<niels_t> d_table;      // msm_table_entries(n, geom) entries
   std::map<size_t, std::unique_ptr<HostBase>> host_bases;  // built on first use, kept with the stream
-  MsmTable table() const { return MsmTable{d_table.p, n}; }
+  MsmTable table() const { return MsmTable{d_table.p, n, geom}; }
   const HostBase *host_base(size_t index) {
     auto it = host_bases.find(index);
     if (it != host_bases.end()) return it->second.get();

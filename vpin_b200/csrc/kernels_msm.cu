@@ -50,21 +50,21 @@ __device__ __forceinline__ void st_niels(niels_t *p, const niels_t &n) { st_fp(&
 
 // ------------------------------------------------------------------------------------------------ table build
 // step 1: table[j][0] = affine Niels form of base j
-__global__ void __launch_bounds__(128) k_bases_to_niels(const ge_t *bases, size_t n, niels_t *table) {
+__global__ void __launch_bounds__(128) k_bases_to_niels(const ge_t *bases, size_t n, int tsize, niels_t *table) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   ge_t g = ld_ge(bases + j);
-  st_niels(table + j * kMsmTable, ge_to_niels(g, fp_invert(g.Z)));
+  st_niels(table + j * tsize, ge_to_niels(g, fp_invert(g.Z)));
 }
 // step 2: thread (j, c) fills multiples c*CH+1 .. c*CH+CH of base j; one inversion per chunk (Montgomery's trick)
 static const int kTblChunk = 32;
-__global__ void __launch_bounds__(128) k_table_fill(size_t n, niels_t *table) {
-  const int chunks = kMsmTable / kTblChunk;
+__global__ void __launch_bounds__(128) k_table_fill(size_t n, int tsize, niels_t *table) {
+  const int chunks = tsize / kTblChunk;
   size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n * chunks) return;
   size_t j = tid / chunks;
   int c = (int)(tid % chunks);
-  niels_t *slots = table + j * kMsmTable;
+  niels_t *slots = table + j * tsize;
   niels_t g1 = ld_niels(slots);
   int first = c == 0 ? 1 : 0;  // slot 0 is already final and is being read by the other chunks
   // P = (c*CH + 1 + first) * G by double-and-add
@@ -102,51 +102,51 @@ __global__ void __launch_bounds__(128) k_points_dbl_n(const ge_t *in, size_t n, 
   for (int i = 0; i < ndbl; i++) g = ge_dbl(g);
   st_ge(out + j, g);
 }
-void launch_table_build(const ge_t *d_bases, size_t n, niels_t *d_table, ge_t *d_scratch, cudaStream_t st) {
+void launch_table_build(const ge_t *d_bases, size_t n, const MsmGeom &g, niels_t *d_table, ge_t *d_scratch, cudaStream_t st) {
   const ge_t *cur = d_bases;
-  size_t threads = n * (kMsmTable / kTblChunk);
+  size_t threads = n * (g.table / kTblChunk);
   for (int t = 0; t < kMsmSub; t++) {
     if (t > 0) {
-      ++g_kernel_launches, k_points_dbl_n<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cur, n, kMsmW * kMsmGroup, d_scratch);
+      ++g_kernel_launches, k_points_dbl_n<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cur, n, g.W * g.group, d_scratch);
       cur = d_scratch;
     }
-    niels_t *tbl = d_table + (size_t)t * n * kMsmTable;
-    ++g_kernel_launches, k_bases_to_niels<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cur, n, tbl);
-    ++g_kernel_launches, k_table_fill<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(n, tbl);
+    niels_t *tbl = d_table + (size_t)t * n * g.table;
+    ++g_kernel_launches, k_bases_to_niels<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cur, n, g.table, tbl);
+    ++g_kernel_launches, k_table_fill<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(n, g.table, tbl);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ recode
-__device__ __forceinline__ uint32_t recode_one(const fl_t *src, uint16_t *dst, size_t plane) {
+__device__ __forceinline__ uint32_t recode_one(const fl_t *src, const MsmGeom &g, uint16_t *dst, size_t plane) {
   if (!src) {
-    for (int w = 0; w < kMsmWindows; w++) dst[(size_t)w * plane] = 0;
+    for (int w = 0; w < g.windows; w++) dst[(size_t)w * plane] = 0;
     return 0;
   }
   const uint4 *q = reinterpret_cast<const uint4 *>(src);
   uint4 lo = __ldg(q), hi = __ldg(q + 1);
   fl_t x;
   x.v[0] = lo.x; x.v[1] = lo.y; x.v[2] = lo.z; x.v[3] = lo.w; x.v[4] = hi.x; x.v[5] = hi.y; x.v[6] = hi.z; x.v[7] = hi.w;
-  return msm_recode_value(x, dst, plane);
+  return msm_recode_value(x, g, dst, plane);
 }
-__global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows, size_t cols, size_t ld, const fl_t *extra,
+__global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows, size_t cols, size_t ld, const fl_t *extra, MsmGeom g,
                                                 size_t stride, uint16_t *digits, unsigned long long *nonzero) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nz = 0;
   if (idx < rows * stride) {
     size_t row = idx / stride, col = idx % stride;
     const fl_t *src = col < cols ? scalars + row * ld + col : (col == cols && extra ? extra + row : nullptr);
-    nz = recode_one(src, digits + row * stride + col, rows * stride);
+    nz = recode_one(src, g, digits + row * stride + col, rows * stride);
   }
   if (nonzero) {
     nz = __reduce_add_sync(0xffffffffu, nz);
     if ((threadIdx.x & 31) == 0 && nz) atomicAdd(nonzero, (unsigned long long)nz);
   }
 }
-void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, const fl_t *d_extra, uint16_t *d_digits,
+void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, const fl_t *d_extra, const MsmGeom &g, uint16_t *d_digits,
                    unsigned long long *d_nonzero, cudaStream_t st) {
   size_t stride = msm_col_stride(cols + (d_extra ? 1 : 0));
   size_t total = rows * stride;
-  ++g_kernel_launches, k_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_scalars, rows, cols, ld, d_extra, stride, d_digits, d_nonzero);
+  ++g_kernel_launches, k_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_scalars, rows, cols, ld, d_extra, g, stride, d_digits, d_nonzero);
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate
@@ -166,9 +166,9 @@ __device__ __forceinline__ void madd_signed(ge_t &p, const niels_t *e, uint32_t 
   p.X = fp_mul(e_, f); p.Y = fp_mul(g, h); p.Z = fp_mul(f, g); p.T = fp_mul(e_, h);
 }
 // grid (ceil(rows / 128), kMsmGroup, segs), block 128: thread = (row, local window w', column segment)
-__global__ void __launch_bounds__(kMsmRowsPerBlock) k_msm_accumulate(const niels_t *table, const uint16_t *digits, size_t rows, size_t cols,
-                                                                     size_t cols_total, size_t extra_base, size_t stride, size_t n_bases,
-                                                                     size_t seg_len, ge_t *partial) {
+__global__ void __launch_bounds__(kMsmRowsPerBlock) k_msm_accumulate(const niels_t *table, MsmGeom g, const uint16_t *digits, size_t rows,
+                                                                     size_t cols, size_t cols_total, size_t extra_base, size_t stride,
+                                                                     size_t n_bases, size_t seg_len, ge_t *partial) {
   size_t row = (size_t)blockIdx.x * kMsmRowsPerBlock + threadIdx.x;
   if (row >= rows) return;
   const int wl = blockIdx.y;
@@ -181,13 +181,13 @@ __global__ void __launch_bounds__(kMsmRowsPerBlock) k_msm_accumulate(const niels
     size_t base = col < cols ? col : extra_base;
 #pragma unroll 1
     for (int t = 0; t < kMsmSub; t++) {  // not unrolled: one copy of the 7-multiplication body keeps the loop inside the I-cache
-      int w = t * kMsmGroup + wl;
-      if (w >= kMsmWindows) break;
+      int w = t * g.group + wl;
+      if (w >= g.windows) break;
       uint32_t d = dg[(size_t)w * plane + col];
-      if (d) madd_signed(acc, table + ((size_t)t * n_bases + base) * kMsmTable + ((d & 0x7fffu) - 1u), d >> 15);
+      if (d) madd_signed(acc, table + ((size_t)t * n_bases + base) * g.table + ((d & 0x7fffu) - 1u), d >> 15);
     }
   }
-  st_ge(partial + (row * kMsmGroup + wl) * segs + seg, acc);
+  st_ge(partial + (row * g.group + wl) * segs + seg, acc);
 }
 __device__ __forceinline__ ge_t shfl_down_ge(const ge_t &g, int off) {
   ge_t r;
@@ -203,7 +203,7 @@ __device__ __forceinline__ ge_t shfl_down_ge(const ge_t &g, int off) {
 // Few rows (the bullet-reduction L / R rows, single Pedersen commitments): rows cannot fill a warp, so the lanes of a warp
 // take the COLUMNS of one (row, local window, segment) instead and the 32 partial sums are added by a shuffle tree.
 // grid (segs, kMsmGroup, rows), one warp per block.
-__global__ void __launch_bounds__(32) k_msm_accumulate_small(const niels_t *table, const uint16_t *digits, size_t rows, size_t cols,
+__global__ void __launch_bounds__(32) k_msm_accumulate_small(const niels_t *table, MsmGeom g, const uint16_t *digits, size_t rows, size_t cols,
                                                              size_t cols_total, size_t extra_base, size_t stride, size_t n_bases,
                                                              size_t seg_len, ge_t *partial) {
   const size_t row = blockIdx.z, seg = blockIdx.x, segs = gridDim.x;
@@ -216,10 +216,10 @@ __global__ void __launch_bounds__(32) k_msm_accumulate_small(const niels_t *tabl
     size_t base = col < cols ? col : extra_base;
 #pragma unroll 1
     for (int t = 0; t < kMsmSub; t++) {
-      int w = t * kMsmGroup + wl;
-      if (w >= kMsmWindows) break;
+      int w = t * g.group + wl;
+      if (w >= g.windows) break;
       uint32_t d = dg[(size_t)w * plane + col];
-      if (d) madd_signed(acc, table + ((size_t)t * n_bases + base) * kMsmTable + ((d & 0x7fffu) - 1u), d >> 15);
+      if (d) madd_signed(acc, table + ((size_t)t * n_bases + base) * g.table + ((d & 0x7fffu) - 1u), d >> 15);
     }
   }
 #pragma unroll 1
@@ -227,20 +227,20 @@ __global__ void __launch_bounds__(32) k_msm_accumulate_small(const niels_t *tabl
     ge_t o = shfl_down_ge(acc, off);
     acc = ge_add(acc, o);
   }
-  if (lane == 0) st_ge(partial + (row * kMsmGroup + wl) * segs + seg, acc);
+  if (lane == 0) st_ge(partial + (row * g.group + wl) * segs + seg, acc);
 }
 static const size_t kMsmSmallRows = 16;
-size_t msm_num_segments(size_t rows, size_t cols_total) {
+size_t msm_num_segments(size_t rows, size_t cols_total, const MsmGeom &g) {
   if (rows <= kMsmSmallRows) {
     const size_t want_warps = (size_t)148 * 16;
-    size_t per = rows * kMsmGroup;
+    size_t per = rows * g.group;
     size_t segs = (want_warps + per - 1) / per;
     size_t max_segs = (cols_total + 63) / 64;  // at least two columns per lane
     if (segs > max_segs) segs = max_segs;
     return segs < 1 ? 1 : segs;
   }
   const size_t want_threads = (size_t)148 * 1024;
-  size_t per = rows * kMsmGroup;
+  size_t per = rows * g.group;
   size_t segs = (want_threads + per - 1) / per;
   size_t max_segs = (cols_total + 7) / 8;  // at least 8 columns per thread
   if (segs > max_segs) segs = max_segs;
@@ -254,13 +254,13 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
   size_t stride = msm_col_stride(cols_total);
   size_t seg_len = (cols_total + segs - 1) / segs;
   if (rows <= kMsmSmallRows) {
-    dim3 grid((unsigned)segs, kMsmGroup, (unsigned)rows);
-    ++g_kernel_launches, k_msm_accumulate_small<<<grid, 32, 0, st>>>(t.d_table, d_digits, rows, cols, cols_total, extra_base, stride,
+    dim3 grid((unsigned)segs, t.geom.group, (unsigned)rows);
+    ++g_kernel_launches, k_msm_accumulate_small<<<grid, 32, 0, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride,
                                                                       t.n_bases, seg_len, d_partial);
     return;
   }
-  dim3 grid((unsigned)((rows + kMsmRowsPerBlock - 1) / kMsmRowsPerBlock), kMsmGroup, (unsigned)segs);
-  ++g_kernel_launches, k_msm_accumulate<<<grid, kMsmRowsPerBlock, 0, st>>>(t.d_table, d_digits, rows, cols, cols_total, extra_base, stride,
+  dim3 grid((unsigned)((rows + kMsmRowsPerBlock - 1) / kMsmRowsPerBlock), t.geom.group, (unsigned)segs);
+  ++g_kernel_launches, k_msm_accumulate<<<grid, kMsmRowsPerBlock, 0, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride,
                                                                            t.n_bases, seg_len, d_partial);
 }
 
@@ -288,13 +288,13 @@ __global__ void __launch_bounds__(128) k_msm_segsum(const ge_t *partial, size_t 
   if (lane == 0) st_ge(sums + pair, acc);
 }
 // finish, step 2: one thread per row runs the Horner pass over the kMsmGroup window sums and encodes the point
-__global__ void __launch_bounds__(32) k_msm_horner(const ge_t *sums, size_t rows, ge_t *out, uint8_t *comp) {
+__global__ void __launch_bounds__(32) k_msm_horner(const ge_t *sums, size_t rows, MsmGeom g, ge_t *out, uint8_t *comp) {
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
-  const ge_t *p = sums + row * kMsmGroup;
-  ge_t h = ld_ge(p + kMsmGroup - 1);
-  for (int w = kMsmGroup - 2; w >= 0; w--) {
-    for (int i = 0; i < kMsmW; i++) h = ge_dbl(h);
+  const ge_t *p = sums + row * g.group;
+  ge_t h = ld_ge(p + g.group - 1);
+  for (int w = g.group - 2; w >= 0; w--) {
+    for (int i = 0; i < g.W; i++) h = ge_dbl(h);
     h = ge_add(h, ld_ge(p + w));
   }
   if (out) st_ge(out + row, h);
@@ -308,18 +308,19 @@ __global__ void __launch_bounds__(32) k_msm_horner(const ge_t *sums, size_t rows
     q[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
-void launch_msm_segsum(const ge_t *d_partial, size_t rows, size_t segs, ge_t *d_sums, cudaStream_t st) {
-  size_t pairs = rows * kMsmGroup;
+void launch_msm_segsum(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, cudaStream_t st) {
+  size_t pairs = rows * g.group;
   ++g_kernel_launches, k_msm_segsum<<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(d_partial, pairs, segs, d_sums);
 }
-void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, ge_t *d_sums, ge_t *d_out, uint8_t *d_comp, cudaStream_t st) {
+void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, ge_t *d_out, uint8_t *d_comp,
+                       cudaStream_t st) {
   const ge_t *sums = d_partial;
   if (segs > 1) {
-    size_t pairs = rows * kMsmGroup;
+    size_t pairs = rows * g.group;
     ++g_kernel_launches, k_msm_segsum<<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(d_partial, pairs, segs, d_sums);
     sums = d_sums;
   }
-  ++g_kernel_launches, k_msm_horner<<<(unsigned)((rows + 31) / 32), 32, 0, st>>>(sums, rows, d_out, d_comp);
+  ++g_kernel_launches, k_msm_horner<<<(unsigned)((rows + 31) / 32), 32, 0, st>>>(sums, rows, g, d_out, d_comp);
 }
 
 // ------------------------------------------------------------------------------------------------ encodings

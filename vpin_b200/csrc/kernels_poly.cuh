@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "fl.cuh"
+#include "kernels_msm.cuh"
 
 namespace vpin {
 
@@ -70,6 +71,7 @@ struct BulletRoundArgs {
   size_t n, len;              // len: vector length after the pending fold
   fl_t u, uinv, d;            // previous challenge; d: the final blind multiplier (final mode)
   int fold, final;
+  MsmGeom geom;               // window geometry of the generator table the rows are multiplied against
   uint16_t *digits;           // MSM digits [window][row][stride], rows = final ? 1 : 2 (row 0 = L, row 1 = R)
   size_t stride;
   unsigned long long *nonzero;

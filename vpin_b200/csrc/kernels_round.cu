@@ -304,18 +304,18 @@ __global__ void __launch_bounds__(kRedThreads) k_bullet_round(BulletRoundArgs p)
         str(p.W + j, w);
       }
       if (p.final) {
-        nz = msm_recode_value(fl_mul(p.d, w), p.digits + j, plane);
+        nz = msm_recode_value(fl_mul(p.d, w), p.geom, p.digits + j, plane);
       } else {
         size_t rem = j & (len - 1);
         bool upper = rem >= cur;  // a_L against G_R -> row 0 (L); a_R against G_L -> row 1 (R)
         fl_t s = fl_mul(A(upper ? rem - cur : rem + cur), w);
-        nz = msm_recode_value(s, p.digits + (upper ? 0 : p.stride) + j, plane);
+        nz = msm_recode_value(s, p.geom, p.digits + (upper ? 0 : p.stride) + j, plane);
         uint16_t *other = p.digits + (upper ? p.stride : 0) + j;
-        for (int wdw = 0; wdw < kMsmWindows; wdw++) other[(size_t)wdw * plane] = 0;
+        for (int wdw = 0; wdw < p.geom.windows; wdw++) other[(size_t)wdw * plane] = 0;
       }
     } else {
       for (int row = 0; row < (p.final ? 1 : 2); row++)
-        for (int wdw = 0; wdw < kMsmWindows; wdw++) p.digits[(size_t)wdw * plane + row * p.stride + j] = 0;
+        for (int wdw = 0; wdw < p.geom.windows; wdw++) p.digits[(size_t)wdw * plane + row * p.stride + j] = 0;
     }
   }
   if (p.nonzero) {

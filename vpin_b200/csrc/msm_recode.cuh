@@ -11,11 +11,11 @@ __device__ __forceinline__ uint32_t msm_half_l_limb(int i) {  // (l - 1) / 2
     case 7: return 0x08000000u; default: return 0u;
   }
 }
-// x: Montgomery form. Writes the kMsmWindows digits of the representative of smallest absolute value (|s| <= (l-1)/2) to
+// x: Montgomery form. Writes the g.windows digits of the representative of smallest absolute value (|s| <= (l-1)/2) to
 // dst[w * plane] as magnitude | sign << 15 and returns the number of non-zero digits.
-__device__ __forceinline__ uint32_t msm_recode_value(const fl_t &x, uint16_t *dst, size_t plane) {
+__device__ __forceinline__ uint32_t msm_recode_value(const fl_t &x, const MsmGeom &g, uint16_t *dst, size_t plane) {
   if (fl_is_zero(x)) {
-    for (int w = 0; w < kMsmWindows; w++) dst[(size_t)w * plane] = 0;
+    for (int w = 0; w < g.windows; w++) dst[(size_t)w * plane] = 0;
     return 0;
   }
   fl_t s = fl_from_mont(x);
@@ -37,13 +37,18 @@ __device__ __forceinline__ uint32_t msm_recode_value(const fl_t &x, uint16_t *ds
   }
   v[8] = 0;
   uint32_t carry = 0, nz = 0;
+  // limb indexing by a run-time window: v lives in local memory for this loop only when the compiler cannot resolve it;
+  // the funnel over (v[limb], v[limb + 1]) is written with a select chain to stay in registers
+  const uint32_t wmask = (1u << g.W) - 1u;
+  for (int w = 0; w < g.windows; w++) {
+    int bit = w * g.W, limb = bit >> 5, sh = bit & 31;
+    uint32_t lo = 0, hi = 0;
 #pragma unroll
-  for (int w = 0; w < kMsmWindows; w++) {
-    int bit = w * kMsmW, limb = bit >> 5, sh = bit & 31;
-    uint64_t two = (uint64_t)v[limb] | ((uint64_t)(limb + 1 < 9 ? v[limb + 1] : 0u) << 32);
-    uint32_t raw = (limb < 8 ? (uint32_t)(two >> sh) & ((1u << kMsmW) - 1u) : 0u) + carry;
-    uint32_t neg = raw > (uint32_t)kMsmTable ? 1u : 0u;
-    uint32_t mag = neg ? (1u << kMsmW) - raw : raw;
+    for (int i = 0; i < 8; i++) { lo = limb == i ? v[i] : lo; hi = limb == i ? v[i + 1] : hi; }
+    uint64_t two = (uint64_t)lo | ((uint64_t)hi << 32);
+    uint32_t raw = ((uint32_t)(two >> sh) & wmask) + carry;
+    uint32_t neg = raw > (uint32_t)g.table ? 1u : 0u;
+    uint32_t mag = neg ? (1u << g.W) - raw : raw;
     carry = neg;
     uint32_t sign = (neg ^ (gt ? 1u : 0u)) & (mag != 0 ? 1u : 0u);
     nz += mag != 0 ? 1u : 0u;

@@ -456,9 +456,10 @@ struct Prover {
     VPIN_CUDA(cudaMemcpyAsync(av[0], d_x, n * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
     VPIN_CUDA(cudaMemcpyAsync(bv[0], d_a, n * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
     launch_fill_one(W.p, n, st);
-    size_t segs = msm_num_segments(2, n), stride = msm_col_stride(n);
-    DevVec<uint16_t> digits(msm_digits_count(2, n), st);
-    DevVec<ge_t> partial(2 * kMsmGroup * segs, st), sums(2 * kMsmGroup, st);
+    const MsmGeom geom = lg.geom;
+    size_t segs = msm_num_segments(2, n, geom), stride = msm_col_stride(n);
+    DevVec<uint16_t> digits(msm_digits_count(2, n, geom), st);
+    DevVec<ge_t> partial(2 * geom.group * segs, st);
     DotLogS out;
     t_bullet_pre += now_ms() - tb0;
     int src = 0, slot = 0;
@@ -471,7 +472,7 @@ struct Prover {
       p.a_old = av[src]; p.b_old = bv[src]; p.a_new = av[src ^ 1]; p.b_new = bv[src ^ 1];
       p.W = W.p; p.n = n; p.len = len; p.u = u; p.uinv = u_inv; p.d = d;
       p.fold = fold ? 1 : 0; p.final = final ? 1 : 0;
-      p.digits = digits.p; p.stride = stride; p.nonzero = ctx->d_counters.p;
+      p.geom = geom; p.digits = digits.p; p.stride = stride; p.nonzero = ctx->d_counters.p;
       uint32_t seq0;
       p.ctl = round_ctl(slot, &seq0);
       size_t rows = final ? 1 : 2;
@@ -480,7 +481,7 @@ struct Prover {
         ProfScope ps(ctx, PROF_BULLET, pts, 0);
         launch_bullet_round(p, st);
       }
-      size_t sg = final ? msm_num_segments(1, n) : segs;
+      size_t sg = final ? msm_num_segments(1, n, geom) : segs;
       if (sg > segs) sg = segs;
       {
         ProfScope ps(ctx, PROF_MSM_ACCUMULATE, pts, 0);
@@ -488,20 +489,20 @@ struct Prover {
       }
       {  // window sums straight into the host-mapped slot: vals[8 ..] = rows x kMsmGroup points
         ProfScope ps(ctx, PROF_MSM_FINISH, pts, 0);
-        launch_msm_segsum(partial.p, rows, sg, reinterpret_cast<ge_t *>(ctx->d_slots[slot].vals + 8), st);
+        launch_msm_segsum(partial.p, rows, sg, geom, reinterpret_cast<ge_t *>(ctx->d_slots[slot].vals + 8), st);
       }
       *seq_out = ++ctx->round_seq;
       launch_publish_seq(ctx->d_slots + slot, *seq_out, st);
       if (fold && !final) src ^= 1;
     };
-    static_assert(8 * sizeof(fl_t) + 2 * kMsmGroup * sizeof(ge_t) <= kRoundSlotVals * sizeof(fl_t), "slot too small for two rows");
-    // Horner pass over the kMsmGroup window sums of one row (kernels_msm.cuh), on the host
+    static_assert(8 * sizeof(fl_t) + 2 * kMsmMaxGroup * sizeof(ge_t) <= kRoundSlotVals * sizeof(fl_t), "slot too small for two rows");
+    // Horner pass over the geom.group window sums of one row (kernels_msm.cuh), on the host
     auto horner = [&](const fl_t *vals, size_t row) {
-      ge_t w[kMsmGroup];
-      memcpy(w, reinterpret_cast<const uint8_t *>(vals + 8) + row * sizeof(w), sizeof(w));
-      hge_t h = hf::ge_from_dev(w[kMsmGroup - 1]);
-      for (int k = kMsmGroup - 2; k >= 0; k--) {
-        for (int i = 0; i < kMsmW; i++) h = hf::ge_dbl(h);
+      ge_t w[kMsmMaxGroup];
+      memcpy(w, reinterpret_cast<const uint8_t *>(vals + 8) + row * geom.group * sizeof(ge_t), geom.group * sizeof(ge_t));
+      hge_t h = hf::ge_from_dev(w[geom.group - 1]);
+      for (int k = geom.group - 2; k >= 0; k--) {
+        for (int i = 0; i < geom.W; i++) h = hf::ge_dbl(h);
         h = hf::ge_add(h, hf::ge_from_dev(w[k]));
       }
       return h;
