@@ -189,6 +189,19 @@ vpin_status vpin_sumcheck_quad_round(vpin_ctx *ctx, const uint8_t *A32, const ui
 /* eval_point_0, _2, _3 with comb = A*B*C   SP/sumcheck.rs:296-320 */
 vpin_status vpin_sumcheck_cubic3_round(vpin_ctx *ctx, const uint8_t *A32, const uint8_t *B32, const uint8_t *C32,
                                        uint64_t len, uint8_t out96[96]);
+/* A whole sumcheck driven with caller-supplied challenges through the prover's FUSED round kernels (bind with r_{j-1} and
+ * evaluate round j in one launch, results in host-mapped memory): the device side of prove_cubic_with_additive_term
+ * (degree 3: comb = A*(B*C - D), SP/sumcheck.rs:619-676) or prove_quad (degree 2: comb = A*B, :456-486; C32, D32 NULL).
+ * len = 2^rounds scalars per table, r32 = rounds challenges. evals_out: rounds x degree scalars (eval_point_0, _2[, _3]
+ * of every round); finals_out: the tables bound at all challenges (4 or 2 scalars = poly[0] after the last bind). */
+vpin_status vpin_sumcheck_fused(vpin_ctx *ctx, uint32_t degree, const uint8_t *A32, const uint8_t *B32, const uint8_t *C32,
+                                const uint8_t *D32, uint64_t len, const uint8_t *r32, uint8_t *evals_out, uint8_t *finals_out);
+/* AddrTimestamps::new (SP/sparse_mlpoly.rs:232-265) for one side (rows or columns) of the three matrices: addr_k = n_k
+ * addresses < M in COO order, padded with address 0 to N operations each (SP/sparse_mlpoly.rs:370-378). Outputs: the 3N
+ * padded addresses and read timestamps (A | B | C) and the M audit timestamps, all u32. */
+vpin_status vpin_spark_timestamps(vpin_ctx *ctx, const uint32_t *addr_a, uint64_t n_a, const uint32_t *addr_b, uint64_t n_b,
+                                  const uint32_t *addr_c, uint64_t n_c, uint64_t N, uint64_t M, uint32_t *addr_out,
+                                  uint32_t *read_ts_out, uint32_t *audit_ts_out);
 /* bound_poly_var_top   SP/dense_mlpoly.rs:229-236; Z32 (len scalars) is overwritten, first len/2 are the result */
 vpin_status vpin_bind_top(vpin_ctx *ctx, uint8_t *Z32, uint64_t len, const uint8_t r32[32]);
 /* DensePolynomial::bound(L)   SP/dense_mlpoly.rs:220-227: out has R = 2^ceil(ell/2) scalars */

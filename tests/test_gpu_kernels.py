@@ -141,3 +141,65 @@ def test_instance_errors(ctx):
     with pytest.raises(api.VpinError) as e:
         api.Instance(ctx, 4, 4, 1, ok, bad_val, ok)
     assert e.value.name == "InvalidScalar"
+
+
+# ---- fused sumcheck rounds (kernels_round.cu) against the plain definition, big-int arithmetic --------------------------
+def _sumcheck_reference(degree, tables, r):
+    """SP/sumcheck.rs:619-676 / :456-486 with the challenges given: per round eval at 0, 2(, 3), then bound_poly_var_top"""
+    p = O.L_ORDER
+    T = [list(t) for t in tables]
+    evals = []
+    for rj in r:
+        half = len(T[0]) // 2
+        pts = (0, 2, 3) if degree == 3 else (0, 2)
+        for t in pts:
+            acc = 0
+            for i in range(half):
+                v = [(tab[i] + t * (tab[half + i] - tab[i])) % p for tab in T]
+                acc += v[0] * (v[1] * v[2] - v[3]) if degree == 3 else v[0] * v[1]
+            evals.append(acc % p)
+        T = [[(tab[i] + rj * (tab[half + i] - tab[i])) % p for i in range(half)] for tab in T]
+    return evals, [tab[0] for tab in T]
+
+
+@pytest.mark.parametrize("degree,ell", [(3, 1), (3, 2), (3, 7), (3, 11), (2, 1), (2, 5), (2, 12)])
+def test_fused_sumcheck_rounds(ctx, degree, ell):
+    n = 1 << ell
+    ntab = 4 if degree == 3 else 2
+    tables = [H.rand_scalars(n, seed=1000 * degree + 10 * ell + k) for k in range(ntab)]
+    r = H.rand_scalars(ell, seed=77 + ell, edge=False)
+    evals, finals = ctx.sumcheck_fused(degree, [O.ints_to_bytes(t) for t in tables], O.ints_to_bytes(r))
+    want_evals, want_finals = _sumcheck_reference(degree, tables, r)
+    assert O.bytes_to_ints(evals) == want_evals
+    assert O.bytes_to_ints(finals) == want_finals
+
+
+# ---- SPARK timestamps (kernels_sort.cu) against the reference's sequential replay ------------------------------------
+def _replay(addrs, N, M):
+    """AddrTimestamps::new, SP/sparse_mlpoly.rs:237-257: one counter per cell, shared by the three matrices"""
+    audit = [0] * M
+    addr_out, ts_out = [], []
+    for a in addrs:
+        for i in range(N):
+            x = int(a[i]) if i < len(a) else 0  # padding entries are (0, 0, 0) and do bump address 0 (:370-378)
+            addr_out.append(x)
+            ts_out.append(audit[x])
+            audit[x] += 1
+    return addr_out, ts_out, audit
+
+
+@pytest.mark.parametrize("N,M,sizes,hot", [(8, 4, (8, 5, 0), 0.0), (4096, 512, (4096, 4000, 1), 0.5), (8192, 1 << 17, (8000, 8192, 7777), 0.2),
+                                           (1 << 15, 1 << 9, (1 << 15, 30000, 12345), 0.9), (16, 1 << 20, (0, 0, 0), 0.0)])
+def test_spark_timestamps_match_the_sequential_replay(ctx, N, M, sizes, hot):
+    import numpy as np
+    rng = np.random.default_rng(N + M)
+    addrs = []
+    for n in sizes:
+        a = rng.integers(0, M, size=n, dtype=np.uint32)
+        a[rng.random(n) < hot] = min(3, M - 1)  # a hot cell, like the constant-1 column of vPIN's instances
+        addrs.append(a)
+    got_addr, got_ts, got_audit = ctx.spark_timestamps(addrs, N, M)
+    want_addr, want_ts, want_audit = _replay(addrs, N, M)
+    assert got_addr.tolist() == want_addr
+    assert got_ts.tolist() == want_ts
+    assert got_audit.tolist() == want_audit

@@ -153,6 +153,25 @@ class Context:
         self.check(lib().vpin_sumcheck_cubic3_round(self._h, A, B, Cc, C.c_uint64(len(A) // 32), out))
         return out.raw
 
+    def sumcheck_fused(self, degree, tables, r):
+        """whole sumcheck through the fused bind+evaluate kernels -> (rounds x degree evals, finals), canonical bytes"""
+        n = len(tables[0]) // 32
+        rounds = n.bit_length() - 1
+        evals = C.create_string_buffer(32 * rounds * degree)
+        finals = C.create_string_buffer(32 * len(tables))
+        t = list(tables) + [None] * (4 - len(tables))
+        self.check(lib().vpin_sumcheck_fused(self._h, C.c_uint32(degree), t[0], t[1], t[2], t[3], C.c_uint64(n), r, evals, finals))
+        return evals.raw, finals.raw
+
+    def spark_timestamps(self, addrs, N, M):
+        """AddrTimestamps::new for one side: addrs = three uint32 numpy arrays -> (addr[3N], read_ts[3N], audit_ts[M])"""
+        a = [np.ascontiguousarray(x, dtype=np.uint32) for x in addrs]
+        out_addr, out_ts, out_audit = np.empty(3 * N, np.uint32), np.empty(3 * N, np.uint32), np.empty(M, np.uint32)
+        ptr = lambda x: x.ctypes.data_as(C.c_void_p) if len(x) else None
+        self.check(lib().vpin_spark_timestamps(self._h, ptr(a[0]), C.c_uint64(len(a[0])), ptr(a[1]), C.c_uint64(len(a[1])), ptr(a[2]),
+                                               C.c_uint64(len(a[2])), C.c_uint64(N), C.c_uint64(M), ptr(out_addr), ptr(out_ts), ptr(out_audit)))
+        return out_addr, out_ts, out_audit
+
     def bind_top(self, Z, r):
         buf = C.create_string_buffer(Z, len(Z))
         self.check(lib().vpin_bind_top(self._h, buf, C.c_uint64(len(Z) // 32), r))

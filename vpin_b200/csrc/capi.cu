@@ -596,6 +596,76 @@ vpin_status vpin_sumcheck_cubic_round(vpin_ctx *ctx, const uint8_t *A32, const u
   download_scalars(c_, c_->d_small.p, 3, out96);
   VPIN_CATCH
 }
+vpin_status vpin_sumcheck_fused(vpin_ctx *ctx, uint32_t degree, const uint8_t *A32, const uint8_t *B32, const uint8_t *C32, const uint8_t *D32,
+                                uint64_t len, const uint8_t *r32, uint8_t *evals_out, uint8_t *finals_out) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE((degree == 2 || degree == 3) && A32 && B32 && r32 && evals_out && finals_out && is_pow2(len) && len >= 2 &&
+                   (degree == 2 || (C32 && D32)), VPIN_ERR_BAD_ARGUMENT, "bad argument");
+  cudaStream_t st = c_->st;
+  size_t rounds = log2_ceil(len), ntab = degree == 3 ? 4 : 2;
+  DevVec<fl_t> t[4];
+  const uint8_t *src[4] = {A32, B32, C32, D32};
+  for (size_t k = 0; k < ntab; k++) t[k] = upload_scalars(c_, src[k], len);
+  std::vector<fl_t> r(rounds), evals(rounds * degree), fin(ntab);
+  for (size_t j = 0; j < rounds; j++) VPIN_REQUIRE(fl_from_bytes(r32 + 32 * j, &r[j]), VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
+  auto wait = [&](int slot, uint32_t seq) {
+    volatile uint32_t *flag = &c_->h_slots[slot].seq;
+    while (*flag != seq) {
+      cudaError_t e = cudaStreamQuery(st);
+      if (e == cudaSuccess && *flag != seq) throw Error(VPIN_ERR_CUDA, "round result never arrived");
+      if (e != cudaSuccess && e != cudaErrorNotReady) VPIN_CUDA(e);
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return c_->h_slots[slot].vals;
+  };
+  auto launch = [&](size_t j, uint32_t *seq) {  // round j: bind with r[j-1] (j > 0), evaluate over q = len >> (j+1) items
+    RoundCtl ctl{c_->d_partials.p, c_->d_round_counters.p, c_->d_slots + (j & 1), *seq = ++c_->round_seq};
+    size_t q = len >> (j + 1);
+    fl_t rp = j ? r[j - 1] : fl_zero();
+    if (degree == 3) launch_round_cubic_additive(t[0].p, t[1].p, t[2].p, t[3].p, q, j > 0, rp, ctl, st);
+    else launch_round_quad(t[0].p, t[1].p, q, j > 0, rp, ctl, st);
+  };
+  uint32_t seq;
+  launch(0, &seq);
+  for (size_t j = 0; j < rounds; j++) {
+    memcpy(&evals[j * degree], wait((int)(j & 1), seq), degree * sizeof(fl_t));
+    if (j + 1 < rounds) launch(j + 1, &seq);
+  }
+  FinalArgs fa;
+  fa.n = (int)ntab;
+  for (size_t k = 0; k < ntab; k++) fa.p[k] = t[k].p;
+  RoundCtl ctl{c_->d_partials.p, c_->d_round_counters.p, c_->d_slots + (rounds & 1), seq = ++c_->round_seq};
+  launch_round_final(fa, true, r[rounds - 1], ctl, st);
+  memcpy(fin.data(), wait((int)(rounds & 1), seq), ntab * sizeof(fl_t));
+  for (size_t i = 0; i < evals.size(); i++) fl_to_bytes(evals[i], evals_out + 32 * i);
+  for (size_t i = 0; i < ntab; i++) fl_to_bytes(fin[i], finals_out + 32 * i);
+  VPIN_CATCH
+}
+vpin_status vpin_spark_timestamps(vpin_ctx *ctx, const uint32_t *addr_a, uint64_t n_a, const uint32_t *addr_b, uint64_t n_b,
+                                  const uint32_t *addr_c, uint64_t n_c, uint64_t N, uint64_t M, uint32_t *addr_out, uint32_t *read_ts_out,
+                                  uint32_t *audit_ts_out) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE(addr_out && read_ts_out && audit_ts_out && N && M && n_a <= N && n_b <= N && n_c <= N && 3 * N < ((uint64_t)1 << 32) &&
+                   (addr_a || !n_a) && (addr_b || !n_b) && (addr_c || !n_c), VPIN_ERR_BAD_ARGUMENT, "bad argument");
+  cudaStream_t st = c_->st;
+  const uint32_t *src[3] = {addr_a, addr_b, addr_c};
+  size_t nnz[3] = {n_a, n_b, n_c};
+  for (int k = 0; k < 3; k++)
+    for (size_t i = 0; i < nnz[k]; i++) VPIN_REQUIRE(src[k][i] < M, VPIN_ERR_INVALID_INDEX, "address out of range");
+  DevVec<uint32_t> d_in[3], d_addr(3 * N, st), d_ts(3 * N, st), d_audit(M, st), scratch(spark_timestamps_scratch_words(N, M), st);
+  const uint32_t *dp[3];
+  for (int k = 0; k < 3; k++) {
+    d_in[k].alloc(std::max<size_t>(nnz[k], 1), st);
+    if (nnz[k]) d_in[k].upload(src[k], nnz[k]);
+    dp[k] = d_in[k].p;
+  }
+  launch_spark_timestamps(dp, nnz, N, M, d_addr.p, d_ts.p, d_audit.p, scratch.p, st);
+  d_addr.download(addr_out, 3 * N);
+  d_ts.download(read_ts_out, 3 * N);
+  d_audit.download(audit_ts_out, M);
+  c_->sync();
+  VPIN_CATCH
+}
 vpin_status vpin_dev_cubic_round(vpin_ctx *ctx, const void *dA, const void *dB, const void *dC, const void *dD, uint64_t len, void *d_out3) {
   VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
   launch_cubic_additive_round((const fl_t *)dA, (const fl_t *)dB, (const fl_t *)dC, (const fl_t *)dD, len / 2, (fl_t *)d_out3, c_->d_partials.p, c_->st);

@@ -253,38 +253,6 @@ __global__ void __launch_bounds__(256) k_coo_unpack(const vpin_coo_entry *raw, s
   atomicAdd(row_cnt + r, 1u);
   atomicAdd(col_cnt + cc, 1u);
 }
-// exclusive prefix sum of n + 1 counters (cnt[n] == 0 on entry) by one block; n is at most 2^27 here
-__global__ void __launch_bounds__(1024) k_exclusive_scan(uint32_t *cnt, size_t n_plus_1) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (size_t base = 0; base < n_plus_1; base += 1024 * 4) {
-    size_t i = base + (size_t)threadIdx.x * 4;
-    uint32_t v[4], t = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { v[k] = i + k < n_plus_1 ? cnt[i + k] : 0u; t += v[k]; }
-    uint32_t incl = t;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = warp_sums[lane], wi = w;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += o; }
-      warp_sums[lane] = wi - w;  // exclusive
-    }
-    __syncthreads();
-    uint32_t excl = carry + warp_sums[warp] + incl - t;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { if (i + k < n_plus_1) cnt[i + k] = excl; excl += v[k]; }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl;
-    __syncthreads();
-  }
-}
 __global__ void __launch_bounds__(256) k_coo_scatter(const uint32_t *row, const uint32_t *col, const fl_t *val, size_t n, uint32_t *row_cur,
                                                      uint32_t *col_cur, uint32_t *csr_col, fl_t *csr_val, uint32_t *csc_row, fl_t *csc_val) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -345,8 +313,11 @@ uint32_t build_matrix(Ctx *ctx, MatrixDev &m, const vpin_coo_entry *entries, siz
   VPIN_CUDA(cudaMemcpyAsync(&err, d_err.p, sizeof(err), cudaMemcpyDeviceToHost, st));
   ctx->sync();
   if (err != ~0ull) return (uint32_t)(err & 3);
-  ++g_kernel_launches, k_exclusive_scan<<<1, 1024, 0, st>>>(m.csr_ptr.p, num_rows + 1);
-  ++g_kernel_launches, k_exclusive_scan<<<1, 1024, 0, st>>>(m.csc_ptr.p, num_cols + 1);
+  {  // exclusive prefix sums of the n + 1 counters (cnt[n] == 0 on entry) -> CSR / CSC pointers
+    DevVec<uint32_t> scratch(exclusive_scan_scratch_words(std::max(num_rows, num_cols) + 1), st);
+    launch_exclusive_scan_u32(m.csr_ptr.p, num_rows + 1, scratch.p, st);
+    launch_exclusive_scan_u32(m.csc_ptr.p, num_cols + 1, scratch.p, st);
+  }
   DevVec<uint32_t> row_cur(num_rows + 1, st), col_cur(num_cols + 1, st), n_long(1, st);
   VPIN_CUDA(cudaMemcpyAsync(row_cur.p, m.csr_ptr.p, (num_rows + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   VPIN_CUDA(cudaMemcpyAsync(col_cur.p, m.csc_ptr.p, (num_cols + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));

@@ -112,6 +112,9 @@ void launch_sparse_eval(const uint32_t *rows, const uint32_t *cols, const fl_t *
 void launch_gather(const uint32_t *addr, const fl_t *mem, size_t n, fl_t *out, cudaStream_t st);
 // out[i] = fl(u32 in[i])
 void launch_u32_to_fl(const uint32_t *in, size_t n, fl_t *out, cudaStream_t st);
+// in-place exclusive prefix sum of n u32 counters (multi-block); d_scratch: exclusive_scan_scratch_words(n) words
+size_t exclusive_scan_scratch_words(size_t n);
+void launch_exclusive_scan_u32(uint32_t *d, size_t n, uint32_t *d_scratch, cudaStream_t st);
 // memory-checking timestamps (:232-265) by a stable radix sort instead of the reference's sequential replay (kernels_sort.cu).
 // addr[k]: nnz[k] addresses of matrix k (row or column indices, COO order), padded with address 0 to N operations each.
 // Outputs: d_addr_out, d_read_ts (3N words, A | B | C) and d_audit_ts (M words). d_scratch: spark_timestamps_scratch_words.

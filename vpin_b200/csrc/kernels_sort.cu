@@ -47,43 +47,69 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t *keys
   __syncthreads();
   hist[(size_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
 }
-// in-place exclusive prefix sum by one block (the histogram has 256 * tiles entries)
-__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t *a, size_t n) {
+// ---- in-place exclusive prefix sum of n 32-bit counters, three launches: (1) every block scans its 4096-element chunk and
+// records the chunk total, (2) one block scans the chunk totals, (3) every block adds its chunk's offset ----
+const int kScanChunk = 4096;  // 1024 threads x 4
+__device__ __forceinline__ uint32_t block_exclusive_scan4(uint32_t (&v)[4], uint32_t *total) {
   __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (size_t base = 0; base < n; base += 4096) {
-    size_t i = base + (size_t)threadIdx.x * 4;
-    uint32_t v[4], t = 0;
+  uint32_t t = v[0] + v[1] + v[2] + v[3], incl = t;
 #pragma unroll
-    for (int k = 0; k < 4; k++) { v[k] = i + k < n ? a[i + k] : 0u; t += v[k]; }
-    uint32_t incl = t;
+  for (int off = 1; off < 32; off <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += o;
+  }
+  __syncthreads();  // warp_sums may still be read by a previous call
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_sums[lane], wi = w;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += o;
+      uint32_t o = __shfl_up_sync(0xffffffffu, wi, off);
+      if (lane >= off) wi += o;
     }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = warp_sums[lane], wi = w;
+    warp_sums[lane] = wi - w;  // exclusive
+    if (lane == 31 && total) *total = wi;
+  }
+  __syncthreads();
+  return warp_sums[warp] + incl - t;  // exclusive prefix of this thread's first element
+}
+__global__ void __launch_bounds__(1024) k_scan_chunks(uint32_t *a, size_t n, uint32_t *chunk_totals) {
+  size_t i = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * 4;
+  uint32_t v[4];
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        uint32_t o = __shfl_up_sync(0xffffffffu, wi, off);
-        if (lane >= off) wi += o;
-      }
-      warp_sums[lane] = wi - w;  // exclusive
-    }
-    __syncthreads();
-    uint32_t excl = carry + warp_sums[warp] + incl - t;
+  for (int k = 0; k < 4; k++) v[k] = i + k < n ? a[i + k] : 0u;
+  __shared__ uint32_t total;
+  uint32_t excl = block_exclusive_scan4(v, &total);
 #pragma unroll
-    for (int k = 0; k < 4; k++) { if (i + k < n) a[i + k] = excl; excl += v[k]; }
+  for (int k = 0; k < 4; k++) { if (i + k < n) a[i + k] = excl; excl += v[k]; }
+  if (threadIdx.x == 0) chunk_totals[blockIdx.x] = total;
+}
+// one block: exclusive scan of m chunk totals (m is at most a few thousand per pass; loops with a carry beyond 4096)
+__global__ void __launch_bounds__(1024) k_scan_totals(uint32_t *t, size_t m) {
+  __shared__ uint32_t total, carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < m; base += kScanChunk) {
+    size_t i = base + (size_t)threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = i + k < m ? t[i + k] : 0u;
+    uint32_t excl = carry + block_exclusive_scan4(v, &total);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (i + k < m) t[i + k] = excl; excl += v[k]; }
     __syncthreads();
-    if (threadIdx.x == 1023) carry = excl;
+    if (threadIdx.x == 0) carry += total;
     __syncthreads();
   }
+}
+__global__ void __launch_bounds__(1024) k_scan_add(uint32_t *a, size_t n, const uint32_t *chunk_offsets) {
+  size_t i = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * 4;
+  uint32_t off = chunk_offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (i + k < n) a[i + k] += off;
 }
 // stable scatter of one tile: a warp owns 512 consecutive elements and walks them 32 at a time, so the order inside
 // the tile is (warp, iteration, lane) = the original order
@@ -144,14 +170,25 @@ __global__ void __launch_bounds__(256) k_ts_ranks(const uint32_t *keys, const ui
 
 }  // namespace
 
+size_t exclusive_scan_scratch_words(size_t n) { return (n + kScanChunk - 1) / kScanChunk + 1; }
+void launch_exclusive_scan_u32(uint32_t *d, size_t n, uint32_t *d_scratch, cudaStream_t st) {
+  if (!n) return;
+  size_t chunks = (n + kScanChunk - 1) / kScanChunk;
+  ++g_kernel_launches, k_scan_chunks<<<(unsigned)chunks, 1024, 0, st>>>(d, n, d_scratch);
+  if (chunks > 1) {
+    ++g_kernel_launches, k_scan_totals<<<1, 1024, 0, st>>>(d_scratch, chunks);
+    ++g_kernel_launches, k_scan_add<<<(unsigned)chunks, 1024, 0, st>>>(d, n, d_scratch);
+  }
+}
 size_t spark_timestamps_scratch_words(size_t N, size_t M) {
   size_t n = 3 * N, tiles = (n + kSortTile - 1) / kSortTile;
-  return 4 * n + 256 * tiles + M;
+  return 4 * n + 256 * tiles + M + exclusive_scan_scratch_words(256 * tiles);
 }
 void launch_spark_timestamps(const uint32_t *const addr[3], const size_t nnz[3], size_t N, size_t M, uint32_t *d_addr_out, uint32_t *d_read_ts,
                              uint32_t *d_audit_ts, uint32_t *d_scratch, cudaStream_t st) {
   const size_t n = 3 * N, tiles = (n + kSortTile - 1) / kSortTile;
   uint32_t *keys = d_scratch, *vals = keys + n, *keys2 = vals + n, *vals2 = keys2 + n, *hist = vals2 + n, *start = hist + 256 * tiles;
+  uint32_t *scan_scratch = start + M;
   cudaMemsetAsync(d_audit_ts, 0, M * sizeof(uint32_t), st);
   unsigned eb = (unsigned)((n + 255) / 256);
   ++g_kernel_launches, k_ts_init<<<eb, 256, 0, st>>>(addr[0], addr[1], addr[2], nnz[0], nnz[1], nnz[2], N, keys, vals, d_audit_ts);
@@ -159,7 +196,7 @@ void launch_spark_timestamps(const uint32_t *const addr[3], const size_t nnz[3],
   while (((size_t)1 << bits) < M) bits++;
   for (int shift = 0; shift < bits; shift += 8) {
     ++g_kernel_launches, k_sort_hist<<<(unsigned)tiles, kSortThreads, 0, st>>>(keys, n, shift, hist, tiles);
-    ++g_kernel_launches, k_sort_scan<<<1, 1024, 0, st>>>(hist, 256 * tiles);
+    launch_exclusive_scan_u32(hist, 256 * tiles, scan_scratch, st);
     ++g_kernel_launches, k_sort_scatter<<<(unsigned)tiles, kSortThreads, 0, st>>>(keys, vals, n, shift, hist, tiles, keys2, vals2);
     uint32_t *t = keys; keys = keys2; keys2 = t;
     t = vals; vals = vals2; vals2 = t;
