@@ -16,6 +16,13 @@ __global__ void k_spin(long long cycles) {
   long long t0 = clock64();
   while (clock64() - t0 < cycles) {}
 }
+// speculative launch: the kernel is already resident and polls a host-mapped word for its go signal
+__global__ void k_poll_flag(volatile uint32_t *go, uint32_t want, RoundSlot *slot, uint32_t seq) {
+  long long t0 = clock64();
+  while (*go != want) { if (clock64() - t0 > 4000000000LL) return; }
+  __threadfence_system();
+  *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
+}
 static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int main() {
@@ -44,6 +51,27 @@ int main() {
     double t0 = now_us();
     for (int i = 0; i < reps; i++) { ++seq; k_empty_flag<<<1, 1, 0, st>>>(d, seq); wait(0); }
     printf("empty kernel -> flag            : %6.2f us\n", (now_us() - t0) / reps);
+  }
+  {
+    uint32_t *go_h, *go_d;
+    cudaHostAlloc((void **)&go_h, 64, cudaHostAllocMapped);
+    *go_h = 0;
+    cudaHostGetDevicePointer((void **)&go_d, go_h, 0);
+    double t0 = now_us();
+    uint32_t tick = 0;
+    ++seq; ++tick;
+    k_poll_flag<<<1, 1, 0, st>>>(go_d, tick, d, seq);
+    for (int i = 0; i < reps; i++) {
+      uint32_t cur_seq = seq, cur_tick = tick;
+      ++seq; ++tick;
+      k_poll_flag<<<1, 1, 0, st>>>(go_d, tick, d, seq);  // next one queued behind the current one
+      *(volatile uint32_t *)go_h = cur_tick;              // release the current one
+      volatile uint32_t *f = &h[0].seq;
+      while (*f != cur_seq) __builtin_ia32_pause();
+    }
+    *(volatile uint32_t *)go_h = tick;
+    cudaStreamSynchronize(st);
+    printf("pre-launched kernel, go via mapped : %6.2f us\n", (now_us() - t0) / reps);
   }
   BatchedRoundArgs a;
   memset(&a, 0, sizeof(a));
