@@ -78,3 +78,25 @@ def test_unsatisfied_witness_is_reported(ctx):
     bad = bytearray(v)
     bad[0] ^= 1
     assert inst.is_sat(v, inputs) and not inst.is_sat(bytes(bad), inputs)
+
+
+@pytest.mark.parametrize("tag", ["conv3", "conv5", "A"])
+def test_named_vpin_shapes_verify(ctx, tag):
+    """BASELINE.json's named shapes at full size (point-mult instance): too large for the CPU prover inside a test, so the
+    check is the size-independent one — the oracle's restatement of my_lib_verify (O(sqrt n)) must accept the CUDA proof,
+    reject a corrupted one, and the combined commitment must be the row-wise sum (proof_point_add.rs:69-80)."""
+    from vpin_b200 import api
+
+    m, _ = W.SHAPES[tag]
+    weights, px, py = W.synth_point_mult(m)
+    dims, inst, vp, vi, v, inputs = api.point_mult(ctx, weights, px, py)
+    sq, sp = W.tape_seeds()
+    got = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp)
+    assert ctx.commitments_add(got["comm_vars_para"], got["comm_vars_input"]) == got["comm_vars"]
+    assert O.verify(dims, got["proof"], got["comm"], inputs, got["comm_vars_para"], got["comm_vars_input"]) == 1
+    bad = bytearray(got["proof"])
+    bad[len(bad) // 3] ^= 0x10
+    assert O.verify(dims, bytes(bad), got["comm"], inputs, got["comm_vars_para"], got["comm_vars_input"]) != 1
+    # determinism: the same seeds give the same bytes
+    again = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp)
+    assert again["proof"] == got["proof"] and again["comm"] == got["comm"]

@@ -99,6 +99,7 @@ void vpin_ctx_destroy(vpin_ctx *ctx_) {
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
   ctx->d_round_counters.release();
+  ctx->workspace.release();
   cudaStreamSynchronize(ctx->st);
   cudaStreamDestroy(ctx->st);
   delete ctx;

@@ -129,6 +129,18 @@ struct vpin_ctx_impl {
   RoundSlot *h_slots = nullptr, *d_slots = nullptr;
   DevVec<unsigned> d_round_counters;
   uint32_t round_seq = 0;
+  // per-proof workspace for the SPARK tables (derefs, product trees, dot-product clones): one slab that only ever grows, so
+  // a steady-state proof allocates nothing large (multi-GB cudaMallocAsync calls were measured at 10-150 ms when the pool
+  // has to grow or is fragmented)
+  DevVec<fl_t> workspace;
+  fl_t *workspace_reserve(size_t elems) {
+    if (workspace.n < elems) {
+      workspace.release();
+      sync();
+      workspace.alloc(elems, st);
+    }
+    return workspace.p;
+  }
   std::vector<std::pair<const char *, double>> phases;
   Prof prof;
   // multi-GPU (one process per GPU): NCCL communicator over NVLink/NVSwitch, created by vpin_ctx_init_distributed

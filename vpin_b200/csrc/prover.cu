@@ -884,8 +884,10 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   VPIN_REQUIRE(((size_t)1 << rx_ext.size()) == M, VPIN_ERR_SIZE_MISMATCH, "memory size");
   DevVec<fl_t> mem_rx = P.eq_table(rx_ext), mem_ry = P.eq_table(ry_ext);
   // derefs (:525-530, :267-282) merged as row A,B,C | col A,B,C | 0 | 0 (:61)
-  DevVec<fl_t> derefs(8 * N, st);
-  derefs.zero();
+  // workspace slab: derefs 8N | mem trees 8M | ops trees 24N | dot-product clones 9N
+  fl_t *ws = ctx->workspace_reserve(41 * N + 8 * M);
+  struct { fl_t *p; } derefs{ws}, mem_trees{ws + 8 * N}, ops_trees{ws + 8 * N + 8 * M}, dotp_tables{ws + 32 * N + 8 * M};
+  VPIN_CUDA(cudaMemsetAsync(derefs.p, 0, 8 * N * sizeof(fl_t), st));
   for (int k = 0; k < 3; k++) {
     ProfScope ps(ctx, PROF_GATHER, 2.0 * N, 2.0 * N * 68, 2);
     launch_gather(dec.row_addr[k].p, mem_rx.p, N, derefs.p + (size_t)k * N, st);
@@ -913,7 +915,7 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   t0 = now_ms();
   // hash layers + product trees (:547-671). Packed trees: 2 for init/audit per side (M leaves), 6 per side for ops (N leaves)
   const fl_t *d_gt = P.up(r_mem_check);
-  DevVec<fl_t> mem_trees(4 * 2 * M, st), ops_trees(12 * 2 * N, st);
+  phase("network_alloc", t0);
   fl_t *row_init = mem_trees.p, *row_audit = mem_trees.p + 2 * M, *col_init = mem_trees.p + 4 * M, *col_audit = mem_trees.p + 6 * M;
   {
     ProfScope ps(ctx, PROF_HASH, 2.0 * M, 2.0 * M * 100, 2);
@@ -928,6 +930,7 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
     launch_hash_ops(dec.row_addr[k].p, derefs.p + (size_t)k * N, dec.row_read_ts[k].p, N, d_gt, ops_ptr[k], ops_ptr[3 + k], st);
     launch_hash_ops(dec.col_addr[k].p, derefs.p + (size_t)(3 + k) * N, dec.col_read_ts[k].p, N, d_gt, ops_ptr[6 + k], ops_ptr[9 + k], st);
   }
+  phase("network_hash", t0);
   for (auto p : mem_ptr) build_tree(ctx, p, M, st);
   for (auto p : ops_ptr) build_tree(ctx, p, N, st);
   phase("build_layered_network", t0);
@@ -969,7 +972,6 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   t.scalars("claim_col_eval_write", ec.write);
   t.scalar("claim_col_eval_audit", ec.audit);
   // dot-product circuits on clones (row_ops_val, col_ops_val, val), split in halves (:1105-1130)
-  DevVec<fl_t> dotp_tables(9 * N, st);
   std::vector<Prover::DotpTables> dotp(6);
   std::vector<fl_t> eval_dotp_left(3), eval_dotp_right(3);
   for (int k = 0; k < 3; k++) {
@@ -997,9 +999,6 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   BatchedS proof_mem = P.batched_prove(mem_ptr, M, {}, mem_evals, &rand_mem);
   phase("product_circuits_mem", t1);
   t1 = now_ms();
-  ops_trees.release();
-  mem_trees.release();
-  dotp_tables.release();
 
   // HashLayerProof::prove (:740-849)
   t.protocol_name("Sparse polynomial hash layer proof");
