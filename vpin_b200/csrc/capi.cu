@@ -62,10 +62,7 @@ vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out) {
     ctx->device = cuda_device;
     VPIN_CUDA(cudaSetDevice(cuda_device));
     VPIN_CUDA(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
-    cudaMemPool_t pool;
-    VPIN_CUDA(cudaDeviceGetDefaultMemPool(&pool, cuda_device));
-    uint64_t thr = UINT64_MAX;
-    VPIN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    block_cache_register(ctx->st);
     ctx->d_partials.alloc((size_t)3 * kRedBlocks * 32, ctx->st);
     ctx->d_small.alloc(256, ctx->st);
     ctx->d_counters.alloc(4, ctx->st);
@@ -101,6 +98,7 @@ void vpin_ctx_destroy(vpin_ctx *ctx_) {
   ctx->d_round_counters.release();
   ctx->workspace.release();
   cudaStreamSynchronize(ctx->st);
+  block_cache_unregister(ctx->st);
   cudaStreamDestroy(ctx->st);
   delete ctx;
 }

@@ -4,10 +4,105 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <mutex>
 
 namespace vpin {
 
 std::atomic<uint64_t> g_kernel_launches{0};
+
+// ------------------------------------------------------------------------------------------------ block cache
+struct BlockCache {
+  std::mutex mu;
+  std::map<size_t, std::vector<void *>> free_;   // rounded size -> idle blocks
+  std::map<void *, size_t> live_;                // every block handed out by this cache -> rounded size
+};
+namespace {
+std::mutex g_cache_mu;
+std::map<cudaStream_t, std::unique_ptr<BlockCache>> g_caches;
+std::map<void *, size_t> g_orphans;  // blocks whose cache died while they were in use (freed on release)
+size_t round_block(size_t bytes) {
+  if (bytes <= 256) return 256;
+  if (bytes >= ((size_t)2 << 20)) return (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  size_t r = 256;
+  while (r < bytes) r <<= 1;
+  return r;
+}
+}  // namespace
+BlockCache *block_cache_of(cudaStream_t st) {
+  std::lock_guard<std::mutex> g(g_cache_mu);
+  auto it = g_caches.find(st);
+  return it == g_caches.end() ? nullptr : it->second.get();
+}
+void block_cache_register(cudaStream_t st) {
+  std::lock_guard<std::mutex> g(g_cache_mu);
+  g_caches[st] = std::make_unique<BlockCache>();
+}
+void block_cache_unregister(cudaStream_t st) {
+  std::unique_ptr<BlockCache> c;
+  {
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    auto it = g_caches.find(st);
+    if (it == g_caches.end()) return;
+    c = std::move(it->second);
+    g_caches.erase(it);
+    for (auto &kv : c->live_) g_orphans.insert(kv);  // still owned by some handle: freed when it lets go
+  }
+  for (auto &kv : c->free_)
+    for (void *p : kv.second) cudaFree(p);
+}
+void *block_cache_alloc(BlockCache *c, size_t bytes) {
+  size_t r = round_block(bytes);
+  void *p = nullptr;
+  if (c) {
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->free_.find(r);
+    if (it != c->free_.end() && !it->second.empty()) {
+      p = it->second.back();
+      it->second.pop_back();
+      c->live_[p] = r;
+      return p;
+    }
+  }
+  cudaError_t e = cudaMalloc(&p, r);
+  if (e != cudaSuccess && c) {  // give idle blocks back to the driver and retry once
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> g(c->mu);
+      for (auto &kv : c->free_)
+        for (void *q : kv.second) cudaFree(q);
+      c->free_.clear();
+    }
+    e = cudaMalloc(&p, r);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Error(VPIN_ERR_OOM, std::string("cudaMalloc(") + std::to_string(r) + "): " + cudaGetErrorString(e));
+  }
+  if (c) {
+    std::lock_guard<std::mutex> g(c->mu);
+    c->live_[p] = r;
+  } else {
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    g_orphans[p] = r;
+  }
+  return p;
+}
+void block_cache_free(BlockCache *c, void *p) {
+  if (c) {
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->live_.find(p);
+    if (it != c->live_.end()) {
+      c->free_[it->second].push_back(p);
+      c->live_.erase(it);
+      return;
+    }
+  }
+  {
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    g_orphans.erase(p);
+  }
+  cudaFree(p);  // implicit device synchronisation: nothing can still be using it
+}
 
 // ------------------------------------------------------------------------------------------------ profiling
 const char *prof_class_name(int cls) {

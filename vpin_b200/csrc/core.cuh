@@ -36,7 +36,19 @@ struct Error : std::runtime_error {
 
 extern std::atomic<uint64_t> g_kernel_launches;
 
-// stream-ordered HBM array
+// Per-stream caching allocator. Every context drives ONE stream from one host thread, so a block released by a DevVec may be
+// handed to the next DevVec on the same stream without any synchronisation (stream order protects it). Blocks come from
+// cudaMalloc, are kept in exact-size free lists and only go back to the driver when the context dies: a steady-state
+// proof makes no driver allocation at all. (cudaMallocAsync was measured to cost 10-450 ms per proof once two contexts
+// share the default pool or the pool fragments — its reuse across streams either stalls or maps fresh memory.)
+struct BlockCache;
+BlockCache *block_cache_of(cudaStream_t st);            // nullptr when the stream has no cache (context gone)
+void *block_cache_alloc(BlockCache *c, size_t bytes);   // throws Error(VPIN_ERR_OOM)
+void block_cache_free(BlockCache *c, void *p);
+void block_cache_register(cudaStream_t st);
+void block_cache_unregister(cudaStream_t st);           // frees every cached block; outstanding blocks are freed on release
+
+// HBM array owned through the stream's block cache
 template <class T>
 struct DevVec {
   T *p = nullptr;
@@ -55,10 +67,10 @@ struct DevVec {
   void alloc(size_t n_, cudaStream_t st_) {
     release();
     n = n_; st = st_;
-    if (n) VPIN_CUDA(cudaMallocAsync((void **)&p, n * sizeof(T), st));
+    if (n) p = static_cast<T *>(block_cache_alloc(block_cache_of(st), n * sizeof(T)));
   }
   void release() {
-    if (p) cudaFreeAsync(p, st);
+    if (p) block_cache_free(block_cache_of(st), p);
     p = nullptr; n = 0;
   }
   void upload(const T *h, size_t cnt) { VPIN_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st)); }
