@@ -247,11 +247,11 @@ std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, si
   launch_from_uniform_bytes(d_stream.p, n, g->d_pts.p, ctx->st);
   g->h_pts.resize(n);
   g->d_pts.download(g->h_pts.data(), n);
-  // window width: the widest whose table takes at most a quarter of the free HBM (and at most 48 GiB); VPIN_MSM_W pins it
+  // window width: the widest whose table takes at most 30 % of the free HBM (and at most 64 GiB); VPIN_MSM_W pins it
   {
     size_t free_b = 0, total_b = 0;
     VPIN_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = std::min<size_t>(free_b / 4, (size_t)48 << 30);
+    size_t budget = std::min<size_t>(free_b / 10 * 3, (size_t)64 << 30);
     int W = kMsmMinW;
     while (W < kMsmMaxW && msm_table_bytes_per_base(W + 1) * n <= budget) W++;
     if (const char *e = getenv("VPIN_MSM_W")) {

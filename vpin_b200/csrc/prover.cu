@@ -6,6 +6,7 @@
 #include <time.h>
 
 #include <array>
+#include <thread>
 
 namespace vpin {
 
@@ -326,17 +327,27 @@ struct Prover {
   }
   // DotProductProof::prove with gens_n = gens_3 / gens_4 and gens_1 of the sat gens (:315-374). Cx is the already
   // computed commitment to x_vec under blind_x (the round's comm_poly).
+  // the prover's random draws of one DotProductProof (d_vec, r_delta, r_beta: SP/nizk/mod.rs:326-333) and the commitment
+  // delta = d_vec.commit(r_delta), which depends on nothing else and can therefore be computed ahead of its round
+  struct DotDraw { std::vector<fl_t> d_vec; fl_t r_delta, r_beta; Comp delta; };
+  DotDraw dot_draw(size_t n) {
+    DotDraw d;
+    d.d_vec = tape.vector("d_vec", n);
+    d.r_delta = tape.scalar("r_delta");
+    d.r_beta = tape.scalar("r_beta");
+    return d;
+  }
   DotProductProofS dotproduct_prove(const std::vector<fl_t> &x_vec, const fl_t &blind_x, const Comp &Cx, const std::vector<fl_t> &a_vec,
-                                    const fl_t &y, const fl_t &blind_y) {
+                                    const fl_t &y, const fl_t &blind_y, const DotDraw &draw) {
     t.protocol_name("dot product proof");
     size_t n = x_vec.size();
-    std::vector<fl_t> d_vec = tape.vector("d_vec", n);
-    fl_t r_delta = tape.scalar("r_delta"), r_beta = tape.scalar("r_beta");
+    const std::vector<fl_t> &d_vec = draw.d_vec;
+    const fl_t &r_delta = draw.r_delta, &r_beta = draw.r_beta;
     t.point("Cx", Cx.data());
     Comp Cy = compress_host(commit1(g.sat_pc, y, blind_y));
     t.point("Cy", Cy.data());
     t.scalars("a", a_vec);
-    Comp delta = compress_host(commit_coeffs(d_vec, r_delta));
+    const Comp &delta = draw.delta;
     t.point("delta", delta.data());
     fl_t dot = fl_zero();
     for (size_t i = 0; i < n; i++) dot = dot + a_vec[i] * d_vec[i];
@@ -361,6 +372,19 @@ struct Prover {
                           FinalFn launch_final, size_t nfinal, std::vector<fl_t> *r_out, fl_t *blind_post, std::vector<fl_t> *finals) {
     std::vector<fl_t> blinds_poly = tape.vector("blinds_poly", num_rounds);
     std::vector<fl_t> blinds_evals = tape.vector("blinds_evals", num_rounds);
+    // The tape is touched by nothing but the per-round DotProductProofs from here to the end of the sumcheck, so their
+    // draws can be taken now in the same order, and a worker thread commits to the d_vecs (5 fixed-base multiplications
+    // and an encoding per round) while this thread runs the rounds.
+    std::vector<DotDraw> draws(num_rounds);
+    for (size_t j = 0; j < num_rounds; j++) draws[j] = dot_draw((size_t)degree + 1);
+    std::atomic<size_t> deltas_ready{0};
+    std::thread delta_worker([&] {
+      for (size_t j = 0; j < num_rounds; j++) {
+        draws[j].delta = compress_host(commit_coeffs(draws[j].d_vec, draws[j].r_delta));
+        deltas_ready.store(j + 1, std::memory_order_release);
+      }
+    });
+    struct Joiner { std::thread &th; ~Joiner() { if (th.joinable()) th.join(); } } joiner{delta_worker};
     fl_t claim_per_round = claim;
     Comp comm_claim_per_round = compress_host(commit1(g.sat_pc, claim_per_round, blind_claim));
     ZkSumcheckS out;
@@ -397,7 +421,8 @@ struct Prover {
         a[i] = w[0] * a_sc + w[1] * pw;
         pw = pw * r_j;
       }
-      out.proofs.push_back(dotproduct_prove(poly, blinds_poly[j], comm_poly, a, target, blind));
+      while (deltas_ready.load(std::memory_order_acquire) <= j) __builtin_ia32_pause();
+      out.proofs.push_back(dotproduct_prove(poly, blinds_poly[j], comm_poly, a, target, blind, draws[j]));
       claim_per_round = eval;
       comm_claim_per_round = comm_eval;
       r.push_back(r_j);
