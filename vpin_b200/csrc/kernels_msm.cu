@@ -239,7 +239,7 @@ size_t msm_num_segments(size_t rows, size_t cols_total, const MsmGeom &g) {
     if (segs > max_segs) segs = max_segs;
     return segs < 1 ? 1 : segs;
   }
-  const size_t want_threads = (size_t)148 * 1024;
+  const size_t want_threads = (size_t)148 * 6144;  // ~6 waves of blocks: short blocks balance the SMs (measured: 610 -> 736 Mpoints/s from 1024)
   size_t per = rows * g.group;
   size_t segs = (want_threads + per - 1) / per;
   size_t max_segs = (cols_total + 7) / 8;  // at least 8 columns per thread
