@@ -63,6 +63,11 @@ vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out) {
     VPIN_CUDA(cudaSetDevice(cuda_device));
     VPIN_CUDA(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
     block_cache_register(ctx->st);
+    block_cache_set_pressure_hook(ctx->st, [ctx]() {
+      if (ctx->workspace_busy || !ctx->workspace.p) return false;
+      ctx->workspace.release();  // back to the cache's idle list; the allocator returns that to the driver next
+      return true;
+    });
     ctx->d_partials.alloc((size_t)3 * kRedBlocks * 32, ctx->st);
     ctx->d_small.alloc(256, ctx->st);
     ctx->d_counters.alloc(4, ctx->st);

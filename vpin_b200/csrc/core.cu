@@ -15,6 +15,7 @@ struct BlockCache {
   std::mutex mu;
   std::map<size_t, std::vector<void *>> free_;   // rounded size -> idle blocks
   std::map<void *, size_t> live_;                // every block handed out by this cache -> rounded size
+  std::function<bool()> pressure;                // see block_cache_set_pressure_hook
 };
 namespace {
 std::mutex g_cache_mu;
@@ -36,6 +37,11 @@ BlockCache *block_cache_of(cudaStream_t st) {
 void block_cache_register(cudaStream_t st) {
   std::lock_guard<std::mutex> g(g_cache_mu);
   g_caches[st] = std::make_unique<BlockCache>();
+}
+void block_cache_set_pressure_hook(cudaStream_t st, std::function<bool()> hook) {
+  std::lock_guard<std::mutex> g(g_cache_mu);
+  auto it = g_caches.find(st);
+  if (it != g_caches.end()) it->second->pressure = std::move(hook);
 }
 void block_cache_unregister(cudaStream_t st) {
   std::unique_ptr<BlockCache> c;
@@ -64,8 +70,11 @@ void *block_cache_alloc(BlockCache *c, size_t bytes) {
     }
   }
   cudaError_t e = cudaMalloc(&p, r);
-  if (e != cudaSuccess && c) {  // give idle blocks back to the driver and retry once
+  // out of memory: give the idle blocks back to the driver and retry; then ask the owner to let go of what it can spare
+  // (the idle SPARK workspace of a previous proof) and retry once more
+  for (int attempt = 0; e != cudaSuccess && c && attempt < 2; attempt++) {
     cudaGetLastError();
+    if (attempt == 1 && !(c->pressure && c->pressure())) break;
     {
       std::lock_guard<std::mutex> g(c->mu);
       for (auto &kv : c->free_)
@@ -226,7 +235,7 @@ void dist_allgather_inplace(Ctx *ctx, void *buf, size_t bytes_per_rank) {
 }
 
 // ------------------------------------------------------------------------------------------------ generators
-std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n) {
+std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n, size_t table_budget) {
   auto it = ctx->label_gens.find(label);
   if (it != ctx->label_gens.end() && it->second->n >= n) return it->second;
   auto g = std::make_shared<LabelGens>();
@@ -247,11 +256,12 @@ std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, si
   launch_from_uniform_bytes(d_stream.p, n, g->d_pts.p, ctx->st);
   g->h_pts.resize(n);
   g->d_pts.download(g->h_pts.data(), n);
-  // window width: the widest whose table takes at most 30 % of the free HBM (and at most 64 GiB); VPIN_MSM_W pins it
+  // window width: the widest whose table fits the caller's budget (snark_gens_create plans both tables of a shape against
+  // the proof's working set) or, without one, 30 % of the free HBM; at most 64 GiB either way. VPIN_MSM_W pins it.
   {
     size_t free_b = 0, total_b = 0;
     VPIN_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = std::min<size_t>(free_b / 10 * 3, (size_t)64 << 30);
+    size_t budget = std::min<size_t>(table_budget ? std::min(table_budget, free_b) : free_b / 10 * 3, (size_t)64 << 30);
     int W = kMsmMinW;
     while (W < kMsmMaxW && msm_table_bytes_per_base(W + 1) * n <= budget) W++;
     if (const char *e = getenv("VPIN_MSM_W")) {

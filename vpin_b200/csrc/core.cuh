@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -47,6 +48,9 @@ void *block_cache_alloc(BlockCache *c, size_t bytes);   // throws Error(VPIN_ERR
 void block_cache_free(BlockCache *c, void *p);
 void block_cache_register(cudaStream_t st);
 void block_cache_unregister(cudaStream_t st);           // frees every cached block; outstanding blocks are freed on release
+// `hook` is called (without the cache lock) when the driver is out of memory even after the idle blocks went back to it;
+// it releases whatever the owner can spare (the context's idle SPARK workspace) and returns true if that was anything.
+void block_cache_set_pressure_hook(cudaStream_t st, std::function<bool()> hook);
 
 // HBM array owned through the stream's block cache
 template <class T>
@@ -145,6 +149,7 @@ struct vpin_ctx_impl {
   // a steady-state proof allocates nothing large (multi-GB cudaMallocAsync calls were measured at 10-150 ms when the pool
   // has to grow or is fragmented)
   DevVec<fl_t> workspace;
+  bool workspace_busy = false;  // a proof is using the slab (set by the prover): the out-of-memory hook must leave it alone
   fl_t *workspace_reserve(size_t elems) {
     if (workspace.n < elems) {
       workspace.release();
@@ -172,7 +177,8 @@ void dist_get_unique_id(uint8_t out[128]);
 void dist_init(Ctx *ctx, int rank, int world, const uint8_t id[128]);
 void dist_destroy(Ctx *ctx);
 
-std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n);
+// table_budget: bytes the fixed-base table may take (0 = 30 % of the free HBM)
+std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n, size_t table_budget = 0);
 
 // Hyrax rows: out[i] = sum_j Z[i*ld + j] * G_j (+ blind_i * G_{blind_base}). d_points (rows ge_t) and d_comp (rows*32 B)
 // are optional outputs.

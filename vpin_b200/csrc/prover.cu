@@ -88,15 +88,35 @@ std::unique_ptr<SnarkGens> snark_gens_create(Ctx *ctx, uint64_t num_cons, uint64
   auto g = std::make_unique<SnarkGens>();
   size_t ell_sat = math_log2(num_vars_padded);
   size_t R_sat = (size_t)1 << (ell_sat - ell_sat / 2);
-  g->sat_label = get_label_gens(ctx, "gens_r1cs_sat", std::max<size_t>(R_sat + 2, 5));
-  make_pc(ctx, *g->sat_label, ell_sat, &g->sat_pc);
-  for (int i = 0; i < 5; i++) g->sat_g[i] = g->sat_label->host_base(i);
   size_t nvx = math_log2(num_cons), nvy = math_log2(2 * num_vars_padded);
   size_t k = math_log2(next_pow2(num_nz_entries));
   size_t ell_ops = k + math_log2(next_pow2(3 * 5)), ell_mem = std::max(nvx, nvy) + 1, ell_derefs = k + math_log2(next_pow2(3 * 2));
   size_t ell_max = std::max(ell_ops, std::max(ell_mem, ell_derefs));
   size_t R_max = (size_t)1 << (ell_max - ell_max / 2);
-  g->eval_label = get_label_gens(ctx, "gens_r1cs_eval", R_max + 2);
+  // HBM plan for this shape: what one proof keeps alive next to the two generator tables — the SPARK workspace slab
+  // (41 N + 8 M elements, snark_prove), the decommitment (comb_ops 16 N, comb_mem 2 M, address / timestamp words), the
+  // instance (COO + CSR + CSC), the witness-sized tables of the satisfiability proof, MSM / sort temporaries — plus a
+  // margin. The tables share what is left: 80 % at most for the evaluation generators (derefs 8 N and comb_ops 16 N
+  // scalars go through them), the rest for the satisfiability generators. LeNet layer 5 (N = 2^25) keeps ~115 GB alive:
+  // without the plan the first table took 30 % of an empty GPU and the second proof ran out of memory.
+  size_t table_budget_eval = 0, table_budget_sat = 0;
+  {
+    size_t N = (size_t)1 << k, M = (size_t)1 << std::max(nvx, nvy), c = (size_t)1 << nvx, v = num_vars_padded;
+    size_t working = (41 * N + 8 * M) * 32 + (16 * N + 2 * M) * 32 + 64 * N + 3 * N * 112 + (8 * v + 5 * c) * 32 + ((size_t)4 << 30);
+    size_t free_b = 0, total_b = 0;
+    VPIN_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t margin = (size_t)6 << 30;
+    size_t avail = free_b > working + margin ? free_b - working - margin : 0;
+    table_budget_eval = std::max<size_t>(avail / 5 * 4, 1);
+    auto it = ctx->label_gens.find("gens_r1cs_eval");
+    bool eval_cached = it != ctx->label_gens.end() && it->second->n >= R_max + 2;
+    g->eval_label = get_label_gens(ctx, "gens_r1cs_eval", R_max + 2, table_budget_eval);
+    size_t eval_bytes = eval_cached ? 0 : msm_table_entries(g->eval_label->n, g->eval_label->geom) * sizeof(niels_t);
+    table_budget_sat = std::max<size_t>(avail > eval_bytes ? avail - eval_bytes : 0, 1);
+  }
+  g->sat_label = get_label_gens(ctx, "gens_r1cs_sat", std::max<size_t>(R_sat + 2, 5), table_budget_sat);
+  make_pc(ctx, *g->sat_label, ell_sat, &g->sat_pc);
+  for (int i = 0; i < 5; i++) g->sat_g[i] = g->sat_label->host_base(i);
   make_pc(ctx, *g->eval_label, ell_ops, &g->ops_pc);
   make_pc(ctx, *g->eval_label, ell_mem, &g->mem_pc);
   make_pc(ctx, *g->eval_label, ell_derefs, &g->derefs_pc);
@@ -910,6 +930,11 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   DevVec<fl_t> mem_rx = P.eq_table(rx_ext), mem_ry = P.eq_table(ry_ext);
   // derefs (:525-530, :267-282) merged as row A,B,C | col A,B,C | 0 | 0 (:61)
   // workspace slab: derefs 8N | mem trees 8M | ops trees 24N | dot-product clones 9N
+  struct WorkspaceBusy {  // keeps the out-of-memory hook (capi.cu) away from the slab until this proof is done with it
+    Ctx *c;
+    explicit WorkspaceBusy(Ctx *c_) : c(c_) { c->workspace_busy = true; }
+    ~WorkspaceBusy() { c->workspace_busy = false; }
+  } workspace_busy(ctx);
   fl_t *ws = ctx->workspace_reserve(41 * N + 8 * M);
   struct { fl_t *p; } derefs{ws}, mem_trees{ws + 8 * N}, ops_trees{ws + 8 * N + 8 * M}, dotp_tables{ws + 32 * N + 8 * M};
   VPIN_CUDA(cudaMemsetAsync(derefs.p, 0, 8 * N * sizeof(fl_t), st));
