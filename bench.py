@@ -426,6 +426,19 @@ def run_b200(args):
     prof, madds, prof_ms = ({}, 0, 0.0) if args.no_profile else leg.profile_pass()
     e2e_s, h2d, d2h = leg.time_e2e()
     msm = msm_uniform_bench(leg.ctx, torch, leg.dev, leg.stream, imad_peak) if world == 1 else None
+    # witness expansion + R1CS emission of the point-mult instance on the device (vpin_build_point_mult_device), assignments left
+    # in HBM: the step of vPIN's timed region that precedes the prover (proof_point_mult.rs:24, point_mult.rs:7-664)
+    from vpin_b200 import api as _api
+    t_build = []
+    for _ in range(3):
+        leg.sync_all()
+        t0 = time.time()
+        built = _api.point_mult_device(leg.ctx, *wl["mult"])
+        leg.ctx.sync()
+        t_build.append(time.time() - t0)
+        del built
+    witness_build = {"point_mult_build_s": min(t_build), "what": "witness expansion (256 inversions per multiplication) + COO emission + "
+                     "Instance::new on the device from the JSON-level inputs (weights, point coordinates); not part of `value`"}
     instances = [{"kind": s.kind, "num_cons": s.dims[0], "num_vars": s.dims[1], "nnz_param": s.dims[3], "hyrax_grid": [s.gens.L, s.gens.R]}
                  for s in leg.states]
     leg.close()
@@ -494,6 +507,7 @@ def run_b200(args):
         "rooflines": rooflines[:8],
         "msm": msm,
         "one_proof_sharded": sharded,
+        "witness_build": witness_build,
         "phases_ms_point_mult": res["phases"],
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -153,6 +153,16 @@ uint32_t vpin_last_phase_times(const vpin_ctx *ctx, const char **names_out, doub
 vpin_status vpin_build_point_mult(vpin_ctx *ctx, uint64_t m, const uint64_t *weights_lo_hi, const uint8_t *px32,
                                   const uint8_t *py32, vpin_instance **inst, uint64_t dims_out[4],
                                   uint8_t *vars_para32, uint8_t *vars_input32, uint8_t *vars32, uint8_t *inputs32);
+/* The same builder with the three assignments left in HBM: d_vars_para / d_vars_input / d_vars are device arrays of
+ * `padded` 32-byte elements each (padded >= num_vars; normally the power of two the prover pads to, see
+ * vpin_instance_dims), written in Montgomery form and zero beyond num_vars — exactly what vpin_dev_poly_commit* and
+ * vpin_witness_from_device take. Witness expansion (VP/point_mult.rs:328-602, 256 field inversions per multiplication)
+ * and COO emission (:85-322) both run on the device; the reference does them on one core inside its timed region
+ * (VP/proof_point_mult.rs:24-101). */
+vpin_status vpin_build_point_mult_device(vpin_ctx *ctx, uint64_t m, const uint64_t *weights_lo_hi, const uint8_t *px32,
+                                         const uint8_t *py32, vpin_instance **inst, uint64_t dims_out[4],
+                                         void *d_vars_para, void *d_vars_input, void *d_vars, uint64_t padded,
+                                         uint8_t *inputs32);
 vpin_status vpin_build_point_add(vpin_ctx *ctx, uint64_t n, const uint8_t *px32, const uint8_t *py32,
                                  const uint8_t *rx32, const uint8_t *ry32, const int64_t *rz_flags,
                                  vpin_instance **inst, uint64_t dims_out[4], uint8_t *vars_para32,

@@ -58,6 +58,39 @@ def test_point_mult_flow_m7(ctx):
     _check(ctx, built, dims, inst, vp, vi, v, inputs)
 
 
+@pytest.mark.parametrize("m", [1, 7, 33])
+def test_point_mult_device_builder(ctx, m):
+    """vpin_build_point_mult_device (witness expansion and COO emission on the device, assignments left in HBM in Montgomery
+    form) against the oracle's restatement of point_mult.rs: every assignment byte, every COO triple in the reference's
+    order, zero padding, and satisfiability."""
+    import numpy as np
+    import torch
+    from vpin_b200 import api
+
+    weights, px, py = W.synth_point_mult(m, seed=W.SEED + 17 * m)
+    if m > 1:  # edge weights: zero, one, all 128 bits set
+        weights = [0, 1, (1 << 128) - 1] + list(weights[3:])
+    built = O.build_point_mult(weights, px, py)
+    dims, inst, d_para, d_input, d_vars, inputs, padded = api.point_mult_device(ctx, weights, px, py)
+    assert dims == built.dims
+    A, B, Cm, ovp, ovi, ov, oin = built.arrays()
+    assert inputs == oin
+    nv = dims[1]
+    for d, want in ((d_para, ovp), (d_input, ovi), (d_vars, ov)):
+        canon = torch.empty_like(d)
+        api.dev_from_mont(ctx, d, padded, canon)
+        ctx.sync()
+        got = canon.cpu().numpy().tobytes()
+        assert got[: 32 * nv] == want
+        assert got[32 * nv:] == bytes(32 * (padded - nv))
+    for got, want in zip(inst.export_coo(nv), (A, B, Cm)):
+        assert np.array_equal(got, want)
+    assert inst.is_sat(ov, oin)
+    # the host-buffer builder is the same device code plus a download
+    dims2, inst2, vp, vi, v, inputs2 = api.point_mult(ctx, weights, px, py)
+    assert (dims2, vp, vi, v, inputs2) == (dims, ovp, ovi, ov, oin)
+
+
 @pytest.mark.parametrize("num_cons,num_vars,num_inputs", [(1, 2, 1), (16, 16, 3), (64, 32, 5), (1024, 1024, 10), (37, 50, 2)])
 def test_synthetic_r1cs_flow(ctx, num_cons, num_vars, num_inputs):
     """shapes of the reference's own round-trip tests (Spartan/src/lib.rs:615-774, r1csproof.rs:586-619) incl. padding"""

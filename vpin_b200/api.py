@@ -68,6 +68,7 @@ class Context:
 
     def __init__(self, device=0):
         self._h = C.c_void_p()
+        self.device = device
         st = lib().vpin_ctx_create(C.c_int32(device), C.byref(self._h))
         if st != 0:
             raise VpinError(st, "vpin_ctx_create failed (no usable CUDA device?)")
@@ -331,6 +332,27 @@ def point_mult(ctx, weights, px, py):
     return tuple(dims), inst, bufs[0].raw, bufs[1].raw, bufs[2].raw, inputs.raw
 
 
+def point_mult_device(ctx, weights, px, py):
+    """point_mult with the three assignments left in HBM (vpin_build_point_mult_device): returns
+    (dims, inst, d_vars_para, d_vars_input, d_vars, inputs, padded) — torch uint8 device tensors of padded x 32 bytes in
+    Montgomery form, ready for dev_poly_commit* / DeviceWitness."""
+    import torch
+    m = len(weights)
+    dims = (C.c_uint64 * 4)()
+    lib().vpin_point_mult_dims(C.c_uint64(m), dims)
+    padded = 1 << max(1, (int(dims[1]) - 1).bit_length())
+    dev = torch.device("cuda", ctx.device)
+    bufs = [torch.empty(32 * padded, dtype=torch.uint8, device=dev) for _ in range(3)]
+    torch.cuda.synchronize(dev)
+    w = (C.c_uint64 * (2 * m))(*[x for ww in weights for x in (ww & (2**64 - 1), ww >> 64)])
+    inputs = C.create_string_buffer(32)
+    h = C.c_void_p()
+    ctx.check(lib().vpin_build_point_mult_device(ctx._h, C.c_uint64(m), w, px, py, C.byref(h), dims, _dp(bufs[0]), _dp(bufs[1]), _dp(bufs[2]),
+                                                 C.c_uint64(padded), inputs))
+    inst = Instance(ctx, 0, 0, 0, None, None, None, _handle=h)
+    return tuple(dims), inst, bufs[0], bufs[1], bufs[2], inputs.raw, padded
+
+
 def point_addition(ctx, px, py, rx, ry, rz):
     """point_addition(network) of vPIN_proof_generation/src/point_addition.rs:5-326."""
     n = len(rz)
@@ -466,6 +488,10 @@ def _dp(x):
 
 def dev_to_mont(ctx, d_in, n, d_out):
     ctx.check(lib().vpin_dev_to_mont(ctx._h, _dp(d_in), C.c_uint64(n), _dp(d_out)))
+
+
+def dev_from_mont(ctx, d_in, n, d_out):
+    ctx.check(lib().vpin_dev_from_mont(ctx._h, _dp(d_in), C.c_uint64(n), _dp(d_out)))
 
 
 def dev_poly_commit(ctx, gens, d_Z, n, tape, d_points_out, d_blinds_out):

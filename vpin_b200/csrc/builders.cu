@@ -138,146 +138,248 @@ std::unique_ptr<Instance> build_point_add(Ctx *ctx, uint64_t n, const uint8_t *p
                          E.M[2].size());
 }
 
+// ------------------------------------------------------------------------------------------------ point_mult on the device
+// point_mult.rs:7-704 is inside the reference's timed region (proof_point_mult.rs:24-101): 256 field inversions per
+// multiplication and 12.9 K COO triples per multiplication on one core — 8.4 s for LeNet layer 5 with the host expansion
+// that used to live here, eight times the proof itself. Both halves now run on the device:
+//  * the constraint system is a closed-form pattern: the (row, col, value) triples of ONE multiplication block are emitted
+//    on the host by the table below (entry order inside A, B, C is the reference's, because SPARK commits to the COO order)
+//    and k_pm_emit replicates them for every multiplication with the block's row / variable offsets;
+//  * k_pm_expand runs the 128 double-and-add steps of one multiplication per thread (the two inversions of a step share one
+//    exponentiation through Montgomery's trick) and writes the assignment in Montgomery form where the prover reads it.
+namespace {
+const uint64_t kColSentinel = (uint64_t)1 << 40;  // template column codes: sentinel = constant 1, sentinel + 1 = public input 0
+const long PM_N = 128;                            // bits per scalar (load_data.rs:62)
+// variable layout of one block (point_mult.rs:517-601)
+enum : long {
+  BIT = 0, A_SC = PM_N, AX = PM_N + 1, AY = 2 * PM_N + 2, BX = 3 * PM_N + 3, BY = 4 * PM_N + 4, BZ = 5 * PM_N + 5, CX = 6 * PM_N + 6,
+  CY = 7 * PM_N + 6, DX = 8 * PM_N + 6, DY = 9 * PM_N + 6, QX = 10 * PM_N + 6, QY = 10 * PM_N + 7, PX = 10 * PM_N + 8, PY = 10 * PM_N + 9,
+  C_PA = 10 * PM_N + 10, S1_PA = 11 * PM_N + 10, S2_PA = 12 * PM_N + 10, S3_PA = 13 * PM_N + 10, T1_PA = 14 * PM_N + 10,
+  T2_PA = 15 * PM_N + 10, T3_PA = 16 * PM_N + 10, T4_PA = 17 * PM_N + 10, C_PD = 18 * PM_N + 10, T1_PD = 19 * PM_N + 10,
+  S1_PD = 20 * PM_N + 10, S2_PD = 21 * PM_N + 10, T2_PD = 22 * PM_N + 10, Z1 = 23 * PM_N + 10, Z2 = 24 * PM_N + 10, Z3 = 25 * PM_N + 10,
+  Z4 = 26 * PM_N + 10
+};
+const size_t PM_ONC = 27 * PM_N + 8, PM_ONV = 27 * PM_N + 10;
+
+// the constraints of one multiplication block with row offset R and variable offset V (point_mult.rs:85-322)
+void emit_point_mult_block(Emitter &E, size_t R, size_t V) {
+  const long n = PM_N;
+  uint8_t pow2[32];
+  fl_t tb = fl_one(), two = fl_one() + fl_one();
+  for (long i = 0; i < n; i++) {  // sum_i 2^i bit_i * 1 = a
+    vpin_coo_entry e;
+    fl_to_bytes(tb, pow2);
+    tb = tb * two;
+    e.row = R; e.col = V + i;
+    memcpy(e.val, pow2, 32);
+    E.M[0].push_back(e);
+  }
+  E.con(R, V, {}, {{K1, ONE}}, {{A_SC, ONE}});
+  for (long i = 1; i <= n; i++) E.con(R + i, V, {{BIT + i - 1, ONE}}, {{BIT + i - 1, ONE}}, {{BIT + i - 1, ONE}});  // booleanity
+  E.con(R + n + 1, V, {{AX, ONE}, {PX, MINUS_ONE}}, {{K1, ONE}}, {});
+  E.con(R + n + 2, V, {{AY, ONE}, {PY, MINUS_ONE}}, {{K1, ONE}}, {});
+  E.con(R + n + 3, V, {{BX, ONE}}, {{K1, ONE}}, {});
+  E.con(R + n + 4, V, {{BY, ONE}}, {{K1, ONE}}, {});
+  E.con(R + n + 5, V, {{BZ, ONE}, {K1, MINUS_ONE}}, {{K1, ONE}}, {});
+  for (long i = 0; i < n; i++) {
+    size_t r = R + n + 26 * i;
+    // C = B + A (point addition with infinity flag Bz)  :129-198
+    E.con(r + 6, V, {{C_PA + i, ONE}}, {{BX + i, ONE}, {AX + i, MINUS_ONE}}, {{K1, ONE}});
+    E.con(r + 7, V, {{BY + i, ONE}, {AY + i, MINUS_ONE}}, {{C_PA + i, ONE}}, {{S1_PA + i, ONE}});
+    E.con(r + 8, V, {{S1_PA + i, ONE}}, {{S1_PA + i, ONE}}, {{S2_PA + i, ONE}});
+    E.con(r + 9, V, {{S2_PA + i, ONE}, {AX + i, MINUS_ONE}, {BX + i, MINUS_ONE}}, {{K1, ONE}, {BZ + i, MINUS_ONE}}, {{T1_PA + i, ONE}});
+    E.con(r + 10, V, {{AX + i, ONE}}, {{BZ + i, ONE}}, {{T2_PA + i, ONE}});
+    E.con(r + 11, V, {{T1_PA + i, ONE}, {T2_PA + i, ONE}}, {{K1, ONE}}, {{CX + i, ONE}});
+    E.con(r + 12, V, {{S1_PA + i, ONE}}, {{AX + i, ONE}, {CX + i, MINUS_ONE}}, {{S3_PA + i, ONE}});
+    E.con(r + 13, V, {{S3_PA + i, ONE}, {AY + i, MINUS_ONE}}, {{K1, ONE}, {BZ + i, MINUS_ONE}}, {{T3_PA + i, ONE}});
+    E.con(r + 14, V, {{AY + i, ONE}}, {{BZ + i, ONE}}, {{T4_PA + i, ONE}});
+    E.con(r + 15, V, {{T3_PA + i, ONE}, {T4_PA + i, ONE}}, {{K1, ONE}}, {{CY + i, ONE}});
+    // D = 2A (point doubling, curve coefficient a is public input 0)  :206-250
+    E.con(r + 16, V, {{C_PD + i, ONE}}, {{AY + i, TWO}}, {{K1, ONE}});
+    E.con(r + 17, V, {{AX + i, ONE}}, {{AX + i, ONE}}, {{T1_PD + i, ONE}});
+    E.con(r + 18, V, {{T1_PD + i, THREE}, {IN0, ONE}}, {{C_PD + i, ONE}}, {{S1_PD + i, ONE}});
+    E.con(r + 19, V, {{S1_PD + i, ONE}}, {{S1_PD + i, ONE}}, {{S2_PD + i, ONE}});
+    E.con(r + 20, V, {{S2_PD + i, ONE}, {AX + i, MINUS_TWO}}, {{K1, ONE}}, {{DX + i, ONE}});
+    E.con(r + 21, V, {{S1_PD + i, ONE}}, {{AX + i, ONE}, {DX + i, MINUS_ONE}}, {{T2_PD + i, ONE}});
+    E.con(r + 22, V, {{T2_PD + i, ONE}, {AY + i, MINUS_ONE}}, {{K1, ONE}}, {{DY + i, ONE}});
+    // B' = bit ? C : B ;  A' = D   :256-304
+    E.con(r + 23, V, {{CX + i, ONE}}, {{BIT + i, ONE}}, {{Z1 + i, ONE}});
+    E.con(r + 24, V, {{BX + i, ONE}}, {{K1, ONE}, {BIT + i, MINUS_ONE}}, {{Z2 + i, ONE}});
+    E.con(r + 25, V, {{Z1 + i, ONE}, {Z2 + i, ONE}}, {{K1, ONE}}, {{BX + 1 + i, ONE}});
+    E.con(r + 26, V, {{CY + i, ONE}}, {{BIT + i, ONE}}, {{Z3 + i, ONE}});
+    E.con(r + 27, V, {{BY + i, ONE}}, {{K1, ONE}, {BIT + i, MINUS_ONE}}, {{Z4 + i, ONE}});
+    E.con(r + 28, V, {{Z3 + i, ONE}, {Z4 + i, ONE}}, {{K1, ONE}}, {{BY + 1 + i, ONE}});
+    E.con(r + 29, V, {{BZ + i, ONE}}, {{K1, ONE}, {BIT + i, MINUS_ONE}}, {{BZ + 1 + i, ONE}});
+    E.con(r + 30, V, {{AX + 1 + i, ONE}, {DX + i, MINUS_ONE}}, {{K1, ONE}}, {});
+    E.con(r + 31, V, {{AY + 1 + i, ONE}, {DY + i, MINUS_ONE}}, {{K1, ONE}}, {});
+  }
+  E.con(R + PM_ONC - 2, V, {{QX, ONE}, {BX + n, MINUS_ONE}}, {{K1, ONE}}, {});
+  E.con(R + PM_ONC - 1, V, {{QY, ONE}, {BY + n, MINUS_ONE}}, {{K1, ONE}}, {});
+}
+
+// out[j * per + k] = tmpl[k] moved to block j: rows += onc * j; columns below the sentinel += onv * j, the two codes above it
+// become num_vars (constant 1) and num_vars + 1 (public input 0)
+__global__ void __launch_bounds__(256) k_pm_emit(const vpin_coo_entry *tmpl, size_t per, size_t m, uint64_t onc, uint64_t onv, uint64_t num_vars,
+                                                 vpin_coo_entry *out) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per * m) return;
+  size_t j = idx / per, k = idx % per;
+  const uint4 *q = reinterpret_cast<const uint4 *>(tmpl + k);
+  uint4 rc = __ldg(q), v0 = __ldg(q + 1), v1 = __ldg(q + 2);
+  uint64_t r = ((uint64_t)rc.x | ((uint64_t)rc.y << 32)) + onc * j, c = (uint64_t)rc.z | ((uint64_t)rc.w << 32);
+  c = c >= kColSentinel ? num_vars + (c - kColSentinel) : c + onv * j;
+  uint4 *o = reinterpret_cast<uint4 *>(out + idx);
+  o[0] = make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)c, (uint32_t)(c >> 32));
+  o[1] = v0;
+  o[2] = v1;
+}
+
+__device__ __forceinline__ void stw(fl_t *W, size_t i, const fl_t &x) {
+  uint4 *q = reinterpret_cast<uint4 *>(W + i);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+__device__ __forceinline__ fl_t ld_raw32(const uint8_t *p) {  // 32 little-endian bytes -> raw limbs (16-byte aligned input)
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  fl_t r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+// witness expansion of multiplication j (point_mult.rs:328-602; pa :667-685, pd :687-704), one thread per multiplication.
+// W: the assignment `vars` in Montgomery form (zero-filled by the caller). Inversion maps 0 to 0 like dalek's.
+__global__ void __launch_bounds__(32) k_pm_expand(size_t m, const uint64_t *weights, const uint8_t *px, const uint8_t *py, fl_t a_pd, fl_t *W) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const size_t V = PM_ONV * j;
+  const uint64_t wl = weights[2 * j], wh = weights[2 * j + 1];
+  const fl_t one = fl_one(), zero = fl_zero();
+  {
+    fl_t a = zero;
+    a.v[0] = (uint32_t)wl; a.v[1] = (uint32_t)(wl >> 32); a.v[2] = (uint32_t)wh; a.v[3] = (uint32_t)(wh >> 32);
+    stw(W, V + A_SC, fl_to_mont(a));
+  }
+  // Scalar::from_bytes_mod_order: x R^2 / R reduces any 256-bit x
+  fl_t ax = fl_mul(ld_raw32(px + 32 * j), fl_r2()), ay = fl_mul(ld_raw32(py + 32 * j), fl_r2());
+  fl_t bx = zero, by = zero, bz = one;
+  stw(W, V + AX, ax); stw(W, V + AY, ay); stw(W, V + BZ, one);
+  stw(W, V + PX, ax); stw(W, V + PY, ay);
+#pragma unroll 1
+  for (int i = 0; i < PM_N; i++) {
+    const bool bit_set = ((i < 64 ? wl >> i : wh >> (i - 64)) & 1) != 0;
+    const fl_t bit = bit_set ? one : zero, nbit = bit_set ? zero : one;
+    // c = 1 / (bx - ax), c_pd = 1 / (2 ay) from one exponentiation
+    fl_t u = fl_sub(bx, ax), v2 = fl_dbl(ay);
+    const bool uz = fl_is_zero(u), vz = fl_is_zero(v2);
+    fl_t uu = uz ? one : u, vv = vz ? one : v2;
+    fl_t winv = fl_invert(fl_mul(uu, vv));
+    fl_t c = uz ? zero : fl_mul(winv, vv), c_pd = vz ? zero : fl_mul(winv, uu);
+    fl_t nbz1 = fl_sub(one, bz);
+    fl_t s1 = fl_mul(fl_sub(by, ay), c);
+    fl_t s2 = fl_sqr(s1);
+    fl_t t1 = fl_mul(fl_sub(fl_sub(s2, ax), bx), nbz1);
+    fl_t t2 = fl_mul(ax, bz);
+    fl_t cx = fl_add(t1, t2);
+    fl_t s3 = fl_mul(s1, fl_sub(ax, cx));
+    fl_t t3 = fl_mul(fl_sub(s3, ay), nbz1);
+    fl_t t4 = fl_mul(ay, bz);
+    fl_t cy = fl_add(t3, t4);
+    stw(W, V + C_PA + i, c); stw(W, V + S1_PA + i, s1); stw(W, V + S2_PA + i, s2); stw(W, V + S3_PA + i, s3);
+    stw(W, V + T1_PA + i, t1); stw(W, V + T2_PA + i, t2); stw(W, V + T3_PA + i, t3); stw(W, V + T4_PA + i, t4);
+    stw(W, V + CX + i, cx); stw(W, V + CY + i, cy);
+    fl_t t1_pd = fl_sqr(ax);
+    fl_t s1_pd = fl_mul(fl_add(fl_add(fl_dbl(t1_pd), t1_pd), a_pd), c_pd);
+    fl_t s2_pd = fl_sqr(s1_pd);
+    fl_t dx = fl_sub(s2_pd, fl_dbl(ax));
+    fl_t t2_pd = fl_mul(s1_pd, fl_sub(ax, dx));
+    fl_t dy = fl_sub(t2_pd, ay);
+    stw(W, V + C_PD + i, c_pd); stw(W, V + T1_PD + i, t1_pd); stw(W, V + S1_PD + i, s1_pd); stw(W, V + S2_PD + i, s2_pd);
+    stw(W, V + T2_PD + i, t2_pd); stw(W, V + DX + i, dx); stw(W, V + DY + i, dy);
+    // z1 = cx * bit, z2 = bx * (1 - bit), ... : multiplications by 0 / 1
+    fl_t z1 = bit_set ? cx : zero, z2 = bit_set ? zero : bx, z3 = bit_set ? cy : zero, z4 = bit_set ? zero : by;
+    fl_t nbx = bit_set ? cx : bx, nby = bit_set ? cy : by, nbz = bit_set ? zero : bz;
+    stw(W, V + BIT + i, bit);
+    stw(W, V + Z1 + i, z1); stw(W, V + Z2 + i, z2); stw(W, V + Z3 + i, z3); stw(W, V + Z4 + i, z4);
+    stw(W, V + AX + 1 + i, dx); stw(W, V + AY + 1 + i, dy);
+    stw(W, V + BX + 1 + i, nbx); stw(W, V + BY + 1 + i, nby); stw(W, V + BZ + 1 + i, nbz);
+    ax = dx; ay = dy; bx = nbx; by = nby; bz = nbz;
+    (void)nbit;
+  }
+  stw(W, V + QX, bx); stw(W, V + QY, by);
+}
+// vars_para holds only the scalar a of every block; vars_input everything else (point_mult.rs:517-571)
+__global__ void __launch_bounds__(256) k_pm_split(const fl_t *W, size_t nv, size_t blocks_end, fl_t *para, fl_t *input) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nv) return;
+  const uint4 *q = reinterpret_cast<const uint4 *>(W + k);
+  uint4 a = q[0], b = q[1], z = make_uint4(0, 0, 0, 0);
+  bool is_a = k < blocks_end && (k % PM_ONV) == (size_t)A_SC;
+  uint4 *p = reinterpret_cast<uint4 *>(para + k), *in = reinterpret_cast<uint4 *>(input + k);
+  p[0] = is_a ? a : z; p[1] = is_a ? b : z;
+  in[0] = is_a ? z : a; in[1] = is_a ? z : b;
+}
+}  // namespace
+
+std::unique_ptr<Instance> build_point_mult_dev(Ctx *ctx, uint64_t m, const uint64_t *weights_lo_hi, const uint8_t *px32, const uint8_t *py32,
+                                               uint64_t dims[4], fl_t *d_para, fl_t *d_input, fl_t *d_vars, size_t padded, uint8_t *inputs32) {
+  point_mult_dims(m, dims);
+  cudaStream_t st = ctx->st;
+  const size_t nv = dims[1];
+  VPIN_REQUIRE(m > 0 && padded >= nv, VPIN_ERR_SIZE_MISMATCH, "point_mult: assignment buffers too small");
+  static const uint8_t a_pd_byte[32] = {157, 27, 50, 101, 63, 42, 38, 142, 68, 159, 245, 15, 16, 47, 75, 58,
+                                        203, 87, 15, 3, 219, 183, 77, 94, 64, 118, 147, 233, 124, 16, 184, 7};  // :341
+  fl_t a_pd = from_bytes_mod_order(a_pd_byte);
+  fl_to_bytes(a_pd, inputs32);
+  // ---- witness ----
+  DevVec<uint64_t> d_w(2 * m, st);
+  DevVec<uint8_t> d_px(32 * m, st), d_py(32 * m, st);
+  d_w.upload(weights_lo_hi, 2 * m);
+  d_px.upload(px32, 32 * m);
+  d_py.upload(py32, 32 * m);
+  VPIN_CUDA(cudaMemsetAsync(d_vars, 0, padded * sizeof(fl_t), st));
+  VPIN_CUDA(cudaMemsetAsync(d_para, 0, padded * sizeof(fl_t), st));
+  VPIN_CUDA(cudaMemsetAsync(d_input, 0, padded * sizeof(fl_t), st));
+  ++g_kernel_launches, k_pm_expand<<<(unsigned)((m + 31) / 32), 32, 0, st>>>(m, d_w.p, d_px.p, d_py.p, a_pd, d_vars);
+  ++g_kernel_launches, k_pm_split<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(d_vars, nv, PM_ONV * m, d_para, d_input);
+  // ---- constraint system ----
+  Emitter E;
+  E.num_vars = kColSentinel;
+  emit_point_mult_block(E, 0, 0);
+  std::unique_ptr<Instance> inst;
+  {
+    DevVec<vpin_coo_entry> tmpl[3], full[3];
+    for (int k = 0; k < 3; k++) {
+      size_t per = E.M[k].size();
+      tmpl[k].alloc(per, st);
+      tmpl[k].upload(E.M[k].data(), per);
+      full[k].alloc(per * m, st);
+      ++g_kernel_launches, k_pm_emit<<<(unsigned)((per * m + 255) / 256), 256, 0, st>>>(tmpl[k].p, per, m, PM_ONC, PM_ONV, nv, full[k].p);
+    }
+    ctx->sync();  // the template vectors of E go out of use here
+    inst = instance_create(ctx, dims[0], dims[1], dims[2], full[0].p, E.M[0].size() * m, full[1].p, E.M[1].size() * m, full[2].p,
+                           E.M[2].size() * m, true);
+  }
+  return inst;
+}
+
+// host-buffer variant (the JSON-driven flow of proof_point_mult.rs): the same device build, assignments downloaded as
+// canonical bytes
 std::unique_ptr<Instance> build_point_mult(Ctx *ctx, uint64_t m, const uint64_t *weights_lo_hi, const uint8_t *px32, const uint8_t *py32,
                                            uint64_t dims[4], uint8_t *vars_para32, uint8_t *vars_input32, uint8_t *vars32,
                                            uint8_t *inputs32) {
   point_mult_dims(m, dims);
-  const long n = 128;
-  const size_t onc = 27 * n + 8, onv = 27 * n + 10;
-  Emitter E;
-  E.num_vars = dims[1];
-  // variable layout of one block (point_mult.rs:517-601)
-  const long BIT = 0, A_SC = n, AX = n + 1, AY = 2 * n + 2, BX = 3 * n + 3, BY = 4 * n + 4, BZ = 5 * n + 5, CX = 6 * n + 6, CY = 7 * n + 6,
-             DX = 8 * n + 6, DY = 9 * n + 6, QX = 10 * n + 6, QY = 10 * n + 7, PX = 10 * n + 8, PY = 10 * n + 9, C_PA = 10 * n + 10,
-             S1_PA = 11 * n + 10, S2_PA = 12 * n + 10, S3_PA = 13 * n + 10, T1_PA = 14 * n + 10, T2_PA = 15 * n + 10, T3_PA = 16 * n + 10,
-             T4_PA = 17 * n + 10, C_PD = 18 * n + 10, T1_PD = 19 * n + 10, S1_PD = 20 * n + 10, S2_PD = 21 * n + 10, T2_PD = 22 * n + 10,
-             Z1 = 23 * n + 10, Z2 = 24 * n + 10, Z3 = 25 * n + 10, Z4 = 26 * n + 10;
-  uint8_t pow2[128][32];
-  {
-    fl_t tb = fl_one(), two = fl_one() + fl_one();
-    for (int i = 0; i < n; i++) { fl_to_bytes(tb, pow2[i]); tb = tb * two; }
-  }
-  for (size_t j = 0; j < m; j++) {  // :85-322
-    size_t R = onc * j, V = onv * j;
-    // sum_i 2^i bit_i * 1 = a
-    for (long i = 0; i < n; i++) {
-      vpin_coo_entry e;
-      e.row = R; e.col = V + i;
-      memcpy(e.val, pow2[i], 32);
-      E.M[0].push_back(e);
-    }
-    E.con(R, V, {}, {{K1, ONE}}, {{A_SC, ONE}});
-    for (long i = 1; i <= n; i++) E.con(R + i, V, {{BIT + i - 1, ONE}}, {{BIT + i - 1, ONE}}, {{BIT + i - 1, ONE}});  // booleanity
-    E.con(R + n + 1, V, {{AX, ONE}, {PX, MINUS_ONE}}, {{K1, ONE}}, {});
-    E.con(R + n + 2, V, {{AY, ONE}, {PY, MINUS_ONE}}, {{K1, ONE}}, {});
-    E.con(R + n + 3, V, {{BX, ONE}}, {{K1, ONE}}, {});
-    E.con(R + n + 4, V, {{BY, ONE}}, {{K1, ONE}}, {});
-    E.con(R + n + 5, V, {{BZ, ONE}, {K1, MINUS_ONE}}, {{K1, ONE}}, {});
-    for (long i = 0; i < n; i++) {
-      size_t r = R + n + 26 * i;
-      // C = B + A (point addition with infinity flag Bz)  :129-198
-      E.con(r + 6, V, {{C_PA + i, ONE}}, {{BX + i, ONE}, {AX + i, MINUS_ONE}}, {{K1, ONE}});
-      E.con(r + 7, V, {{BY + i, ONE}, {AY + i, MINUS_ONE}}, {{C_PA + i, ONE}}, {{S1_PA + i, ONE}});
-      E.con(r + 8, V, {{S1_PA + i, ONE}}, {{S1_PA + i, ONE}}, {{S2_PA + i, ONE}});
-      E.con(r + 9, V, {{S2_PA + i, ONE}, {AX + i, MINUS_ONE}, {BX + i, MINUS_ONE}}, {{K1, ONE}, {BZ + i, MINUS_ONE}}, {{T1_PA + i, ONE}});
-      E.con(r + 10, V, {{AX + i, ONE}}, {{BZ + i, ONE}}, {{T2_PA + i, ONE}});
-      E.con(r + 11, V, {{T1_PA + i, ONE}, {T2_PA + i, ONE}}, {{K1, ONE}}, {{CX + i, ONE}});
-      E.con(r + 12, V, {{S1_PA + i, ONE}}, {{AX + i, ONE}, {CX + i, MINUS_ONE}}, {{S3_PA + i, ONE}});
-      E.con(r + 13, V, {{S3_PA + i, ONE}, {AY + i, MINUS_ONE}}, {{K1, ONE}, {BZ + i, MINUS_ONE}}, {{T3_PA + i, ONE}});
-      E.con(r + 14, V, {{AY + i, ONE}}, {{BZ + i, ONE}}, {{T4_PA + i, ONE}});
-      E.con(r + 15, V, {{T3_PA + i, ONE}, {T4_PA + i, ONE}}, {{K1, ONE}}, {{CY + i, ONE}});
-      // D = 2A (point doubling, curve coefficient a is public input 0)  :206-250
-      E.con(r + 16, V, {{C_PD + i, ONE}}, {{AY + i, TWO}}, {{K1, ONE}});
-      E.con(r + 17, V, {{AX + i, ONE}}, {{AX + i, ONE}}, {{T1_PD + i, ONE}});
-      E.con(r + 18, V, {{T1_PD + i, THREE}, {IN0, ONE}}, {{C_PD + i, ONE}}, {{S1_PD + i, ONE}});
-      E.con(r + 19, V, {{S1_PD + i, ONE}}, {{S1_PD + i, ONE}}, {{S2_PD + i, ONE}});
-      E.con(r + 20, V, {{S2_PD + i, ONE}, {AX + i, MINUS_TWO}}, {{K1, ONE}}, {{DX + i, ONE}});
-      E.con(r + 21, V, {{S1_PD + i, ONE}}, {{AX + i, ONE}, {DX + i, MINUS_ONE}}, {{T2_PD + i, ONE}});
-      E.con(r + 22, V, {{T2_PD + i, ONE}, {AY + i, MINUS_ONE}}, {{K1, ONE}}, {{DY + i, ONE}});
-      // B' = bit ? C : B ;  A' = D   :256-304
-      E.con(r + 23, V, {{CX + i, ONE}}, {{BIT + i, ONE}}, {{Z1 + i, ONE}});
-      E.con(r + 24, V, {{BX + i, ONE}}, {{K1, ONE}, {BIT + i, MINUS_ONE}}, {{Z2 + i, ONE}});
-      E.con(r + 25, V, {{Z1 + i, ONE}, {Z2 + i, ONE}}, {{K1, ONE}}, {{BX + 1 + i, ONE}});
-      E.con(r + 26, V, {{CY + i, ONE}}, {{BIT + i, ONE}}, {{Z3 + i, ONE}});
-      E.con(r + 27, V, {{BY + i, ONE}}, {{K1, ONE}, {BIT + i, MINUS_ONE}}, {{Z4 + i, ONE}});
-      E.con(r + 28, V, {{Z3 + i, ONE}, {Z4 + i, ONE}}, {{K1, ONE}}, {{BY + 1 + i, ONE}});
-      E.con(r + 29, V, {{BZ + i, ONE}}, {{K1, ONE}, {BIT + i, MINUS_ONE}}, {{BZ + 1 + i, ONE}});
-      E.con(r + 30, V, {{AX + 1 + i, ONE}, {DX + i, MINUS_ONE}}, {{K1, ONE}}, {});
-      E.con(r + 31, V, {{AY + 1 + i, ONE}, {DY + i, MINUS_ONE}}, {{K1, ONE}}, {});
-    }
-    E.con(R + onc - 2, V, {{QX, ONE}, {BX + n, MINUS_ONE}}, {{K1, ONE}}, {});
-    E.con(R + onc - 1, V, {{QY, ONE}, {BY + n, MINUS_ONE}}, {{K1, ONE}}, {});
-  }
-
-  // ---- witness expansion (:328-602, pa :667-685, pd :687-704) ----
-  static const uint8_t a_pd_byte[32] = {157, 27, 50, 101, 63, 42, 38, 142, 68, 159, 245, 15, 16, 47, 75, 58,
-                                        203, 87, 15, 3, 219, 183, 77, 94, 64, 118, 147, 233, 124, 16, 184, 7};  // :341
-  fl_t a_pd = from_bytes_mod_order(a_pd_byte);
   size_t nv = dims[1];
-  std::vector<fl_t> W(nv, fl_zero());  // the full assignment `vars`
-  fl_t one = fl_one(), zero = fl_zero(), two = one + one, three = two + one;
-  std::vector<fl_t> ax(m), ay(m), bx(m, zero), by(m, zero), bz(m, one), inv(2 * m);
-  for (size_t j = 0; j < m; j++) {
-    size_t V = onv * j;
-    fl_t a = fl_zero();
-    a.v[0] = (uint32_t)weights_lo_hi[2 * j]; a.v[1] = (uint32_t)(weights_lo_hi[2 * j] >> 32);
-    a.v[2] = (uint32_t)weights_lo_hi[2 * j + 1]; a.v[3] = (uint32_t)(weights_lo_hi[2 * j + 1] >> 32);
-    W[V + A_SC] = fl_to_mont(a);
-    ax[j] = from_bytes_mod_order(px32 + 32 * j);
-    ay[j] = from_bytes_mod_order(py32 + 32 * j);
-    W[V + AX] = ax[j]; W[V + AY] = ay[j]; W[V + BX] = zero; W[V + BY] = zero; W[V + BZ] = one;
-    W[V + PX] = ax[j]; W[V + PY] = ay[j];
+  cudaStream_t st = ctx->st;
+  DevVec<fl_t> d_para(nv, st), d_input(nv, st), d_vars(nv, st);
+  auto inst = build_point_mult_dev(ctx, m, weights_lo_hi, px32, py32, dims, d_para.p, d_input.p, d_vars.p, nv, inputs32);
+  uint8_t *outs[3] = {vars_para32, vars_input32, vars32};
+  fl_t *srcs[3] = {d_para.p, d_input.p, d_vars.p};
+  for (int k = 0; k < 3; k++) {
+    launch_from_mont(srcs[k], nv, srcs[k], st);
+    VPIN_CUDA(cudaMemcpyAsync(outs[k], srcs[k], nv * sizeof(fl_t), cudaMemcpyDeviceToHost, st));
   }
-  for (long i = 0; i < n; i++) {
-    for (size_t j = 0; j < m; j++) { inv[2 * j] = bx[j] - ax[j]; inv[2 * j + 1] = two * ay[j]; }
-    batch_invert(inv);
-    for (size_t j = 0; j < m; j++) {
-      size_t V = onv * j;
-      uint64_t wl = weights_lo_hi[2 * j], wh = weights_lo_hi[2 * j + 1];
-      fl_t bit = ((i < 64 ? wl >> i : wh >> (i - 64)) & 1) ? one : zero;
-      fl_t c = inv[2 * j];
-      fl_t s1 = (by[j] - ay[j]) * c;
-      fl_t s2 = s1 * s1;
-      fl_t t1 = (s2 - ax[j] - bx[j]) * (one - bz[j]);
-      fl_t t2 = ax[j] * bz[j];
-      fl_t cx = t1 + t2;
-      fl_t s3 = s1 * (ax[j] - cx);
-      fl_t t3 = (s3 - ay[j]) * (one - bz[j]);
-      fl_t t4 = ay[j] * bz[j];
-      fl_t cy = t3 + t4;
-      fl_t c_pd = inv[2 * j + 1];
-      fl_t t1_pd = ax[j] * ax[j];
-      fl_t s1_pd = (three * t1_pd + a_pd) * c_pd;
-      fl_t s2_pd = s1_pd * s1_pd;
-      fl_t dx = s2_pd - two * ax[j];
-      fl_t t2_pd = s1_pd * (ax[j] - dx);
-      fl_t dy = t2_pd - ay[j];
-      fl_t z1 = cx * bit, z2 = bx[j] * (one - bit), z3 = cy * bit, z4 = by[j] * (one - bit);
-      fl_t nbx = z1 + z2, nby = z3 + z4, nbz = bz[j] * (one - bit);
-      W[V + BIT + i] = bit;
-      W[V + AX + 1 + i] = dx; W[V + AY + 1 + i] = dy;
-      W[V + BX + 1 + i] = nbx; W[V + BY + 1 + i] = nby; W[V + BZ + 1 + i] = nbz;
-      W[V + CX + i] = cx; W[V + CY + i] = cy; W[V + DX + i] = dx; W[V + DY + i] = dy;
-      W[V + C_PA + i] = c; W[V + S1_PA + i] = s1; W[V + S2_PA + i] = s2; W[V + S3_PA + i] = s3;
-      W[V + T1_PA + i] = t1; W[V + T2_PA + i] = t2; W[V + T3_PA + i] = t3; W[V + T4_PA + i] = t4;
-      W[V + C_PD + i] = c_pd; W[V + T1_PD + i] = t1_pd; W[V + S1_PD + i] = s1_pd; W[V + S2_PD + i] = s2_pd; W[V + T2_PD + i] = t2_pd;
-      W[V + Z1 + i] = z1; W[V + Z2 + i] = z2; W[V + Z3 + i] = z3; W[V + Z4 + i] = z4;
-      ax[j] = dx; ay[j] = dy; bx[j] = nbx; by[j] = nby; bz[j] = nbz;
-    }
-  }
-  for (size_t j = 0; j < m; j++) { W[onv * j + QX] = bx[j]; W[onv * j + QY] = by[j]; }
-  // vars_para holds only the scalar a; vars_input everything else (:517-571)
-  memset(vars_para32, 0, 32 * nv);
-  for (size_t k = 0; k < nv; k++) fl_to_bytes(W[k], vars32 + 32 * k);
-  memcpy(vars_input32, vars32, 32 * nv);
-  for (size_t j = 0; j < m; j++) {
-    size_t k = onv * j + A_SC;
-    memcpy(vars_para32 + 32 * k, vars32 + 32 * k, 32);
-    memset(vars_input32 + 32 * k, 0, 32);
-  }
-  fl_to_bytes(a_pd, inputs32);
-  return instance_create(ctx, dims[0], dims[1], dims[2], E.M[0].data(), E.M[0].size(), E.M[1].data(), E.M[1].size(), E.M[2].data(),
-                         E.M[2].size());
+  ctx->sync();
+  return inst;
 }
 
 }  // namespace vpin

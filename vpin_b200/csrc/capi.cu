@@ -481,6 +481,16 @@ vpin_status vpin_build_point_mult(vpin_ctx *ctx, uint64_t m, const uint64_t *wei
   *inst = reinterpret_cast<vpin_instance *>(build_point_mult(c_, m, weights_lo_hi, px32, py32, dims_out, vars_para32, vars_input32, vars32, inputs32).release());
   VPIN_CATCH
 }
+vpin_status vpin_build_point_mult_device(vpin_ctx *ctx, uint64_t m, const uint64_t *weights_lo_hi, const uint8_t *px32, const uint8_t *py32,
+                                         vpin_instance **inst, uint64_t dims_out[4], void *d_vars_para, void *d_vars_input, void *d_vars,
+                                         uint64_t padded, uint8_t *inputs32) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE(weights_lo_hi && px32 && py32 && inst && dims_out && d_vars_para && d_vars_input && d_vars && inputs32, VPIN_ERR_BAD_ARGUMENT,
+               "null argument");
+  *inst = reinterpret_cast<vpin_instance *>(build_point_mult_dev(c_, m, weights_lo_hi, px32, py32, dims_out, (fl_t *)d_vars_para,
+                                                                 (fl_t *)d_vars_input, (fl_t *)d_vars, padded, inputs32).release());
+  VPIN_CATCH
+}
 vpin_status vpin_build_point_add(vpin_ctx *ctx, uint64_t n, const uint8_t *px32, const uint8_t *py32, const uint8_t *rx32,
                                  const uint8_t *ry32, const int64_t *rz_flags, vpin_instance **inst, uint64_t dims_out[4],
                                  uint8_t *vars_para32, uint8_t *vars_input32, uint8_t *vars32) {

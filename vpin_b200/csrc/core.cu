@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(256) k_find_long_cols(const uint32_t *cptr, si
 }
 
 // returns 0, or the error kind of the first invalid entry
-uint32_t build_matrix(Ctx *ctx, MatrixDev &m, const vpin_coo_entry *entries, size_t n, size_t n_pad, uint64_t num_cons, uint64_t num_vars,
-                      uint64_t num_inputs, size_t num_rows, size_t num_vars_padded) {
+uint32_t build_matrix(Ctx *ctx, MatrixDev &m, const vpin_coo_entry *entries, bool entries_on_device, size_t n, size_t n_pad, uint64_t num_cons,
+                      uint64_t num_vars, uint64_t num_inputs, size_t num_rows, size_t num_vars_padded) {
   cudaStream_t st = ctx->st;
   size_t num_cols = 2 * num_vars_padded, nnz = n + n_pad;
   m.nnz = nnz;
@@ -396,8 +396,9 @@ uint32_t build_matrix(Ctx *ctx, MatrixDev &m, const vpin_coo_entry *entries, siz
     pad[i].row = n + i;
     pad[i].col = num_vars;
   }
-  DevVec<vpin_coo_entry> raw(nnz, st);
-  if (n) VPIN_CUDA(cudaMemcpyAsync(raw.p, entries, n * sizeof(vpin_coo_entry), cudaMemcpyHostToDevice, st));
+  DevVec<vpin_coo_entry> raw(entries_on_device ? 0 : nnz, st);
+  if (n && !entries_on_device) VPIN_CUDA(cudaMemcpyAsync(raw.p, entries, n * sizeof(vpin_coo_entry), cudaMemcpyHostToDevice, st));
+  const vpin_coo_entry *d_raw = entries_on_device ? entries : raw.p;
   m.coo_row.alloc(nnz, st); m.coo_col.alloc(nnz, st); m.coo_val.alloc(nnz, st);
   m.csr_ptr.alloc(num_rows + 1, st); m.csc_ptr.alloc(num_cols + 1, st);
   m.csr_col.alloc(nnz, st); m.csr_val.alloc(nnz, st); m.csc_row.alloc(nnz, st); m.csc_val.alloc(nnz, st);
@@ -405,7 +406,7 @@ uint32_t build_matrix(Ctx *ctx, MatrixDev &m, const vpin_coo_entry *entries, siz
   DevVec<unsigned long long> d_err(1, st);
   VPIN_CUDA(cudaMemsetAsync(d_err.p, 0xff, sizeof(unsigned long long), st));
   if (n)
-    ++g_kernel_launches, k_coo_unpack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw.p, n, num_cons, num_vars, ncols_in, shift, m.coo_row.p, m.coo_col.p,
+    ++g_kernel_launches, k_coo_unpack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_raw, n, num_cons, num_vars, ncols_in, shift, m.coo_row.p, m.coo_col.p,
                                                                                  m.coo_val.p, m.csr_ptr.p, m.csc_ptr.p, d_err.p);
   if (n_pad) {  // padding rows carry the unshifted column num_vars and are exempt from the index checks
     DevVec<vpin_coo_entry> dpad(n_pad, st);
@@ -446,7 +447,7 @@ uint32_t build_matrix(Ctx *ctx, MatrixDev &m, const vpin_coo_entry *entries, siz
 // the SNARK path and is not computed.
 std::unique_ptr<Instance> instance_create(Ctx *ctx, uint64_t num_cons, uint64_t num_vars, uint64_t num_inputs,
                                           const vpin_coo_entry *A, uint64_t nA, const vpin_coo_entry *B, uint64_t nB,
-                                          const vpin_coo_entry *C, uint64_t nC) {
+                                          const vpin_coo_entry *C, uint64_t nC, bool entries_on_device) {
   size_t num_vars_padded = next_pow2(std::max<size_t>(num_vars, num_inputs + 1));
   size_t num_cons_padded = num_cons;
   if (num_cons_padded == 0 || num_cons_padded == 1) num_cons_padded = 2;
@@ -461,7 +462,7 @@ std::unique_ptr<Instance> instance_create(Ctx *ctx, uint64_t num_cons, uint64_t 
   uint64_t cnt[3] = {nA, nB, nC};
   for (int k = 0; k < 3; k++) {
     size_t n_pad = (num_cons == 0 || num_cons == 1) && cnt[k] < num_cons_padded ? num_cons_padded - cnt[k] : 0;
-    uint32_t err = build_matrix(ctx, inst->M[k], src[k], cnt[k], n_pad, num_cons, num_vars, num_inputs, num_cons_padded, num_vars_padded);
+    uint32_t err = build_matrix(ctx, inst->M[k], src[k], entries_on_device, cnt[k], n_pad, num_cons, num_vars, num_inputs, num_cons_padded, num_vars_padded);
     VPIN_REQUIRE(err != 2, VPIN_ERR_INVALID_INDEX, "InvalidIndex");
     VPIN_REQUIRE(err != 1, VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
   }

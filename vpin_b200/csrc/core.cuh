@@ -204,7 +204,7 @@ typedef vpin_instance_impl Instance;
 
 std::unique_ptr<Instance> instance_create(Ctx *ctx, uint64_t num_cons, uint64_t num_vars, uint64_t num_inputs,
                                           const vpin_coo_entry *A, uint64_t nA, const vpin_coo_entry *B, uint64_t nB,
-                                          const vpin_coo_entry *C, uint64_t nC);
+                                          const vpin_coo_entry *C, uint64_t nC, bool entries_on_device = false);
 
 static inline size_t log2_ceil(size_t x) { size_t l = 0; while (((size_t)1 << l) < x) l++; return l; }
 static inline size_t next_pow2(size_t x) { return (size_t)1 << log2_ceil(x); }

@@ -64,6 +64,11 @@ void point_add_dims(uint64_t n, uint64_t dims_out[4]);
 std::unique_ptr<Instance> build_point_mult(Ctx *ctx, uint64_t m, const uint64_t *weights_lo_hi, const uint8_t *px32, const uint8_t *py32,
                                            uint64_t dims_out[4], uint8_t *vars_para32, uint8_t *vars_input32, uint8_t *vars32,
                                            uint8_t *inputs32);
+// device-resident variant: the three assignments are written in Montgomery form into caller-provided device arrays of
+// `padded` elements each (zero beyond num_vars)
+std::unique_ptr<Instance> build_point_mult_dev(Ctx *ctx, uint64_t m, const uint64_t *weights_lo_hi, const uint8_t *px32, const uint8_t *py32,
+                                               uint64_t dims_out[4], fl_t *d_para, fl_t *d_input, fl_t *d_vars, size_t padded,
+                                               uint8_t *inputs32);
 std::unique_ptr<Instance> build_point_add(Ctx *ctx, uint64_t n, const uint8_t *px32, const uint8_t *py32, const uint8_t *rx32,
                                           const uint8_t *ry32, const int64_t *rz_flags, uint64_t dims_out[4], uint8_t *vars_para32,
                                           uint8_t *vars_input32, uint8_t *vars32);
