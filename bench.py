@@ -273,8 +273,11 @@ class Leg:
         builders = ([("point_add", lambda c: api.point_addition(c, *wl["add"]))] if wl["add"] is not None else []) + \
                    [("point_mult", lambda c: api.point_mult(c, *wl["mult"]))]
         self.states = []
+        prio = os.environ.get("VPIN_BENCH_PRIORITY", "1") == "1"
         for kind, build in builders:
-            c = api.Context(self.local_rank)
+            # the point-mult proof is the critical path of the step: its stream gets the urgent priority, so the point-add
+            # instance's kernels fill the gaps instead of delaying its latency-bound rounds
+            c = api.Context(self.local_rank, high_priority=prio and kind == "point_mult")
             if distributed:
                 c.init_distributed(self.rank, self.world, dist)
             self.states.append(InstanceState(c, kind, build(c), torch))

@@ -58,6 +58,10 @@ typedef struct vpin_coo_entry {
 
 /* ---- context ---------------------------------------------------------------------------------------------- */
 vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out);
+/* high_priority != 0: the context's stream is created at the device's most urgent stream priority, so that when several
+ * contexts share a GPU (a network's independent instances are proved concurrently, one context each) the thread blocks
+ * of this one are scheduled first — give it to the instance on the critical path (the point-mult proof). */
+vpin_status vpin_ctx_create_ex(int32_t cuda_device, int32_t high_priority, vpin_ctx **out);
 void vpin_ctx_destroy(vpin_ctx *ctx);
 /* Multi-GPU, one process (and one context) per GPU. Rank 0 calls vpin_nccl_unique_id and ships the 128 bytes to the other
  * ranks by any means (bench.py: a torch.distributed broadcast); every rank then calls vpin_ctx_init_distributed. After

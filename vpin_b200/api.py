@@ -66,10 +66,10 @@ def _buf(b):
 class Context:
     """One per host thread (the reference API is single-threaded: &mut Transcript, &mut RandomTape)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, high_priority=False):
         self._h = C.c_void_p()
         self.device = device
-        st = lib().vpin_ctx_create(C.c_int32(device), C.byref(self._h))
+        st = lib().vpin_ctx_create_ex(C.c_int32(device), C.c_int32(1 if high_priority else 0), C.byref(self._h))
         if st != 0:
             raise VpinError(st, "vpin_ctx_create failed (no usable CUDA device?)")
 

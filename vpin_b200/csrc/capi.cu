@@ -52,7 +52,8 @@ bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
 
 extern "C" {
 
-vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out) {
+vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out) { return vpin_ctx_create_ex(cuda_device, 0, out); }
+vpin_status vpin_ctx_create_ex(int32_t cuda_device, int32_t high_priority, vpin_ctx **out) {
   if (!out) return VPIN_ERR_BAD_ARGUMENT;
   *out = nullptr;
   int ndev = 0;
@@ -61,7 +62,11 @@ vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out) {
   try {
     ctx->device = cuda_device;
     VPIN_CUDA(cudaSetDevice(cuda_device));
-    VPIN_CUDA(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    {
+      int lo = 0, hi = 0;  // (numerically lower = more urgent; default streams sit at `lo`)
+      VPIN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      VPIN_CUDA(cudaStreamCreateWithPriority(&ctx->st, cudaStreamNonBlocking, high_priority ? hi : lo));
+    }
     block_cache_register(ctx->st);
     block_cache_set_pressure_hook(ctx->st, [ctx]() {
       if (ctx->workspace_busy || !ctx->workspace.p) return false;
