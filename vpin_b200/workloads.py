@@ -25,8 +25,10 @@ SEED = 0x7650494E
 SHAPES = {
     "conv3": (18, 16), "conv5": (50, 48), "conv7": (98, 96),
     "A": (178, 2144), "B": (210, 2208), "C": (562, 2144), "D": (594, 2208), "E": (658, 2336),
-    "L1": (300, 0), "L3": (800, 0), "L5": (6000, 5760), "L6": (240, 0), "L7": (168, 0),
+    # LeNet, per layer (point multiplications, point additions): the slices of src/LeNet/Server.py:690-698 and :753-761
+    "L1": (300, 288), "L2": (0, 7056), "L3": (800, 768), "L4": (0, 2400), "L5": (6000, 5760), "L6": (240, 406), "L7": (168, 186),
 }
+LENET_LAYERS = ("L1", "L2", "L3", "L4", "L5", "L6", "L7")
 
 
 def ec_add(p, q):
