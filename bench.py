@@ -377,14 +377,18 @@ class Leg:
     def time_e2e(self):
         """the same step through the host-buffer C ABI: pinned host inputs up, proof bytes down, every step"""
         args = self.args
-        for _ in range(max(1, min(args.warmup, 2))):
+        for _ in range(max(1, args.warmup)):
             e2e_out = self.one_step_e2e()
         self.barrier()
+        per_step = []
         t0 = time.time()
         for _ in range(args.steps):
+            t1 = time.time()
             e2e_out = self.one_step_e2e()
+            per_step.append(time.time() - t1)
         self.barrier()
         e2e_s = self.max_over_ranks((time.time() - t0) / args.steps)
+        self.e2e_steps_ms = [round(1e3 * x, 2) for x in per_step]
         for (c1, p1), (c2, p2, _) in zip(self.last, e2e_out):
             assert c1 == c2 and p1 == p2, "resident and host-buffer legs disagree"
         h2d = sum(s.h2d_bytes() for s in self.states)
@@ -428,6 +432,7 @@ def run_b200(args):
     step_s = res["step_s"]
     prof, madds, prof_ms = ({}, 0, 0.0) if args.no_profile else leg.profile_pass()
     e2e_s, h2d, d2h = leg.time_e2e()
+    e2e_steps_ms = leg.e2e_steps_ms
     msm = msm_uniform_bench(leg.ctx, torch, leg.dev, leg.stream, imad_peak) if world == 1 else None
     # witness expansion + R1CS emission of the point-mult instance on the device (vpin_build_point_mult_device), assignments left
     # in HBM: the step of vPIN's timed region that precedes the prover (proof_point_mult.rs:24, point_mult.rs:7-664)
@@ -503,7 +508,7 @@ def run_b200(args):
         "wall_s_per_step": res["wall_step_s"],
         "gpu_launches": res["launches"],
         "clocks": res["clocks"],
-        "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_ms": e2e_steps_ms},
         "roofline": top,
         "roofline_pass": {"ms_per_step": prof_ms / args.steps if prof_ms else None,
                           "how": "same K steps repeated after the timed region with CUDA-event scopes on the launching stream, instances sequential"},

@@ -23,7 +23,7 @@ hdr = rows[0]
 ik, im, iu, iv, ii = (hdr.index(x) for x in ("Kernel Name", "Metric Name", "Metric Unit", "Metric Value", "ID"))
 launches = OrderedDict()
 for r in rows[1:]:
-    d = launches.setdefault(r[ii], {"kernel": re.sub(r"\(.*", "", r[ik]).replace("vpin::<unnamed>::", "").replace("vpin::", "")})
+    d = launches.setdefault(r[ii], {"kernel": re.sub(r"\(.*", "", r[ik]).replace("vpin::", "").replace("<unnamed>::", "").replace("void ", "")})
     v = float(r[iv].replace(",", ""))
     u = r[iu]
     scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)

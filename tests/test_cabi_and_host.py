@@ -39,6 +39,8 @@ def test_dims_entry_points_need_no_gpu():
     # every named shape: the nnz parameter must round to the same power of two as the true padded max nnz (41n+12 per mult)
     from vpin_b200 import workloads as W
     for tag, (m, n_add) in W.SHAPES.items():
+        if m == 0:  # LeNet's pooling layers have point additions only
+            continue
         lib.vpin_point_mult_dims(C.c_uint64(m), d)
         true_nnz = m * (41 * 128 + 12)
         assert (int(d[3]) - 1).bit_length() == (true_nnz - 1).bit_length(), tag

@@ -6,6 +6,9 @@
 #include <time.h>
 
 #include <array>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 namespace vpin {
@@ -188,12 +191,86 @@ std::unique_ptr<Decomm> snark_encode(Ctx *ctx, const Instance &inst, const Snark
 // ------------------------------------------------------------------------------------------------ prover
 namespace {
 
+// A few helper threads for the O(1) elliptic-curve work next to the transcript (the per-round commitments of the ZK
+// sumchecks, the L / R points of a bullet-reduction round): ~10 fixed-base multiplications of 5-10 us each per round that
+// are independent of one another. Helpers spin while a scope is active (hand-off ~0.3 us) and sleep otherwise.
+class HostPool {
+ public:
+  explicit HostPool(int n) : slots_(n) {
+    for (int i = 0; i < n; i++) th_.emplace_back([this, i] { loop(i); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_.store(true);
+    }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  int size() const { return (int)slots_.size(); }
+  void set_active(bool on) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      active_.store(on);
+    }
+    if (on) cv_.notify_all();
+  }
+  template <class F>
+  void run(int i, F &&f) {
+    slots_[i].fn = std::forward<F>(f);
+    slots_[i].state.store(1, std::memory_order_release);
+  }
+  void wait(int i) {
+    while (slots_[i].state.load(std::memory_order_acquire) != 2) __builtin_ia32_pause();
+    slots_[i].state.store(0, std::memory_order_relaxed);
+  }
+  struct Scope {  // helpers spin for the lifetime of the scope
+    HostPool &p;
+    explicit Scope(HostPool &p_) : p(p_) { p.set_active(true); }
+    ~Scope() { p.set_active(false); }
+  };
+
+ private:
+  struct alignas(64) Slot {
+    std::atomic<int> state{0};  // 0 idle, 1 task posted, 2 task done
+    std::function<void()> fn;
+  };
+  void loop(int i) {
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return active_.load() || stop_.load(); });
+      }
+      if (stop_.load()) return;
+      while (active_.load(std::memory_order_relaxed) && !stop_.load(std::memory_order_relaxed)) {
+        if (slots_[i].state.load(std::memory_order_acquire) == 1) {
+          slots_[i].fn();
+          slots_[i].state.store(2, std::memory_order_release);
+        } else {
+          __builtin_ia32_pause();
+        }
+      }
+      // a task posted just before the scope closed must still run
+      if (slots_[i].state.load(std::memory_order_acquire) == 1) {
+        slots_[i].fn();
+        slots_[i].state.store(2, std::memory_order_release);
+      }
+    }
+  }
+  std::vector<Slot> slots_;
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::atomic<bool> active_{false}, stop_{false};
+};
+
 struct Prover {
   Ctx *ctx;
   cudaStream_t st;
   MerlinTranscript &t;
   ProverTape &tape;
   const SnarkGens &g;
+  HostPool pool{3};
   size_t ring = 0;
   // accumulating wall-clock timers (reported next to the phases)
   double t_bullet_gpu = 0, t_bullet_host = 0, t_bullet_pre = 0, t_b_wait = 0, t_b_host = 0, t_b_launch = 0, t_b_small_wait = 0;
@@ -269,6 +346,25 @@ struct Prover {
     for (size_t i = 0; i < c.size(); i++) g.sat_g[i]->mul_acc(c[i], &acc);
     g.sat_g[c.size()]->mul_acc(blind, &acc);
     return acc;
+  }
+  // the same two commitments with their fixed-base multiplications spread over the helper threads (inside a HostPool::Scope);
+  // the group element, hence the encoding, does not depend on the order of the additions
+  hge_t commit1_par(const PcGens &pc, const fl_t &x, const fl_t &blind) {
+    hge_t part = hf::ge_identity(), acc = hf::ge_identity();
+    pool.run(0, [&] { pc.g1->mul_acc(x, &part); });
+    pc.h->mul_acc(blind, &acc);
+    pool.wait(0);
+    return hf::ge_add(acc, part);
+  }
+  hge_t commit_coeffs_par(const std::vector<fl_t> &c, const fl_t &blind) {
+    const size_t n = c.size();  // 3 (quadratic round) or 4 (cubic round) coefficients + the blind
+    hge_t part[2] = {hf::ge_identity(), hf::ge_identity()}, acc = hf::ge_identity();
+    pool.run(0, [&] { g.sat_g[0]->mul_acc(c[0], &part[0]); g.sat_g[1]->mul_acc(c[1], &part[0]); });
+    pool.run(1, [&] { g.sat_g[2]->mul_acc(c[2], &part[1]); if (n > 3) g.sat_g[3]->mul_acc(c[3], &part[1]); });
+    g.sat_g[n]->mul_acc(blind, &acc);
+    pool.wait(0);
+    pool.wait(1);
+    return hf::ge_add(hf::ge_add(acc, part[0]), part[1]);
   }
 
   // ---- SP/unipoly.rs:23-54 ----
@@ -363,15 +459,28 @@ struct Prover {
     size_t n = x_vec.size();
     const std::vector<fl_t> &d_vec = draw.d_vec;
     const fl_t &r_delta = draw.r_delta, &r_beta = draw.r_beta;
+    // Cy = y G1 + blind_y h and beta = <a, d> G1 + r_beta h depend on nothing the transcript produces in between: the four
+    // multiplications run side by side (called inside zk_sumcheck's HostPool::Scope), then the two encodings
+    fl_t dot = fl_zero();
+    for (size_t i = 0; i < n; i++) dot = dot + a_vec[i] * d_vec[i];
+    hge_t p_y = hf::ge_identity(), p_by = hf::ge_identity(), p_dot = hf::ge_identity(), p_rb = hf::ge_identity();
+    pool.run(0, [&] { g.sat_pc.g1->mul_acc(y, &p_y); });
+    pool.run(1, [&] { g.sat_pc.h->mul_acc(blind_y, &p_by); });
+    pool.run(2, [&] { g.sat_pc.g1->mul_acc(dot, &p_dot); });
+    g.sat_pc.h->mul_acc(r_beta, &p_rb);
+    pool.wait(2);
+    Comp beta;
+    hge_t beta_pt = hf::ge_add(p_dot, p_rb);
+    pool.run(2, [&] { beta = compress_host(beta_pt); });
+    pool.wait(0);
+    pool.wait(1);
+    Comp Cy = compress_host(hf::ge_add(p_y, p_by));
+    pool.wait(2);
     t.point("Cx", Cx.data());
-    Comp Cy = compress_host(commit1(g.sat_pc, y, blind_y));
     t.point("Cy", Cy.data());
     t.scalars("a", a_vec);
     const Comp &delta = draw.delta;
     t.point("delta", delta.data());
-    fl_t dot = fl_zero();
-    for (size_t i = 0; i < n; i++) dot = dot + a_vec[i] * d_vec[i];
-    Comp beta = compress_host(commit1(g.sat_pc, dot, r_beta));
     t.point("beta", beta.data());
     fl_t c = t.challenge_scalar("c");
     DotProductProofS p;
@@ -405,6 +514,7 @@ struct Prover {
       }
     });
     struct Joiner { std::thread &th; ~Joiner() { if (th.joinable()) th.join(); } } joiner{delta_worker};
+    HostPool::Scope helpers(pool);
     fl_t claim_per_round = claim;
     Comp comm_claim_per_round = compress_host(commit1(g.sat_pc, claim_per_round, blind_claim));
     ZkSumcheckS out;
@@ -417,14 +527,14 @@ struct Prover {
       std::vector<fl_t> evals = degree == 3 ? std::vector<fl_t>{ev[0], claim_per_round - ev[0], ev[1], ev[2]}
                                             : std::vector<fl_t>{ev[0], claim_per_round - ev[0], ev[1]};
       std::vector<fl_t> poly = unipoly_from_evals(evals);
-      Comp comm_poly = compress_host(commit_coeffs(poly, blinds_poly[j]));
+      Comp comm_poly = compress_host(commit_coeffs_par(poly, blinds_poly[j]));
       t.point("comm_poly", comm_poly.data());
       out.comm_polys.push_back(comm_poly);
       fl_t r_j = t.challenge_scalar("challenge_nextround");
       if (j + 1 < num_rounds) launch_round(len >> (j + 2), true, r_j, round_ctl((int)((j + 1) & 1), &seq));
       else launch_final(r_j, round_ctl((int)((j + 1) & 1), &seq));
       fl_t eval = unipoly_eval(poly, r_j);
-      Comp comm_eval = compress_host(commit1(g.sat_pc, eval, blinds_evals[j]));
+      Comp comm_eval = compress_host(commit1_par(g.sat_pc, eval, blinds_evals[j]));
       t.point("comm_claim_per_round", comm_claim_per_round.data());
       t.point("comm_eval", comm_eval.data());
       std::vector<fl_t> w = t.challenge_vector("combine_two_claims_to_one", 2);
@@ -553,6 +663,7 @@ struct Prover {
       return h;
     };
     size_t len = n;
+    HostPool::Scope helpers(pool);
     for (size_t round = 0; len != 1; round++) {
       double tr0 = now_ms();
       uint32_t seq;
@@ -560,14 +671,22 @@ struct Prover {
       const fl_t *vals = round_wait(slot, seq);
       fl_t c[2] = {vals[0], vals[1]};
       double tr1 = now_ms();
-      hge_t LR[2] = {horner(vals, 0), horner(vals, 1)};
       t_bullet_gpu += tr1 - tr0;
       const fl_t &blind_L = bv1[round], &blind_R = bv2[round];
+      // L and R are independent (Horner pass, two fixed-base multiplications, encoding each): R on a helper thread
+      hge_t LR[2];
+      Comp Lc, Rc;
+      pool.run(0, [&] {
+        LR[1] = horner(vals, 1);
+        pc.g1->mul_acc(c[1] * r, &LR[1]);
+        pc.h->mul_acc(blind_R, &LR[1]);
+        Rc = compress_host(LR[1]);
+      });
+      LR[0] = horner(vals, 0);
       pc.g1->mul_acc(c[0] * r, &LR[0]);
       pc.h->mul_acc(blind_L, &LR[0]);
-      pc.g1->mul_acc(c[1] * r, &LR[1]);
-      pc.h->mul_acc(blind_R, &LR[1]);
-      Comp Lc = compress_host(LR[0]), Rc = compress_host(LR[1]);
+      Lc = compress_host(LR[0]);
+      pool.wait(0);
       t.point("L", Lc.data());
       t.point("R", Rc.data());
       u = t.challenge_scalar("u");
