@@ -419,6 +419,10 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_src = load_peaks()
+    # host threads per rank: 2 instance threads (they spin on the round slots), 2 delta workers, up to 6 spinning helpers for
+    # the sigma-protocol commitments; without ~12 cores per rank the helpers would only steal from the spinning main threads
+    if (os.cpu_count() or 1) // world < 12:
+        os.environ.setdefault("VPIN_HOST_HELPERS", "0")
 
     # ---- headline arrangement. N = 1: the named network on one B200. N > 1: the unit the path partitions into with no
     # data-path collective is the PROOF — every rank proves its own network of the named shape (different witnesses per
@@ -503,6 +507,7 @@ def run_b200(args):
                    "parallelism": "1 GPU" if world == 1 else
                                   f"{world} GPUs prove {world} different {tag} networks side by side (one per rank, no data-path "
                                   "collective); value = seconds until the slowest rank's proof is done"},
+        "host": {"cores": os.cpu_count(), "helpers_per_prover": int(os.environ.get("VPIN_HOST_HELPERS", "3"))},
         "networks_per_step": world,
         "networks_per_s": world / step_s,
         "wall_s_per_step": res["wall_step_s"],

@@ -217,12 +217,26 @@ class HostPool {
   }
   template <class F>
   void run(int i, F &&f) {
-    slots_[i].fn = std::forward<F>(f);
-    slots_[i].state.store(1, std::memory_order_release);
+    if (slots_.empty()) { f(); return; }  // no helpers (VPIN_HOST_HELPERS=0, or few cores per rank): do it here
+    Slot &s = slots_[i % slots_.size()];
+    if (s.state.load(std::memory_order_acquire) != 0) { f(); return; }  // slot busy (fewer helpers than tasks)
+    s.fn = std::forward<F>(f);
+    s.state.store(1, std::memory_order_release);
   }
   void wait(int i) {
-    while (slots_[i].state.load(std::memory_order_acquire) != 2) __builtin_ia32_pause();
-    slots_[i].state.store(0, std::memory_order_relaxed);
+    if (slots_.empty()) return;
+    Slot &s = slots_[i % slots_.size()];
+    if (s.state.load(std::memory_order_acquire) == 0) return;  // ran inline
+    while (s.state.load(std::memory_order_acquire) != 2) __builtin_ia32_pause();
+    s.state.store(0, std::memory_order_relaxed);
+  }
+  // helper threads per prover: VPIN_HOST_HELPERS (default 3), never more than the cores this process can spare
+  static int default_size() {
+    int n = 3;
+    if (const char *e = getenv("VPIN_HOST_HELPERS")) n = atoi(e);
+    unsigned hc = std::thread::hardware_concurrency();
+    if (hc && hc < 8) n = 0;
+    return n < 0 ? 0 : (n > 3 ? 3 : n);
   }
   struct Scope {  // helpers spin for the lifetime of the scope
     HostPool &p;
@@ -270,7 +284,7 @@ struct Prover {
   MerlinTranscript &t;
   ProverTape &tape;
   const SnarkGens &g;
-  HostPool pool{3};
+  HostPool pool{HostPool::default_size()};
   size_t ring = 0;
   // accumulating wall-clock timers (reported next to the phases)
   double t_bullet_gpu = 0, t_bullet_host = 0, t_bullet_pre = 0, t_b_wait = 0, t_b_host = 0, t_b_launch = 0, t_b_small_wait = 0;
