@@ -421,8 +421,9 @@ def run_b200(args):
     hbm_peak, peak_src = load_peaks()
     # host threads per rank: 2 instance threads (they spin on the round slots), 2 delta workers, up to 6 spinning helpers for
     # the sigma-protocol commitments; without ~12 cores per rank the helpers would only steal from the spinning main threads
-    if (os.cpu_count() or 1) // world < 12:
-        os.environ.setdefault("VPIN_HOST_HELPERS", "0")
+    cores_per_rank = (os.cpu_count() or 1) // world
+    if cores_per_rank < 12:
+        os.environ.setdefault("VPIN_HOST_HELPERS", "1" if cores_per_rank >= 8 else "0")
 
     # ---- headline arrangement. N = 1: the named network on one B200. N > 1: the unit the path partitions into with no
     # data-path collective is the PROOF — every rank proves its own network of the named shape (different witnesses per

@@ -113,6 +113,42 @@ def test_unsatisfied_witness_is_reported(ctx):
     assert inst.is_sat(v, inputs) and not inst.is_sat(bytes(bad), inputs)
 
 
+def test_two_contexts_prove_concurrently():
+    """A network's independent instances are proved from two host threads with one context each (bench.py does this for the
+    point-add / point-mult pair, the point-mult context on the urgent stream priority): both proofs must be the oracle's."""
+    from concurrent.futures import ThreadPoolExecutor
+    from vpin_b200 import api
+
+    sq, sp = W.tape_seeds()
+    jobs = []
+    px, py, rx, ry, rz = W.synth_point_add(24, infinity_every=7)
+    jobs.append(("add", False, O.build_point_add(px, py, rx, ry, rz), lambda c: api.point_addition(c, px, py, rx, ry, rz)))
+    weights, mx, my = W.synth_point_mult(2)
+    jobs.append(("mult", True, O.build_point_mult(weights, mx, my), lambda c: api.point_mult(c, weights, mx, my)))
+
+    def run(job):
+        _, urgent, _, build = job
+        c = api.Context(0, high_priority=urgent)
+        dims, inst, vp, vi, v, inputs = build(c)
+        res = []
+        for _ in range(2):
+            o = api.prove_flow(c, dims, inst, vp, vi, v, inputs, sq, sp)
+            res.append((o["comm"], o["comm_vars"], o["proof"]))
+            del o  # the generator / decommitment handles go before the context that owns their stream
+        del inst
+        c.close()
+        return res
+
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        results = list(pool.map(run, jobs))
+    for (name, _, built, _), outs in zip(jobs, results):
+        ref = O.Flow(built, sq, sp, verify=True)
+        assert ref.verified
+        for comm, comm_vars, proof in outs:
+            assert (comm, comm_vars) == (ref.comm, ref.comm_vars), name
+            assert proof == ref.proof, name
+
+
 @pytest.mark.parametrize("tag", ["conv3", "conv5", "A"])
 def test_named_vpin_shapes_verify(ctx, tag):
     """BASELINE.json's named shapes at full size (point-mult instance): too large for the CPU prover inside a test, so the
