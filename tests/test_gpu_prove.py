@@ -123,7 +123,7 @@ def test_two_contexts_prove_concurrently():
     jobs = []
     px, py, rx, ry, rz = W.synth_point_add(24, infinity_every=7)
     jobs.append(("add", False, O.build_point_add(px, py, rx, ry, rz), lambda c: api.point_addition(c, px, py, rx, ry, rz)))
-    weights, mx, my = W.synth_point_mult(2)
+    weights, mx, my = W.synth_point_mult(7)  # the smallest count whose hard-coded nnz parameter fits
     jobs.append(("mult", True, O.build_point_mult(weights, mx, my), lambda c: api.point_mult(c, weights, mx, my)))
 
     def run(job):

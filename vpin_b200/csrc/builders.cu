@@ -145,8 +145,9 @@ std::unique_ptr<Instance> build_point_add(Ctx *ctx, uint64_t n, const uint8_t *p
 //  * the constraint system is a closed-form pattern: the (row, col, value) triples of ONE multiplication block are emitted
 //    on the host by the table below (entry order inside A, B, C is the reference's, because SPARK commits to the COO order)
 //    and k_pm_emit replicates them for every multiplication with the block's row / variable offsets;
-//  * k_pm_expand runs the 128 double-and-add steps of one multiplication per thread (the two inversions of a step share one
-//    exponentiation through Montgomery's trick) and writes the assignment in Montgomery form where the prover reads it.
+//  * the witness is expanded by the k_pm_chain / k_pm_invert / k_pm_affine / k_pm_fill pipeline below (Jacobian chains, two
+//    batched inversions per multiplication instead of 256 sequential ones) and written in Montgomery form where the prover
+//    reads it.
 namespace {
 const uint64_t kColSentinel = (uint64_t)1 << 40;  // template column codes: sentinel = constant 1, sentinel + 1 = public input 0
 const long PM_N = 128;                            // bits per scalar (load_data.rs:62)
@@ -246,66 +247,172 @@ __device__ __forceinline__ fl_t ld_raw32(const uint8_t *p) {  // 32 little-endia
   r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
   return r;
 }
-// witness expansion of multiplication j (point_mult.rs:328-602; pa :667-685, pd :687-704), one thread per multiplication.
-// W: the assignment `vars` in Montgomery form (zero-filled by the caller). Inversion maps 0 to 0 like dalek's.
-__global__ void __launch_bounds__(32) k_pm_expand(size_t m, const uint64_t *weights, const uint8_t *px, const uint8_t *py, fl_t a_pd, fl_t *W) {
+// ---- witness expansion (point_mult.rs:328-602; pa :667-685, pd :687-704) --------------------------------------------------
+// The reference walks the 128 double-and-add steps in affine coordinates: two field inversions per step, 256 in a row per
+// multiplication. Every witness value of step i is a function of the affine points A_i = 2^i P, B_i = (k mod 2^i) P (with its
+// infinity flag), the bit, and the two inverses c_i = 1 / (bx_i - ax_i), c_pd_i = 1 / (2 ay_i). So:
+//   k_pm_chain   one thread per multiplication: both chains in Jacobian coordinates, no inversion (10 multiplications per
+//                doubling, 16 per addition actually taken);
+//   k_pm_invert  one thread per multiplication: Montgomery's trick over its 256 Z coordinates (one exponentiation);
+//   k_pm_affine  one thread per (multiplication, step): affine A_i, B_i and the 256 denominators;
+//   k_pm_invert  again, on the denominators;
+//   k_pm_fill    one thread per (multiplication, step): the 27 values of the step, written in Montgomery form where the
+//                prover reads them.
+// ~5 K sequential field multiplications per multiplication instead of ~45 K; the values are the same field elements, hence the
+// same bytes. Degenerate additions (B_i = +-A_i) cannot occur for a point of large prime order (B_i = (k mod 2^i) P with
+// 0 < k mod 2^i < 2^i), and the reference itself would divide by zero there. Inversion maps 0 to 0 like dalek's.
+struct jac_t { fl_t X, Y, Z; };
+__device__ __forceinline__ fl_t ldw(const fl_t *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = q[0], b = q[1];
+  fl_t r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+// dbl-2007-bl for y^2 = x^3 + a x + b
+__device__ __forceinline__ jac_t jac_dbl(const jac_t &p, const fl_t &a) {
+  fl_t XX = fl_sqr(p.X), YY = fl_sqr(p.Y), YYYY = fl_sqr(YY), ZZ = fl_sqr(p.Z);
+  fl_t S = fl_dbl(fl_sub(fl_sub(fl_sqr(fl_add(p.X, YY)), XX), YYYY));
+  fl_t M = fl_add(fl_add(fl_dbl(XX), XX), fl_mul(a, fl_sqr(ZZ)));
+  jac_t r;
+  r.X = fl_sub(fl_sqr(M), fl_dbl(S));
+  fl_t y8 = fl_dbl(fl_dbl(fl_dbl(YYYY)));
+  r.Y = fl_sub(fl_mul(M, fl_sub(S, r.X)), y8);
+  r.Z = fl_sub(fl_sub(fl_sqr(fl_add(p.Y, p.Z)), YY), ZZ);
+  return r;
+}
+// add-2007-bl (distinct points, neither at infinity)
+__device__ __forceinline__ jac_t jac_add(const jac_t &p, const jac_t &q) {
+  fl_t Z1Z1 = fl_sqr(p.Z), Z2Z2 = fl_sqr(q.Z);
+  fl_t U1 = fl_mul(p.X, Z2Z2), U2 = fl_mul(q.X, Z1Z1);
+  fl_t S1 = fl_mul(fl_mul(p.Y, q.Z), Z2Z2), S2 = fl_mul(fl_mul(q.Y, p.Z), Z1Z1);
+  fl_t H = fl_sub(U2, U1);
+  fl_t I = fl_sqr(fl_dbl(H));
+  fl_t J = fl_mul(H, I);
+  fl_t rr = fl_dbl(fl_sub(S2, S1));
+  fl_t V = fl_mul(U1, I);
+  jac_t r;
+  r.X = fl_sub(fl_sub(fl_sqr(rr), J), fl_dbl(V));
+  r.Y = fl_sub(fl_mul(rr, fl_sub(V, r.X)), fl_dbl(fl_mul(S1, J)));
+  r.Z = fl_mul(fl_sub(fl_sub(fl_sqr(fl_add(p.Z, q.Z)), Z1Z1), Z2Z2), H);
+  return r;
+}
+// chains[(j * 128 + i) * 2 + 0] = A_i, [.. + 1] = B_i (Z = 0 for the point at infinity); zs[j * 256 + 2 i + {0, 1}] = their Z
+__global__ void __launch_bounds__(32) k_pm_chain(size_t m, const uint64_t *weights, const uint8_t *px, const uint8_t *py, fl_t a_pd, jac_t *chains,
+                                                 fl_t *zs) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
+  const uint64_t wl = weights[2 * j], wh = weights[2 * j + 1];
+  jac_t A, B;
+  A.X = fl_mul(ld_raw32(px + 32 * j), fl_r2());  // Scalar::from_bytes_mod_order: x R^2 / R reduces any 256-bit x
+  A.Y = fl_mul(ld_raw32(py + 32 * j), fl_r2());
+  A.Z = fl_one();
+  B.X = B.Y = B.Z = fl_zero();
+  bool b_inf = true;
+  jac_t *out = chains + j * PM_N * 2;
+  fl_t *z = zs + j * PM_N * 2;
+#pragma unroll 1
+  for (int i = 0; i < PM_N; i++) {
+    stw(&out[2 * i].X, 0, A.X); stw(&out[2 * i].Y, 0, A.Y); stw(&out[2 * i].Z, 0, A.Z);
+    stw(&out[2 * i + 1].X, 0, B.X); stw(&out[2 * i + 1].Y, 0, B.Y); stw(&out[2 * i + 1].Z, 0, B.Z);
+    stw(z, 2 * i, A.Z); stw(z, 2 * i + 1, B.Z);
+    if ((i < 64 ? wl >> i : wh >> (i - 64)) & 1) {
+      if (b_inf) { B = A; b_inf = false; }
+      else B = jac_add(B, A);
+    }
+    A = jac_dbl(A, a_pd);
+  }
+}
+// v[j * per .. (j + 1) * per) := element-wise inverses (zeros stay zero); tmp: same size, prefix products
+__global__ void __launch_bounds__(32) k_pm_invert(size_t m, int per, fl_t *v, fl_t *tmp) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  fl_t *x = v + j * per, *pre = tmp + j * per;
+  fl_t run = fl_one();
+#pragma unroll 1
+  for (int k = 0; k < per; k++) {
+    stw(pre, k, run);
+    fl_t e = ldw(x + k);
+    if (!fl_is_zero(e)) run = fl_mul(run, e);
+  }
+  fl_t inv = fl_invert(run);
+#pragma unroll 1
+  for (int k = per - 1; k >= 0; k--) {
+    fl_t e = ldw(x + k);
+    if (fl_is_zero(e)) continue;
+    stw(x, k, fl_mul(inv, ldw(pre + k)));
+    inv = fl_mul(inv, e);
+  }
+}
+// affine coordinates of A_i, B_i from the inverted Z's; aff[(j * 128 + i) * 4 + {0..3}] = ax, ay, bx, by;
+// den[j * 256 + 2 i + {0, 1}] = bx - ax, 2 ay
+__global__ void __launch_bounds__(128) k_pm_affine(size_t total, const jac_t *chains, const fl_t *zinv, fl_t *aff, fl_t *den) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  fl_t xy[4];
+#pragma unroll
+  for (int w = 0; w < 2; w++) {
+    const jac_t *p = chains + 2 * t + w;
+    fl_t zi = ldw(zinv + 2 * t + w);  // 0 for the point at infinity -> (0, 0)
+    fl_t zi2 = fl_sqr(zi);
+    xy[2 * w] = fl_mul(ldw(&p->X), zi2);
+    xy[2 * w + 1] = fl_mul(ldw(&p->Y), fl_mul(zi2, zi));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) stw(aff, 4 * t + k, xy[k]);
+  stw(den, 2 * t, fl_sub(xy[2], xy[0]));
+  stw(den, 2 * t + 1, fl_dbl(xy[1]));
+}
+// the 27 witness values of step i of multiplication j (+ the block's header / trailer values from steps 0 and 127)
+__global__ void __launch_bounds__(128) k_pm_fill(size_t total, const uint64_t *weights, const jac_t *chains, const fl_t *aff, const fl_t *dinv,
+                                                 fl_t a_pd, fl_t *W) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const size_t j = t / PM_N;
+  const int i = (int)(t % PM_N);
   const size_t V = PM_ONV * j;
   const uint64_t wl = weights[2 * j], wh = weights[2 * j + 1];
   const fl_t one = fl_one(), zero = fl_zero();
-  {
+  const bool bit_set = ((i < 64 ? wl >> i : wh >> (i - 64)) & 1) != 0;
+  fl_t ax = ldw(aff + 4 * t), ay = ldw(aff + 4 * t + 1), bx = ldw(aff + 4 * t + 2), by = ldw(aff + 4 * t + 3);
+  const bool b_inf = fl_is_zero(ldw(&chains[2 * t + 1].Z));
+  fl_t bz = b_inf ? one : zero, nbz1 = b_inf ? zero : one;
+  fl_t c = ldw(dinv + 2 * t), c_pd = ldw(dinv + 2 * t + 1);
+  if (i == 0) {
     fl_t a = zero;
     a.v[0] = (uint32_t)wl; a.v[1] = (uint32_t)(wl >> 32); a.v[2] = (uint32_t)wh; a.v[3] = (uint32_t)(wh >> 32);
     stw(W, V + A_SC, fl_to_mont(a));
+    stw(W, V + AX, ax); stw(W, V + AY, ay); stw(W, V + BZ, one);
+    stw(W, V + PX, ax); stw(W, V + PY, ay);
   }
-  // Scalar::from_bytes_mod_order: x R^2 / R reduces any 256-bit x
-  fl_t ax = fl_mul(ld_raw32(px + 32 * j), fl_r2()), ay = fl_mul(ld_raw32(py + 32 * j), fl_r2());
-  fl_t bx = zero, by = zero, bz = one;
-  stw(W, V + AX, ax); stw(W, V + AY, ay); stw(W, V + BZ, one);
-  stw(W, V + PX, ax); stw(W, V + PY, ay);
-#pragma unroll 1
-  for (int i = 0; i < PM_N; i++) {
-    const bool bit_set = ((i < 64 ? wl >> i : wh >> (i - 64)) & 1) != 0;
-    const fl_t bit = bit_set ? one : zero, nbit = bit_set ? zero : one;
-    // c = 1 / (bx - ax), c_pd = 1 / (2 ay) from one exponentiation
-    fl_t u = fl_sub(bx, ax), v2 = fl_dbl(ay);
-    const bool uz = fl_is_zero(u), vz = fl_is_zero(v2);
-    fl_t uu = uz ? one : u, vv = vz ? one : v2;
-    fl_t winv = fl_invert(fl_mul(uu, vv));
-    fl_t c = uz ? zero : fl_mul(winv, vv), c_pd = vz ? zero : fl_mul(winv, uu);
-    fl_t nbz1 = fl_sub(one, bz);
-    fl_t s1 = fl_mul(fl_sub(by, ay), c);
-    fl_t s2 = fl_sqr(s1);
-    fl_t t1 = fl_mul(fl_sub(fl_sub(s2, ax), bx), nbz1);
-    fl_t t2 = fl_mul(ax, bz);
-    fl_t cx = fl_add(t1, t2);
-    fl_t s3 = fl_mul(s1, fl_sub(ax, cx));
-    fl_t t3 = fl_mul(fl_sub(s3, ay), nbz1);
-    fl_t t4 = fl_mul(ay, bz);
-    fl_t cy = fl_add(t3, t4);
-    stw(W, V + C_PA + i, c); stw(W, V + S1_PA + i, s1); stw(W, V + S2_PA + i, s2); stw(W, V + S3_PA + i, s3);
-    stw(W, V + T1_PA + i, t1); stw(W, V + T2_PA + i, t2); stw(W, V + T3_PA + i, t3); stw(W, V + T4_PA + i, t4);
-    stw(W, V + CX + i, cx); stw(W, V + CY + i, cy);
-    fl_t t1_pd = fl_sqr(ax);
-    fl_t s1_pd = fl_mul(fl_add(fl_add(fl_dbl(t1_pd), t1_pd), a_pd), c_pd);
-    fl_t s2_pd = fl_sqr(s1_pd);
-    fl_t dx = fl_sub(s2_pd, fl_dbl(ax));
-    fl_t t2_pd = fl_mul(s1_pd, fl_sub(ax, dx));
-    fl_t dy = fl_sub(t2_pd, ay);
-    stw(W, V + C_PD + i, c_pd); stw(W, V + T1_PD + i, t1_pd); stw(W, V + S1_PD + i, s1_pd); stw(W, V + S2_PD + i, s2_pd);
-    stw(W, V + T2_PD + i, t2_pd); stw(W, V + DX + i, dx); stw(W, V + DY + i, dy);
-    // z1 = cx * bit, z2 = bx * (1 - bit), ... : multiplications by 0 / 1
-    fl_t z1 = bit_set ? cx : zero, z2 = bit_set ? zero : bx, z3 = bit_set ? cy : zero, z4 = bit_set ? zero : by;
-    fl_t nbx = bit_set ? cx : bx, nby = bit_set ? cy : by, nbz = bit_set ? zero : bz;
-    stw(W, V + BIT + i, bit);
-    stw(W, V + Z1 + i, z1); stw(W, V + Z2 + i, z2); stw(W, V + Z3 + i, z3); stw(W, V + Z4 + i, z4);
-    stw(W, V + AX + 1 + i, dx); stw(W, V + AY + 1 + i, dy);
-    stw(W, V + BX + 1 + i, nbx); stw(W, V + BY + 1 + i, nby); stw(W, V + BZ + 1 + i, nbz);
-    ax = dx; ay = dy; bx = nbx; by = nby; bz = nbz;
-    (void)nbit;
-  }
-  stw(W, V + QX, bx); stw(W, V + QY, by);
+  fl_t s1 = fl_mul(fl_sub(by, ay), c);
+  fl_t s2 = fl_sqr(s1);
+  fl_t t1 = fl_mul(fl_sub(fl_sub(s2, ax), bx), nbz1);
+  fl_t t2 = fl_mul(ax, bz);
+  fl_t cx = fl_add(t1, t2);
+  fl_t s3 = fl_mul(s1, fl_sub(ax, cx));
+  fl_t t3 = fl_mul(fl_sub(s3, ay), nbz1);
+  fl_t t4 = fl_mul(ay, bz);
+  fl_t cy = fl_add(t3, t4);
+  stw(W, V + C_PA + i, c); stw(W, V + S1_PA + i, s1); stw(W, V + S2_PA + i, s2); stw(W, V + S3_PA + i, s3);
+  stw(W, V + T1_PA + i, t1); stw(W, V + T2_PA + i, t2); stw(W, V + T3_PA + i, t3); stw(W, V + T4_PA + i, t4);
+  stw(W, V + CX + i, cx); stw(W, V + CY + i, cy);
+  fl_t t1_pd = fl_sqr(ax);
+  fl_t s1_pd = fl_mul(fl_add(fl_add(fl_dbl(t1_pd), t1_pd), a_pd), c_pd);
+  fl_t s2_pd = fl_sqr(s1_pd);
+  fl_t dx = fl_sub(s2_pd, fl_dbl(ax));
+  fl_t t2_pd = fl_mul(s1_pd, fl_sub(ax, dx));
+  fl_t dy = fl_sub(t2_pd, ay);
+  stw(W, V + C_PD + i, c_pd); stw(W, V + T1_PD + i, t1_pd); stw(W, V + S1_PD + i, s1_pd); stw(W, V + S2_PD + i, s2_pd);
+  stw(W, V + T2_PD + i, t2_pd); stw(W, V + DX + i, dx); stw(W, V + DY + i, dy);
+  // z1 = cx * bit, z2 = bx * (1 - bit), ... : multiplications by 0 / 1
+  fl_t z1 = bit_set ? cx : zero, z2 = bit_set ? zero : bx, z3 = bit_set ? cy : zero, z4 = bit_set ? zero : by;
+  fl_t nbx = bit_set ? cx : bx, nby = bit_set ? cy : by, nbz = bit_set ? zero : bz;
+  stw(W, V + BIT + i, bit_set ? one : zero);
+  stw(W, V + Z1 + i, z1); stw(W, V + Z2 + i, z2); stw(W, V + Z3 + i, z3); stw(W, V + Z4 + i, z4);
+  stw(W, V + AX + 1 + i, dx); stw(W, V + AY + 1 + i, dy);
+  stw(W, V + BX + 1 + i, nbx); stw(W, V + BY + 1 + i, nby); stw(W, V + BZ + 1 + i, nbz);
+  if (i == PM_N - 1) { stw(W, V + QX, nbx); stw(W, V + QY, nby); }
 }
 // vars_para holds only the scalar a of every block; vars_input everything else (point_mult.rs:517-571)
 __global__ void __launch_bounds__(256) k_pm_split(const fl_t *W, size_t nv, size_t blocks_end, fl_t *para, fl_t *input) {
@@ -339,7 +446,17 @@ std::unique_ptr<Instance> build_point_mult_dev(Ctx *ctx, uint64_t m, const uint6
   VPIN_CUDA(cudaMemsetAsync(d_vars, 0, padded * sizeof(fl_t), st));
   VPIN_CUDA(cudaMemsetAsync(d_para, 0, padded * sizeof(fl_t), st));
   VPIN_CUDA(cudaMemsetAsync(d_input, 0, padded * sizeof(fl_t), st));
-  ++g_kernel_launches, k_pm_expand<<<(unsigned)((m + 31) / 32), 32, 0, st>>>(m, d_w.p, d_px.p, d_py.p, a_pd, d_vars);
+  {
+    const size_t steps = m * PM_N;
+    DevVec<jac_t> chains(2 * steps, st);
+    DevVec<fl_t> zs(2 * steps, st), tmp(2 * steps, st), aff(4 * steps, st), den(2 * steps, st);
+    const unsigned jb = (unsigned)((m + 31) / 32), sb = (unsigned)((steps + 127) / 128);
+    ++g_kernel_launches, k_pm_chain<<<jb, 32, 0, st>>>(m, d_w.p, d_px.p, d_py.p, a_pd, chains.p, zs.p);
+    ++g_kernel_launches, k_pm_invert<<<jb, 32, 0, st>>>(m, 2 * (int)PM_N, zs.p, tmp.p);
+    ++g_kernel_launches, k_pm_affine<<<sb, 128, 0, st>>>(steps, chains.p, zs.p, aff.p, den.p);
+    ++g_kernel_launches, k_pm_invert<<<jb, 32, 0, st>>>(m, 2 * (int)PM_N, den.p, tmp.p);
+    ++g_kernel_launches, k_pm_fill<<<sb, 128, 0, st>>>(steps, d_w.p, chains.p, aff.p, den.p, a_pd, d_vars);
+  }
   ++g_kernel_launches, k_pm_split<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(d_vars, nv, PM_ONV * m, d_para, d_input);
   // ---- constraint system ----
   Emitter E;
