@@ -235,9 +235,22 @@ void dist_allgather_inplace(Ctx *ctx, void *buf, size_t bytes_per_rank) {
 }
 
 // ------------------------------------------------------------------------------------------------ generators
-std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n, size_t table_budget) {
+namespace {
+std::mutex g_gens_mu;  // held while a table is being built, so that concurrent contexts wait for it instead of building their own
+std::map<std::pair<int, std::string>, std::weak_ptr<LabelGens>> g_gens;
+}  // namespace
+std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n, size_t table_budget, bool *built) {
+  if (built) *built = false;
   auto it = ctx->label_gens.find(label);
   if (it != ctx->label_gens.end() && it->second->n >= n) return it->second;
+  std::lock_guard<std::mutex> global_lock(g_gens_mu);
+  {
+    auto gi = g_gens.find({ctx->device, label});
+    if (gi != g_gens.end())
+      if (auto shared = gi->second.lock())
+        if (shared->n >= n) return ctx->label_gens[label] = shared;
+  }
+  if (built) *built = true;
   auto g = std::make_shared<LabelGens>();
   g->label = label;
   g->n = n;
@@ -277,6 +290,7 @@ std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, si
   }
   ctx->sync();
   ctx->label_gens[label] = g;
+  g_gens[{ctx->device, label}] = g;
   return g;
 }
 

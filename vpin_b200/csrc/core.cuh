@@ -6,6 +6,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -94,8 +95,10 @@ struct LabelGens {
   MsmGeom geom = msm_geom(kMsmMinW);  // window width of this stream's table (chosen when the table is built)
   DevVec<niels_t> d_table;      // msm_table_entries(n, geom) entries
   std::map<size_t, std::unique_ptr<HostBase>> host_bases;  // built on first use, kept with the stream
+  std::mutex mu;                // a stream's generators are shared by every context of the process on the same device
   MsmTable table() const { return MsmTable{d_table.p, n, geom}; }
   const HostBase *host_base(size_t index) {
+    std::lock_guard<std::mutex> lock(mu);
     auto it = host_bases.find(index);
     if (it != host_bases.end()) return it->second.get();
     auto b = std::make_unique<HostBase>();
@@ -177,8 +180,10 @@ void dist_get_unique_id(uint8_t out[128]);
 void dist_init(Ctx *ctx, int rank, int world, const uint8_t id[128]);
 void dist_destroy(Ctx *ctx);
 
-// table_budget: bytes the fixed-base table may take (0 = 30 % of the free HBM)
-std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n, size_t table_budget = 0);
+// table_budget: bytes the fixed-base table may take (0 = 30 % of the free HBM). Generators and tables are public parameters:
+// one copy per (device, label) serves every context of the process (a second context proving the same shape neither
+// rebuilds nor duplicates 30 GB of tables); *built tells whether this call had to build one.
+std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n, size_t table_budget = 0, bool *built = nullptr);
 
 // Hyrax rows: out[i] = sum_j Z[i*ld + j] * G_j (+ blind_i * G_{blind_base}). d_points (rows ge_t) and d_comp (rows*32 B)
 // are optional outputs.

@@ -111,10 +111,9 @@ std::unique_ptr<SnarkGens> snark_gens_create(Ctx *ctx, uint64_t num_cons, uint64
     size_t margin = (size_t)6 << 30;
     size_t avail = free_b > working + margin ? free_b - working - margin : 0;
     table_budget_eval = std::max<size_t>(avail / 5 * 4, 1);
-    auto it = ctx->label_gens.find("gens_r1cs_eval");
-    bool eval_cached = it != ctx->label_gens.end() && it->second->n >= R_max + 2;
-    g->eval_label = get_label_gens(ctx, "gens_r1cs_eval", R_max + 2, table_budget_eval);
-    size_t eval_bytes = eval_cached ? 0 : msm_table_entries(g->eval_label->n, g->eval_label->geom) * sizeof(niels_t);
+    bool eval_built = false;
+    g->eval_label = get_label_gens(ctx, "gens_r1cs_eval", R_max + 2, table_budget_eval, &eval_built);
+    size_t eval_bytes = eval_built ? msm_table_entries(g->eval_label->n, g->eval_label->geom) * sizeof(niels_t) : 0;
     table_budget_sat = std::max<size_t>(avail > eval_bytes ? avail - eval_bytes : 0, 1);
   }
   g->sat_label = get_label_gens(ctx, "gens_r1cs_sat", std::max<size_t>(R_sat + 2, 5), table_budget_sat);
