@@ -388,7 +388,7 @@ class SNARK:
         d = C.c_void_p()
         st = lib().vpin_encode(ctx._h, inst._h, gens._h, out, C.c_uint64(cap), C.byref(n), C.byref(d))
         ctx.check(st)
-        return out.raw[: n.value], Decommitment(d)
+        return C.string_at(out, n.value), Decommitment(d)
 
 
 class Decommitment:
@@ -437,27 +437,35 @@ class Witness:
 _PROOF_CAP = 8 << 20
 
 
+def _proof_buffer(ctx):
+    """one 8 MB output buffer per context, reused (allocating and zeroing a fresh one costs ~1 ms per proof)"""
+    buf = getattr(ctx, "_proof_buf", None)
+    if buf is None:
+        buf = ctx._proof_buf = C.create_string_buffer(_PROOF_CAP)
+    return buf
+
+
 def my_lib_prove(inst, decomm, vars_bytes, inputs_bytes, gens, transcript_label, comm_vars, blinds_vars, tape_seed, n=None):
     """my_lib_prove (vPIN_proof_generation/src/commit_test.rs:59-133): host buffers in, bincode(SNARK) out.
     `vars_bytes` doubles as poly_vars (DensePolynomial::new(padded_vars.assignment))."""
     ctx = inst.ctx
-    out = C.create_string_buffer(_PROOF_CAP)
+    out = _proof_buffer(ctx)
     n_vars = len(vars_bytes) // 32 if n is None else n
     n = C.c_uint64()
     ctx.check(lib().vpin_prove(ctx._h, inst._h, decomm._h, vars_bytes, C.c_uint64(n_vars), inputs_bytes,
                                C.c_uint64(len(inputs_bytes) // 32), gens._h, transcript_label, C.c_uint64(len(transcript_label)),
                                comm_vars, blinds_vars, C.c_uint64(gens.L), tape_seed, out, C.c_uint64(_PROOF_CAP), C.byref(n)))
-    return out.raw[: n.value]
+    return C.string_at(out, n.value)
 
 
 def my_lib_prove_resident(inst, decomm, witness, inputs_bytes, gens, transcript_label, tape_seed):
     ctx = inst.ctx
-    out = C.create_string_buffer(_PROOF_CAP)
+    out = _proof_buffer(ctx)
     n = C.c_uint64()
     ctx.check(lib().vpin_prove_resident(ctx._h, inst._h, decomm._h, witness._h, inputs_bytes, C.c_uint64(len(inputs_bytes) // 32), gens._h,
                                         transcript_label, C.c_uint64(len(transcript_label)), tape_seed, out, C.c_uint64(_PROOF_CAP),
                                         C.byref(n)))
-    return out.raw[: n.value]
+    return C.string_at(out, n.value)
 
 
 def prove_flow(ctx, dims, inst, vars_para, vars_input, vars_, inputs, seed_q, seed_p, label=b"snark_example"):
