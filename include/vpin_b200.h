@@ -220,6 +220,17 @@ vpin_status vpin_spark_timestamps(vpin_ctx *ctx, const uint32_t *addr_a, uint64_
 vpin_status vpin_bind_top(vpin_ctx *ctx, uint8_t *Z32, uint64_t len, const uint8_t r32[32]);
 /* DensePolynomial::bound(L)   SP/dense_mlpoly.rs:220-227: out has R = 2^ceil(ell/2) scalars */
 vpin_status vpin_bound(vpin_ctx *ctx, const uint8_t *Z32, uint64_t len, const uint8_t *L32, uint8_t *out32);
+/* ProductCircuit::new (SP/product_tree.rs:36-56, compute_layer :18-34): the packed tree of n = 2^k leaves,
+ * tree = [V_0 | V_1 | ...] with V_0 = leaves and V_{j+1}[i] = V_j[i] * V_j[i + |V_j|/2], down to the layer of length 2 (the two
+ * factors of the root): 2n - 2 elements out. n >= 2. */
+vpin_status vpin_product_tree(vpin_ctx *ctx, const uint8_t *leaves32, uint64_t n, uint8_t *tree32);
+/* Layers::build_hash_layer (SP/sparse_mlpoly.rs:547-622) for n operations: read[i] = ts[i] gamma^2 + val[i] gamma + addr[i] - tau,
+ * write[i] = read[i] + gamma^2 (write_ts = read_ts + 1). With addr[i] = i and ts = 0 / audit_ts it is the init / audit layer. */
+vpin_status vpin_hash_layer(vpin_ctx *ctx, const uint32_t *addr, const uint8_t *val32, const uint32_t *ts, uint64_t n,
+                            const uint8_t gamma32[32], const uint8_t tau32[32], uint8_t *read32, uint8_t *write32);
+/* deref_mem (SP/sparse_mlpoly.rs:267-276): out[i] = mem[addr[i]] */
+vpin_status vpin_deref_gather(vpin_ctx *ctx, const uint32_t *addr, uint64_t n, const uint8_t *mem32, uint64_t num_cells,
+                              uint8_t *out32);
 
 /* Device-resident forms for benchmarks: pointers are CUDA device pointers to 32-byte MONTGOMERY elements (the
  * in-HBM table format, identical to the reference's serde of Scalar, SP/scalar/ristretto255.rs:199-200).

@@ -203,3 +203,39 @@ def test_spark_timestamps_match_the_sequential_replay(ctx, N, M, sizes, hot):
     assert got_addr.tolist() == want_addr
     assert got_ts.tolist() == want_ts
     assert got_audit.tolist() == want_audit
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 11])
+def test_product_tree_layers(ctx, k):
+    """ProductCircuit::new (Spartan/src/product_tree.rs:18-56): every layer is the element-wise product of the two halves of the
+    layer below, down to the two factors of the root (big-int restatement; edge values 0, 1, l - 1 among the leaves)."""
+    n = 1 << k
+    leaves = H.rand_scalars(n, seed=40 + k)
+    want, layer = list(leaves), list(leaves)
+    while len(layer) > 2:
+        half = len(layer) // 2
+        layer = [layer[i] * layer[i + half] % H.L for i in range(half)]
+        want += layer
+    got = O.bytes_to_ints(ctx.product_tree(O.ints_to_bytes(leaves)))
+    assert len(got) == 2 * n - 2 and got == want
+
+
+@pytest.mark.parametrize("n", [1, 33, 4096])
+def test_hash_layer_and_deref_gather(ctx, n):
+    """deref_mem (Spartan/src/sparse_mlpoly.rs:267-276) and build_hash_layer (:547-622): h = ts gamma^2 + val gamma + addr - tau,
+    the write set one timestamp later; addresses and timestamps at their extremes (0, 2^32 - 1)."""
+    import random
+    rng = random.Random(n)
+    cells = 64
+    mem = H.rand_scalars(cells, seed=n + 1)
+    addr = [rng.randrange(cells) for _ in range(n)]
+    vals = O.bytes_to_ints(ctx.deref_gather(addr, O.ints_to_bytes(mem)))
+    assert vals == [mem[a] for a in addr]
+    big_addr = [rng.choice([0, 1, 2**32 - 1, rng.randrange(2**32)]) for _ in range(n)]
+    ts = [rng.choice([0, 1, 2**32 - 1, rng.randrange(1 << 20)]) for _ in range(n)]
+    gamma, tau = rng.randrange(H.L), rng.randrange(H.L)
+    rd, wr = ctx.hash_layer(big_addr, O.ints_to_bytes(vals), ts, O.le32(gamma), O.le32(tau))
+    g2 = gamma * gamma % H.L
+    want = [(t * g2 + v * gamma + a - tau) % H.L for a, v, t in zip(big_addr, vals, ts)]
+    assert O.bytes_to_ints(rd) == want
+    assert O.bytes_to_ints(wr) == [(w + g2) % H.L for w in want]

@@ -186,6 +186,24 @@ class Context:
         self.check(lib().vpin_bound(self._h, Z, C.c_uint64(n), Lvec, out))
         return out.raw
 
+    def product_tree(self, leaves):
+        n = len(leaves) // 32
+        out = C.create_string_buffer(32 * (2 * n - 2))
+        self.check(lib().vpin_product_tree(self._h, leaves, C.c_uint64(n), out))
+        return out.raw
+
+    def hash_layer(self, addr, vals, ts, gamma, tau):
+        n = len(addr)
+        rd, wr = C.create_string_buffer(32 * n), C.create_string_buffer(32 * n)
+        self.check(lib().vpin_hash_layer(self._h, (C.c_uint32 * n)(*addr), vals, (C.c_uint32 * n)(*ts), C.c_uint64(n), gamma, tau, rd, wr))
+        return rd.raw, wr.raw
+
+    def deref_gather(self, addr, mem):
+        n = len(addr)
+        out = C.create_string_buffer(32 * n)
+        self.check(lib().vpin_deref_gather(self._h, (C.c_uint32 * n)(*addr), C.c_uint64(n), mem, C.c_uint64(len(mem) // 32), out))
+        return out.raw
+
     def commitments_add(self, c1, c2):
         out = C.create_string_buffer(len(c1))
         self.check(lib().vpin_commitments_add(self._h, c1, c2, C.c_uint64(len(c1) // 32), out))

@@ -739,6 +739,50 @@ vpin_status vpin_bound(vpin_ctx *ctx, const uint8_t *Z32, uint64_t len, const ui
   download_scalars(c_, out.p, R, out32);
   VPIN_CATCH
 }
+vpin_status vpin_product_tree(vpin_ctx *ctx, const uint8_t *leaves32, uint64_t n, uint8_t *tree32) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE(leaves32 && tree32 && is_pow2(n) && n >= 2, VPIN_ERR_BAD_ARGUMENT, "bad argument");
+  DevVec<fl_t> tree(2 * n, c_->st);
+  tree.zero();
+  {
+    DevVec<fl_t> leaves = upload_scalars(c_, leaves32, n);
+    VPIN_CUDA(cudaMemcpyAsync(tree.p, leaves.p, n * sizeof(fl_t), cudaMemcpyDeviceToDevice, c_->st));
+    c_->sync();
+  }
+  build_tree(c_, tree.p, n, c_->st);
+  download_scalars(c_, tree.p, 2 * n - 2, tree32);
+  VPIN_CATCH
+}
+vpin_status vpin_hash_layer(vpin_ctx *ctx, const uint32_t *addr, const uint8_t *val32, const uint32_t *ts, uint64_t n,
+                            const uint8_t gamma32[32], const uint8_t tau32[32], uint8_t *read32, uint8_t *write32) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE(addr && val32 && ts && gamma32 && tau32 && read32 && write32 && n, VPIN_ERR_BAD_ARGUMENT, "bad argument");
+  DevVec<fl_t> val = upload_scalars(c_, val32, n);
+  uint8_t gt[64];
+  memcpy(gt, gamma32, 32);
+  memcpy(gt + 32, tau32, 32);
+  DevVec<fl_t> d_gt = upload_scalars(c_, gt, 2);
+  DevVec<uint32_t> d_addr(n, c_->st), d_ts(n, c_->st);
+  d_addr.upload(addr, n);
+  d_ts.upload(ts, n);
+  DevVec<fl_t> rd(n, c_->st), wr(n, c_->st);
+  launch_hash_ops(d_addr.p, val.p, d_ts.p, n, d_gt.p, rd.p, wr.p, c_->st);
+  download_scalars(c_, rd.p, n, read32);
+  download_scalars(c_, wr.p, n, write32);
+  VPIN_CATCH
+}
+vpin_status vpin_deref_gather(vpin_ctx *ctx, const uint32_t *addr, uint64_t n, const uint8_t *mem32, uint64_t num_cells, uint8_t *out32) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE(addr && mem32 && out32 && n && num_cells, VPIN_ERR_BAD_ARGUMENT, "bad argument");
+  for (uint64_t i = 0; i < n; i++) VPIN_REQUIRE(addr[i] < num_cells, VPIN_ERR_INVALID_INDEX, "address out of range");
+  DevVec<fl_t> mem = upload_scalars(c_, mem32, num_cells);
+  DevVec<uint32_t> d_addr(n, c_->st);
+  d_addr.upload(addr, n);
+  DevVec<fl_t> out(n, c_->st);
+  launch_gather(d_addr.p, mem.p, n, out.p, c_->st);
+  download_scalars(c_, out.p, n, out32);
+  VPIN_CATCH
+}
 vpin_status vpin_dev_to_mont(vpin_ctx *ctx, const void *d_in, uint64_t n, void *d_out) {
   VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
   launch_to_mont((const fl_t *)d_in, n, (fl_t *)d_out, c_->st);

@@ -877,7 +877,10 @@ struct Prover {
   }
 };
 
-// builds the packed product tree of `n` leaves already stored at tree[0..n) (SP/product_tree.rs:18-56)
+}  // namespace
+
+// builds the packed product tree of `n` leaves already stored at tree[0..n) (SP/product_tree.rs:18-56): layers of length
+// n, n/2, ..., 2 (the two factors of the root), 2n - 2 elements in all
 void build_tree(Ctx *ctx, fl_t *tree, size_t n, cudaStream_t st) {
   size_t off = 0;
   for (size_t vlen = n; vlen > 2; vlen /= 2) {
@@ -886,8 +889,6 @@ void build_tree(Ctx *ctx, fl_t *tree, size_t n, cudaStream_t st) {
     off += vlen;
   }
 }
-
-}  // namespace
 
 bool instance_is_sat(Ctx *ctx, const Instance &inst, const uint8_t *vars32, uint64_t n_vars, const uint8_t *inputs32, uint64_t n_inputs) {
   cudaStream_t st = ctx->st;

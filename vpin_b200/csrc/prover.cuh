@@ -58,6 +58,9 @@ static inline size_t eq_tmp_elems(size_t ell) {
 }
 double measure_imad_peak(Ctx *ctx);
 
+// packed product tree of n leaves stored at tree[0..n): 2n - 2 elements (prover.cu)
+void build_tree(Ctx *ctx, fl_t *tree, size_t n, cudaStream_t st);
+
 // builders.cu — vPIN_proof_generation/src/point_mult.rs, point_addition.rs
 void point_mult_dims(uint64_t m, uint64_t dims_out[4]);
 void point_add_dims(uint64_t n, uint64_t dims_out[4]);
