@@ -70,16 +70,44 @@ void *block_cache_alloc(BlockCache *c, size_t bytes) {
     }
   }
   cudaError_t e = cudaMalloc(&p, r);
-  // out of memory: give the idle blocks back to the driver and retry; then ask the owner to let go of what it can spare
-  // (the idle SPARK workspace of a previous proof) and retry once more
+  // Out of memory: give idle blocks back to the driver, largest first and only until the request fits (returning everything
+  // makes the next proof re-allocate it all: at LeNet layer 5, where the cache holds ~170 of the 180 GB, that thrash doubled
+  // the time of whole phases); then ask the owner to let go of what it can spare (the idle SPARK workspace of a previous
+  // proof) and repeat.
   for (int attempt = 0; e != cudaSuccess && c && attempt < 2; attempt++) {
     cudaGetLastError();
     if (attempt == 1 && !(c->pressure && c->pressure())) break;
+    for (;;) {
+      size_t freed = 0;
+      {
+        std::lock_guard<std::mutex> g(c->mu);
+        for (auto it = c->free_.rbegin(); it != c->free_.rend() && freed < r; ++it) {
+          while (!it->second.empty() && freed < r) {
+            cudaFree(it->second.back());
+            it->second.pop_back();
+            freed += it->first;
+          }
+        }
+        for (auto it = c->free_.begin(); it != c->free_.end();) it = it->second.empty() ? c->free_.erase(it) : std::next(it);
+      }
+      e = cudaMalloc(&p, r);
+      if (e == cudaSuccess || freed == 0) break;  // done, or nothing left to give back
+      cudaGetLastError();
+    }
+  }
+  if (e != cudaSuccess) {  // last resort: the idle blocks of every other context of the process (concurrent proofs share the GPU)
+    cudaGetLastError();
+    std::vector<BlockCache *> others;
     {
-      std::lock_guard<std::mutex> g(c->mu);
-      for (auto &kv : c->free_)
-        for (void *q : kv.second) cudaFree(q);
-      c->free_.clear();
+      std::lock_guard<std::mutex> g(g_cache_mu);
+      for (auto &kv : g_caches)
+        if (kv.second.get() != c) others.push_back(kv.second.get());
+      for (BlockCache *o : others) {  // (under g_cache_mu: a cache cannot be unregistered meanwhile)
+        std::lock_guard<std::mutex> go(o->mu);
+        for (auto &kv : o->free_)
+          for (void *q : kv.second) cudaFree(q);
+        o->free_.clear();
+      }
     }
     e = cudaMalloc(&p, r);
   }
