@@ -10,6 +10,7 @@
 //   hi' = T[i+q] + r (T[i+3q] - T[i+q])    (element i + q   of the bound table)
 // are stored in place (no other thread touches these four slots) and (lo', hi') is the pair the evaluation needs.
 #include <atomic>
+#include <cstdlib>
 
 #include "kernels_poly.cuh"
 #include "msm_recode.cuh"
@@ -209,7 +210,8 @@ __global__ void __launch_bounds__(kRedThreads, 2) k_round_cubic_batched(BatchedR
 // ---- the same for tiny rounds (q <= kSmallQ): ONE block, half a warp per instance, no inter-block traffic at all.
 // Roughly 250 of the ~400 rounds of the two product-circuit proofs of a 2^20 instance are of this kind, and their cost
 // is pure latency (launch -> loads -> a handful of multiplications -> shuffle tree -> PCIe store).
-static const size_t kSmallQ = 64;
+static const size_t kSmallQ = 64;         // what the kernel supports
+static const size_t kSmallQDefault = 16;  // measured on a B200: 16 beats 64 by 0.6 ms per CNN-A proof (a lane then has one item)
 template <bool kBind>
 __global__ void __launch_bounds__(16 * kMaxBatched + 16) k_round_cubic_batched_small(BatchedRoundArgs a, int ninst, size_t q, fl_t r,
                                                                                     RoundSlot *slot, uint32_t seq) {
@@ -349,9 +351,17 @@ void launch_round_quad(fl_t *A, fl_t *B, size_t q, bool bind, const fl_t &r, con
   if (bind) k_round_quad<true><<<nb, kRedThreads, 0, st>>>(A, B, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
   else k_round_quad<false><<<nb, kRedThreads, 0, st>>>(A, B, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
 }
+static size_t small_q_threshold() {  // VPIN_SMALL_Q overrides (experiments)
+  static const size_t v = [] {
+    const char *e = getenv("VPIN_SMALL_Q");
+    long x = e ? atol(e) : (long)kSmallQDefault;
+    return (size_t)(x < 0 ? 0 : (x > (long)kSmallQ ? (long)kSmallQ : x));
+  }();
+  return v;
+}
 void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
   ++g_kernel_launches;
-  if (q <= kSmallQ) {
+  if (q <= small_q_threshold()) {
     int threads = (16 * ninst + 31) / 32 * 32;
     if (bind) k_round_cubic_batched_small<true><<<1, threads, 0, st>>>(a, ninst, q, r, c.slot, c.seq);
     else k_round_cubic_batched_small<false><<<1, threads, 0, st>>>(a, ninst, q, r, c.slot, c.seq);
