@@ -335,16 +335,17 @@ static void hyrax_rows_local(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_
   size_t segs = msm_num_segments(chunk, cols_total, geom);
   DevVec<uint16_t> digits(msm_digits_count(chunk, cols_total, geom), ctx->st);
   DevVec<ge_t> partial(chunk * geom.group * segs, ctx->st), sums(segs > 1 ? chunk * geom.group : 0, ctx->st);
+  uint32_t *d_wmask = reinterpret_cast<uint32_t *>(ctx->d_counters.p + 2);  // windows in use, per recode launch
   for (size_t r0 = 0; r0 < rows; r0 += chunk) {
     size_t nr = rows - r0 < chunk ? rows - r0 : chunk;
     double pts = (double)nr * cols_total;
     {
       ProfScope ps(ctx, PROF_MSM_RECODE, pts, pts * (32 + 2 * geom.windows));
-      launch_recode(dZ + r0 * ld, nr, cols, ld, d_blinds ? d_blinds + r0 : nullptr, geom, digits.p, ctx->d_counters.p, ctx->st);
+      launch_recode(dZ + r0 * ld, nr, cols, ld, d_blinds ? d_blinds + r0 : nullptr, geom, digits.p, ctx->d_counters.p, ctx->st, d_wmask);
     }
     {
       ProfScope ps(ctx, PROF_MSM_ACCUMULATE, pts, 0);
-      launch_msm_accumulate(g.table(), digits.p, nr, cols, d_blinds != nullptr, blind_base, segs, partial.p, ctx->st);
+      launch_msm_accumulate(g.table(), digits.p, nr, cols, d_blinds != nullptr, blind_base, segs, partial.p, ctx->st, d_wmask);
     }
     ProfScope ps(ctx, PROF_MSM_FINISH, pts, 0);
     launch_msm_finish(partial.p, nr, segs, geom, sums.p, d_points ? d_points + r0 : nullptr, d_comp ? d_comp + 32 * r0 : nullptr, ctx->st);

@@ -117,7 +117,8 @@ void launch_table_build(const ge_t *d_bases, size_t n, const MsmGeom &g, niels_t
 }
 
 // ------------------------------------------------------------------------------------------------ recode
-__device__ __forceinline__ uint32_t recode_one(const fl_t *src, const MsmGeom &g, uint16_t *dst, size_t plane) {
+__device__ __forceinline__ uint32_t recode_one(const fl_t *src, const MsmGeom &g, uint16_t *dst, size_t plane, uint32_t *used) {
+  *used = 0;
   if (!src) {
     for (int w = 0; w < g.windows; w++) dst[(size_t)w * plane] = 0;
     return 0;
@@ -126,16 +127,20 @@ __device__ __forceinline__ uint32_t recode_one(const fl_t *src, const MsmGeom &g
   uint4 lo = __ldg(q), hi = __ldg(q + 1);
   fl_t x;
   x.v[0] = lo.x; x.v[1] = lo.y; x.v[2] = lo.z; x.v[3] = lo.w; x.v[4] = hi.x; x.v[5] = hi.y; x.v[6] = hi.z; x.v[7] = hi.w;
-  return msm_recode_value(x, g, dst, plane);
+  return msm_recode_value(x, g, dst, plane, used);
 }
 __global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows, size_t cols, size_t ld, const fl_t *extra, MsmGeom g,
-                                                size_t stride, uint16_t *digits, unsigned long long *nonzero) {
+                                                size_t stride, uint16_t *digits, unsigned long long *nonzero, uint32_t *wmask) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nz = 0;
+  uint32_t nz = 0, used = 0;
   if (idx < rows * stride) {
     size_t row = idx / stride, col = idx % stride;
     const fl_t *src = col < cols ? scalars + row * ld + col : (col == cols && extra ? extra + row : nullptr);
-    nz = recode_one(src, g, digits + row * stride + col, rows * stride);
+    nz = recode_one(src, g, digits + row * stride + col, rows * stride, &used);
+  }
+  if (wmask) {  // windows that hold a non-zero digit anywhere in this launch (the accumulate kernel skips the others)
+    used = __reduce_or_sync(0xffffffffu, used);
+    if ((threadIdx.x & 31) == 0 && used) atomicOr(wmask, used);
   }
   if (nonzero) {
     nz = __reduce_add_sync(0xffffffffu, nz);
@@ -143,10 +148,12 @@ __global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows
   }
 }
 void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, const fl_t *d_extra, const MsmGeom &g, uint16_t *d_digits,
-                   unsigned long long *d_nonzero, cudaStream_t st) {
+                   unsigned long long *d_nonzero, cudaStream_t st, uint32_t *d_wmask) {
   size_t stride = msm_col_stride(cols + (d_extra ? 1 : 0));
   size_t total = rows * stride;
-  ++g_kernel_launches, k_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_scalars, rows, cols, ld, d_extra, g, stride, d_digits, d_nonzero);
+  if (d_wmask) cudaMemsetAsync(d_wmask, 0, sizeof(uint32_t), st);
+  ++g_kernel_launches, k_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_scalars, rows, cols, ld, d_extra, g, stride, d_digits, d_nonzero,
+                                                                                 d_wmask);
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate
@@ -166,13 +173,23 @@ __device__ __forceinline__ void madd_signed(ge_t &p, const niels_t *e, uint32_t 
   p.X = fp_mul(e_, f); p.Y = fp_mul(g, h); p.Z = fp_mul(f, g); p.T = fp_mul(e_, h);
 }
 // grid (ceil(rows / 128), kMsmGroup, segs), block 128: thread = (row, local window w', column segment)
-__global__ void __launch_bounds__(kMsmRowsPerBlock) k_msm_accumulate(const niels_t *table, MsmGeom g, const uint16_t *digits, size_t rows,
+__global__ void __launch_bounds__(kMsmRowsPerBlock, 6) k_msm_accumulate(const niels_t *table, MsmGeom g, const uint16_t *digits, size_t rows,
                                                                      size_t cols, size_t cols_total, size_t extra_base, size_t stride,
-                                                                     size_t n_bases, size_t seg_len, ge_t *partial) {
+                                                                     size_t n_bases, size_t seg_len, ge_t *partial, const uint32_t *wmask) {
   size_t row = (size_t)blockIdx.x * kMsmRowsPerBlock + threadIdx.x;
   if (row >= rows) return;
   const int wl = blockIdx.y;
   const size_t seg = blockIdx.z, segs = gridDim.z;
+  // a local window none of whose sub-table windows holds a non-zero digit anywhere (small scalars: addresses, timestamps,
+  // 128-bit weights) is finished at once; its digits are not even read
+  {
+    uint32_t live = wmask ? *wmask : 0xffffffffu, mine = 0;
+    for (int t = 0; t < kMsmSub; t++) mine |= (t * g.group + wl) < g.windows ? (live >> (t * g.group + wl)) & 1u : 0u;
+    if (!mine) {
+      st_ge(partial + (row * g.group + wl) * segs + seg, ge_identity());
+      return;
+    }
+  }
   size_t c0 = seg * seg_len, c1 = c0 + seg_len < cols_total ? c0 + seg_len : cols_total;
   const size_t plane = rows * stride;
   const uint16_t *dg = digits + row * stride;
@@ -249,7 +266,7 @@ size_t msm_num_segments(size_t rows, size_t cols_total, const MsmGeom &g) {
   return segs;
 }
 void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t rows, size_t cols, bool has_extra, size_t extra_base,
-                           size_t segs, ge_t *d_partial, cudaStream_t st) {
+                           size_t segs, ge_t *d_partial, cudaStream_t st, const uint32_t *d_wmask) {
   size_t cols_total = cols + (has_extra ? 1 : 0);
   size_t stride = msm_col_stride(cols_total);
   size_t seg_len = (cols_total + segs - 1) / segs;
@@ -261,7 +278,7 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
   }
   dim3 grid((unsigned)((rows + kMsmRowsPerBlock - 1) / kMsmRowsPerBlock), t.geom.group, (unsigned)segs);
   ++g_kernel_launches, k_msm_accumulate<<<grid, kMsmRowsPerBlock, 0, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride,
-                                                                           t.n_bases, seg_len, d_partial);
+                                                                           t.n_bases, seg_len, d_partial, d_wmask);
 }
 
 // finish, step 1 (only when a row was split into segments): one warp per (row, local window) adds the segment partials

@@ -58,16 +58,18 @@ static inline size_t msm_col_stride(size_t cols) { return (cols + kMsmColsPerBlo
 static inline size_t msm_digits_count(size_t rows, size_t cols, const MsmGeom &g) { return (size_t)g.windows * rows * msm_col_stride(cols); }
 // scalars: rows x cols Montgomery elements, row-major with leading dimension ld. extra: optional one more scalar per row
 // (the blind, multiplied by base index `cols`), or nullptr. Padding columns get digit 0.
+// d_wmask (optional): device word that receives the set of windows holding a non-zero digit (zeroed here first); handed to
+// launch_msm_accumulate it lets the kernel skip the other windows without reading their digits.
 // d_nonzero (optional): device counter incremented by the number of non-zero digits written (= mixed additions the
 // accumulate kernel will execute)
 void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, const fl_t *d_extra, const MsmGeom &g, uint16_t *d_digits,
-                   unsigned long long *d_nonzero, cudaStream_t st);
+                   unsigned long long *d_nonzero, cudaStream_t st, uint32_t *d_wmask = nullptr);
 // number of column segments the accumulate kernel splits a row into (enough threads to fill 148 SMs)
 size_t msm_num_segments(size_t rows, size_t cols_total, const MsmGeom &g);
 // partial[(row * geom.group + w') * segs + seg] = sum over the segment's columns and the kMsmSub sub-tables; the optional extra
 // column (index cols) uses table base `extra_base`
 void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t rows, size_t cols, bool has_extra, size_t extra_base,
-                           size_t segs, ge_t *d_partial, cudaStream_t st);
+                           size_t segs, ge_t *d_partial, cudaStream_t st, const uint32_t *d_wmask = nullptr);
 // out[row] = sum_w' 2^(W*w') sum_seg partial[row][w'][seg]; d_sums: rows * geom.group scratch points (used when segs > 1);
 // d_out (points) and d_comp (32-byte encodings) are optional
 void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, ge_t *d_out, uint8_t *d_comp,

@@ -12,8 +12,10 @@ __device__ __forceinline__ uint32_t msm_half_l_limb(int i) {  // (l - 1) / 2
   }
 }
 // x: Montgomery form. Writes the g.windows digits of the representative of smallest absolute value (|s| <= (l-1)/2) to
-// dst[w * plane] as magnitude | sign << 15 and returns the number of non-zero digits.
-__device__ __forceinline__ uint32_t msm_recode_value(const fl_t &x, const MsmGeom &g, uint16_t *dst, size_t plane) {
+// dst[w * plane] as magnitude | sign << 15 and returns the number of non-zero digits; *used_windows (optional) receives the set of
+// windows that got a non-zero digit.
+__device__ __forceinline__ uint32_t msm_recode_value(const fl_t &x, const MsmGeom &g, uint16_t *dst, size_t plane, uint32_t *used_windows = nullptr) {
+  if (used_windows) *used_windows = 0;
   if (fl_is_zero(x)) {
     for (int w = 0; w < g.windows; w++) dst[(size_t)w * plane] = 0;
     return 0;
@@ -36,7 +38,7 @@ __device__ __forceinline__ uint32_t msm_recode_value(const fl_t &x, const MsmGeo
     for (int i = 0; i < 8; i++) v[i] = s.v[i];
   }
   v[8] = 0;
-  uint32_t carry = 0, nz = 0;
+  uint32_t carry = 0, nz = 0, used = 0;
   // limb indexing by a run-time window: v lives in local memory for this loop only when the compiler cannot resolve it;
   // the funnel over (v[limb], v[limb + 1]) is written with a select chain to stay in registers
   const uint32_t wmask = (1u << g.W) - 1u;
@@ -52,8 +54,10 @@ __device__ __forceinline__ uint32_t msm_recode_value(const fl_t &x, const MsmGeo
     carry = neg;
     uint32_t sign = (neg ^ (gt ? 1u : 0u)) & (mag != 0 ? 1u : 0u);
     nz += mag != 0 ? 1u : 0u;
+    used |= mag != 0 ? (1u << w) : 0u;
     dst[(size_t)w * plane] = (uint16_t)(mag | (sign << 15));
   }
+  if (used_windows) *used_windows = used;
   return nz;
 }
 
