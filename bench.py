@@ -172,18 +172,24 @@ class InstanceState:
         """host buffers in, host bytes out — every call a Rust shim of the reference driver would make"""
         from vpin_b200 import api
         import numpy as np
+        T = [time.time()]
         A, B, Cm = (np.frombuffer(t.numpy()[: n * api.COO_DTYPE.itemsize], dtype=api.COO_DTYPE) for t, n in self.h_coo)
-        inst = api.Instance(ctx, self.dims[0], self.dims[1], self.dims[2], A, B, Cm)
+        inst = api.Instance(ctx, self.dims[0], self.dims[1], self.dims[2], A, B, Cm); T.append(time.time())
         vp, vi, v = (t.numpy() for t in self.h_assign)
         sq, sp = seeds
-        gens = api.SNARKGens(ctx, *self.dims)
-        comm, decomm = api.SNARK.encode(inst, gens)
+        gens = api.SNARKGens(ctx, *self.dims); T.append(time.time())
+        comm, decomm = api.SNARK.encode(inst, gens); T.append(time.time())
         tape = api.RandomTape(b"\x02", sq)
         c_para, b_para = api.dense_mlpoly_commit(ctx, gens, api._buf(vp), tape, n=self.n)
         c_input, b_input = api.dense_mlpoly_commit(ctx, gens, api._buf(vi), tape, n=self.n)
         c_vars, b_vars = api.my_dense_mlpoly_commit(ctx, gens, api._buf(v), b_para, b_input, n=self.n)
-        combined = ctx.commitments_add(c_para, c_input)
-        proof = api.my_lib_prove(inst, decomm, api._buf(v), self.inputs, gens, TRANSCRIPT_LABEL, combined, b_vars, sp, n=self.n)
+        combined = ctx.commitments_add(c_para, c_input); T.append(time.time())
+        proof = api.my_lib_prove(inst, decomm, api._buf(v), self.inputs, gens, TRANSCRIPT_LABEL, combined, b_vars, sp, n=self.n); T.append(time.time())
+        del inst, decomm, gens
+        T.append(time.time())
+        # per-call wall times of this step (Instance::new, SNARKGens::new, encode, commits, prove, handle release), kept for the
+        # slowest step of the leg (bench line: e2e.slowest_step_calls_ms)
+        self.last_e2e_calls_ms = [round(1e3 * (b - a), 2) for a, b in zip(T, T[1:])]
         return comm, proof, (c_para, c_input, c_vars)
 
 
@@ -394,14 +400,18 @@ class Leg:
         gc.disable()
         per_step = []
         t0 = time.time()
+        slowest, slowest_calls = 0.0, None
         for _ in range(args.steps):
             t1 = time.time()
             e2e_out = self.one_step_e2e()
             per_step.append(time.time() - t1)
+            if per_step[-1] > slowest:
+                slowest, slowest_calls = per_step[-1], {s_.kind: s_.last_e2e_calls_ms for s_ in self.states}
         self.barrier()
         e2e_s = self.max_over_ranks((time.time() - t0) / args.steps)
         gc.enable()
         self.e2e_steps_ms = [round(1e3 * x, 2) for x in per_step]
+        self.e2e_slowest_calls = slowest_calls
         for (c1, p1), (c2, p2, _) in zip(self.last, e2e_out):
             assert c1 == c2 and p1 == p2, "resident and host-buffer legs disagree"
         h2d = sum(s.h2d_bytes() for s in self.states)
@@ -451,6 +461,7 @@ def run_b200(args):
     prof, madds, prof_ms = ({}, 0, 0.0) if args.no_profile else leg.profile_pass()
     e2e_s, h2d, d2h = leg.time_e2e()
     e2e_steps_ms = leg.e2e_steps_ms
+    e2e_slowest_calls = leg.e2e_slowest_calls
     msm = msm_uniform_bench(leg.ctx, torch, leg.dev, leg.stream, imad_peak) if world == 1 else None
     # witness expansion + R1CS emission of the point-mult instance on the device (vpin_build_point_mult_device), assignments left
     # in HBM: the step of vPIN's timed region that precedes the prover (proof_point_mult.rs:24, point_mult.rs:7-664)
@@ -545,7 +556,9 @@ def run_b200(args):
         "wall_s_per_step": res["wall_step_s"],
         "gpu_launches": res["launches"],
         "clocks": res["clocks"],
-        "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_ms": e2e_steps_ms},
+        "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_ms": e2e_steps_ms,
+                "slowest_step_calls_ms": e2e_slowest_calls,
+                "calls": ["Instance::new", "SNARKGens::new", "SNARK::encode", "3 commits + combine", "my_lib_prove", "release"]},
         "roofline": top,
         "roofline_pass": {"ms_per_step": prof_ms / args.steps if prof_ms else None,
                           "how": "same K steps repeated after the timed region with CUDA-event scopes on the launching stream, instances sequential"},
