@@ -103,6 +103,31 @@ def test_synthetic_r1cs_flow(ctx, num_cons, num_vars, num_inputs):
     _check(ctx, built, (num_cons, num_vars, num_inputs, nnz), inst, vp, vi, v, inputs)
 
 
+def test_padded_constraints_instance_of_the_reference(ctx):
+    """The instance of Spartan's own `test_padded_constraints` (Spartan/src/lib.rs:694-774): ONE constraint a^2 = z - 13 - b over
+    zero variables and three public inputs (z = 16, a = 1, b = 2) — the constraint count is padded to 2, the variable count to
+    4 (max(num_vars, num_inputs + 1) rounded up), and the witness is empty. Through vPIN's flow, against the oracle."""
+    import numpy as np
+    from vpin_b200 import api
+
+    L = O.L_ORDER
+    num_cons, num_vars, num_inputs, nnz = 1, 0, 3, 3
+    def ent(rows):
+        a = np.zeros(len(rows), O.COO_DTYPE)
+        for k, (r, c, val) in enumerate(rows):
+            a[k] = (r, c, np.frombuffer(O.le32(val % L), dtype=np.uint8))
+        return a
+    A = ent([(0, num_vars + 2, 1)])
+    B = ent([(0, num_vars + 2, 1)])
+    Cm = ent([(0, num_vars + 1, 1), (0, num_vars, -13), (0, num_vars + 3, -1)])
+    inputs = O.le32(16) + O.le32(1) + O.le32(2)
+    built = O.build_custom(num_cons, num_vars, num_inputs, nnz, A, B, Cm, b"", b"", b"", inputs)
+    inst = api.Instance(ctx, num_cons, num_vars, num_inputs, A, B, Cm)
+    assert inst.is_sat(b"", inputs)
+    assert not inst.is_sat(b"", O.le32(17) + O.le32(1) + O.le32(2))
+    _check(ctx, built, (num_cons, num_vars, num_inputs, nnz), inst, b"", b"", b"", inputs)
+
+
 def test_unsatisfied_witness_is_reported(ctx):
     from vpin_b200 import api
 
