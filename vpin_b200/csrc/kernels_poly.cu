@@ -461,6 +461,43 @@ __global__ void __launch_bounds__(256) k_mul_halves(const fl_t *in, size_t n, fl
 void launch_mul_halves(const fl_t *in, size_t n, fl_t *out, cudaStream_t st) {
   ++g_kernel_launches, k_mul_halves<<<stream_blocks(n), 256, 0, st>>>(in, n, out);
 }
+// the same layer of several packed trees in one launch (tree = blockIdx.y)
+__global__ void __launch_bounds__(256) k_mul_halves_multi(TreeBatch b, size_t off, size_t half) {
+  fl_t *t = b.p[blockIdx.y];
+  const fl_t *in = t + off;
+  fl_t *out = t + off + 2 * half;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride)
+    st_fl(out + i, fl_mul(ldg_fl(in + i), ldg_fl(in + half + i)));
+}
+// every remaining layer of a tree (current layer of `vlen` <= kTreeTail elements at `off`) by ONE block per tree: the upper
+// layers are a chain of ever shorter launches otherwise (12 trees x 13 layers of <= 4096 products each)
+__global__ void __launch_bounds__(1024) k_tree_tail(TreeBatch b, size_t off, size_t vlen) {
+  fl_t *t = b.p[blockIdx.x];
+  while (vlen > 2) {
+    size_t half = vlen / 2;
+    for (size_t i = threadIdx.x; i < half; i += blockDim.x) {
+      const uint4 *pa = reinterpret_cast<const uint4 *>(t + off + i), *pb = reinterpret_cast<const uint4 *>(t + off + half + i);
+      fl_t x, y;
+      uint4 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];  // plain loads: the layer below was written by this block
+      x.v[0] = a0.x; x.v[1] = a0.y; x.v[2] = a0.z; x.v[3] = a0.w; x.v[4] = a1.x; x.v[5] = a1.y; x.v[6] = a1.z; x.v[7] = a1.w;
+      y.v[0] = b0.x; y.v[1] = b0.y; y.v[2] = b0.z; y.v[3] = b0.w; y.v[4] = b1.x; y.v[5] = b1.y; y.v[6] = b1.z; y.v[7] = b1.w;
+      st_fl(t + off + vlen + i, fl_mul(x, y));
+    }
+    __syncthreads();
+    off += vlen;
+    vlen = half;
+  }
+}
+void launch_build_trees(const TreeBatch &b, size_t n, cudaStream_t st) {
+  size_t off = 0, vlen = n;
+  for (; vlen > kTreeTail; vlen /= 2) {
+    dim3 grid(stream_blocks(vlen / 2), b.n);
+    ++g_kernel_launches, k_mul_halves_multi<<<grid, 256, 0, st>>>(b, off, vlen / 2);
+    off += vlen;
+  }
+  if (vlen > 2) ++g_kernel_launches, k_tree_tail<<<b.n, 1024, 0, st>>>(b, off, vlen);
+}
 __global__ void __launch_bounds__(256) k_lincomb3(const fl_t *A, const fl_t *B, const fl_t *C, const fl_t *d_abc, size_t n, fl_t *out) {
   fl_t a = ld_fl(d_abc), b = ld_fl(d_abc + 1), c = ld_fl(d_abc + 2);
   size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -129,6 +129,11 @@ void launch_hash_ops(const uint32_t *addr, const fl_t *deref, const uint32_t *re
                      fl_t *write, cudaStream_t st);
 // product tree layer (Spartan/src/product_tree.rs:18-34): out[i] = in[i] * in[i + n] for i < n (out may not alias in)
 void launch_mul_halves(const fl_t *in, size_t n, fl_t *out, cudaStream_t st);
+// packed product trees (layers n, n/2, ..., 2 of each tree, leaves already at p[k][0..n)) of up to 16 circuits at once: one
+// launch per layer for all trees while a layer is longer than kTreeTail, then one block per tree for the rest
+static const size_t kTreeTail = 8192;
+struct TreeBatch { fl_t *p[16]; int n; };
+void launch_build_trees(const TreeBatch &b, size_t n, cudaStream_t st);
 // out[i] = a*A[i] + b*B[i] + c*C[i] ; d_abc = {a,b,c} on device
 void launch_lincomb3(const fl_t *A, const fl_t *B, const fl_t *C, const fl_t *d_abc, size_t n, fl_t *out, cudaStream_t st);
 

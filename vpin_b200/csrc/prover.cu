@@ -881,14 +881,17 @@ struct Prover {
 
 // builds the packed product tree of `n` leaves already stored at tree[0..n) (SP/product_tree.rs:18-56): layers of length
 // n, n/2, ..., 2 (the two factors of the root), 2n - 2 elements in all
-void build_tree(Ctx *ctx, fl_t *tree, size_t n, cudaStream_t st) {
-  size_t off = 0;
-  for (size_t vlen = n; vlen > 2; vlen /= 2) {
-    ProfScope ps(ctx, PROF_TREE, (double)vlen / 2, 48.0 * vlen);
-    launch_mul_halves(tree + off, vlen / 2, tree + off + vlen, st);
-    off += vlen;
-  }
+void build_trees(Ctx *ctx, const std::vector<fl_t *> &trees, size_t n, cudaStream_t st) {
+  VPIN_REQUIRE(trees.size() <= 16, VPIN_ERR_PROVER, "too many trees in one batch");
+  if (trees.empty() || n <= 2) return;
+  TreeBatch b;
+  b.n = (int)trees.size();
+  for (int k = 0; k < b.n; k++) b.p[k] = trees[k];
+  // every layer reads 2 x 32 B and writes 32 B per product: 48 B x (n + n/2 + ... + 4) per tree
+  ProfScope ps(ctx, PROF_TREE, (double)b.n * (double)n, 48.0 * 2.0 * (double)n * b.n, 8);
+  launch_build_trees(b, n, st);
 }
+void build_tree(Ctx *ctx, fl_t *tree, size_t n, cudaStream_t st) { build_trees(ctx, std::vector<fl_t *>{tree}, n, st); }
 
 bool instance_is_sat(Ctx *ctx, const Instance &inst, const uint8_t *vars32, uint64_t n_vars, const uint8_t *inputs32, uint64_t n_inputs) {
   cudaStream_t st = ctx->st;
@@ -1115,8 +1118,8 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
     launch_hash_ops(dec.col_addr[k].p, derefs.p + (size_t)(3 + k) * N, dec.col_read_ts[k].p, N, d_gt, ops_ptr[6 + k], ops_ptr[9 + k], st);
   }
   phase("network_hash", t0);
-  for (auto p : mem_ptr) build_tree(ctx, p, M, st);
-  for (auto p : ops_ptr) build_tree(ctx, p, N, st);
+  build_trees(ctx, mem_ptr, M, st);
+  build_trees(ctx, ops_ptr, N, st);
   phase("build_layered_network", t0);
 
   t0 = now_ms();

@@ -60,6 +60,7 @@ double measure_imad_peak(Ctx *ctx);
 
 // packed product tree of n leaves stored at tree[0..n): 2n - 2 elements (prover.cu)
 void build_tree(Ctx *ctx, fl_t *tree, size_t n, cudaStream_t st);
+void build_trees(Ctx *ctx, const std::vector<fl_t *> &trees, size_t n, cudaStream_t st);
 
 // builders.cu — vPIN_proof_generation/src/point_mult.rs, point_addition.rs
 void point_mult_dims(uint64_t m, uint64_t dims_out[4]);
