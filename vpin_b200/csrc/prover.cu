@@ -579,18 +579,6 @@ struct Prover {
     return out;
   }
 
-  // ---- one fixed-base MSM row set returning extended points on the host ----
-  std::vector<hge_t> msm_rows_host(const LabelGens &lg, const fl_t *d_scalars, size_t rows, size_t cols, size_t ld) {
-    DevVec<ge_t> pts(rows, st);
-    hyrax_rows(ctx, lg, d_scalars, rows, cols, ld, nullptr, 0, pts.p, nullptr);
-    std::vector<ge_t> h(rows);
-    pts.download(h.data(), rows);
-    ctx->sync();
-    std::vector<hge_t> out(rows);
-    for (size_t i = 0; i < rows; i++) out[i] = hf::ge_from_dev(h[i]);
-    return out;
-  }
-
   // ---- DotProductProofLog::prove (SP/nizk/mod.rs:447-531) + BulletReductionProof::prove (SP/nizk/bullet.rs:32-132).
   // x_vec, a_vec: device vectors of length n = pc.R. The reference folds the generators every round
   // (G_L[i] = u^-1 G_L[i] + u G_R[i]); here the folded generators are never materialised: a weight vector W over the
@@ -604,19 +592,51 @@ struct Prover {
     fl_t r_delta = tape.scalar("r_delta");
     fl_t r_beta = tape.scalar("r_delta");  // sic (mod.rs:466)
     std::vector<fl_t> bv1 = tape.vector("blinds_vec_1", 2 * lg_n), bv2 = tape.vector("blinds_vec_2", 2 * lg_n);
-    // Cx = x_vec.commit(blind_x, gens_n)
-    hge_t cx = msm_rows_host(lg, d_x, 1, n, n)[0];
+    const MsmGeom geom = lg.geom;
+    // Horner pass over the geom.group window sums of one row (kernels_msm.cuh), on the host: 60 doublings cost 14 us here
+    // and 130-250 us in a lone GPU thread
+    auto horner = [&](const fl_t *vals, size_t row) {
+      ge_t w[kMsmMaxGroup];
+      memcpy(w, reinterpret_cast<const uint8_t *>(vals + 8) + row * geom.group * sizeof(ge_t), geom.group * sizeof(ge_t));
+      hge_t h = hf::ge_from_dev(w[geom.group - 1]);
+      for (int k = geom.group - 2; k >= 0; k--) {
+        for (int i = 0; i < geom.W; i++) h = hf::ge_dbl(h);
+        h = hf::ge_add(h, hf::ge_from_dev(w[k]));
+      }
+      return h;
+    };
+    // Cx = x_vec.commit(blind_x, gens_n): one-row fixed-base MSM whose window sums land in the host-mapped slot; the copy of
+    // a_vec for the transcript travels behind it on the same stream
+    hge_t cx;
+    std::vector<fl_t> a_host(n);
+    {
+      size_t segs1 = msm_num_segments(1, n, geom);
+      DevVec<uint16_t> dg(msm_digits_count(1, n, geom), st);
+      DevVec<ge_t> part(geom.group * segs1, st);
+      {
+        ProfScope ps(ctx, PROF_MSM_RECODE, (double)n, (double)n * (32 + 2 * geom.windows));
+        launch_recode(d_x, 1, n, n, nullptr, geom, dg.p, ctx->d_counters.p, st);
+      }
+      {
+        ProfScope ps(ctx, PROF_MSM_ACCUMULATE, (double)n, 0);
+        launch_msm_accumulate(lg.table(), dg.p, 1, n, false, 0, segs1, part.p, st);
+      }
+      {
+        ProfScope ps(ctx, PROF_MSM_FINISH, (double)n, 0);
+        launch_msm_segsum(part.p, 1, segs1, geom, reinterpret_cast<ge_t *>(ctx->d_slots[0].vals + 8), st);
+      }
+      uint32_t seq = ++ctx->round_seq;
+      launch_publish_seq(ctx->d_slots + 0, seq, st);
+      VPIN_CUDA(cudaMemcpyAsync(a_host.data(), d_a, n * sizeof(fl_t), cudaMemcpyDeviceToHost, st));
+      cx = horner(round_wait(0, seq), 0);
+    }
     pc.h->mul_acc(blind_x, &cx);
     Comp Cx = compress_host(cx);
     t.point("Cx", Cx.data());
     Comp Cy = compress_host(commit1(pc, y, blind_y));
     t.point("Cy", Cy.data());
-    {
-      std::vector<fl_t> a_host(n);
-      VPIN_CUDA(cudaMemcpyAsync(a_host.data(), d_a, n * sizeof(fl_t), cudaMemcpyDeviceToHost, st));
-      ctx->sync();
-      t.scalars("a", a_host);
-    }
+    ctx->sync();  // a_host has arrived
+    t.scalars("a", a_host);
     fl_t r = t.challenge_scalar("r");  // Q = r * gens_1.G[0]
     fl_t blind_fin = blind_x + r * blind_y;
     // a / b ping-pong buffers, weights over the original generators, MSM scratch for two rows (kernels_round.cu)
@@ -625,7 +645,6 @@ struct Prover {
     VPIN_CUDA(cudaMemcpyAsync(av[0], d_x, n * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
     VPIN_CUDA(cudaMemcpyAsync(bv[0], d_a, n * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
     launch_fill_one(W.p, n, st);
-    const MsmGeom geom = lg.geom;
     size_t segs = msm_num_segments(2, n, geom), stride = msm_col_stride(n);
     DevVec<uint16_t> digits(msm_digits_count(2, n, geom), st);
     DevVec<ge_t> partial(2 * geom.group * segs, st);
@@ -665,17 +684,6 @@ struct Prover {
       if (fold && !final) src ^= 1;
     };
     static_assert(8 * sizeof(fl_t) + 2 * kMsmMaxGroup * sizeof(ge_t) <= kRoundSlotVals * sizeof(fl_t), "slot too small for two rows");
-    // Horner pass over the geom.group window sums of one row (kernels_msm.cuh), on the host
-    auto horner = [&](const fl_t *vals, size_t row) {
-      ge_t w[kMsmMaxGroup];
-      memcpy(w, reinterpret_cast<const uint8_t *>(vals + 8) + row * geom.group * sizeof(ge_t), geom.group * sizeof(ge_t));
-      hge_t h = hf::ge_from_dev(w[geom.group - 1]);
-      for (int k = geom.group - 2; k >= 0; k--) {
-        for (int i = 0; i < geom.W; i++) h = hf::ge_dbl(h);
-        h = hf::ge_add(h, hf::ge_from_dev(w[k]));
-      }
-      return h;
-    };
     size_t len = n;
     HostPool::Scope helpers(pool);
     for (size_t round = 0; len != 1; round++) {
