@@ -1134,13 +1134,16 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   t.protocol_name("Sparse polynomial evaluation proof");     // PolyEvalNetworkProof (:1333, :1345)
   t.protocol_name("Sparse polynomial product layer proof");  // ProductLayerProof::prove (:1057)
   // circuit outputs = product of the two elements of the last layer (SP/product_tree.rs:58-63)
+  // (one launch gathers the two factors of every root into the host-mapped slot)
   auto tree_evals = [&](const std::vector<fl_t *> &ptrs, size_t n) {
-    std::vector<fl_t> last(2 * ptrs.size());
-    DevVec<fl_t> dl(2 * ptrs.size(), st);
-    for (size_t i = 0; i < ptrs.size(); i++)
-      VPIN_CUDA(cudaMemcpyAsync(dl.p + 2 * i, ptrs[i] + 2 * n - 4, 2 * sizeof(fl_t), cudaMemcpyDeviceToDevice, st));
-    dl.download(last.data(), last.size());
-    ctx->sync();
+    FinalArgs fa;
+    fa.n = 0;
+    for (size_t i = 0; i < ptrs.size(); i++) { fa.p[fa.n++] = ptrs[i] + 2 * n - 4; fa.p[fa.n++] = ptrs[i] + 2 * n - 3; }
+    VPIN_REQUIRE(fa.n <= kRoundSlotVals, VPIN_ERR_PROVER, "too many circuits");
+    uint32_t seq;
+    RoundCtl ctl = P.round_ctl(0, &seq);
+    launch_round_final(fa, false, fl_zero(), ctl, st);
+    const fl_t *last = P.round_wait(0, seq);
     std::vector<fl_t> ev(ptrs.size());
     for (size_t i = 0; i < ptrs.size(); i++) ev[i] = last[2 * i] * last[2 * i + 1];
     return ev;
