@@ -103,6 +103,7 @@ void vpin_ctx_destroy(vpin_ctx *ctx_) {
   ctx->d_counters.release();
   for (auto &p : ctx->prof.pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
+  if (ctx->ev_marker) cudaEventDestroy(ctx->ev_marker);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
   ctx->d_round_counters.release();

@@ -168,6 +168,13 @@ struct vpin_ctx_impl {
   void *nccl_comm = nullptr;
   DevVec<unsigned long long> d_counters;  // [0] = non-zero MSM digits recoded (= mixed additions executed)
   void sync() { VPIN_CUDA(cudaStreamSynchronize(st)); }
+  // a marker on the stream that the host can wait for without draining what is queued behind it
+  cudaEvent_t ev_marker = nullptr;
+  void mark() {
+    if (!ev_marker) VPIN_CUDA(cudaEventCreateWithFlags(&ev_marker, cudaEventDisableTiming));
+    VPIN_CUDA(cudaEventRecord(ev_marker, st));
+  }
+  void wait_mark() { VPIN_CUDA(cudaEventSynchronize(ev_marker)); }
 };
 
 // rows [*r0, *r1) of an L-row Hyrax grid that rank `rank` of `world` commits to; the whole range when the grid is too

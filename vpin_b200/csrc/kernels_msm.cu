@@ -283,26 +283,39 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
 
 // finish, step 1 (only when a row was split into segments): one warp per (row, local window) adds the segment partials
 // (lane-strided, then a shuffle tree) -> sums[row][w'].
-__global__ void __launch_bounds__(128) k_msm_segsum(const ge_t *partial, size_t pairs, size_t segs, ge_t *sums) {
+// publish: optional {counter, host-mapped sequence word, value}: the last block to finish stores the value there (system scope),
+// which tells the host that every window sum has landed in its mapped slot — saves the separate one-thread launch
+struct SegsumPublish { unsigned *counter; volatile uint32_t *seq_word; uint32_t seq; };
+__global__ void __launch_bounds__(128) k_msm_segsum(const ge_t *partial, size_t pairs, size_t segs, ge_t *sums, SegsumPublish pub) {
   size_t pair = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);  // (row, w') flattened
-  if (pair >= pairs) return;
   const int lane = threadIdx.x & 31;
-  const ge_t *p = partial + pair * segs;
-  ge_t acc = ge_identity();
-  bool first = true;
-  for (size_t s = lane; s < segs; s += 32) {
-    ge_t q = ld_ge(p + s);
-    acc = first ? q : ge_add(acc, q);
-    first = false;
+  if (pair < pairs) {
+    const ge_t *p = partial + pair * segs;
+    ge_t acc = ge_identity();
+    bool first = true;
+    for (size_t s = lane; s < segs; s += 32) {
+      ge_t q = ld_ge(p + s);
+      acc = first ? q : ge_add(acc, q);
+      first = false;
+    }
+    int width = segs >= 32 ? 32 : (int)segs;
+    for (int off = 16; off > 0; off >>= 1) {
+      if (off < width) {  // warp-uniform; lanes beyond the data hold the identity
+        ge_t o = shfl_down_ge(acc, off);
+        acc = ge_add(acc, o);
+      }
+    }
+    if (lane == 0) st_ge(sums + pair, acc);
   }
-  int width = segs >= 32 ? 32 : (int)segs;
-  for (int off = 16; off > 0; off >>= 1) {
-    if (off < width) {  // warp-uniform; lanes beyond the data hold the identity
-      ge_t o = shfl_down_ge(acc, off);
-      acc = ge_add(acc, o);
+  if (pub.counter) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(pub.counter, 1u) == gridDim.x - 1) {
+      *pub.counter = 0;
+      __threadfence_system();
+      *pub.seq_word = pub.seq;
     }
   }
-  if (lane == 0) st_ge(sums + pair, acc);
 }
 // finish, step 2: one thread per row runs the Horner pass over the kMsmGroup window sums and encodes the point
 __global__ void __launch_bounds__(32) k_msm_horner(const ge_t *sums, size_t rows, MsmGeom g, ge_t *out, uint8_t *comp) {
@@ -325,16 +338,18 @@ __global__ void __launch_bounds__(32) k_msm_horner(const ge_t *sums, size_t rows
     q[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
-void launch_msm_segsum(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, cudaStream_t st) {
+void launch_msm_segsum(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, cudaStream_t st, unsigned *d_counter,
+                       uint32_t *d_seq_word, uint32_t seq) {
   size_t pairs = rows * g.group;
-  ++g_kernel_launches, k_msm_segsum<<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(d_partial, pairs, segs, d_sums);
+  SegsumPublish pub{d_counter, d_seq_word, seq};
+  ++g_kernel_launches, k_msm_segsum<<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(d_partial, pairs, segs, d_sums, pub);
 }
 void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, ge_t *d_out, uint8_t *d_comp,
                        cudaStream_t st) {
   const ge_t *sums = d_partial;
   if (segs > 1) {
     size_t pairs = rows * g.group;
-    ++g_kernel_launches, k_msm_segsum<<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(d_partial, pairs, segs, d_sums);
+    ++g_kernel_launches, k_msm_segsum<<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(d_partial, pairs, segs, d_sums, SegsumPublish{nullptr, nullptr, 0});
     sums = d_sums;
   }
   ++g_kernel_launches, k_msm_horner<<<(unsigned)((rows + 31) / 32), 32, 0, st>>>(sums, rows, g, d_out, d_comp);

@@ -77,7 +77,10 @@ void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, const Ms
 // first half of the finish only: d_sums[row * geom.group + w'] = sum_seg partial[row][w'][seg] (the caller runs the Horner
 // pass itself — the prover's bullet-reduction rounds do it on the host, 60 doublings being far cheaper there than in a
 // single GPU thread)
-void launch_msm_segsum(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, cudaStream_t st);
+// d_counter / d_seq_word / seq (optional): the last block stores `seq` to *d_seq_word (a host-mapped word) once every sum is
+// written — d_sums then normally points into the same mapped slot; d_counter: a zeroed device word, left zero again
+void launch_msm_segsum(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, cudaStream_t st,
+                       unsigned *d_counter = nullptr, uint32_t *d_seq_word = nullptr, uint32_t seq = 0);
 // RFC 9496 encoding of n points -> n x 32 bytes
 void launch_compress(const ge_t *d_pts, size_t n, uint8_t *d_out, cudaStream_t st);
 // decode n x 32 bytes -> points; d_ok[i] = 1 if valid

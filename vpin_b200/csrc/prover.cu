@@ -608,6 +608,7 @@ struct Prover {
     // Cx = x_vec.commit(blind_x, gens_n): one-row fixed-base MSM whose window sums land in the host-mapped slot; the copy of
     // a_vec for the transcript travels behind it on the same stream
     hge_t cx;
+    uint32_t cx_seq = 0;
     std::vector<fl_t> a_host(n);
     {
       size_t segs1 = msm_num_segments(1, n, geom);
@@ -621,24 +622,16 @@ struct Prover {
         ProfScope ps(ctx, PROF_MSM_ACCUMULATE, (double)n, 0);
         launch_msm_accumulate(lg.table(), dg.p, 1, n, false, 0, segs1, part.p, st);
       }
-      {
-        ProfScope ps(ctx, PROF_MSM_FINISH, (double)n, 0);
-        launch_msm_segsum(part.p, 1, segs1, geom, reinterpret_cast<ge_t *>(ctx->d_slots[0].vals + 8), st);
-      }
       uint32_t seq = ++ctx->round_seq;
-      launch_publish_seq(ctx->d_slots + 0, seq, st);
+      {  // the last block of the segment-sum kernel publishes the sequence number (slot 1: slot 0 belongs to round 0 below)
+        ProfScope ps(ctx, PROF_MSM_FINISH, (double)n, 0);
+        launch_msm_segsum(part.p, 1, segs1, geom, reinterpret_cast<ge_t *>(ctx->d_slots[1].vals + 8), st, ctx->d_round_counters.p + 31,
+                          &ctx->d_slots[1].seq, seq);
+      }
       VPIN_CUDA(cudaMemcpyAsync(a_host.data(), d_a, n * sizeof(fl_t), cudaMemcpyDeviceToHost, st));
-      cx = horner(round_wait(0, seq), 0);
+      ctx->mark();
+      cx_seq = seq;
     }
-    pc.h->mul_acc(blind_x, &cx);
-    Comp Cx = compress_host(cx);
-    t.point("Cx", Cx.data());
-    Comp Cy = compress_host(commit1(pc, y, blind_y));
-    t.point("Cy", Cy.data());
-    ctx->sync();  // a_host has arrived
-    t.scalars("a", a_host);
-    fl_t r = t.challenge_scalar("r");  // Q = r * gens_1.G[0]
-    fl_t blind_fin = blind_x + r * blind_y;
     // a / b ping-pong buffers, weights over the original generators, MSM scratch for two rows (kernels_round.cu)
     DevVec<fl_t> abuf(2 * n, st), bbuf(2 * n, st), W(n, st);
     fl_t *av[2] = {abuf.p, abuf.p + n}, *bv[2] = {bbuf.p, bbuf.p + n};
@@ -649,7 +642,6 @@ struct Prover {
     DevVec<uint16_t> digits(msm_digits_count(2, n, geom), st);
     DevVec<ge_t> partial(2 * geom.group * segs, st);
     DotLogS out;
-    t_bullet_pre += now_ms() - tb0;
     int src = 0, slot = 0;
     bool fold = false;
     fl_t u = fl_zero(), u_inv = fl_zero();
@@ -675,21 +667,38 @@ struct Prover {
         ProfScope ps(ctx, PROF_MSM_ACCUMULATE, pts, 0);
         launch_msm_accumulate(lg.table(), digits.p, rows, n, false, 0, sg, partial.p, st);
       }
-      {  // window sums straight into the host-mapped slot: vals[8 ..] = rows x kMsmGroup points
-        ProfScope ps(ctx, PROF_MSM_FINISH, pts, 0);
-        launch_msm_segsum(partial.p, rows, sg, geom, reinterpret_cast<ge_t *>(ctx->d_slots[slot].vals + 8), st);
-      }
       *seq_out = ++ctx->round_seq;
-      launch_publish_seq(ctx->d_slots + slot, *seq_out, st);
+      {  // window sums straight into the host-mapped slot: vals[8 ..] = rows x kMsmGroup points; the kernel's last block publishes
+        ProfScope ps(ctx, PROF_MSM_FINISH, pts, 0);
+        launch_msm_segsum(partial.p, rows, sg, geom, reinterpret_cast<ge_t *>(ctx->d_slots[slot].vals + 8), st, ctx->d_round_counters.p + 31,
+                          &ctx->d_slots[slot].seq, *seq_out);
+      }
       if (fold && !final) src ^= 1;
     };
     static_assert(8 * sizeof(fl_t) + 2 * kMsmMaxGroup * sizeof(ge_t) <= kRoundSlotVals * sizeof(fl_t), "slot too small for two rows");
+    // Round 0 needs nothing from the transcript (no fold yet): its kernels are queued now and run while the host finishes Cx
+    // and absorbs the n scalars of a_vec (0.3 ms of Keccak at n = 4096)
     size_t len = n;
+    uint32_t seq_round0 = 0;
+    const bool prelaunched = len != 1;
+    if (prelaunched) launch(len, false, &seq_round0);
+    cx = horner(round_wait(1, cx_seq), 0);
+    pc.h->mul_acc(blind_x, &cx);
+    Comp Cx = compress_host(cx);
+    t.point("Cx", Cx.data());
+    Comp Cy = compress_host(commit1(pc, y, blind_y));
+    t.point("Cy", Cy.data());
+    ctx->wait_mark();  // a_host has arrived (it travels behind the Cx kernels and ahead of round 0, which keeps running)
+    t.scalars("a", a_host);
+    fl_t r = t.challenge_scalar("r");  // Q = r * gens_1.G[0]
+    fl_t blind_fin = blind_x + r * blind_y;
+    t_bullet_pre += now_ms() - tb0;
     HostPool::Scope helpers(pool);
     for (size_t round = 0; len != 1; round++) {
       double tr0 = now_ms();
       uint32_t seq;
-      launch(len, false, &seq);
+      if (round == 0 && prelaunched) seq = seq_round0;
+      else launch(len, false, &seq);
       const fl_t *vals = round_wait(slot, seq);
       fl_t c[2] = {vals[0], vals[1]};
       double tr1 = now_ms();
