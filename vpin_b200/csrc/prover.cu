@@ -805,9 +805,6 @@ struct Prover {
           args.Cin[nc + k] = dotp[k].w; args.Cout[nc + k] = dotp[k].w;
         }
       fl_t *eq_cur = eqC.p, *eq_other = eq_pong.p;
-      std::vector<fl_t> coeffs = t.challenge_vector("rand_coeffs_next_layer", claims_to_verify.size());
-      fl_t e = fl_zero();
-      for (size_t i = 0; i < coeffs.size(); i++) e = e + claims_to_verify[i] * coeffs[i];
       LayerS layer;
       std::vector<fl_t> rand_prod;
       double tables = 2.0 * nc + 1 + (with_dotp ? 3.0 * dotp.size() : 0);
@@ -824,6 +821,10 @@ struct Prover {
       };
       fl_t r_j = fl_zero();
       if (num_rounds) launch(0, r_j);
+      // the first round's kernel needs neither the coefficients nor the claim: both are drawn / formed while it runs
+      std::vector<fl_t> coeffs = t.challenge_vector("rand_coeffs_next_layer", claims_to_verify.size());
+      fl_t e = fl_zero();
+      for (size_t i = 0; i < coeffs.size(); i++) e = e + claims_to_verify[i] * coeffs[i];
       std::vector<fl_t> ev(3 * ninst);
       for (size_t j = 0; j < num_rounds; j++) {
         double tw0 = now_ms();
