@@ -1,0 +1,44 @@
+"""CPU: the driver-facing contract of bench.py that can be checked without a GPU — the reference arm prints exactly one JSON
+line with the agreed keys, and the B200 arm refuses to run without a CUDA device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "conv3", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "spartan_prove_time_s" and d["unit"] == "s"
+    assert d["higher_is_better"] is False and d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["config"]["workload"] == "conv3" and d["config"]["point_mults"] == 18
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_b200_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)
+    assert not [l for l in p.stdout.splitlines() if l.strip().startswith("{")]  # no number without the CUDA path
+
+
+def test_workload_replicas_differ_and_facts_load():
+    sys.path.insert(0, ROOT)
+    import bench
+    a, b = bench.make_workload("conv3"), bench.make_workload("conv3", replica=1)
+    assert a["mult"] != b["mult"] and a["add"] != b["add"] and a["seeds"] == b["seeds"]
+    facts = bench.load_ncu_facts()
+    assert facts and 100 < facts["dram_bytes_per_madd"] < 300 and 0.5 < facts["fmaheavy_pipe_util"] <= 1.0
