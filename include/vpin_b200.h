@@ -68,7 +68,9 @@ void vpin_ctx_destroy(vpin_ctx *ctx);
  * that every rank runs the SAME calls with the SAME inputs (the Fiat-Shamir transcript is replayed identically on every
  * rank, so no challenge is ever broadcast); the L independent rows of every Hyrax commitment (SP/dense_mlpoly.rs:160-175,
  * the reference's one rayon par_iter) are split across ranks and exchanged with one in-place NCCL all-gather of 32 B
- * per row. vpin_shard_rows tells which rows a rank owns (whole range when the grid is too small to shard). */
+ * per row. vpin_shard_rows tells which rows a rank owns (whole range when the grid is too small to shard).
+ * With VPIN_SHARD_SUMCHECK=1 in the environment the instances of the large batched product-circuit sumcheck layers are dealt to the
+ * ranks as well (one NCCL all-gather of <= 3 KB per round); the proof bytes do not change. */
 vpin_status vpin_nccl_unique_id(uint8_t id_out[128]);
 vpin_status vpin_ctx_init_distributed(vpin_ctx *ctx, int32_t rank, int32_t world, const uint8_t nccl_id[128]);
 void vpin_shard_rows(uint64_t rows, int32_t rank, int32_t world, uint64_t *r0, uint64_t *r1, int32_t *sharded);

@@ -167,6 +167,10 @@ struct vpin_ctx_impl {
   int rank = 0, world = 1;
   void *nccl_comm = nullptr;
   DevVec<unsigned long long> d_counters;  // [0] = non-zero MSM digits recoded (= mixed additions executed)
+  // sharded sumcheck rounds (one proof on several GPUs, VPIN_SHARD_SUMCHECK=1): device-side result slots of the round kernels
+  // and the all-gather buffer (kRoundSlotVals elements)
+  DevVec<RoundSlot> d_dev_slots;
+  DevVec<fl_t> d_gather;
   void sync() { VPIN_CUDA(cudaStreamSynchronize(st)); }
   // a marker on the stream that the host can wait for without draining what is queued behind it
   cudaEvent_t ev_marker = nullptr;

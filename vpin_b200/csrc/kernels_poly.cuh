@@ -37,7 +37,7 @@ void launch_cubic_batched_round(const fl_t *const *d_A, const fl_t *const *d_B, 
 
 // ---- fused rounds (kernels_round.cu): bind with the previous challenge + evaluate the next round in one launch, results
 // delivered to host-mapped pinned memory. ----
-static const int kRoundSlotVals = 64;
+static const int kRoundSlotVals = 96;  // >= 3 x the instances of a batched layer spread over up to 8 ranks (sharded rounds)
 struct RoundSlot {                 // lives in cudaHostAllocMapped memory
   fl_t vals[kRoundSlotVals];
   uint32_t seq;                    // written last (after a system-wide fence) with the launch's sequence number
@@ -79,6 +79,10 @@ struct BulletRoundArgs {
 };
 void launch_bullet_round(const BulletRoundArgs &p, cudaStream_t st);
 void launch_publish_seq(RoundSlot *slot, uint32_t seq, cudaStream_t st);
+// sharded rounds (one proof on several GPUs): dst[0..n_total) = src[0..n_valid) followed by zeros (this rank's segment of the
+// all-gather buffer); then, after the all-gather, slot->vals[0..count) = src[0..count) and the sequence number
+void launch_stage_vals(const fl_t *src, int n_valid, int n_total, fl_t *dst, cudaStream_t st);
+void launch_publish_vals(const fl_t *src, int count, RoundSlot *slot, uint32_t seq, cudaStream_t st);
 // eq table with the point passed by value (no device-side copy of r needed); same output as launch_eq_evals
 struct EqPoint { fl_t r[32]; };
 void launch_eq_evals_pt(const EqPoint &pt, int ell, fl_t *d_out, fl_t *d_tmp, cudaStream_t st);

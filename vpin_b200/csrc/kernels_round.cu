@@ -331,6 +331,21 @@ __global__ void k_publish_seq(RoundSlot *slot, uint32_t seq) {
   *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
 }
 
+__global__ void k_stage_vals(const fl_t *src, int n_valid, int n_total, fl_t *dst) {
+  int k = threadIdx.x;
+  if (k < n_total) str(dst + k, k < n_valid ? ldr(src + k) : fl_zero());
+}
+__global__ void k_publish_vals(const fl_t *src, int count, RoundSlot *slot, uint32_t seq) {
+  int k = threadIdx.x;
+  if (k < count) str(slot->vals + k, ldr(src + k));
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
+  }
+}
+
 inline int round_blocks(size_t q, int cap) {
   size_t b = (q + kRedThreads - 1) / kRedThreads;
   if (b < 1) b = 1;
@@ -375,6 +390,12 @@ void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, 
 void launch_bullet_round(const BulletRoundArgs &p, cudaStream_t st) {
   unsigned nb = (unsigned)((p.stride + kRedThreads - 1) / kRedThreads);
   ++g_kernel_launches, k_bullet_round<<<nb, kRedThreads, 0, st>>>(p);
+}
+void launch_stage_vals(const fl_t *src, int n_valid, int n_total, fl_t *dst, cudaStream_t st) {
+  ++g_kernel_launches, k_stage_vals<<<1, 128, 0, st>>>(src, n_valid, n_total, dst);
+}
+void launch_publish_vals(const fl_t *src, int count, RoundSlot *slot, uint32_t seq, cudaStream_t st) {
+  ++g_kernel_launches, k_publish_vals<<<1, 128, 0, st>>>(src, count, slot, seq);
 }
 void launch_publish_seq(RoundSlot *slot, uint32_t seq, cudaStream_t st) { ++g_kernel_launches, k_publish_seq<<<1, 1, 0, st>>>(slot, seq); }
 void launch_round_final(const FinalArgs &a, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {

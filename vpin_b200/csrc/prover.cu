@@ -190,6 +190,14 @@ std::unique_ptr<Decomm> snark_encode(Ctx *ctx, const Instance &inst, const Snark
 // ------------------------------------------------------------------------------------------------ prover
 namespace {
 
+// Sharded sumcheck rounds of ONE proof across GPUs: opt-in (VPIN_SHARD_SUMCHECK=1) and only for layers of at least this many
+// thread items, see batched_prove.
+static const size_t kShardMinLayer = (size_t)1 << 14;
+static bool shard_sumcheck_enabled(const Ctx *ctx) {
+  static const bool on = [] { const char *e = getenv("VPIN_SHARD_SUMCHECK"); return e && atoi(e) != 0; }();
+  return on && ctx->world > 1 && ctx->nccl_comm != nullptr;
+}
+
 // A few helper threads for the O(1) elliptic-curve work next to the transcript (the per-round commitments of the ZK
 // sumchecks, the L / R points of a bullet-reduction round): ~10 fixed-base multiplications of 5-10 us each per round that
 // are independent of one another. Helpers spin while a scope is active (hand-off ~0.3 us) and sleep otherwise.
@@ -810,9 +818,60 @@ struct Prover {
       double tables = 2.0 * nc + 1 + (with_dotp ? 3.0 * dotp.size() : 0);
       uint32_t seq = 0;
       int slot = 0;
+      // One proof on several GPUs (opt-in, VPIN_SHARD_SUMCHECK=1): the instances of a LARGE layer are dealt round-robin to the
+      // ranks. Every layer starts from tree data that all ranks hold, and nothing outside the layer's sumcheck reads its
+      // tables, so a rank only ever evaluates and binds its own instances; per round the 3 sums of every instance are
+      // exchanged with one small in-place NCCL all-gather (and the final claims once per layer), then every rank continues
+      // with the same transcript. Small layers are not worth the ~15 us of the collective per round and stay replicated.
+      const int world = ctx->world, rank = ctx->rank;
+      const bool sharded = shard_sumcheck_enabled(ctx) && len_half >= kShardMinLayer;
+      const size_t max_own = (ninst + world - 1) / world;
+      std::vector<size_t> own;  // this rank's instances, in order
+      BatchedRoundArgs own_args;
+      memset(&own_args, 0, sizeof(own_args));
+      if (sharded) {
+        for (size_t i = rank; i < ninst; i += world) own.push_back(i);
+        VPIN_REQUIRE(3 * max_own * world <= (size_t)kRoundSlotVals, VPIN_ERR_PROVER, "sharded round does not fit the slot");
+        if (!ctx->d_dev_slots.p) { ctx->d_dev_slots.alloc(2, st); ctx->d_gather.alloc(kRoundSlotVals, st); }
+        for (size_t k = 0; k < own.size(); k++) {
+          own_args.A[k] = args.A[own[k]]; own_args.B[k] = args.B[own[k]];
+          own_args.Cin[k] = args.Cin[own[k]]; own_args.Cout[k] = args.Cout[own[k]];  // (dot-product instances own their third factor)
+        }
+      }
+      // after a sharded launch: stage this rank's values, all-gather, publish everything to the host-mapped slot
+      auto exchange = [&](int per_inst) {
+        const int seg = per_inst * (int)max_own;
+        launch_stage_vals(ctx->d_dev_slots.p[slot].vals, per_inst * (int)own.size(), seg, ctx->d_gather.p + (size_t)rank * seg, st);
+        dist_allgather_inplace(ctx, ctx->d_gather.p, (size_t)seg * sizeof(fl_t));
+        seq = ++ctx->round_seq;
+        launch_publish_vals(ctx->d_gather.p, seg * world, ctx->d_slots + slot, seq, st);
+      };
+      // gathered layout -> instance order: instance i sits at rank (i % world), position (i / world)
+      auto ungather = [&](const fl_t *g, int per_inst, size_t i, int k) -> const fl_t & {
+        return g[(i % world) * (per_inst * max_own) + (i / world) * per_inst + k];
+      };
       // round j: bind with r_{j-1} (j > 0) and evaluate over q = len_half >> (j+1) thread items
       auto launch = [&](size_t j, const fl_t &r_prev) {
         size_t q = len_half >> (j + 1);
+        if (sharded) {
+          bool first_prod = true;  // the first product instance of this rank writes the bound eq table, the others read it
+          for (size_t k = 0; k < own.size(); k++)
+            if (own[k] < nc) {
+              own_args.Cin[k] = eq_cur;
+              own_args.Cout[k] = (j > 0 && first_prod) ? eq_other : nullptr;
+              first_prod = false;
+            }
+          if (!own.empty()) {
+            uint32_t dev_seq;
+            RoundCtl ctl = round_ctl(slot, &dev_seq);
+            ctl.slot = ctx->d_dev_slots.p + slot;  // results stay on the device until the exchange
+            ProfScope ps(ctx, PROF_SC_BATCHED, (double)own.size() * q, (2.0 * own.size() + 1) * (j > 0 ? 6 : 2) * q * 32);
+            launch_round_cubic_batched(own_args, (int)own.size(), q, j > 0, r_prev, ctl, st);
+          }
+          exchange(3);
+          if (j > 0) std::swap(eq_cur, eq_other);
+          return;
+        }
         for (size_t c = 0; c < nc; c++) { args.Cin[c] = eq_cur; args.Cout[c] = nullptr; }
         if (j > 0) { args.Cout[0] = eq_other; }
         ProfScope ps(ctx, PROF_SC_BATCHED, (double)ninst * q, tables * (j > 0 ? 6 : 2) * q * 32);
@@ -828,7 +887,15 @@ struct Prover {
       std::vector<fl_t> ev(3 * ninst);
       for (size_t j = 0; j < num_rounds; j++) {
         double tw0 = now_ms();
-        memcpy(ev.data(), round_wait(slot, seq), 3 * ninst * sizeof(fl_t));
+        {
+          const fl_t *got = round_wait(slot, seq);
+          if (sharded) {
+            for (size_t i = 0; i < ninst; i++)
+              for (int k = 0; k < 3; k++) ev[3 * i + k] = ungather(got, 3, i, k);
+          } else {
+            memcpy(ev.data(), got, 3 * ninst * sizeof(fl_t));
+          }
+        }
         double tw1 = now_ms();
         t_b_wait += tw1 - tw0;
         n_b_rounds++;
@@ -862,12 +929,33 @@ struct Prover {
       if (with_dotp)
         for (size_t k = 0; k < dotp.size(); k++) { fa.p[fa.n++] = dotp[k].l; fa.p[fa.n++] = dotp[k].r; fa.p[fa.n++] = dotp[k].w; }
       VPIN_REQUIRE(fa.n <= kRoundSlotVals, VPIN_ERR_PROVER, "too many final claims");
-      {
+      std::vector<fl_t> fin(fa.n);
+      if (sharded) {  // three final claims per own instance (left, right, third factor), exchanged like the round sums
+        FinalArgs fo;
+        fo.n = 0;
+        for (size_t k = 0; k < own.size(); k++) {
+          fo.p[fo.n++] = own_args.A[k];
+          fo.p[fo.n++] = own_args.B[k];
+          fo.p[fo.n++] = own[k] < nc ? eq_cur : own_args.Cin[k];
+        }
+        if (fo.n) {
+          uint32_t dev_seq;
+          RoundCtl ctl = round_ctl(slot, &dev_seq);
+          ctl.slot = ctx->d_dev_slots.p + slot;
+          launch_round_final(fo, num_rounds > 0, r_j, ctl, st);
+        }
+        exchange(3);
+        const fl_t *got = round_wait(slot, seq);
+        for (size_t c = 0; c < nc; c++) { fin[2 * c] = ungather(got, 3, c, 0); fin[2 * c + 1] = ungather(got, 3, c, 1); }
+        fin[2 * nc] = ungather(got, 3, 0, 2);
+        if (with_dotp)
+          for (size_t k = 0; k < dotp.size(); k++)
+            for (int x = 0; x < 3; x++) fin[2 * nc + 1 + 3 * k + x] = ungather(got, 3, nc + k, x);
+      } else {
         ProfScope ps(ctx, PROF_FINAL, (double)fa.n, 0);
         launch_round_final(fa, num_rounds > 0, r_j, round_ctl(slot, &seq), st);
+        memcpy(fin.data(), round_wait(slot, seq), fa.n * sizeof(fl_t));
       }
-      std::vector<fl_t> fin(fa.n);
-      memcpy(fin.data(), round_wait(slot, seq), fa.n * sizeof(fl_t));
       for (size_t c = 0; c < nc; c++) { layer.left.push_back(fin[2 * c]); layer.right.push_back(fin[2 * c + 1]); }
       for (size_t c = 0; c < nc; c++) {
         t.scalar("claim_prod_left", layer.left[c]);
