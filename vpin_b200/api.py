@@ -401,7 +401,9 @@ class SNARK:
         """SNARK::encode(&inst, &gens) -> (ComputationCommitment as bincode bytes, ComputationDecommitment handle)"""
         ctx = inst.ctx
         cap = 64 + 32 * (1 << 16) * 2
-        out = C.create_string_buffer(cap)
+        out = getattr(ctx, "_comm_buf", None)  # one 4 MB output buffer per context, reused (no mmap / munmap per call)
+        if out is None:
+            out = ctx._comm_buf = C.create_string_buffer(cap)
         n = C.c_uint64()
         d = C.c_void_p()
         st = lib().vpin_encode(ctx._h, inst._h, gens._h, out, C.c_uint64(cap), C.byref(n), C.byref(d))
