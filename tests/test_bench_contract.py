@@ -24,6 +24,14 @@ def test_reference_arm_prints_one_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_other_ranks_exit_quietly():
+    """under torchrun only rank 0 runs and prints the reference arm; the other ranks exit 0 without work"""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
 def test_b200_arm_needs_a_gpu():
     import torch
     if torch.cuda.is_available():
