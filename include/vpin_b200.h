@@ -77,7 +77,7 @@ void vpin_shard_rows(uint64_t rows, int32_t rank, int32_t world, uint64_t *r0, u
 /* message of the last failure on this context (never NULL) */
 const char *vpin_last_error(const vpin_ctx *ctx);
 /* number of this library's kernels launched on the context so far (bench.py's gpu_launches) */
-uint64_t vpin_kernel_launches(const vpin_ctx *ctx);
+uint64_t vpin_kernel_launches(const vpin_ctx *ctx); /* kernels launched by calls on this context (ctx == NULL: by the process) */
 
 /* ---- public parameters: SNARKGens::new(num_cons, num_vars, num_inputs, num_nz_entries)   SP/lib.rs:305 ---------- */
 vpin_status vpin_gens_create(vpin_ctx *ctx, uint64_t num_cons, uint64_t num_vars, uint64_t num_inputs,
@@ -264,8 +264,13 @@ vpin_status vpin_witness_from_device(vpin_ctx *ctx, const vpin_gens *gens, const
 vpin_status vpin_profile_enable(vpin_ctx *ctx, int32_t on, double min_units);
 uint32_t vpin_profile_read(vpin_ctx *ctx, const char **names_out, double *ms_out, uint64_t *launches_out, double *units_out,
                            double *bytes_out, uint32_t cap, uint64_t *msm_madds_out);
-/* dependency-free mad.wide.u32 microbenchmark: returns multiply-accumulates per second (the integer roofline) */
+/* The integer roofline, measured live: 32 x 32 + 64 -> 64 multiply-accumulates per second of a dependency-free stream of real
+ * IMAD.WIDE.U32 instructions (one factor changes every iteration, so nothing is hoisted). forms[0]: plain product (no addend)
+ * combined into the accumulator on the ALU pipe; forms[1]: single-instruction multiply-accumulate (64-bit addend), the form
+ * the field arithmetic uses. vpin_imad_peak returns the better of the two. IMAD.WIDE is a half-rate instruction on sm_100a:
+ * ~8.0 / 7.6 T/s on a B200 (the round-1 figure of 18.4 T/s timed IADD3 pairs - its product had been hoisted by ptxas). */
 vpin_status vpin_imad_peak(vpin_ctx *ctx, double *macs_per_second);
+vpin_status vpin_imad_peak_forms(vpin_ctx *ctx, double forms[2]);
 
 #ifdef __cplusplus
 }

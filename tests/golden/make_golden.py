@@ -53,7 +53,49 @@ def run(kind, kw):
                 comm_vars_sha256=digest(f.comm_vars), proof_head=f.proof[:64].hex())
 
 
+
+
+# ---- BASELINE.json's named shapes at full size (golden_named.json) ----------------------------------------------------------
+# The CPU oracle needs seconds (conv3) to minutes (CNN E) per instance, far too long for a test, so the digests are generated
+# once here and committed; tests/test_gpu_golden.py::test_named_shape_matches_golden compares the CUDA flow with them byte
+# for byte (sha256 of the proof and of the four commitments, proof length, first 64 proof bytes).
+#     python tests/golden/make_golden.py named [tags...]      # default tags: conv3 conv5 conv7 A E
+NAMED_DEFAULT = ["conv3", "conv5", "conv7", "A", "E"]
+
+
+def run_named(tag, which):
+    import time
+    m, n_add = W.SHAPES[tag]
+    if which == "mult":
+        built, args = O.build_point_mult(*W.synth_point_mult(m)), dict(m=m)
+    else:
+        built, args = O.build_point_add(*W.synth_point_add(n_add)), dict(n=n_add, infinity_every=0)
+    sq, sp = W.tape_seeds()
+    t0 = time.time()
+    f = O.Flow(built, sq, sp, verify=True)
+    assert f.verified
+    print(f"  {tag}/{which}: dims {built.dims}, proof {len(f.proof)} B, oracle flow {time.time() - t0:.1f} s", flush=True)
+    return dict(tag=tag, kind="point_" + which, args=args, dims=list(built.dims), proof_len=len(f.proof), proof_sha256=digest(f.proof),
+                comm_sha256=digest(f.comm), comm_vars_para_sha256=digest(f.comm_vars_para),
+                comm_vars_input_sha256=digest(f.comm_vars_input), comm_vars_sha256=digest(f.comm_vars), proof_head=f.proof[:64].hex())
+
+
+def main_named(tags):
+    path = os.path.join(HERE, "golden_named.json")
+    out = json.load(open(path)) if os.path.exists(path) else dict(tape_seeds=[s.hex() for s in W.tape_seeds()],
+                                                                   transcript_label="snark_example", cases=[])
+    for tag in tags:
+        for which in ("mult", "add"):
+            out["cases"] = [c for c in out["cases"] if not (c["tag"] == tag and c["kind"] == "point_" + which)]
+            out["cases"].append(run_named(tag, which))
+            json.dump(out, open(path, "w"), indent=1)
+    print("wrote", len(out["cases"]), "named cases")
+
+
 if __name__ == "__main__":
-    out = dict(tape_seeds=[s.hex() for s in W.tape_seeds()], transcript_label="snark_example", cases=[run(k, kw) for k, kw in CASES])
-    json.dump(out, open(os.path.join(HERE, "golden_flows.json"), "w"), indent=1)
-    print("wrote", len(out["cases"]), "cases")
+    if len(sys.argv) > 1 and sys.argv[1] == "named":
+        main_named(sys.argv[2:] or NAMED_DEFAULT)
+    else:
+        out = dict(tape_seeds=[s.hex() for s in W.tape_seeds()], transcript_label="snark_example", cases=[run(k, kw) for k, kw in CASES])
+        json.dump(out, open(os.path.join(HERE, "golden_flows.json"), "w"), indent=1)
+        print("wrote", len(out["cases"]), "cases")

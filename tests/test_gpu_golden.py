@@ -39,3 +39,30 @@ def test_cuda_flow_matches_golden(ctx, case):
     assert sha(got["comm_vars_para"]) == case["comm_vars_para_sha256"]
     assert sha(got["comm_vars_input"]) == case["comm_vars_input_sha256"]
     assert sha(got["comm_vars"]) == case["comm_vars_sha256"]
+
+
+NAMED = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_named.json")))
+
+
+@pytest.mark.parametrize("case", NAMED["cases"], ids=lambda c: f"{c['tag']}-{c['kind']}")
+def test_named_shape_matches_golden(ctx, case):
+    """BASELINE.json's named shapes at FULL size - conv 3/5/7, CNN A..E, LeNet layers 1 and 3, both instances of each network -
+    byte-compared with the CPU oracle through committed digests (tests/golden/make_golden.py named; the oracle needs 7 s ..
+    5 min per instance, so its outputs are frozen there). These sizes take the code paths the small cases never reach:
+    multi-block batched rounds, k_spmv_csc_long, MSM rows split into segments, multi-launch product-tree layers, W = 15 tables."""
+    from vpin_b200 import api
+    kw = case["args"]
+    if case["kind"] == "point_add":
+        dims, inst, vp, vi, v, inputs = api.point_addition(ctx, *W.synth_point_add(kw["n"], infinity_every=kw["infinity_every"]))
+    else:
+        dims, inst, vp, vi, v, inputs = api.point_mult(ctx, *W.synth_point_mult(kw["m"]))
+    assert list(dims) == case["dims"]
+    sq, sp = (bytes.fromhex(s) for s in NAMED["tape_seeds"])
+    got = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp, label=NAMED["transcript_label"].encode())
+    assert len(got["proof"]) == case["proof_len"]
+    assert got["proof"][:64].hex() == case["proof_head"]
+    assert sha(got["proof"]) == case["proof_sha256"]
+    assert sha(got["comm"]) == case["comm_sha256"]
+    assert sha(got["comm_vars_para"]) == case["comm_vars_para_sha256"]
+    assert sha(got["comm_vars_input"]) == case["comm_vars_input_sha256"]
+    assert sha(got["comm_vars"]) == case["comm_vars_sha256"]

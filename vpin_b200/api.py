@@ -231,6 +231,12 @@ class Context:
         self.check(lib().vpin_imad_peak(self._h, C.byref(v)))
         return v.value
 
+    def imad_peak_forms(self):
+        """(plain IMAD.WIDE product + ALU combine, single-instruction IMAD.WIDE multiply-accumulate) in MAC/s"""
+        v = (C.c_double * 2)()
+        self.check(lib().vpin_imad_peak_forms(self._h, v))
+        return v[0], v[1]
+
 
 def exchange_unique_id(dist, rank, make_id=None):
     """rank 0 makes the 128-byte NCCL unique id (vpin_nccl_unique_id), everyone receives it through `dist`."""

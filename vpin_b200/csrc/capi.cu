@@ -7,6 +7,7 @@ using namespace vpin;
 #define VPIN_TRY(ctx_)                      \
   Ctx *c_ = (ctx_);                         \
   if (c_) cudaSetDevice(c_->device); /* contexts may be driven from different host threads */ \
+  LaunchCounter::current() = c_ ? &c_->kernel_launches : nullptr; /* launches of this call count for this context */ \
   try {
 #define VPIN_CATCH                                                    \
   }                                                                   \
@@ -136,7 +137,9 @@ void vpin_shard_rows(uint64_t rows, int32_t rank, int32_t world, uint64_t *r0, u
   if (sharded) *sharded = s ? 1 : 0;
 }
 const char *vpin_last_error(const vpin_ctx *ctx) { return ctx ? reinterpret_cast<const Ctx *>(ctx)->err.c_str() : "null context"; }
-uint64_t vpin_kernel_launches(const vpin_ctx *) { return g_kernel_launches.load(); }
+uint64_t vpin_kernel_launches(const vpin_ctx *ctx) {  // launches made by calls on THIS context (process total when ctx is NULL)
+  return ctx ? reinterpret_cast<const Ctx *>(ctx)->kernel_launches.load() : g_kernel_launches.load();
+}
 void *vpin_stream(vpin_ctx *ctx) { return reinterpret_cast<Ctx *>(ctx)->st; }
 vpin_status vpin_sync(vpin_ctx *ctx) {
   VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
@@ -798,6 +801,12 @@ vpin_status vpin_imad_peak(vpin_ctx *ctx, double *macs_per_second) {
   VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
   VPIN_REQUIRE(macs_per_second, VPIN_ERR_BAD_ARGUMENT, "null argument");
   *macs_per_second = measure_imad_peak(c_);
+  VPIN_CATCH
+}
+vpin_status vpin_imad_peak_forms(vpin_ctx *ctx, double forms[2]) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE(forms, VPIN_ERR_BAD_ARGUMENT, "null argument");
+  measure_imad_peaks(c_, forms);
   VPIN_CATCH
 }
 

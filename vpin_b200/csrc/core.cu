@@ -8,7 +8,7 @@
 
 namespace vpin {
 
-std::atomic<uint64_t> g_kernel_launches{0};
+LaunchCounter g_kernel_launches;
 
 // ------------------------------------------------------------------------------------------------ block cache
 struct BlockCache {

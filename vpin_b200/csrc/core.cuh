@@ -1,5 +1,6 @@
 // Context, HBM buffers, generator streams + fixed-base tables, Hyrax commitment driver, R1CS instance storage.
 #pragma once
+#include "launch_count.hpp"
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -36,7 +37,6 @@ struct Error : std::runtime_error {
     if (!(cond)) throw ::vpin::Error((code), (msg));     \
   } while (0)
 
-extern std::atomic<uint64_t> g_kernel_launches;
 
 // Per-stream caching allocator. Every context drives ONE stream from one host thread, so a block released by a DevVec may be
 // handed to the next DevVec on the same stream without any synchronisation (stream order protects it). Blocks come from
@@ -139,6 +139,7 @@ struct vpin_ctx_impl {
   int device = 0;
   cudaStream_t st = nullptr;
   std::string err;
+  std::atomic<uint64_t> kernel_launches{0};  // launches made by C-ABI calls on this context (launch_count.hpp)
   std::map<std::string, std::shared_ptr<LabelGens>> label_gens;
   DevVec<fl_t> d_partials;   // reduction scratch
   DevVec<fl_t> d_small;      // small device results / parameters

@@ -80,6 +80,23 @@ VPIN_HD fp_t fp_sub(const fp_t &a, const fp_t &b) {
   return r;
 }
 VPIN_HD fp_t fp_neg(const fp_t &a) { return fp_sub(fp_zero(), a); }
+// a / 2: (a + (a odd ? p : 0)) >> 1, again lazily reduced below 2^256
+VPIN_HD fp_t fp_half(const fp_t &a) {
+  const uint32_t odd = 0u - (a.v[0] & 1u);
+  uint32_t t[9];
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.v[i] + ((i == 0 ? 0xffffffedu : (i == 7 ? 0x7fffffffu : 0xffffffffu)) & odd);
+    t[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  t[8] = (uint32_t)c;
+  fp_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+  return r;
+}
 
 // t (16 limbs) -> t mod 2^256-38, lazily reduced into [0, 2^256)
 VPIN_HD fp_t fp_reduce_wide(const uint32_t t[16]) {
@@ -116,6 +133,13 @@ VPIN_HD fp_t fp_mul(const fp_t &a, const fp_t &b) {
   return fp_reduce_wide(t);
 }
 VPIN_HD fp_t fp_sqr(const fp_t &a) { return fp_mul(a, a); }
+// fp_mul with the accumulation of chosen product rows moved to the ALU pipe (limbs.cuh mul_8x8_p); same value
+template <uint32_t kAluRows>
+VPIN_HD fp_t fp_mul_p(const fp_t &a, const fp_t &b) {
+  uint32_t t[16];
+  limb::mul_8x8_p<kAluRows>(t, a.v, b.v);
+  return fp_reduce_wide(t);
+}
 
 // canonical bytes (value in [0, p))
 VPIN_HD void fp_canon(const fp_t &a, uint32_t out[8]) {
@@ -250,6 +274,14 @@ VPIN_HD niels_t ge_to_niels(const ge_t &p, const fp_t &zinv) {
   niels_t n;
   n.yp = fp_add(y, x); n.ym = fp_sub(y, x); n.t2d = fp_mul(fp_mul(x, y), fp_d2());
   return n;
+}
+// the same entry with every coordinate halved ((y+x)/2, (y-x)/2, d*x*y): what the MSM tables hold. With halved entries the
+// mixed addition uses D = Z1 instead of 2 Z1 and returns (X3/4 : Y3/4 : Z3/4 : T3/4), the same projective point; the
+// radix-2^29 multiplier of the hot loop (fp29.cuh) needs the smaller F = D - C, G = D + C this gives.
+VPIN_HD niels_t niels_half(const niels_t &n) {
+  niels_t h;
+  h.yp = fp_half(n.yp); h.ym = fp_half(n.ym); h.t2d = fp_half(n.t2d);
+  return h;
 }
 // RFC 9496 4.3.2 ENCODE  (dalek RistrettoPoint::compress)
 VPIN_HD void ge_compress(const ge_t &p, uint8_t out[32]) {

@@ -1,13 +1,15 @@
 // Fixed-base MSM kernels for sm_100a (see kernels_msm.cuh for the design). Integer-multiply bound: the hot loop is
 // ge_madd (7 F_p multiplications of 8x8 32-bit limbs) fed by 96-byte table entries fetched with LDG.128.
+#include "launch_count.hpp"
 #include <atomic>
+#include <cstdlib>
 
+#include "fp29.cuh"
 #include "kernels_msm.cuh"
 #include "msm_recode.cuh"
 
 namespace vpin {
 
-extern std::atomic<uint64_t> g_kernel_launches;
 
 __device__ __forceinline__ fp_t ldg_fp(const fp_t *p) {
   const uint4 *q = reinterpret_cast<const uint4 *>(p);
@@ -91,8 +93,14 @@ __global__ void __launch_bounds__(128) k_table_fill(size_t n, int tsize, niels_t
     inv = fp_mul(inv, raw.t2d);
     ge_t q;
     q.X = raw.yp; q.Y = raw.ym; q.Z = raw.t2d; q.T = fp_zero();
-    st_niels(slots + c * kTblChunk + m, ge_to_niels(q, zinv));
+    st_niels(slots + c * kTblChunk + m, niels_half(ge_to_niels(q, zinv)));
   }
+}
+// step 3: slot 0 (read in its full form by every chunk of step 2) is halved last
+__global__ void __launch_bounds__(128) k_table_halve_first(size_t n, int tsize, niels_t *table) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  st_niels(table + j * tsize, niels_half(ld_niels(table + j * tsize)));
 }
 // bases_out[j] = 2^ndbl * bases_in[j]
 __global__ void __launch_bounds__(128) k_points_dbl_n(const ge_t *in, size_t n, int ndbl, ge_t *out) {
@@ -113,6 +121,7 @@ void launch_table_build(const ge_t *d_bases, size_t n, const MsmGeom &g, niels_t
     niels_t *tbl = d_table + (size_t)t * n * g.table;
     ++g_kernel_launches, k_bases_to_niels<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cur, n, g.table, tbl);
     ++g_kernel_launches, k_table_fill<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(n, g.table, tbl);
+    ++g_kernel_launches, k_table_halve_first<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, g.table, tbl);
   }
 }
 
@@ -157,25 +166,52 @@ void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, c
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate
-// acc += (neg ? -e : e) without a divergent branch: the sign swaps the two multiplicands (by address) and F with G.
-__device__ __forceinline__ void madd_signed(ge_t &p, const niels_t *e, uint32_t neg) {
-  const fp_t *p_yp = neg ? &e->ym : &e->yp, *p_ym = neg ? &e->yp : &e->ym;
-  fp_t yp = ldg_fp(p_yp), ym = ldg_fp(p_ym), t2d = ldg_fp(&e->t2d);
-  fp_t a = fp_mul(fp_sub(p.Y, p.X), ym);
-  fp_t b = fp_mul(fp_add(p.Y, p.X), yp);
-  fp_t c = fp_mul(p.T, t2d);
-  fp_t d = fp_add(p.Z, p.Z);
-  fp_t s1 = fp_sub(d, c), s2 = fp_add(d, c);
-  fp_t f, g;
+// Two interchangeable accumulators for the hot loop (same table, same group element, hence the same bytes):
+//   Acc9  : extended coordinates in nine 29-bit limbs each, carry-free multiplier of fp29.cuh (kPolicy: where the 64-bit
+//           accumulations of the partial products run, see f9_mul)
+//   Acc8  : ed.cuh's 8 x u32 limbs with carry-chained IMAD.WIDE rows (the round-1 kernel)
+// Table entries are HALVED ((y+x)/2, (y-x)/2, d x y): Hisil-Wong-Carter-Dawson mixed addition with Z2 = 1 and D = Z1 (instead
+// of 2 Z1), seven multiplications; the sign of the digit swaps the two multiplicands (by address) and negates T.
+template <int kPolicy>
+struct Acc9 {
+  f9 X, Y, Z, T;
+  __device__ __forceinline__ void init() { X = f9_zero(); Y = f9_one(); Z = f9_one(); T = f9_zero(); }
+  __device__ __forceinline__ ge_t get() const { ge_t r; r.X = f9_to_fp(X); r.Y = f9_to_fp(Y); r.Z = f9_to_fp(Z); r.T = f9_to_fp(T); return r; }
+  // operand bounds as stated in fp29.cuh: E, F are differences of two normal values (signed limbs), G, H sums (unsigned product)
+  __device__ __forceinline__ void madd(const niels_t *e, uint32_t neg) {
+    const fp_t *p_yp = neg ? &e->ym : &e->yp, *p_ym = neg ? &e->yp : &e->ym;
+    fp_t wyp = ldg_fp(p_yp), wym = ldg_fp(p_ym), wt = ldg_fp(&e->t2d);
+    f9 a = f9_mul<false, kPolicy>(f9_sub(Y, X), f9_from_fp(wym));
+    f9 b = f9_mul<false, kPolicy>(f9_add(Y, X), f9_from_fp(wyp));
+    f9 c = f9_mul<false, kPolicy>(f9_cneg(T, neg != 0), f9_from_fp(wt));
+    f9 e_ = f9_sub(b, a), h = f9_add(b, a), f = f9_sub(Z, c), g = f9_add(Z, c);
+    X = f9_mul<false, kPolicy>(e_, f); Y = f9_mul<true, kPolicy>(g, h); Z = f9_mul<false, kPolicy>(f, g); T = f9_mul<false, kPolicy>(e_, h);
+  }
+};
+template <uint32_t kAluRows>
+struct Acc8 {
+  ge_t p;
+  __device__ __forceinline__ void init() { p = ge_identity(); }
+  __device__ __forceinline__ ge_t get() const { return p; }
+  __device__ __forceinline__ void madd(const niels_t *e, uint32_t neg) {
+    const fp_t *p_yp = neg ? &e->ym : &e->yp, *p_ym = neg ? &e->yp : &e->ym;
+    fp_t yp = ldg_fp(p_yp), ym = ldg_fp(p_ym), t2d = ldg_fp(&e->t2d);
+    fp_t a = fp_mul_p<kAluRows>(fp_sub(p.Y, p.X), ym);
+    fp_t b = fp_mul_p<kAluRows>(fp_add(p.Y, p.X), yp);
+    fp_t c = fp_mul_p<kAluRows>(p.T, t2d);
+    fp_t s1 = fp_sub(p.Z, c), s2 = fp_add(p.Z, c);
+    fp_t f, g;
 #pragma unroll
-  for (int i = 0; i < 8; i++) { f.v[i] = neg ? s2.v[i] : s1.v[i]; g.v[i] = neg ? s1.v[i] : s2.v[i]; }
-  fp_t e_ = fp_sub(b, a), h = fp_add(b, a);
-  p.X = fp_mul(e_, f); p.Y = fp_mul(g, h); p.Z = fp_mul(f, g); p.T = fp_mul(e_, h);
-}
+    for (int i = 0; i < 8; i++) { f.v[i] = neg ? s2.v[i] : s1.v[i]; g.v[i] = neg ? s1.v[i] : s2.v[i]; }
+    fp_t e_ = fp_sub(b, a), h = fp_add(b, a);
+    p.X = fp_mul_p<kAluRows>(e_, f); p.Y = fp_mul_p<kAluRows>(g, h); p.Z = fp_mul_p<kAluRows>(f, g); p.T = fp_mul_p<kAluRows>(e_, h);
+  }
+};
 // grid (ceil(rows / 128), kMsmGroup, segs), block 128: thread = (row, local window w', column segment)
-__global__ void __launch_bounds__(kMsmRowsPerBlock, 6) k_msm_accumulate(const niels_t *table, MsmGeom g, const uint16_t *digits, size_t rows,
-                                                                     size_t cols, size_t cols_total, size_t extra_base, size_t stride,
-                                                                     size_t n_bases, size_t seg_len, ge_t *partial, const uint32_t *wmask) {
+template <class Acc>
+__device__ __forceinline__ void msm_accumulate_body(const niels_t *table, const MsmGeom &g, const uint16_t *digits, size_t rows, size_t cols,
+                                                    size_t cols_total, size_t extra_base, size_t stride, size_t n_bases, size_t seg_len,
+                                                    ge_t *partial, const uint32_t *wmask) {
   size_t row = (size_t)blockIdx.x * kMsmRowsPerBlock + threadIdx.x;
   if (row >= rows) return;
   const int wl = blockIdx.y;
@@ -193,7 +229,8 @@ __global__ void __launch_bounds__(kMsmRowsPerBlock, 6) k_msm_accumulate(const ni
   size_t c0 = seg * seg_len, c1 = c0 + seg_len < cols_total ? c0 + seg_len : cols_total;
   const size_t plane = rows * stride;
   const uint16_t *dg = digits + row * stride;
-  ge_t acc = ge_identity();
+  Acc acc;
+  acc.init();
   for (size_t col = c0; col < c1; col++) {
     size_t base = col < cols ? col : extra_base;
 #pragma unroll 1
@@ -201,10 +238,25 @@ __global__ void __launch_bounds__(kMsmRowsPerBlock, 6) k_msm_accumulate(const ni
       int w = t * g.group + wl;
       if (w >= g.windows) break;
       uint32_t d = dg[(size_t)w * plane + col];
-      if (d) madd_signed(acc, table + ((size_t)t * n_bases + base) * g.table + ((d & 0x7fffu) - 1u), d >> 15);
+      if (d) acc.madd(table + ((size_t)t * n_bases + base) * g.table + ((d & 0x7fffu) - 1u), d >> 15);
     }
   }
-  st_ge(partial + (row * g.group + wl) * segs + seg, acc);
+  st_ge(partial + (row * g.group + wl) * segs + seg, acc.get());
+}
+#define VPIN_MSM_ACC_ARGS const niels_t *table, MsmGeom g, const uint16_t *digits, size_t rows, size_t cols, size_t cols_total, size_t extra_base, \
+                          size_t stride, size_t n_bases, size_t seg_len, ge_t *partial, const uint32_t *wmask
+#define VPIN_MSM_ACC_PASS table, g, digits, rows, cols, cols_total, extra_base, stride, n_bases, seg_len, partial, wmask
+__global__ void __launch_bounds__(kMsmRowsPerBlock, 6) k_msm_accumulate(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<0>>(VPIN_MSM_ACC_PASS); }
+// 0x8888: the odd-column products of rows 1, 3, 5, 7 accumulate on the ALU pipe (the best of the row patterns tried)
+__global__ void __launch_bounds__(kMsmRowsPerBlock, 5) k_msm_accumulate_a2(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<0x8888u>>(VPIN_MSM_ACC_PASS); }
+__global__ void __launch_bounds__(kMsmRowsPerBlock, 4) k_msm_accumulate_f9p0(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc9<0>>(VPIN_MSM_ACC_PASS); }
+__global__ void __launch_bounds__(kMsmRowsPerBlock, 4) k_msm_accumulate_f9p1(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc9<1>>(VPIN_MSM_ACC_PASS); }
+// VPIN_MSM_VARIANT selects one of the measured alternatives of the hot loop (all bit-identical; 2^22 uniform scalars on a B200,
+// profiles/r2_msm_variants.log): 0 (default) 8 x 32 carry-chained 5.01 ms | 1 radix 2^29, accumulation in the multiplier 6.38 ms |
+// 2 radix 2^29, accumulation on the ALU pipe 7.31 ms | 12 8 x 32 with four rows accumulated on the ALU pipe 5.21 ms
+static int msm_variant() {
+  static const int v = [] { const char *e = getenv("VPIN_MSM_VARIANT"); return e ? atoi(e) : 0; }();
+  return v;
 }
 __device__ __forceinline__ ge_t shfl_down_ge(const ge_t &g, int off) {
   ge_t r;
@@ -228,7 +280,8 @@ __global__ void __launch_bounds__(32) k_msm_accumulate_small(const niels_t *tabl
   size_t c0 = seg * seg_len, c1 = c0 + seg_len < cols_total ? c0 + seg_len : cols_total;
   const size_t plane = rows * stride;
   const uint16_t *dg = digits + row * stride;
-  ge_t acc = ge_identity();
+  Acc8<0> a8;
+  a8.init();
   for (size_t col = c0 + lane; col < c1; col += 32) {
     size_t base = col < cols ? col : extra_base;
 #pragma unroll 1
@@ -236,9 +289,10 @@ __global__ void __launch_bounds__(32) k_msm_accumulate_small(const niels_t *tabl
       int w = t * g.group + wl;
       if (w >= g.windows) break;
       uint32_t d = dg[(size_t)w * plane + col];
-      if (d) madd_signed(acc, table + ((size_t)t * n_bases + base) * g.table + ((d & 0x7fffu) - 1u), d >> 15);
+      if (d) a8.madd(table + ((size_t)t * n_bases + base) * g.table + ((d & 0x7fffu) - 1u), d >> 15);
     }
   }
+  ge_t acc = a8.get();
 #pragma unroll 1
   for (int off = 16; off > 0; off >>= 1) {
     ge_t o = shfl_down_ge(acc, off);
@@ -277,8 +331,15 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
     return;
   }
   dim3 grid((unsigned)((rows + kMsmRowsPerBlock - 1) / kMsmRowsPerBlock), t.geom.group, (unsigned)segs);
-  ++g_kernel_launches, k_msm_accumulate<<<grid, kMsmRowsPerBlock, 0, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride,
-                                                                           t.n_bases, seg_len, d_partial, d_wmask);
+  ++g_kernel_launches;
+#define VPIN_MSM_LAUNCH(K) K<<<grid, kMsmRowsPerBlock, 0, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride, t.n_bases, seg_len, d_partial, d_wmask)
+  switch (msm_variant()) {
+    case 1: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p0); break;
+    case 2: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p1); break;
+    case 12: VPIN_MSM_LAUNCH(k_msm_accumulate_a2); break;
+    default: VPIN_MSM_LAUNCH(k_msm_accumulate); break;
+  }
+#undef VPIN_MSM_LAUNCH
 }
 
 // finish, step 1 (only when a row was split into segments): one warp per (row, local window) adds the segment partials

@@ -1,13 +1,13 @@
 // F_l table kernels for sm_100a: sumcheck round evaluations, binds, eq tables, CSR/CSC SpMV and the SPARK layer
 // builders. HBM-bound integer work: one 32-byte element per 2 x LDG.128, grid-stride loops sized in multiples of the
 // 148 SMs, warp-shuffle + shared-memory reductions of field elements. No tensor cores (nothing here is a contraction).
+#include "launch_count.hpp"
 #include <atomic>
 
 #include "kernels_poly.cuh"
 
 namespace vpin {
 
-extern std::atomic<uint64_t> g_kernel_launches;
 
 __device__ __forceinline__ fl_t ldg_fl(const fl_t *p) {
   const uint4 *q = reinterpret_cast<const uint4 *>(p);

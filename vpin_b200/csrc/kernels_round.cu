@@ -9,6 +9,7 @@
 //   lo' = T[i]   + r (T[i+2q] - T[i])      (element i       of the bound table, length 2q)
 //   hi' = T[i+q] + r (T[i+3q] - T[i+q])    (element i + q   of the bound table)
 // are stored in place (no other thread touches these four slots) and (lo', hi') is the pair the evaluation needs.
+#include "launch_count.hpp"
 #include <atomic>
 #include <cstdlib>
 
@@ -17,7 +18,6 @@
 
 namespace vpin {
 
-extern std::atomic<uint64_t> g_kernel_launches;
 
 namespace {
 

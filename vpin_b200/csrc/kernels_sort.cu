@@ -6,13 +6,13 @@
 // group when the operations are stably sorted by address. That is what runs here: a least-significant-digit radix sort
 // (8 bits per pass, stable) of (address, g), one pass marking where each address group starts, one pass writing
 // rank = position - group start back to slot g; audit_ts is a plain histogram. No host replay, no host<->device copies.
+#include "launch_count.hpp"
 #include <atomic>
 
 #include "kernels_poly.cuh"
 
 namespace vpin {
 
-extern std::atomic<uint64_t> g_kernel_launches;
 
 namespace {
 

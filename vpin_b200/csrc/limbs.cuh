@@ -72,6 +72,37 @@ VPIN_HD void mad_row_nc(uint32_t *r, const uint32_t *a, uint32_t b) {
 #endif
 }
 
+// r[0..8) += (a[0], a[2], a[4], a[6]) * b like mad_row, but as four PLAIN products (IMAD.WIDE without addend) and one
+// 9-word carry chain of IADD3.X. An IMAD.WIDE that also accumulates (64-bit addend, with or without carry-in) occupies the
+// multiply pipe twice as long as a plain product (scripts/ubench/imad_rates2.cu), while the ALU pipe, which issues an IADD3
+// every cycle, is otherwise idle: rows written this way trade 8 multiply-pipe cycles for 9 issue slots.
+VPIN_HD void mad_row_alu(uint32_t *r, const uint32_t *a, uint32_t b, uint32_t &cw) {
+#if defined(__CUDA_ARCH__)
+  uint64_t p0, p1, p2, p3;  // (mul.wide, not mul.lo / mul.hi pairs: those ptxas fuses with the adds below into IMAD.WIDE.X again)
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(p0) : "r"(a[0]), "r"(b));
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(p1) : "r"(a[2]), "r"(b));
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(p2) : "r"(a[4]), "r"(b));
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(p3) : "r"(a[6]), "r"(b));
+  uint32_t q[8] = {(uint32_t)p0, (uint32_t)(p0 >> 32), (uint32_t)p1, (uint32_t)(p1 >> 32),
+                   (uint32_t)p2, (uint32_t)(p2 >> 32), (uint32_t)p3, (uint32_t)(p3 >> 32)};
+  asm("add.cc.u32 %0, %0, %9; addc.cc.u32 %1, %1, %10; addc.cc.u32 %2, %2, %11; addc.cc.u32 %3, %3, %12;"
+      "addc.cc.u32 %4, %4, %13; addc.cc.u32 %5, %5, %14; addc.cc.u32 %6, %6, %15; addc.cc.u32 %7, %7, %16; addc.u32 %8, %8, 0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(cw)
+      : "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]));
+#else
+  mad_row(r, a, b, cw);
+#endif
+}
+template <bool kAlu>
+VPIN_HD void mad_row_sel(uint32_t *r, const uint32_t *a, uint32_t b, uint32_t &cw) {
+  if (kAlu) mad_row_alu(r, a, b, cw);
+  else mad_row(r, a, b, cw);
+}
+// mul_8x8 with a choice per row of where its accumulation runs: bit 2 i of kAluRows -> the even-column products of row i
+// go through mad_row_alu, bit 2 i + 1 -> the odd-column products. kAluRows = 0 is mul_8x8 below.
+template <uint32_t kAluRows>
+VPIN_HD void mul_8x8_p(uint32_t *t, const uint32_t *a, const uint32_t *b);
+
 // t[0..16) = a * b (8 x 8 limbs). 64 IMAD.WIDE + 14 carry words + one 15-limb add chain.
 VPIN_HD void mul_8x8(uint32_t *t, const uint32_t *a, const uint32_t *b) {
   uint32_t ev[16], od[16];  // od[k] has weight 2^(32 (k + 1))
@@ -88,6 +119,51 @@ VPIN_HD void mul_8x8(uint32_t *t, const uint32_t *a, const uint32_t *b) {
     } else {
       mad_row(ev + i, a, b[i], ev[i + 8]);
       mad_row(od + i, a + 1, b[i], od[i + 8]);
+    }
+  }
+  // t = ev + (od << 32)
+  t[0] = ev[0];
+#if defined(__CUDA_ARCH__)
+  uint32_t cy;
+  asm("add.cc.u32 %0, %8, %15; addc.cc.u32 %1, %9, %16; addc.cc.u32 %2, %10, %17; addc.cc.u32 %3, %11, %18;"
+      "addc.cc.u32 %4, %12, %19; addc.cc.u32 %5, %13, %20; addc.cc.u32 %6, %14, %21; addc.u32 %7, 0, 0;"
+      : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(cy)
+      : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+        "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]));
+  asm("add.cc.u32 %8, %8, 0xffffffff;"
+      "addc.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20;"
+      "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.u32 %7, %16, %24;"
+      : "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]), "+r"(cy)
+      : "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
+        "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+#else
+  uint64_t c = 0;
+  for (int k = 1; k < 16; k++) {
+    c += (uint64_t)ev[k] + od[k - 1];
+    t[k] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+}
+
+template <uint32_t kAluRows>
+VPIN_HD void mul_8x8_p(uint32_t *t, const uint32_t *a, const uint32_t *b) {
+  uint32_t ev[16], od[16];  // od[k] has weight 2^(32 (k + 1))
+#pragma unroll
+  for (int k = 8; k < 16; k++) ev[k] = od[k] = 0;
+  mul_row(ev, a, b[0]);
+  mul_row(od, a + 1, b[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    const bool alu_e = ((kAluRows >> (2 * i)) & 1u) != 0, alu_o = ((kAluRows >> (2 * i + 1)) & 1u) != 0;
+    if (i & 1) {
+      if (alu_e) mad_row_alu(od + i - 1, a, b[i], od[i + 7]); else mad_row(od + i - 1, a, b[i], od[i + 7]);
+      if (i + 9 < 16) { if (alu_o) mad_row_alu(ev + i + 1, a + 1, b[i], ev[i + 9]); else mad_row(ev + i + 1, a + 1, b[i], ev[i + 9]); }
+      else if (alu_o) { uint32_t dummy = 0; mad_row_alu(ev + i + 1, a + 1, b[i], dummy); }
+      else mad_row_nc(ev + i + 1, a + 1, b[i]);
+    } else {
+      if (alu_e) mad_row_alu(ev + i, a, b[i], ev[i + 8]); else mad_row(ev + i, a, b[i], ev[i + 8]);
+      if (alu_o) mad_row_alu(od + i, a + 1, b[i], od[i + 8]); else mad_row(od + i, a + 1, b[i], od[i + 8]);
     }
   }
   // t = ev + (od << 32)

@@ -1414,47 +1414,74 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
 }
 
 // ------------------------------------------------------------------------------------------------ integer roofline
+// Peak rate of 32 x 32 + 64 -> 64 multiply-accumulates, measured live. Two forms, both checked in SASS (cuobjdump) to contain
+// what they claim, with one factor changing every iteration so that nothing can be hoisted out of the loop:
+//   form 0: IMAD.WIDE.U32 Rd, Ra, Rb, RZ  + LOP3 pair (product on the multiply pipe, combined into the accumulator on the ALU pipe)
+//   form 1: IMAD.WIDE.U32 Rd, Ra, Rb, Rd  (single-instruction multiply-accumulate, the form the field arithmetic uses)
+// The round-1 kernel that stood here multiplied two loop-invariant registers: ptxas hoisted the product and the loop timed
+// IADD3 / IADD3.X pairs - 18.4 T "MAC"/s without a single multiply. IMAD.WIDE is a half-rate instruction on sm_100a: both
+// forms top out near 32 lanes / clk / SM (8.0 and 7.6 T/s on a B200 at 1.965 GHz; scripts/ubench/imad_rates2.cu).
+template <int kForm>
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t *out, int iters, uint32_t seed) {
-  uint64_t a0 = threadIdx.x + seed, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   uint32_t x = threadIdx.x * 2654435761u + seed, y = x ^ 0x9e3779b9u;
-  for (int i = 0; i < iters; i++) {
+  uint64_t v[12];
+  uint32_t av[12];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0) : "r"(x), "r"(y));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1) : "r"(x), "r"(y));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a2) : "r"(x), "r"(y));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a3) : "r"(x), "r"(y));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a4) : "r"(x), "r"(y));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a5) : "r"(x), "r"(y));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a6) : "r"(x), "r"(y));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a7) : "r"(x), "r"(y));
+  for (int i = 0; i < 12; i++) { v[i] = x + i; av[i] = x * (2 * i + 3); }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      if (kForm == 0) {
+        uint64_t p;
+        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(av[i]), "r"(y));
+        v[i] ^= p;
+      } else {
+        uint32_t lo = (uint32_t)v[i], hi = (uint32_t)(v[i] >> 32);
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(av[i]), "r"(y));
+        v[i] = ((uint64_t)hi << 32) | lo;
+      }
     }
+    y += 0x9e3779b1u;
   }
-  uint64_t s = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+  uint64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) s ^= v[i];
   if (s == 0x123456789abcdefull) out[0] = (uint32_t)s;
 }
-double measure_imad_peak(Ctx *ctx) {
+void measure_imad_peaks(Ctx *ctx, double forms[2]) {
   cudaStream_t st = ctx->st;
   DevVec<uint32_t> out(1, st);
   int blocks = 148 * 8, iters = 4096;
   cudaEvent_t e0, e1;
   VPIN_CUDA(cudaEventCreate(&e0));
   VPIN_CUDA(cudaEventCreate(&e1));
-  ++g_kernel_launches, k_imad_peak<<<blocks, 256, 0, st>>>(out.p, 64, 1);
-  double best = 0;
-  for (int rep = 0; rep < 5; rep++) {
-    VPIN_CUDA(cudaEventRecord(e0, st));
-    ++g_kernel_launches, k_imad_peak<<<blocks, 256, 0, st>>>(out.p, iters, rep);
-    VPIN_CUDA(cudaEventRecord(e1, st));
-    VPIN_CUDA(cudaEventSynchronize(e1));
-    float ms = 0;
-    VPIN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    double macs = (double)blocks * 256 * iters * 64 / (ms * 1e-3);
-    if (macs > best) best = macs;
+  for (int form = 0; form < 2; form++) {
+    auto launch = [&](int n, uint32_t seed) {
+      ++g_kernel_launches;
+      if (form == 0) k_imad_peak<0><<<blocks, 256, 0, st>>>(out.p, n, seed);
+      else k_imad_peak<1><<<blocks, 256, 0, st>>>(out.p, n, seed);
+    };
+    launch(64, 1);
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+      VPIN_CUDA(cudaEventRecord(e0, st));
+      launch(iters, rep);
+      VPIN_CUDA(cudaEventRecord(e1, st));
+      VPIN_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      VPIN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      double macs = (double)blocks * 256 * iters * 12 / (ms * 1e-3);
+      if (macs > best) best = macs;
+    }
+    forms[form] = best;
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  return best;
+}
+double measure_imad_peak(Ctx *ctx) {  // the better of the two forms
+  double f[2];
+  measure_imad_peaks(ctx, f);
+  return f[0] > f[1] ? f[0] : f[1];
 }
 
 }  // namespace vpin

@@ -57,6 +57,7 @@ static inline size_t eq_tmp_elems(size_t ell) {
   return a < 4096 ? 4096 : a;
 }
 double measure_imad_peak(Ctx *ctx);
+void measure_imad_peaks(Ctx *ctx, double forms[2]);
 
 // packed product tree of n leaves stored at tree[0..n): 2n - 2 elements (prover.cu)
 void build_tree(Ctx *ctx, fl_t *tree, size_t n, cudaStream_t st);
