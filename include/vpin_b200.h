@@ -74,6 +74,9 @@ void vpin_ctx_destroy(vpin_ctx *ctx);
 vpin_status vpin_nccl_unique_id(uint8_t id_out[128]);
 vpin_status vpin_ctx_init_distributed(vpin_ctx *ctx, int32_t rank, int32_t world, const uint8_t nccl_id[128]);
 void vpin_shard_rows(uint64_t rows, int32_t rank, int32_t world, uint64_t *r0, uint64_t *r1, int32_t *sharded);
+/* sharded sumcheck rounds for the proofs of this context: 1 = on, 0 = off, -1 = what VPIN_SHARD_SUMCHECK says (the default).
+ * Every rank of the communicator must choose the same value. */
+vpin_status vpin_ctx_set_shard_sumcheck(vpin_ctx *ctx, int32_t on);
 /* message of the last failure on this context (never NULL) */
 const char *vpin_last_error(const vpin_ctx *ctx);
 /* number of this library's kernels launched on the context so far (bench.py's gpu_launches) */

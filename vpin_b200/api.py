@@ -82,6 +82,10 @@ class Context:
         uid = exchange_unique_id(dist, rank)
         self.check(lib().vpin_ctx_init_distributed(self._h, C.c_int32(rank), C.c_int32(world), uid))
 
+    def set_shard_sumcheck(self, on):
+        """sharded sumcheck rounds of one proof across the ranks (1 / 0; -1 = the VPIN_SHARD_SUMCHECK environment default)"""
+        self.check(lib().vpin_ctx_set_shard_sumcheck(self._h, C.c_int32(int(on))))
+
     def close(self):
         if self._h:
             lib().vpin_ctx_destroy(self._h)

@@ -129,6 +129,12 @@ vpin_status vpin_ctx_init_distributed(vpin_ctx *ctx, int32_t rank, int32_t world
   dist_init(c_, rank, world, nccl_id);
   VPIN_CATCH
 }
+vpin_status vpin_ctx_set_shard_sumcheck(vpin_ctx *ctx, int32_t on) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE(c_, VPIN_ERR_BAD_ARGUMENT, "null context");
+  c_->shard_sumcheck = on < 0 ? -1 : (on ? 1 : 0);
+  VPIN_CATCH
+}
 void vpin_shard_rows(uint64_t rows, int32_t rank, int32_t world, uint64_t *r0, uint64_t *r1, int32_t *sharded) {
   size_t a, b;
   bool s = shard_rows(rows, rank, world, &a, &b);

@@ -167,6 +167,7 @@ struct vpin_ctx_impl {
   // multi-GPU (one process per GPU): NCCL communicator over NVLink/NVSwitch, created by vpin_ctx_init_distributed
   int rank = 0, world = 1;
   void *nccl_comm = nullptr;
+  int shard_sumcheck = -1;  // sharded sumcheck rounds of one proof: -1 = VPIN_SHARD_SUMCHECK decides, 0 / 1 = vpin_ctx_set_shard_sumcheck
   DevVec<unsigned long long> d_counters;  // [0] = non-zero MSM digits recoded (= mixed additions executed)
   // sharded sumcheck rounds (one proof on several GPUs, VPIN_SHARD_SUMCHECK=1): device-side result slots of the round kernels
   // and the all-gather buffer (kRoundSlotVals elements)

@@ -194,7 +194,8 @@ namespace {
 // thread items, see batched_prove.
 static const size_t kShardMinLayer = (size_t)1 << 14;
 static bool shard_sumcheck_enabled(const Ctx *ctx) {
-  static const bool on = [] { const char *e = getenv("VPIN_SHARD_SUMCHECK"); return e && atoi(e) != 0; }();
+  static const bool env_on = [] { const char *e = getenv("VPIN_SHARD_SUMCHECK"); return e && atoi(e) != 0; }();
+  const bool on = ctx->shard_sumcheck < 0 ? env_on : ctx->shard_sumcheck != 0;
   return on && ctx->world > 1 && ctx->nccl_comm != nullptr;
 }
 
