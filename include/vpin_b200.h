@@ -40,7 +40,8 @@ enum {
   VPIN_ERR_CUDA = 6,
   VPIN_ERR_OOM = 7,
   VPIN_ERR_PROVER = 8,            /* a prover-side assert! of the reference failed (unsatisfied witness, ...) */
-  VPIN_ERR_BAD_ARGUMENT = 9
+  VPIN_ERR_BAD_ARGUMENT = 9,
+  VPIN_ERR_IO = 10                /* a witness file could not be read / written / parsed (the reference's .expect panics, VP/load_data.rs:14-17) */
 };
 
 typedef struct vpin_ctx vpin_ctx;
@@ -274,6 +275,21 @@ uint32_t vpin_profile_read(vpin_ctx *ctx, const char **names_out, double *ms_out
  * ~8.0 / 7.6 T/s on a B200 (the round-1 figure of 18.4 T/s timed IADD3 pairs - its product had been hoisted by ptxas). */
 vpin_status vpin_imad_peak(vpin_ctx *ctx, double *macs_per_second);
 vpin_status vpin_imad_peak_forms(vpin_ctx *ctx, double forms[2]);
+
+/* ---- native witness I/O (host only)   VP/load_data.rs:5-62, VP/load_data_add.rs:5-102 --------------------------------------
+ * Reads what the Python side writes for the Rust driver: <root>/rust_files/<tag>/pointMult/{weight.json, point_mult_px_byte.json,
+ * point_mult_py_byte.json} and <root>/rust_files/<tag>/pointAdd/point_add_{px,py,rx,ry,rz}_byte.json (the reference opens these
+ * paths relative to its working directory, i.e. root = "."). weights: u128 as (low, high) u64 pairs; coordinates: 32 little-endian
+ * bytes per row; rz[i] = 1 marks R_i = infinity. Call once with all output buffers NULL to learn the count, then with buffers of
+ * `cap` entries. A binary sidecar <dir>/witness.bin (vpin_witness_json_to_bin) holding the same content is preferred when present:
+ * LeNet layer 5's JSON is 3 x 6000 lists of 32 decimal integers. vpin_witness_last_error(): message of this thread's last failure. */
+vpin_status vpin_load_point_mult(const char *root, const char *tag, uint64_t cap, uint64_t *count_out, uint64_t *weights_lo_hi, uint8_t *px32,
+                                 uint8_t *py32);
+vpin_status vpin_load_point_add(const char *root, const char *tag, uint64_t cap, uint64_t *count_out, uint8_t *px32, uint8_t *py32, uint8_t *rx32,
+                                uint8_t *ry32, int64_t *rz);
+/* writes witness.bin next to the JSON files of whichever of the two directories exist; *written_out: bit 0 pointMult, bit 1 pointAdd */
+vpin_status vpin_witness_json_to_bin(const char *root, const char *tag, uint32_t *written_out);
+const char *vpin_witness_last_error(void);
 
 #ifdef __cplusplus
 }

@@ -105,3 +105,54 @@ def test_synthetic_points_are_on_vpins_curve():
         assert (y * y - (x * x * x + W.CURVE_A * x + W.CURVE_B)) % W.FIELD == 0
     assert W.ec_mul(W.ORDER, W.GEN) is None
     assert W.FIELD == 2**252 + 27742317777372353535851937790883648493  # the curve's base field is Spartan's scalar field
+
+
+def test_native_witness_loader_matches_the_python_one(tmp_path):
+    """(f4) vpin_load_point_mult / vpin_load_point_add (C++, VP/load_data.rs:5-62, load_data_add.rs:5-102) return the same bytes
+    as the Python loader from the reference's JSON files, and again from the witness.bin sidecar; malformed input is an error
+    code, not an abort."""
+    import pytest
+    from vpin_b200 import api, workloads as W
+    mult = W.synth_point_mult(37)
+    mult = ([0, 1, (1 << 128) - 1] + list(mult[0][3:]), mult[1], mult[2])   # u128 edge values
+    add = W.synth_point_add(41, infinity_every=5)
+    root = str(tmp_path)
+    W.write_rust_files(root, "netX", mult=mult, add=add)
+    assert W.load_point_mult_native(root, "netX") == W.load_point_mult(root, "netX") == mult
+    got = W.load_point_add_native(root, "netX")
+    assert got[:4] == add[:4] and got[4] == add[4]
+    # sidecar: written once, preferred afterwards (remove the JSON to prove it is what gets read)
+    assert W.witness_json_to_bin(root, "netX") == 3
+    for sub, names in (("pointMult", ["weight.json", "point_mult_px_byte.json", "point_mult_py_byte.json"]),
+                       ("pointAdd", ["point_add_px_byte.json", "point_add_py_byte.json", "point_add_rx_byte.json", "point_add_ry_byte.json",
+                                     "point_add_rz_byte.json"])):
+        for n in names:
+            os.remove(os.path.join(root, "rust_files", "netX", sub, n))
+    assert W.load_point_mult_native(root, "netX") == mult
+    got = W.load_point_add_native(root, "netX")
+    assert got[:4] == add[:4] and got[4] == add[4]
+    # tolerated like serde_json + as_i64: whitespace, short rows (zero padded), non-integer entries skipped
+    d = os.path.join(root, "rust_files", "netY", "pointMult")
+    os.makedirs(d)
+    open(os.path.join(d, "weight.json"), "w").write(' [ "7" ,\n "340282366920938463463374607431768211455" ] ')
+    open(os.path.join(d, "point_mult_px_byte.json"), "w").write("[[1, 2, 3], [255, 1.5, 4]]")
+    open(os.path.join(d, "point_mult_py_byte.json"), "w").write("[[], [9]]")
+    w, px, py = W.load_point_mult_native(root, "netY")
+    assert w == [7, (1 << 128) - 1]
+    assert px == bytes([1, 2, 3]) + bytes(29) + bytes([255, 4]) + bytes(30) and py == bytes(32) + bytes([9]) + bytes(31)
+    # errors
+    with pytest.raises(api.VpinError) as e:
+        W.load_point_mult_native(root, "missing")
+    assert e.value.name == "IoError"
+    open(os.path.join(d, "weight.json"), "w").write('["340282366920938463463374607431768211456", "1"]')   # 2^128
+    with pytest.raises(api.VpinError) as e:
+        W.load_point_mult_native(root, "netY")
+    assert e.value.name == "InvalidScalar"
+    open(os.path.join(d, "weight.json"), "w").write('["7", "8", "9"]')
+    with pytest.raises(api.VpinError) as e:
+        W.load_point_mult_native(root, "netY")
+    assert e.value.name == "SizeMismatch"
+    open(os.path.join(d, "weight.json"), "w").write('["7", "8"')
+    with pytest.raises(api.VpinError) as e:
+        W.load_point_mult_native(root, "netY")
+    assert e.value.name == "IoError"

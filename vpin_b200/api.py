@@ -18,7 +18,7 @@ COO_DTYPE = np.dtype([("row", "<u8"), ("col", "<u8"), ("val", "u1", (32,))])
 
 STATUS = {
     0: "OK", 1: "InvalidScalar", 2: "InvalidIndex", 3: "InvalidNumberOfInputs", 4: "SizeMismatch", 5: "BufferTooSmall",
-    6: "CudaError", 7: "OutOfMemory", 8: "ProverAssertion", 9: "BadArgument",
+    6: "CudaError", 7: "OutOfMemory", 8: "ProverAssertion", 9: "BadArgument", 10: "IoError",
 }
 
 
@@ -41,6 +41,7 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         L = _lib
         vp, u64 = C.c_void_p, C.c_uint64
+        L.vpin_witness_last_error.restype = C.c_char_p
         L.vpin_last_error.restype = C.c_char_p
         L.vpin_last_error.argtypes = [vp]
         L.vpin_kernel_launches.restype = u64

@@ -249,6 +249,9 @@ __device__ __forceinline__ void msm_accumulate_body(const niels_t *table, const 
 __global__ void __launch_bounds__(kMsmRowsPerBlock, 6) k_msm_accumulate(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<0>>(VPIN_MSM_ACC_PASS); }
 // 0x8888: the odd-column products of rows 1, 3, 5, 7 accumulate on the ALU pipe (the best of the row patterns tried)
 __global__ void __launch_bounds__(kMsmRowsPerBlock, 5) k_msm_accumulate_a2(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<0x8888u>>(VPIN_MSM_ACC_PASS); }
+__global__ void __launch_bounds__(kMsmRowsPerBlock, 6) k_msm_accumulate_k6(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<kFpKaratsuba>>(VPIN_MSM_ACC_PASS); }
+__global__ void __launch_bounds__(kMsmRowsPerBlock, 5) k_msm_accumulate_k5(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<kFpKaratsuba>>(VPIN_MSM_ACC_PASS); }
+__global__ void __launch_bounds__(kMsmRowsPerBlock, 4) k_msm_accumulate_k4(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<kFpKaratsuba>>(VPIN_MSM_ACC_PASS); }
 __global__ void __launch_bounds__(kMsmRowsPerBlock, 4) k_msm_accumulate_f9p0(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc9<0>>(VPIN_MSM_ACC_PASS); }
 __global__ void __launch_bounds__(kMsmRowsPerBlock, 4) k_msm_accumulate_f9p1(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc9<1>>(VPIN_MSM_ACC_PASS); }
 // VPIN_MSM_VARIANT selects one of the measured alternatives of the hot loop (all bit-identical; 2^22 uniform scalars on a B200,
@@ -337,6 +340,9 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
     case 1: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p0); break;
     case 2: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p1); break;
     case 12: VPIN_MSM_LAUNCH(k_msm_accumulate_a2); break;
+    case 24: VPIN_MSM_LAUNCH(k_msm_accumulate_k4); break;
+    case 25: VPIN_MSM_LAUNCH(k_msm_accumulate_k5); break;
+    case 26: VPIN_MSM_LAUNCH(k_msm_accumulate_k6); break;
     default: VPIN_MSM_LAUNCH(k_msm_accumulate); break;
   }
 #undef VPIN_MSM_LAUNCH

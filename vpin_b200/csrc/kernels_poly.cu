@@ -135,6 +135,58 @@ void launch_eq_evals_pt(const EqPoint &pt, int ell, fl_t *d_out, fl_t *d_tmp, cu
   unsigned blocks = (unsigned)((n / 256) < 148 * 16 ? (n / 256) : 148 * 16);
   ++g_kernel_launches, k_eq_outer<<<blocks, 256, 0, st>>>(hi, lo, lo_bits, n, d_out);
 }
+// ---- suffix eq tables: S[2^k + x] = eq(r[ell-k .. ell), x) for k = 0..kmax, x < 2^k (S[1] = 1, S[0] unused).
+// The sumcheck kernels factor the shared eq polynomial out of the round polynomial (kernels_round.cu): round j needs
+// eq(r[j+1..ell), .), i.e. exactly the tables this doubling construction passes through when the new variable goes on TOP
+// of the index, so one pass builds the table of every round (2^kmax+1 elements in all, one multiplication per element).
+static const int kEqSuffixSmall = 11;  // levels built by one block
+__global__ void __launch_bounds__(1024) k_eq_suffix_small(EqPoint pt, int ell, int kmax, fl_t *S) {
+  if (threadIdx.x == 0) st_fl(S + 1, fl_one());
+  __syncthreads();
+  for (int k = 0; k < kmax; k++) {  // T_{k+1} from T_k: the new top variable is r[ell - 1 - k]
+    fl_t w = pt.r[ell - 1 - k];
+    int size = 1 << k;
+    for (int x = threadIdx.x; x < size; x += blockDim.x) {
+      fl_t s = ld_fl(S + size + x);
+      fl_t hi = fl_mul(s, w);
+      st_fl(S + 2 * size + size + x, hi);
+      st_fl(S + 2 * size + x, fl_sub(s, hi));
+    }
+    __syncthreads();
+  }
+}
+// thread x < 2^k0 expands T_k0[x] into its descendants of the next `levels` (<= 3) tables
+__global__ void __launch_bounds__(256) k_eq_suffix_expand(EqPoint pt, int ell, int k0, int levels, fl_t *S) {
+  size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n0 = (size_t)1 << k0;
+  if (x >= n0) return;
+  fl_t v[8];
+  v[0] = ld_fl(S + n0 + x);
+#pragma unroll
+  for (int l = 0; l < 3; l++) {
+    if (l >= levels) break;
+    fl_t w = pt.r[ell - 1 - (k0 + l)];
+    fl_t *T = S + (n0 << (l + 1));  // table k0 + l + 1
+#pragma unroll
+    for (int y = 0; y < (1 << l); y++) {
+      fl_t hi = fl_mul(v[y], w);
+      fl_t lo = fl_sub(v[y], hi);
+      v[y] = lo;
+      v[y + (1 << l)] = hi;
+      st_fl(T + x + ((size_t)y << k0), lo);
+      st_fl(T + x + ((size_t)(y + (1 << l)) << k0), hi);
+    }
+  }
+}
+void launch_eq_suffix(const EqPoint &pt, int ell, int kmax, fl_t *S, cudaStream_t st) {
+  int small = kmax < kEqSuffixSmall ? kmax : kEqSuffixSmall;
+  ++g_kernel_launches, k_eq_suffix_small<<<1, small <= 8 ? 256 : 1024, 0, st>>>(pt, ell, small, S);
+  for (int k0 = small; k0 < kmax; k0 += 3) {
+    int levels = kmax - k0 < 3 ? kmax - k0 : 3;
+    size_t n0 = (size_t)1 << k0;
+    ++g_kernel_launches, k_eq_suffix_expand<<<(unsigned)((n0 + 255) / 256), 256, 0, st>>>(pt, ell, k0, levels, S);
+  }
+}
 void launch_eq_evals(const fl_t *d_r, int ell, fl_t *d_out, fl_t *d_tmp, cudaStream_t st) {
   if (ell <= 12) {
     ++g_kernel_launches, k_eq_small<<<1, 1024, 0, st>>>(d_r, ell, d_out, d_tmp);

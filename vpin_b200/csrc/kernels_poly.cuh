@@ -52,13 +52,18 @@ struct RoundCtl {
 static const int kMaxBatched = 18;  // 12 product circuits + 6 dot-product halves (Spartan/src/sparse_mlpoly.rs:1173-1197)
 struct BatchedRoundArgs {
   fl_t *A[kMaxBatched], *B[kMaxBatched];  // bound in place
-  const fl_t *Cin[kMaxBatched];           // third factor; the product circuits share one eq table
-  fl_t *Cout[kMaxBatched];                // where the bound third factor goes (== Cin for an owned table, a ping-pong
-};                                        // buffer for the owner of the shared table, nullptr for its other readers)
+  const fl_t *Cin[kMaxBatched];           // third factor of a dot-product instance (its own table) ...
+  fl_t *Cout[kMaxBatched];                // ... bound in place (Cout == Cin); unused for product instances
+  int nprod;                              // instances [0, nprod) are product circuits: their third factor is the shared eq
+  const fl_t *eq_rest;                    // polynomial, factored out of the round polynomial: eq(rand[j+1..], .) of this
+};                                        // round (q elements, read only); see k_round_cubic_batched
 struct FinalArgs { const fl_t *p[kRoundSlotVals]; int n; };
 // q = number of thread items: half the current length without bind, a quarter of it with bind (the tables then shrink
 // to half their length in place). r is ignored without bind.
 void launch_round_cubic_additive(fl_t *A, fl_t *B, fl_t *C, fl_t *D, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
+// the same round with the eq factor A = eq(tau, .) factored out (s(X) = eq(tau_j, X) E t(X), t quadratic): binds B, C, D and
+// delivers t(0) = sum eq_rest (B C - D) at X = 0 and the leading coefficient t(inf) = sum eq_rest (B1 - B0)(C1 - C0)
+void launch_round_r1cs_split(const fl_t *eq_rest, fl_t *B, fl_t *C, fl_t *D, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
 void launch_round_quad(fl_t *A, fl_t *B, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
 void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
 // vals[k] = p_k[0] + r (p_k[1] - p_k[0]) (bind) or p_k[0]
@@ -86,6 +91,9 @@ void launch_publish_vals(const fl_t *src, int count, RoundSlot *slot, uint32_t s
 // eq table with the point passed by value (no device-side copy of r needed); same output as launch_eq_evals
 struct EqPoint { fl_t r[32]; };
 void launch_eq_evals_pt(const EqPoint &pt, int ell, fl_t *d_out, fl_t *d_tmp, cudaStream_t st);
+// suffix tables of eq(pt, .): S[2^k + x] = eq(pt.r[ell-k .. ell), x) for k = 0..kmax (kmax <= ell), x < 2^k; S has 2^(kmax+1)
+// elements (S[0] unused). Round j of a sumcheck over eq(pt, .) g(.) reads table k = ell - 1 - j (kernels_round.cu).
+void launch_eq_suffix(const EqPoint &pt, int ell, int kmax, fl_t *S, cudaStream_t st);
 
 // dot product sum_i A[i] B[i] (Spartan/src/nizk/mod.rs:442-445). d_out: 1 element; d_partials: kRedBlocks.
 void launch_dot(const fl_t *A, const fl_t *B, size_t n, fl_t *d_out, fl_t *d_partials, cudaStream_t st);

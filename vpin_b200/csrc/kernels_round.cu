@@ -128,20 +128,6 @@ __device__ __forceinline__ void load_pair(fl_t *T, size_t i, size_t q, const fl_
     hi = ldr(T + i + q);
   }
 }
-// same for a table that is read from `in` and (optionally) written to a different buffer `out`
-template <bool kBind>
-__device__ __forceinline__ void load_pair_oop(const fl_t *in, fl_t *out, bool write, size_t i, size_t q, const fl_t &r, fl_t &lo, fl_t &hi) {
-  if (kBind) {
-    fl_t t0 = ldr(in + i), t1 = ldr(in + i + q), t2 = ldr(in + i + 2 * q), t3 = ldr(in + i + 3 * q);
-    lo = bind1(t0, t2, r);
-    hi = bind1(t1, t3, r);
-    if (write) { str(out + i, lo); str(out + i + q, hi); }
-  } else {
-    lo = ldr(in + i);
-    hi = ldr(in + i + q);
-  }
-}
-
 // ---- A (B C - D) at t = 0, 2, 3 ----
 template <bool kBind>
 __global__ void __launch_bounds__(kRedThreads, 2) k_round_cubic_additive(fl_t *A, fl_t *B, fl_t *C, fl_t *D, size_t q, fl_t r, fl_t *partials,
@@ -164,6 +150,29 @@ __global__ void __launch_bounds__(kRedThreads, 2) k_round_cubic_additive(fl_t *A
   publish<3>(acc, 0, 1, partials, counters, slot, seq);
 }
 
+// ---- the same round with A = eq(tau, .) factored out ----
+// s_j(X) = sum_x eq(tau, (r_<j, X, x)) (B C - D)(r_<j, X, x) = E_j eq(tau_j, X) t_j(X) with E_j = prod_{k<j} eq(tau_k, r_k) and
+// t_j(X) = sum_x eq(tau_{>j}, x) (B C - D)(r_<j, X, x), a QUADRATIC. The kernel binds B, C, D and returns t_j(0) and the leading
+// coefficient t_j(inf) = sum_x eq_rest[x] (B1 - B0)(C1 - C0) (D is multilinear, it has no X^2 term); the host recovers t_j(1) from
+// the running claim and forms the three evaluations the reference sends (prover.cu zk_sumcheck). The eq table is neither bound
+// nor streamed four times per round: 10 multiplications and 13 element reads per thread item instead of 14 and 16.
+template <bool kBind>
+__global__ void __launch_bounds__(kRedThreads, 2) k_round_r1cs_split(const fl_t *E, fl_t *B, fl_t *C, fl_t *D, size_t q, fl_t r, fl_t *partials,
+                                                                  unsigned *counters, RoundSlot *slot, uint32_t seq) {
+  fl_t acc[2] = {fl_zero(), fl_zero()};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += stride) {
+    fl_t b0, b1, c0, c1, d0, d1;
+    load_pair<kBind>(B, i, q, r, b0, b1);
+    load_pair<kBind>(C, i, q, r, c0, c1);
+    load_pair<kBind>(D, i, q, r, d0, d1);
+    fl_t e = ldr(E + i);
+    acc[0] = fl_add(acc[0], fl_mul(e, fl_sub(fl_mul(b0, c0), d0)));
+    acc[1] = fl_add(acc[1], fl_mul(e, fl_mul(fl_sub(b1, b0), fl_sub(c1, c0))));
+  }
+  publish<2>(acc, 0, 1, partials, counters, slot, seq);
+}
+
 // ---- A B at t = 0, 2 ----
 template <bool kBind>
 __global__ void __launch_bounds__(kRedThreads) k_round_quad(fl_t *A, fl_t *B, size_t q, fl_t r, fl_t *partials, unsigned *counters,
@@ -181,28 +190,48 @@ __global__ void __launch_bounds__(kRedThreads) k_round_quad(fl_t *A, fl_t *B, si
   publish<2>(acc, 0, 1, partials, counters, slot, seq);
 }
 
-// ---- batched A_k B_k C_k at t = 0, 2, 3; instance = blockIdx.y ----
+// ---- batched rounds; instance = blockIdx.y ----
+// Product-circuit instances (inst < a.nprod) share the third factor eq(rand, .): it is factored out of the round polynomial like
+// in k_round_r1cs_split - s(X) = E eq(rand_j, X) t(X) - so the kernel binds A, B and returns t(0) = sum eq_rest A0 B0 and
+// t(inf) = sum eq_rest (A1 - A0)(B1 - B0) in vals[3 inst], vals[3 inst + 1] (8 multiplications per thread item instead of 12; the
+// eq table is read once per item and never bound). Dot-product instances (own third factor) evaluate A B C at 0, 2, 3 as before.
+__device__ __forceinline__ void batched_item_prod(const fl_t &e, const fl_t &a0, const fl_t &a1, const fl_t &b0, const fl_t &b1, fl_t (&acc)[3]) {
+  acc[0] = fl_add(acc[0], fl_mul(e, fl_mul(a0, b0)));
+  acc[1] = fl_add(acc[1], fl_mul(e, fl_mul(fl_sub(a1, a0), fl_sub(b1, b0))));
+}
+__device__ __forceinline__ void batched_item_dotp(const fl_t &a0, const fl_t &a1, const fl_t &b0, const fl_t &b1, const fl_t &c0, const fl_t &c1,
+                                                  fl_t (&acc)[3]) {
+  acc[0] = fl_add(acc[0], fl_mul(fl_mul(a0, b0), c0));
+  fl_t da = fl_sub(a1, a0), db = fl_sub(b1, b0), dc = fl_sub(c1, c0);
+  fl_t a2 = fl_add(a1, da), b2 = fl_add(b1, db), c2 = fl_add(c1, dc);
+  acc[1] = fl_add(acc[1], fl_mul(fl_mul(a2, b2), c2));
+  fl_t a3 = fl_add(a2, da), b3 = fl_add(b2, db), c3 = fl_add(c2, dc);
+  acc[2] = fl_add(acc[2], fl_mul(fl_mul(a3, b3), c3));
+}
 template <bool kBind>
 __global__ void __launch_bounds__(kRedThreads, 2) k_round_cubic_batched(BatchedRoundArgs a, size_t q, fl_t r, fl_t *partials, unsigned *counters,
                                                                      RoundSlot *slot, uint32_t seq) {
   const int inst = blockIdx.y;
   fl_t *A = a.A[inst], *B = a.B[inst];
-  const fl_t *Cin = a.Cin[inst];
-  fl_t *Cout = a.Cout[inst];
-  const bool writeC = Cout != nullptr;
   fl_t acc[3] = {fl_zero(), fl_zero(), fl_zero()};
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += stride) {
-    fl_t a0, a1, b0, b1, c0, c1;
-    load_pair<kBind>(A, i, q, r, a0, a1);
-    load_pair<kBind>(B, i, q, r, b0, b1);
-    load_pair_oop<kBind>(Cin, Cout, writeC, i, q, r, c0, c1);
-    acc[0] = fl_add(acc[0], fl_mul(fl_mul(a0, b0), c0));
-    fl_t da = fl_sub(a1, a0), db = fl_sub(b1, b0), dc = fl_sub(c1, c0);
-    fl_t a2 = fl_add(a1, da), b2 = fl_add(b1, db), c2 = fl_add(c1, dc);
-    acc[1] = fl_add(acc[1], fl_mul(fl_mul(a2, b2), c2));
-    fl_t a3 = fl_add(a2, da), b3 = fl_add(b2, db), c3 = fl_add(c2, dc);
-    acc[2] = fl_add(acc[2], fl_mul(fl_mul(a3, b3), c3));
+  if (inst < a.nprod) {
+    const fl_t *E = a.eq_rest;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += stride) {
+      fl_t a0, a1, b0, b1;
+      load_pair<kBind>(A, i, q, r, a0, a1);
+      load_pair<kBind>(B, i, q, r, b0, b1);
+      batched_item_prod(ldr(E + i), a0, a1, b0, b1, acc);
+    }
+  } else {
+    fl_t *Cc = a.Cout[inst];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < q; i += stride) {
+      fl_t a0, a1, b0, b1, c0, c1;
+      load_pair<kBind>(A, i, q, r, a0, a1);
+      load_pair<kBind>(B, i, q, r, b0, b1);
+      load_pair<kBind>(Cc, i, q, r, c0, c1);
+      batched_item_dotp(a0, a1, b0, b1, c0, c1, acc);
+    }
   }
   publish<3>(acc, inst, gridDim.y, partials, counters, slot, seq);
 }
@@ -219,20 +248,23 @@ __global__ void __launch_bounds__(16 * kMaxBatched + 16) k_round_cubic_batched_s
   fl_t acc[3] = {fl_zero(), fl_zero(), fl_zero()};
   if (inst < ninst) {
     fl_t *A = a.A[inst], *B = a.B[inst];
-    const fl_t *Cin = a.Cin[inst];
-    fl_t *Cout = a.Cout[inst];
-    const bool writeC = Cout != nullptr;
-    for (size_t i = lane; i < q; i += 16) {
-      fl_t a0, a1, b0, b1, c0, c1;
-      load_pair<kBind>(A, i, q, r, a0, a1);
-      load_pair<kBind>(B, i, q, r, b0, b1);
-      load_pair_oop<kBind>(Cin, Cout, writeC, i, q, r, c0, c1);
-      acc[0] = fl_add(acc[0], fl_mul(fl_mul(a0, b0), c0));
-      fl_t da = fl_sub(a1, a0), db = fl_sub(b1, b0), dc = fl_sub(c1, c0);
-      fl_t a2 = fl_add(a1, da), b2 = fl_add(b1, db), c2 = fl_add(c1, dc);
-      acc[1] = fl_add(acc[1], fl_mul(fl_mul(a2, b2), c2));
-      fl_t a3 = fl_add(a2, da), b3 = fl_add(b2, db), c3 = fl_add(c2, dc);
-      acc[2] = fl_add(acc[2], fl_mul(fl_mul(a3, b3), c3));
+    if (inst < a.nprod) {
+      const fl_t *E = a.eq_rest;
+      for (size_t i = lane; i < q; i += 16) {
+        fl_t a0, a1, b0, b1;
+        load_pair<kBind>(A, i, q, r, a0, a1);
+        load_pair<kBind>(B, i, q, r, b0, b1);
+        batched_item_prod(ldr(E + i), a0, a1, b0, b1, acc);
+      }
+    } else {
+      fl_t *Cc = a.Cout[inst];
+      for (size_t i = lane; i < q; i += 16) {
+        fl_t a0, a1, b0, b1, c0, c1;
+        load_pair<kBind>(A, i, q, r, a0, a1);
+        load_pair<kBind>(B, i, q, r, b0, b1);
+        load_pair<kBind>(Cc, i, q, r, c0, c1);
+        batched_item_dotp(a0, a1, b0, b1, c0, c1, acc);
+      }
     }
   }
   if (q > 1) {  // (q == 1: only lane 0 of each instance holds a term)
@@ -359,6 +391,12 @@ void launch_round_cubic_additive(fl_t *A, fl_t *B, fl_t *C, fl_t *D, size_t q, b
   ++g_kernel_launches;
   if (bind) k_round_cubic_additive<true><<<nb, kRedThreads, 0, st>>>(A, B, C, D, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
   else k_round_cubic_additive<false><<<nb, kRedThreads, 0, st>>>(A, B, C, D, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
+}
+void launch_round_r1cs_split(const fl_t *eq_rest, fl_t *B, fl_t *C, fl_t *D, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
+  int nb = round_blocks(q, kRedBlocks);
+  ++g_kernel_launches;
+  if (bind) k_round_r1cs_split<true><<<nb, kRedThreads, 0, st>>>(eq_rest, B, C, D, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
+  else k_round_r1cs_split<false><<<nb, kRedThreads, 0, st>>>(eq_rest, B, C, D, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
 }
 void launch_round_quad(fl_t *A, fl_t *B, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
   int nb = round_blocks(q, kRedBlocks);

@@ -326,6 +326,55 @@ struct Prover {
     launch_eq_evals_pt(pt, (int)ell, out.p, tmp.p, st);
     return out;
   }
+  // suffix tables of eq(r, .) for the sumchecks that factor the eq polynomial out (launch_eq_suffix): table k at offset 2^k
+  DevVec<fl_t> eq_suffix(const std::vector<fl_t> &r) {
+    size_t ell = r.size();
+    VPIN_REQUIRE(ell <= 32, VPIN_ERR_BAD_ARGUMENT, "eq table: more than 32 variables");
+    int kmax = ell ? (int)ell - 1 : 0;
+    DevVec<fl_t> out((size_t)2 << kmax, st);
+    EqPoint pt;
+    for (size_t i = 0; i < ell; i++) pt.r[i] = r[i];
+    ProfScope ps(ctx, PROF_EQ, (double)((size_t)1 << kmax), 32.0 * (double)((size_t)1 << kmax), 1 + (kmax > 11 ? (kmax - 11 + 2) / 3 : 0));
+    launch_eq_suffix(pt, (int)ell, kmax, out.p, st);
+    return out;
+  }
+  // inverses of every element (Montgomery's trick: one inversion). A zero has no inverse: the split-eq recovery of a round
+  // polynomial divides by the coordinates of the verifier's random point, which vanish with probability 2^-252 each.
+  static std::vector<fl_t> batch_invert(const std::vector<fl_t> &v) {
+    std::vector<fl_t> pre(v.size()), out(v.size());
+    fl_t run = fl_one();
+    for (size_t i = 0; i < v.size(); i++) {
+      VPIN_REQUIRE(!fl_is_zero(v[i]), VPIN_ERR_PROVER, "a coordinate of the random evaluation point is zero");
+      pre[i] = run;
+      run = run * v[i];
+    }
+    fl_t inv = fl_invert(run);
+    for (size_t i = v.size(); i-- > 0;) {
+      out[i] = inv * pre[i];
+      inv = inv * v[i];
+    }
+    return out;
+  }
+  // One round of a sumcheck whose polynomial has the factor eq(w, .) split off: s(X) = E l(X) t(X), l(X) = (1 - w)(1 - X) + w X,
+  // t quadratic. Given t(0), the leading coefficient a = t(inf) and the scaled claim sc = s(0)/E + s(1)/E = l(0) t(0) + l(1) t(1),
+  // returns s(0), s(2), s(3) - the evaluations the reference computes table by table (SP/sumcheck.rs:287-357, :619-652) - and
+  // keeps what the next round needs. Exact field arithmetic: the same polynomial, hence the same bytes.
+  struct SplitEq {
+    fl_t t0, t1, a, w;
+    static void evals(const fl_t &E, const fl_t &w, const fl_t &winv, const fl_t &sc, const fl_t &t0, const fl_t &a, fl_t out[3], SplitEq *keep) {
+      const fl_t one = fl_one();
+      fl_t l0 = one - w;
+      fl_t t1 = (sc - l0 * t0) * winv;
+      fl_t a2 = a + a, t2 = t1 + t1 - t0 + a2, t3 = t2 + t1 - t0 + a2 + a2;  // t(2) = 2 t1 - t0 + 2a, t(3) = 3 t1 - 2 t0 + 6a
+      fl_t w2 = w + w, l2 = w2 + w - one, l3 = l2 + w2 - one;                 // l(2) = 3w - 1, l(3) = 5w - 2
+      out[0] = E * l0 * t0;
+      out[1] = E * l2 * t2;
+      out[2] = E * l3 * t3;
+      keep->t0 = t0; keep->t1 = t1; keep->a = a; keep->w = w;
+    }
+    fl_t l_at(const fl_t &r) const { fl_t l0 = fl_one() - w; return l0 + r * (w - l0); }   // eq(w, r)
+    fl_t t_at(const fl_t &r) const { return t0 + r * ((t1 - t0 - a) + r * a); }          // the next scaled claim
+  };
   // ---- fused rounds: results arrive in host-mapped slots (kernels_round.cu) ----
   RoundCtl round_ctl(int slot, uint32_t *seq_out) {
     uint32_t seq = ++ctx->round_seq;
@@ -520,8 +569,11 @@ struct Prover {
   // delivers the final claims (`nfinal` values, returned in *finals). The kernel of round j+1 is launched as soon as
   // r_j is known, so the device works on it while the host finishes round j's sigma protocol. ----
   template <class RoundFn, class FinalFn>
+  // split_eq (optional): the point tau of an eq(tau, .) factor of the summand that launch_round has split off - the kernel then
+  // delivers (t(0), t(inf)) of the quadratic cofactor instead of three evaluations, and *eq_final receives eq(tau, r).
   ZkSumcheckS zk_sumcheck(const fl_t &claim, const fl_t &blind_claim, size_t num_rounds, size_t len, int degree, RoundFn launch_round,
-                          FinalFn launch_final, size_t nfinal, std::vector<fl_t> *r_out, fl_t *blind_post, std::vector<fl_t> *finals) {
+                          FinalFn launch_final, size_t nfinal, std::vector<fl_t> *r_out, fl_t *blind_post, std::vector<fl_t> *finals,
+                          const std::vector<fl_t> *split_eq = nullptr, fl_t *eq_final = nullptr) {
     std::vector<fl_t> blinds_poly = tape.vector("blinds_poly", num_rounds);
     std::vector<fl_t> blinds_evals = tape.vector("blinds_evals", num_rounds);
     // The tape is touched by nothing but the per-round DotProductProofs from here to the end of the sumcheck, so their
@@ -544,9 +596,19 @@ struct Prover {
     std::vector<fl_t> r;
     uint32_t seq;
     launch_round(len >> 1, false, fl_zero(), round_ctl(0, &seq));
+    std::vector<fl_t> winv;
+    if (split_eq) winv = batch_invert(*split_eq);  // (while the first round's kernel runs)
+    fl_t E = fl_one(), sc = claim;  // E = eq(tau_<j, r_<j); sc = claim_per_round / E
+    SplitEq keep;
     for (size_t j = 0; j < num_rounds; j++) {
       fl_t ev[3];
-      memcpy(ev, round_wait((int)(j & 1), seq), degree * sizeof(fl_t));
+      if (split_eq) {
+        fl_t tv[2];
+        memcpy(tv, round_wait((int)(j & 1), seq), sizeof(tv));
+        SplitEq::evals(E, (*split_eq)[j], winv[j], sc, tv[0], tv[1], ev, &keep);
+      } else {
+        memcpy(ev, round_wait((int)(j & 1), seq), degree * sizeof(fl_t));
+      }
       std::vector<fl_t> evals = degree == 3 ? std::vector<fl_t>{ev[0], claim_per_round - ev[0], ev[1], ev[2]}
                                             : std::vector<fl_t>{ev[0], claim_per_round - ev[0], ev[1]};
       std::vector<fl_t> poly = unipoly_from_evals(evals);
@@ -557,6 +619,7 @@ struct Prover {
       if (j + 1 < num_rounds) launch_round(len >> (j + 2), true, r_j, round_ctl((int)((j + 1) & 1), &seq));
       else launch_final(r_j, round_ctl((int)((j + 1) & 1), &seq));
       fl_t eval = unipoly_eval(poly, r_j);
+      if (split_eq) { E = E * keep.l_at(r_j); sc = keep.t_at(r_j); }
       Comp comm_eval = compress_host(commit1_par(g.sat_pc, eval, blinds_evals[j]));
       t.point("comm_claim_per_round", comm_claim_per_round.data());
       t.point("comm_eval", comm_eval.data());
@@ -583,6 +646,7 @@ struct Prover {
     }
     const fl_t *fin = round_wait((int)(num_rounds & 1), seq);
     finals->assign(fin, fin + nfinal);
+    if (eq_final) *eq_final = E;
     *r_out = r;
     *blind_post = blinds_evals[num_rounds - 1];
     return out;
@@ -791,18 +855,20 @@ struct Prover {
     VPIN_REQUIRE(nc + dotp.size() <= (size_t)kMaxBatched, VPIN_ERR_PROVER, "too many batched instances");
     std::vector<fl_t> claims_to_verify = tree_evals;
     std::vector<fl_t> rand;
-    DevVec<fl_t> eq_pong(std::max<size_t>(n / 4, 1), st);  // second buffer of the shared eq table (see BatchedRoundArgs)
     for (size_t layer_id = num_layers; layer_id-- > 0;) {
       size_t vlen = n >> layer_id;       // |V_layer|
       size_t off = 2 * n - 2 * vlen;     // offset of V_layer inside a packed tree
       size_t len_half = vlen / 2;
-      DevVec<fl_t> eqC = eq_table(rand);
+      // the product circuits share the third factor eq(rand, .): it is split off the round polynomial (k_round_cubic_batched),
+      // round j reads eq(rand_{>j}, .) from the suffix tables and the table is never bound
+      DevVec<fl_t> eqS = eq_suffix(rand);
       VPIN_REQUIRE(((size_t)1 << rand.size()) == len_half, VPIN_ERR_PROVER, "layer size");
       size_t num_rounds = rand.size();
       bool with_dotp = layer_id == 0 && !dotp.empty();
       size_t ninst = nc + (with_dotp ? dotp.size() : 0);
       BatchedRoundArgs args;
       memset(&args, 0, sizeof(args));
+      args.nprod = (int)nc;
       for (size_t c = 0; c < nc; c++) {
         args.A[c] = trees[c] + off;
         args.B[c] = trees[c] + off + len_half;
@@ -813,7 +879,6 @@ struct Prover {
           args.A[nc + k] = dotp[k].l; args.B[nc + k] = dotp[k].r;
           args.Cin[nc + k] = dotp[k].w; args.Cout[nc + k] = dotp[k].w;
         }
-      fl_t *eq_cur = eqC.p, *eq_other = eq_pong.p;
       LayerS layer;
       std::vector<fl_t> rand_prod;
       double tables = 2.0 * nc + 1 + (with_dotp ? 3.0 * dotp.size() : 0);
@@ -837,6 +902,7 @@ struct Prover {
         for (size_t k = 0; k < own.size(); k++) {
           own_args.A[k] = args.A[own[k]]; own_args.B[k] = args.B[own[k]];
           own_args.Cin[k] = args.Cin[own[k]]; own_args.Cout[k] = args.Cout[own[k]];  // (dot-product instances own their third factor)
+          if (own[k] < nc) own_args.nprod = (int)k + 1;  // instances are dealt in increasing order: this rank's product circuits come first
         }
       }
       // after a sharded launch: stage this rank's values, all-gather, publish everything to the host-mapped slot
@@ -854,14 +920,8 @@ struct Prover {
       // round j: bind with r_{j-1} (j > 0) and evaluate over q = len_half >> (j+1) thread items
       auto launch = [&](size_t j, const fl_t &r_prev) {
         size_t q = len_half >> (j + 1);
+        args.eq_rest = own_args.eq_rest = eqS.p + q;  // table k = num_rounds - 1 - j of the suffix family (2^k = q elements)
         if (sharded) {
-          bool first_prod = true;  // the first product instance of this rank writes the bound eq table, the others read it
-          for (size_t k = 0; k < own.size(); k++)
-            if (own[k] < nc) {
-              own_args.Cin[k] = eq_cur;
-              own_args.Cout[k] = (j > 0 && first_prod) ? eq_other : nullptr;
-              first_prod = false;
-            }
           if (!own.empty()) {
             uint32_t dev_seq;
             RoundCtl ctl = round_ctl(slot, &dev_seq);
@@ -870,14 +930,10 @@ struct Prover {
             launch_round_cubic_batched(own_args, (int)own.size(), q, j > 0, r_prev, ctl, st);
           }
           exchange(3);
-          if (j > 0) std::swap(eq_cur, eq_other);
           return;
         }
-        for (size_t c = 0; c < nc; c++) { args.Cin[c] = eq_cur; args.Cout[c] = nullptr; }
-        if (j > 0) { args.Cout[0] = eq_other; }
         ProfScope ps(ctx, PROF_SC_BATCHED, (double)ninst * q, tables * (j > 0 ? 6 : 2) * q * 32);
         launch_round_cubic_batched(args, (int)ninst, q, j > 0, r_prev, round_ctl(slot, &seq), st);
-        if (j > 0) std::swap(eq_cur, eq_other);
       };
       fl_t r_j = fl_zero();
       if (num_rounds) launch(0, r_j);
@@ -886,6 +942,10 @@ struct Prover {
       fl_t e = fl_zero();
       for (size_t i = 0; i < coeffs.size(); i++) e = e + claims_to_verify[i] * coeffs[i];
       std::vector<fl_t> ev(3 * ninst);
+      // split-eq bookkeeping of the product instances (SplitEq): E = eq(rand_<j, r_<j), sc[c] = claim of instance c / E
+      std::vector<fl_t> winv = batch_invert(rand), sc(claims_to_verify.begin(), claims_to_verify.begin() + nc);
+      std::vector<SplitEq> keep(nc);
+      fl_t E = fl_one();
       for (size_t j = 0; j < num_rounds; j++) {
         double tw0 = now_ms();
         {
@@ -896,6 +956,10 @@ struct Prover {
           } else {
             memcpy(ev.data(), got, 3 * ninst * sizeof(fl_t));
           }
+        }
+        for (size_t c = 0; c < nc; c++) {  // (t(0), t(inf)) of the cofactor -> the evaluations at 0, 2, 3 the reference computes
+          fl_t t0 = ev[3 * c], a = ev[3 * c + 1];
+          SplitEq::evals(E, rand[j], winv[j], sc[c], t0, a, &ev[3 * c], &keep[c]);
         }
         double tw1 = now_ms();
         t_b_wait += tw1 - tw0;
@@ -919,6 +983,8 @@ struct Prover {
         t_b_host += tw2 - tw1;
         if (j + 1 < num_rounds) launch(j + 1, r_j);
         t_b_launch += now_ms() - tw2;
+        for (size_t c = 0; c < nc; c++) sc[c] = keep[c].t_at(r_j);
+        if (nc) E = E * keep[0].l_at(r_j);
         e = unipoly_eval(poly, r_j);
         layer.polys.push_back({poly[0], poly[2], poly[3]});  // CompressedUniPoly (SP/unipoly.rs:80-87)
       }
@@ -926,7 +992,7 @@ struct Prover {
       FinalArgs fa;
       fa.n = 0;
       for (size_t c = 0; c < nc; c++) { fa.p[fa.n++] = args.A[c]; fa.p[fa.n++] = args.B[c]; }
-      fa.p[fa.n++] = eq_cur;
+      fa.p[fa.n++] = args.A[0];  // (slot of the eq claim eq(rand, r): equal to E above, not needed by the prover)
       if (with_dotp)
         for (size_t k = 0; k < dotp.size(); k++) { fa.p[fa.n++] = dotp[k].l; fa.p[fa.n++] = dotp[k].r; fa.p[fa.n++] = dotp[k].w; }
       VPIN_REQUIRE(fa.n <= kRoundSlotVals, VPIN_ERR_PROVER, "too many final claims");
@@ -937,7 +1003,7 @@ struct Prover {
         for (size_t k = 0; k < own.size(); k++) {
           fo.p[fo.n++] = own_args.A[k];
           fo.p[fo.n++] = own_args.B[k];
-          fo.p[fo.n++] = own[k] < nc ? eq_cur : own_args.Cin[k];
+          fo.p[fo.n++] = own[k] < nc ? own_args.A[k] : own_args.Cin[k];
         }
         if (fo.n) {
           uint32_t dev_seq;
@@ -1058,7 +1124,7 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   }
   size_t num_rounds_x = math_log2(num_cons), num_rounds_y = math_log2(zlen);
   std::vector<fl_t> tau = t.challenge_vector("challenge_tau", num_rounds_x);
-  DevVec<fl_t> poly_tau = P.eq_table(tau);
+  DevVec<fl_t> tau_suffix = P.eq_suffix(tau);  // eq(tau_{>j}, .) of every round: the eq factor is split off the round polynomial
   DevVec<fl_t> ABCz(3 * num_cons, st);
   for (int k = 0; k < 3; k++) {
     ProfScope ps(ctx, PROF_SPMV, (double)inst.M[k].nnz, 68.0 * inst.M[k].nnz + 36.0 * num_cons);
@@ -1069,20 +1135,22 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   std::vector<fl_t> rx;
   fl_t blind_claim_postsc1;
   std::vector<fl_t> fin1;
+  fl_t tau_claim;
   ZkSumcheckS sc1 = P.zk_sumcheck(
       fl_zero(), fl_zero(), num_rounds_x, num_cons, 3,
       [&](size_t q, bool bind, const fl_t &r, const RoundCtl &c) {
+        // algorithmic bytes of SURVEY.md 8d: 4 tables, each read once and written at half length (the split-off eq table moves less)
         ProfScope ps(ctx, PROF_SC_CUBIC, (double)q, (bind ? 4 * 192.0 : 4 * 64.0) * q);
-        launch_round_cubic_additive(poly_tau.p, Az, Bz, Cz, q, bind, r, c, st);
+        launch_round_r1cs_split(tau_suffix.p + q, Az, Bz, Cz, q, bind, r, c, st);
       },
       [&](const fl_t &r, const RoundCtl &c) {
         FinalArgs fa;
-        fa.p[0] = poly_tau.p; fa.p[1] = Az; fa.p[2] = Bz; fa.p[3] = Cz;
-        fa.n = 4;
+        fa.p[0] = Az; fa.p[1] = Bz; fa.p[2] = Cz;
+        fa.n = 3;
         launch_round_final(fa, true, r, c, st);
       },
-      4, &rx, &blind_claim_postsc1, &fin1);
-  fl_t tau_claim = fin1[0], Az_claim = fin1[1], Bz_claim = fin1[2], Cz_claim = fin1[3];
+      3, &rx, &blind_claim_postsc1, &fin1, &tau, &tau_claim);
+  fl_t Az_claim = fin1[0], Bz_claim = fin1[1], Cz_claim = fin1[2];
   phase("prove_sc_phase_one", t0);
 
   fl_t Az_blind = tape.scalar("Az_blind"), Bz_blind = tape.scalar("Bz_blind"), Cz_blind = tape.scalar("Cz_blind"),

@@ -153,6 +153,53 @@ def load_point_add(root, tag):
     return (*bufs, rz)
 
 
+def load_point_mult_native(root, tag):
+    """the same through the library's native loader (vpin_load_point_mult: JSON or the witness.bin sidecar)"""
+    import ctypes as C
+    from vpin_b200 import api
+    L = api.lib()
+    n = C.c_uint64()
+    st = L.vpin_load_point_mult(root.encode(), tag.encode(), C.c_uint64(0), C.byref(n), None, None, None)
+    if st != 0:
+        raise api.VpinError(st, L.vpin_witness_last_error().decode())
+    m = n.value
+    w = (C.c_uint64 * (2 * m))()
+    px, py = C.create_string_buffer(32 * m), C.create_string_buffer(32 * m)
+    st = L.vpin_load_point_mult(root.encode(), tag.encode(), C.c_uint64(m), C.byref(n), w, px, py)
+    if st != 0:
+        raise api.VpinError(st, L.vpin_witness_last_error().decode())
+    return [int(w[2 * i]) | (int(w[2 * i + 1]) << 64) for i in range(m)], px.raw[: 32 * m], py.raw[: 32 * m]
+
+
+def load_point_add_native(root, tag):
+    import ctypes as C
+    from vpin_b200 import api
+    L = api.lib()
+    n = C.c_uint64()
+    st = L.vpin_load_point_add(root.encode(), tag.encode(), C.c_uint64(0), C.byref(n), None, None, None, None, None)
+    if st != 0:
+        raise api.VpinError(st, L.vpin_witness_last_error().decode())
+    m = n.value
+    bufs = [C.create_string_buffer(32 * m) for _ in range(4)]
+    rz = (C.c_int64 * m)()
+    st = L.vpin_load_point_add(root.encode(), tag.encode(), C.c_uint64(m), C.byref(n), *bufs, rz)
+    if st != 0:
+        raise api.VpinError(st, L.vpin_witness_last_error().decode())
+    return (*[b.raw[: 32 * m] for b in bufs], [int(z) for z in rz])
+
+
+def witness_json_to_bin(root, tag):
+    """writes the witness.bin sidecars (vpin_witness_json_to_bin); returns the bit mask of what was written"""
+    import ctypes as C
+    from vpin_b200 import api
+    L = api.lib()
+    out = C.c_uint32()
+    st = L.vpin_witness_json_to_bin(root.encode(), tag.encode(), C.byref(out))
+    if st != 0:
+        raise api.VpinError(st, L.vpin_witness_last_error().decode())
+    return out.value
+
+
 def tape_seeds():
     """Deterministic stand-ins for the two OsRng scalars: 64 B of SHAKE256 -> mod l."""
     import hashlib
