@@ -134,13 +134,10 @@ VPIN_HD fp_t fp_mul(const fp_t &a, const fp_t &b) {
 }
 VPIN_HD fp_t fp_sqr(const fp_t &a) { return fp_mul(a, a); }
 // fp_mul with the accumulation of chosen product rows moved to the ALU pipe (limbs.cuh mul_8x8_p); same value
-// kAluRows == kFpKaratsuba: one level of subtractive Karatsuba instead (limbs.cuh mul_8x8_k, 48 + 8 multiplies)
-static const uint32_t kFpKaratsuba = 0x10000u;
 template <uint32_t kAluRows>
 VPIN_HD fp_t fp_mul_p(const fp_t &a, const fp_t &b) {
   uint32_t t[16];
-  if (kAluRows == kFpKaratsuba) limb::mul_8x8_k(t, a.v, b.v);
-  else limb::mul_8x8_p<kAluRows>(t, a.v, b.v);
+  limb::mul_8x8_p<kAluRows>(t, a.v, b.v);
   return fp_reduce_wide(t);
 }
 

@@ -249,14 +249,13 @@ __device__ __forceinline__ void msm_accumulate_body(const niels_t *table, const 
 __global__ void __launch_bounds__(kMsmRowsPerBlock, 6) k_msm_accumulate(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<0>>(VPIN_MSM_ACC_PASS); }
 // 0x8888: the odd-column products of rows 1, 3, 5, 7 accumulate on the ALU pipe (the best of the row patterns tried)
 __global__ void __launch_bounds__(kMsmRowsPerBlock, 5) k_msm_accumulate_a2(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<0x8888u>>(VPIN_MSM_ACC_PASS); }
-__global__ void __launch_bounds__(kMsmRowsPerBlock, 6) k_msm_accumulate_k6(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<kFpKaratsuba>>(VPIN_MSM_ACC_PASS); }
-__global__ void __launch_bounds__(kMsmRowsPerBlock, 5) k_msm_accumulate_k5(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<kFpKaratsuba>>(VPIN_MSM_ACC_PASS); }
-__global__ void __launch_bounds__(kMsmRowsPerBlock, 4) k_msm_accumulate_k4(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<kFpKaratsuba>>(VPIN_MSM_ACC_PASS); }
 __global__ void __launch_bounds__(kMsmRowsPerBlock, 4) k_msm_accumulate_f9p0(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc9<0>>(VPIN_MSM_ACC_PASS); }
 __global__ void __launch_bounds__(kMsmRowsPerBlock, 4) k_msm_accumulate_f9p1(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc9<1>>(VPIN_MSM_ACC_PASS); }
 // VPIN_MSM_VARIANT selects one of the measured alternatives of the hot loop (all bit-identical; 2^22 uniform scalars on a B200,
 // profiles/r2_msm_variants.log): 0 (default) 8 x 32 carry-chained 5.01 ms | 1 radix 2^29, accumulation in the multiplier 6.38 ms |
-// 2 radix 2^29, accumulation on the ALU pipe 7.31 ms | 12 8 x 32 with four rows accumulated on the ALU pipe 5.21 ms
+// 2 radix 2^29, accumulation on the ALU pipe 7.31 ms | 12 8 x 32 with four rows accumulated on the ALU pipe 5.21 ms.
+// (One level of subtractive Karatsuba on the 8 x 8 limb product - 48 + 8 instead of 64 + 8 multiplies - was also built: ptxas
+// places the ~60 extra additions and moves on the multiply pipe as IMAD.X / IMAD.MOV, 5.5 - 5.8 ms; dropped.)
 static int msm_variant() {
   static const int v = [] { const char *e = getenv("VPIN_MSM_VARIANT"); return e ? atoi(e) : 0; }();
   return v;
@@ -340,9 +339,6 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
     case 1: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p0); break;
     case 2: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p1); break;
     case 12: VPIN_MSM_LAUNCH(k_msm_accumulate_a2); break;
-    case 24: VPIN_MSM_LAUNCH(k_msm_accumulate_k4); break;
-    case 25: VPIN_MSM_LAUNCH(k_msm_accumulate_k5); break;
-    case 26: VPIN_MSM_LAUNCH(k_msm_accumulate_k6); break;
     default: VPIN_MSM_LAUNCH(k_msm_accumulate); break;
   }
 #undef VPIN_MSM_LAUNCH

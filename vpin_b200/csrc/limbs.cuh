@@ -191,160 +191,6 @@ VPIN_HD void mul_8x8_p(uint32_t *t, const uint32_t *a, const uint32_t *b) {
 #endif
 }
 
-// ---- one level of subtractive Karatsuba: 48 instead of 64 multiplies per 8 x 8 product -------------------------------------
-// IMAD.WIDE is a half-rate instruction on sm_100a (every form of it occupies the multiply pipe for 4 cycles per warp,
-// scripts/ubench/imad_rates2.cu) while IADD3 / LOP3 issue every cycle on a pipe the field arithmetic leaves two thirds idle:
-// trading 16 multiplies for ~60 additions shortens the multiplication.
-//   a = a0 + a1 W, b = b0 + b1 W (W = 2^128):  a b = z0 + (z0 + z2 + (a0 - a1)(b1 - b0)) W + z2 W^2,  z0 = a0 b0, z2 = a1 b1.
-// r[0..4) = (a[0], a[2]) * b as two 64-bit products
-VPIN_HD void mul_row2(uint32_t *r, const uint32_t *a, uint32_t b) {
-#if defined(__CUDA_ARCH__)
-  asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(r[0]), "=r"(r[1]) : "r"(a[0]), "r"(b));
-  asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(r[2]), "=r"(r[3]) : "r"(a[2]), "r"(b));
-#else
-  for (int k = 0; k < 2; k++) {
-    uint64_t p = (uint64_t)a[2 * k] * b;
-    r[2 * k] = (uint32_t)p;
-    r[2 * k + 1] = (uint32_t)(p >> 32);
-  }
-#endif
-}
-// r[0..4) += (a[0], a[2]) * b with one carry chain; cw += carry out
-VPIN_HD void mad_row2(uint32_t *r, const uint32_t *a, uint32_t b, uint32_t &cw) {
-#if defined(__CUDA_ARCH__)
-  asm("mad.lo.cc.u32 %0, %5, %7, %0; madc.hi.cc.u32 %1, %5, %7, %1;"
-      "madc.lo.cc.u32 %2, %6, %7, %2; madc.hi.cc.u32 %3, %6, %7, %3;"
-      "addc.u32 %4, %4, 0;"
-      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(cw)
-      : "r"(a[0]), "r"(a[2]), "r"(b));
-#else
-  uint64_t c = 0;
-  for (int k = 0; k < 2; k++) {
-    uint64_t p = (uint64_t)a[2 * k] * b;
-    uint64_t lo = (uint64_t)r[2 * k] + (uint32_t)p + c;
-    r[2 * k] = (uint32_t)lo;
-    uint64_t hi = (uint64_t)r[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
-    r[2 * k + 1] = (uint32_t)hi;
-    c = hi >> 32;
-  }
-  cw += (uint32_t)c;
-#endif
-}
-VPIN_HD void mad_row2_nc(uint32_t *r, const uint32_t *a, uint32_t b) {
-#if defined(__CUDA_ARCH__)
-  asm("mad.lo.cc.u32 %0, %4, %6, %0; madc.hi.cc.u32 %1, %4, %6, %1;"
-      "madc.lo.cc.u32 %2, %5, %6, %2; madc.hi.u32 %3, %5, %6, %3;"
-      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3])
-      : "r"(a[0]), "r"(a[2]), "r"(b));
-#else
-  uint32_t dummy = 0;
-  mad_row2(r, a, b, dummy);
-#endif
-}
-// t[0..8) = a[0..4) * b[0..4): 16 IMAD.WIDE, even / odd column split like mul_8x8
-VPIN_HD void mul_4x4(uint32_t *t, const uint32_t *a, const uint32_t *b) {
-  uint32_t ev[8], od[8];  // od[k] has weight 2^(32 (k + 1))
-#pragma unroll
-  for (int k = 4; k < 8; k++) ev[k] = od[k] = 0;
-  mul_row2(ev, a, b[0]);
-  mul_row2(od, a + 1, b[0]);
-  mad_row2(od + 0, a, b[1], od[4]);
-  mad_row2(ev + 2, a + 1, b[1], ev[6]);
-  mad_row2(ev + 2, a, b[2], ev[6]);
-  mad_row2(od + 2, a + 1, b[2], od[6]);
-  mad_row2(od + 2, a, b[3], od[6]);
-  mad_row2_nc(ev + 4, a + 1, b[3]);
-  t[0] = ev[0];
-#if defined(__CUDA_ARCH__)
-  asm("add.cc.u32 %0, %7, %14; addc.cc.u32 %1, %8, %15; addc.cc.u32 %2, %9, %16; addc.cc.u32 %3, %10, %17;"
-      "addc.cc.u32 %4, %11, %18; addc.cc.u32 %5, %12, %19; addc.u32 %6, %13, %20;"
-      : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
-      : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
-        "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]));
-#else
-  uint64_t c = 0;
-  for (int k = 1; k < 8; k++) {
-    c += (uint64_t)ev[k] + od[k - 1];
-    t[k] = (uint32_t)c;
-    c >>= 32;
-  }
-#endif
-}
-// d[0..4) = |x - y| for 4-limb x, y; returns 0xffffffff if x < y (the difference was negated), else 0
-VPIN_HD uint32_t abs_diff4(uint32_t *d, const uint32_t *x, const uint32_t *y) {
-#if defined(__CUDA_ARCH__)
-  uint32_t m;
-  asm("sub.cc.u32 %0, %5, %9; subc.cc.u32 %1, %6, %10; subc.cc.u32 %2, %7, %11; subc.cc.u32 %3, %8, %12; subc.u32 %4, 0, 0;"
-      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(m)
-      : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]));
-  // two's complement negation when m is all ones: (d ^ m) + (m & 1)
-  asm("add.cc.u32 %4, %4, 1;"  // carry flag = (m == 0xffffffff); %4 is restored below
-      "addc.cc.u32 %0, %5, 0; addc.cc.u32 %1, %6, 0; addc.cc.u32 %2, %7, 0; addc.u32 %3, %8, 0;"
-      "sub.u32 %4, %4, 1;"
-      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "+r"(m)
-      : "r"(d[0] ^ m), "r"(d[1] ^ m), "r"(d[2] ^ m), "r"(d[3] ^ m));
-  return m;
-#else
-  int64_t br = 0;
-  for (int i = 0; i < 4; i++) { int64_t t = (int64_t)x[i] - (int64_t)y[i] + br; d[i] = (uint32_t)t; br = t >> 32; }
-  uint32_t m = br ? 0xffffffffu : 0u;
-  uint64_t c = m & 1u;
-  for (int i = 0; i < 4; i++) { c += (uint64_t)(d[i] ^ m); d[i] = (uint32_t)c; c >>= 32; }
-  return m;
-#endif
-}
-// t[0..16) = a * b (8 x 8 limbs) with 48 IMAD.WIDE; same value as mul_8x8
-VPIN_HD void mul_8x8_k(uint32_t *t, const uint32_t *a, const uint32_t *b) {
-  uint32_t z0[8], z2[8], zm[8], da[4], db[4];
-  mul_4x4(z0, a, b);
-  mul_4x4(z2, a + 4, b + 4);
-  uint32_t neg = abs_diff4(da, a, a + 4) ^ abs_diff4(db, b + 4, b);  // sign of (a0 - a1)(b1 - b0): all ones = negative
-  mul_4x4(zm, da, db);
-  // mid (9 limbs) = z0 + z2 +- zm  (= a0 b1 + a1 b0 >= 0)
-  uint32_t mid[9];
-#if defined(__CUDA_ARCH__)
-  asm("add.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20;"
-      "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.cc.u32 %7, %16, %24; addc.u32 %8, 0, 0;"
-      : "=r"(mid[0]), "=r"(mid[1]), "=r"(mid[2]), "=r"(mid[3]), "=r"(mid[4]), "=r"(mid[5]), "=r"(mid[6]), "=r"(mid[7]), "=r"(mid[8])
-      : "r"(z0[0]), "r"(z0[1]), "r"(z0[2]), "r"(z0[3]), "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]),
-        "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(z2[4]), "r"(z2[5]), "r"(z2[6]), "r"(z2[7]));
-  {
-    uint32_t cin = neg;  // (zm ^ neg) + (neg & 1), sign-extended by neg into the ninth limb
-    asm("add.cc.u32 %9, %9, 1;"
-        "addc.cc.u32 %0, %0, %10; addc.cc.u32 %1, %1, %11; addc.cc.u32 %2, %2, %12; addc.cc.u32 %3, %3, %13;"
-        "addc.cc.u32 %4, %4, %14; addc.cc.u32 %5, %5, %15; addc.cc.u32 %6, %6, %16; addc.cc.u32 %7, %7, %17; addc.u32 %8, %8, %18;"
-        : "+r"(mid[0]), "+r"(mid[1]), "+r"(mid[2]), "+r"(mid[3]), "+r"(mid[4]), "+r"(mid[5]), "+r"(mid[6]), "+r"(mid[7]), "+r"(mid[8]), "+r"(cin)
-        : "r"(zm[0] ^ neg), "r"(zm[1] ^ neg), "r"(zm[2] ^ neg), "r"(zm[3] ^ neg), "r"(zm[4] ^ neg), "r"(zm[5] ^ neg), "r"(zm[6] ^ neg),
-          "r"(zm[7] ^ neg), "r"(neg));
-  }
-  // t = z0 + mid W + z2 W^2
-#pragma unroll
-  for (int k = 0; k < 4; k++) t[k] = z0[k];
-  asm("add.cc.u32 %0, %12, %24; addc.cc.u32 %1, %13, %25; addc.cc.u32 %2, %14, %26; addc.cc.u32 %3, %15, %27;"
-      "addc.cc.u32 %4, %16, %28; addc.cc.u32 %5, %17, %29; addc.cc.u32 %6, %18, %30; addc.cc.u32 %7, %19, %31;"
-      "addc.cc.u32 %8, %20, %32; addc.cc.u32 %9, %21, 0; addc.cc.u32 %10, %22, 0; addc.u32 %11, %23, 0;"
-      : "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]),
-        "=r"(t[15])
-      : "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]), "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(z2[4]), "r"(z2[5]), "r"(z2[6]),
-        "r"(z2[7]),
-        "r"(mid[0]), "r"(mid[1]), "r"(mid[2]), "r"(mid[3]), "r"(mid[4]), "r"(mid[5]), "r"(mid[6]), "r"(mid[7]), "r"(mid[8]));
-#else
-  uint64_t c = 0;
-  for (int k = 0; k < 8; k++) { c += (uint64_t)z0[k] + z2[k]; mid[k] = (uint32_t)c; c >>= 32; }
-  mid[8] = (uint32_t)c;
-  c = neg & 1u;
-  for (int k = 0; k < 8; k++) { c += (uint64_t)mid[k] + (zm[k] ^ neg); mid[k] = (uint32_t)c; c >>= 32; }
-  mid[8] = (uint32_t)(mid[8] + neg + c);
-  for (int k = 0; k < 4; k++) t[k] = z0[k];
-  c = 0;
-  for (int k = 4; k < 16; k++) {
-    c += (uint64_t)(k < 8 ? z0[k] : z2[k - 8]) + (k - 4 < 9 ? mid[k - 4] : 0u);
-    t[k] = (uint32_t)c;
-    c >>= 32;
-  }
-#endif
-}
-
 // ---- Montgomery reduction rows for l = 2^252 + 27742317777372353535851937790883648493 (limbs P0..P3, 0, 0, 0, 2^28) ----
 #define VPIN_L_P0 0x5cf5d3edu
 #define VPIN_L_P1 0x5812631au
