@@ -16,8 +16,11 @@
  *   - every function returns a vpin_status; no function aborts. There is no CPU fallback: if no CUDA device is
  *     usable, vpin_ctx_create fails with VPIN_ERR_CUDA.
  *   - one context per host thread (the reference API is single-threaded: &mut Transcript, &mut RandomTape).
- *   - determinism hook: the reference seeds its RandomTapes from OsRng (SP/random.rs:16-18); here the 32-byte
- *     `init_randomness` scalar of each tape is an explicit argument.
+ *   - randomness: the reference seeds its RandomTapes from OsRng (SP/random.rs:16-18). Here the 32-byte `init_randomness`
+ *     scalar of each tape is an argument: pass NULL and the library draws it from the operating system's CSPRNG (getrandom,
+ *     64 bytes reduced mod l - what the reference does); pass 32 canonical bytes to reproduce a run (tests, parity vectors).
+ *     A seed is ONE-TIME: the Hyrax blinds and every sigma-protocol nonce derive from it, so proving two different witnesses
+ *     under the same seed leaks them. The fixed seeds in this repository's tests and bench exist for byte comparison only.
  */
 #ifndef VPIN_B200_H
 #define VPIN_B200_H
@@ -117,7 +120,8 @@ void vpin_decomm_destroy(vpin_decomm *decomm);
  * Z: n = 2^ell canonical scalars (the padded assignment). Blinds are drawn from a RandomTape exactly as the
  * reference does: `tape_state` is an opaque 256-byte buffer initialised by vpin_tape_init and advanced by each call,
  * so two consecutive commits on one tape reproduce VP/proof_point_add.rs:44-52. Pass tape_state = NULL for zero
- * blinds. points_out: L x 32 bytes, blinds_out: L x 32 bytes (may be NULL). */
+ * blinds. points_out: L x 32 bytes, blinds_out: L x 32 bytes (may be NULL).
+ * init_randomness32 == NULL: fresh randomness from the OS (production use); otherwise 32 canonical bytes (one-time!). */
 vpin_status vpin_tape_init(uint8_t tape_state[256], const uint8_t *name, uint64_t name_len,
                            const uint8_t init_randomness32[32]);
 vpin_status vpin_poly_commit(vpin_ctx *ctx, const vpin_gens *gens, const uint8_t *Z32, uint64_t n,
@@ -134,7 +138,7 @@ vpin_status vpin_commitments_add(vpin_ctx *ctx, const uint8_t *c1, const uint8_t
  *      VP/commit_test.rs:59-133 ------------------------------------------------------------------------------------
  * vars32: the padded assignment (num_vars_padded scalars) — also the evaluations of poly_vars.
  * transcript_label: the label of Transcript::new (b"snark_example" in VP/proof_point_add.rs:83).
- * tape_seed32: init_randomness of RandomTape::new(b"proof") (VP/commit_test.rs:74).
+ * tape_seed32: init_randomness of RandomTape::new(b"proof") (VP/commit_test.rs:74); NULL = drawn from the OS (see Conventions).
  * proof_out receives bincode(SNARK). */
 vpin_status vpin_prove(vpin_ctx *ctx, const vpin_instance *inst, const vpin_decomm *decomm, const uint8_t *vars32,
                        uint64_t n_vars, const uint8_t *inputs32, uint64_t n_inputs, const vpin_gens *gens,

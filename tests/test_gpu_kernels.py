@@ -112,7 +112,18 @@ def test_spmv_and_transpose(ctx):
         extra[i] = (i, num_vars, np.frombuffer(O.le32(i + 5), dtype=np.uint8))
     extra[num_cons] = (3, 7, np.frombuffer(O.le32(O.L_ORDER - 1), dtype=np.uint8))
     extra[num_cons + 1] = (3, 7, np.frombuffer(O.le32(9), dtype=np.uint8))
-    A2 = np.concatenate([A, extra])
+    # every code of the value dictionary (+-1, +-2, 3: no multiplication, value never read) next to general values in short rows,
+    # and two long rows (> kLongRow entries: the warp-per-row kernel): a 128-term bit decomposition 2^i like vPIN's, and a
+    # mixed one of 40 terms
+    L = O.L_ORDER
+    dict_vals = [1, L - 1, 2, L - 2, 3, 4, L - 3, 0]
+    more = [(10 + k, (5 * k + 1) % num_vars, v) for k, v in enumerate(dict_vals)] + [(10 + k, (3 * k + 2) % num_vars, dict_vals[(k + 3) % 8]) for k in range(8)]
+    more += [(40, i % (num_vars + 1 + num_inputs), 1 << i) for i in range(128)]
+    more += [(41, (7 * i) % num_vars, dict_vals[i % 8] if i % 3 else 12345 + i) for i in range(40)]
+    extra2 = np.zeros(len(more), O.COO_DTYPE)
+    for k, (r, c, v) in enumerate(more):
+        extra2[k] = (r, c, np.frombuffer(O.le32(v), dtype=np.uint8))
+    A2 = np.concatenate([A, extra, extra2])
     inst = api.Instance(ctx, num_cons, num_vars, num_inputs, A2, B, Cm)
     z = O.bytes_to_ints(vars_) + [1] + O.bytes_to_ints(inputs)
     z += [0] * (2 * num_vars - len(z))

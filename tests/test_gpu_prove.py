@@ -138,6 +138,21 @@ def test_unsatisfied_witness_is_reported(ctx):
     assert inst.is_sat(v, inputs) and not inst.is_sat(bytes(bad), inputs)
 
 
+def test_null_seeds_draw_fresh_randomness(ctx):
+    """NULL tape seeds (the production default): the library draws both init_randomness scalars from the OS like the reference's
+    OsRng (SP/random.rs:16-18) - two proofs of one witness then differ in every blinded byte, and both verify."""
+    from vpin_b200 import api
+
+    px, py, rx, ry, rz = W.synth_point_add(8, infinity_every=3)
+    dims, inst, vp, vi, v, inputs = api.point_addition(ctx, px, py, rx, ry, rz)
+    a = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, None, None)
+    b = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, None, None)
+    assert a["comm"] == b["comm"]                      # SNARK::encode is deterministic (no blinds)
+    assert a["comm_vars"] != b["comm_vars"] and a["proof"] != b["proof"] and len(a["proof"]) == len(b["proof"])
+    for got in (a, b):
+        assert O.verify(dims, got["proof"], got["comm"], inputs, got["comm_vars_para"], got["comm_vars_input"]) == 1
+
+
 def test_two_contexts_prove_concurrently():
     """A network's independent instances are proved from two host threads with one context each (bench.py does this for the
     point-add / point-mult pair, the point-mult context on the urgent stream priority): both proofs must be the oracle's."""

@@ -397,9 +397,10 @@ def point_addition(ctx, px, py, rx, ry, rz):
 
 
 class RandomTape:
-    """RandomTape::new(name) with the OsRng scalar supplied (Spartan/src/random.rs:14-21)."""
+    """RandomTape::new(name) (Spartan/src/random.rs:14-21). init_randomness32=None: the library draws the OsRng scalar itself
+    (production); 32 canonical bytes reproduce a run (tests only - a seed must never serve two different witnesses)."""
 
-    def __init__(self, name, init_randomness32):
+    def __init__(self, name, init_randomness32=None):
         self.state = C.create_string_buffer(256)
         st = lib().vpin_tape_init(self.state, name, C.c_uint64(len(name)), init_randomness32)
         if st != 0:

@@ -2,6 +2,9 @@
 // exception -> status mapping. The prover itself is in prover.cu, the kernels in kernels_*.cu.
 #include "prover.cuh"
 
+#include <errno.h>
+#include <sys/random.h>
+
 using namespace vpin;
 
 #define VPIN_TRY(ctx_)                      \
@@ -244,11 +247,33 @@ vpin_status vpin_encode(vpin_ctx *ctx, const vpin_instance *inst, const vpin_gen
 void vpin_decomm_destroy(vpin_decomm *d) { delete reinterpret_cast<Decomm *>(d); }
 
 // ---------------------------------------------------------------------------------------------- commitments
+// init_randomness of a RandomTape (SP/random.rs:16-18): the caller's 32 canonical bytes, or - for NULL - 64 bytes from the
+// operating system's CSPRNG reduced mod l, which is what the reference does (Scalar::random(&mut OsRng)). A tape seed must be
+// used for ONE proof: the blinds and sigma-protocol nonces derive from it, and repeating them under another witness leaks it.
+static bool tape_seed_from(const uint8_t *seed32, fl_t *out) {
+  if (seed32) return fl_from_bytes(seed32, out);
+  uint8_t wide[64];
+  size_t got = 0;
+  while (got < sizeof(wide)) {
+    ssize_t r = getrandom(wide + got, sizeof(wide) - got, 0);
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      throw Error(VPIN_ERR_PROVER, "getrandom failed: no randomness for the prover's tape");
+    }
+    got += (size_t)r;
+  }
+  *out = fl_from_bytes_wide(wide);
+  return true;
+}
 vpin_status vpin_tape_init(uint8_t tape_state[256], const uint8_t *name, uint64_t name_len, const uint8_t init_randomness32[32]) {
   static_assert(sizeof(ProverTape) <= 256, "tape state too small");
-  if (!tape_state || !init_randomness32) return VPIN_ERR_BAD_ARGUMENT;
+  if (!tape_state) return VPIN_ERR_BAD_ARGUMENT;
   fl_t seed;
-  if (!fl_from_bytes(init_randomness32, &seed)) return VPIN_ERR_INVALID_SCALAR;
+  try {
+    if (!tape_seed_from(init_randomness32, &seed)) return VPIN_ERR_INVALID_SCALAR;
+  } catch (const vpin::Error &e) {
+    return e.code;
+  }
   ProverTape t(name, name_len, seed);
   memset(tape_state, 0, 256);
   memcpy(tape_state, &t, sizeof(t));
@@ -342,13 +367,13 @@ vpin_status vpin_prove_resident(vpin_ctx *ctx, const vpin_instance *inst, const 
                                 uint64_t label_len, const uint8_t tape_seed32[32], uint8_t *proof_out, uint64_t proof_cap,
                                 uint64_t *proof_len) {
   VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
-  VPIN_REQUIRE(inst && decomm && w && gens && transcript_label && tape_seed32 && proof_len, VPIN_ERR_BAD_ARGUMENT, "null argument");
+  VPIN_REQUIRE(inst && decomm && w && gens && transcript_label && proof_len, VPIN_ERR_BAD_ARGUMENT, "null argument");
   const Instance *I = reinterpret_cast<const Instance *>(inst);
   VPIN_REQUIRE(n_inputs == I->num_inputs, VPIN_ERR_INVALID_NUM_INPUTS, "InvalidNumberOfInputs");
   std::vector<fl_t> inputs(n_inputs);
   for (size_t i = 0; i < n_inputs; i++) VPIN_REQUIRE(fl_from_bytes(inputs32 + 32 * i, &inputs[i]), VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
   fl_t seed;
-  VPIN_REQUIRE(fl_from_bytes(tape_seed32, &seed), VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
+  VPIN_REQUIRE(tape_seed_from(tape_seed32, &seed), VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
   std::vector<uint8_t> proof = snark_prove(c_, *I, *reinterpret_cast<const Decomm *>(decomm), *reinterpret_cast<const Witness *>(w), inputs,
                                            *reinterpret_cast<const SnarkGens *>(gens), transcript_label, label_len, seed);
   *proof_len = proof.size();

@@ -190,6 +190,7 @@ struct NcclApi {
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi &nccl() {
@@ -207,6 +208,7 @@ NcclApi &nccl() {
   VPIN_NCCL_SYM(AllGather, "ncclAllGather");
   VPIN_NCCL_SYM(AllReduce, "ncclAllReduce");
   VPIN_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+  VPIN_NCCL_SYM(CommAbort, "ncclCommAbort");
   VPIN_NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef VPIN_NCCL_SYM
   api.h = h;
@@ -255,6 +257,17 @@ void dist_destroy(Ctx *ctx) {
   }
   ctx->rank = 0;
   ctx->world = 1;
+}
+// A peer that failed (out of memory, a prover-side assertion) never joins the next collective: the NCCL kernel of the surviving
+// ranks then spins forever and their stream never drains. Called when a round result is overdue on a distributed context: tears
+// the communicator down (which releases the stuck kernel) so that the call can fail with an error instead of hanging.
+void dist_abort(Ctx *ctx) {
+  if (ctx->nccl_comm) {
+    nccl().CommAbort((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    ctx->world = 1;
+    ctx->rank = 0;
+  }
 }
 void dist_allgather_inplace(Ctx *ctx, void *buf, size_t bytes_per_rank) {
   VPIN_REQUIRE(ctx->nccl_comm, VPIN_ERR_BAD_ARGUMENT, "context is not distributed");
@@ -401,26 +414,43 @@ __global__ void __launch_bounds__(256) k_coo_unpack(const vpin_coo_entry *raw, s
   atomicAdd(row_cnt + r, 1u);
   atomicAdd(col_cnt + cc, 1u);
 }
+// Montgomery forms of the dictionary values, code k at index k - 1 (kernels_poly.cuh SpmvCode)
+struct CodeBook { fl_t v[5]; };
+__device__ __forceinline__ uint8_t spmv_code_of(const uint4 &a, const uint4 &b, const CodeBook &cb) {
+  uint8_t code = kCodeGeneral;
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    const uint32_t *w = cb.v[k].v;
+    bool eq = a.x == w[0] && a.y == w[1] && a.z == w[2] && a.w == w[3] && b.x == w[4] && b.y == w[5] && b.z == w[6] && b.w == w[7];
+    code = eq ? (uint8_t)(k + 1) : code;
+  }
+  return code;
+}
 __global__ void __launch_bounds__(256) k_coo_scatter(const uint32_t *row, const uint32_t *col, const fl_t *val, size_t n, uint32_t *row_cur,
-                                                     uint32_t *col_cur, uint32_t *csr_col, fl_t *csr_val, uint32_t *csc_row, fl_t *csc_val) {
+                                                     uint32_t *col_cur, uint32_t *csr_col, fl_t *csr_val, uint32_t *csc_row, fl_t *csc_val,
+                                                     CodeBook cb, uint8_t *csr_code, uint8_t *csc_code) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t r = row[i], c = col[i];
   const uint4 *q = reinterpret_cast<const uint4 *>(val + i);
   uint4 a = __ldg(q), b = __ldg(q + 1);
+  const uint8_t code = spmv_code_of(a, b, cb);
   uint32_t p = atomicAdd(row_cur + r, 1u);
+  csr_code[p] = code;
   csr_col[p] = c;
   reinterpret_cast<uint4 *>(csr_val + p)[0] = a;
   reinterpret_cast<uint4 *>(csr_val + p)[1] = b;
   uint32_t p2 = atomicAdd(col_cur + c, 1u);
+  csc_code[p2] = code;
   csc_row[p2] = r;
   reinterpret_cast<uint4 *>(csc_val + p2)[0] = a;
   reinterpret_cast<uint4 *>(csc_val + p2)[1] = b;
 }
-__global__ void __launch_bounds__(256) k_find_long_cols(const uint32_t *cptr, size_t ncols, uint32_t *long_cols, uint32_t *n_long, uint32_t cap) {
+__global__ void __launch_bounds__(256) k_find_long_cols(const uint32_t *cptr, size_t ncols, uint32_t *long_cols, uint32_t *n_long, uint32_t cap,
+                                                        uint32_t threshold) {
   size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncols) return;
-  if (cptr[c + 1] - cptr[c] > (uint32_t)kLongCol) {
+  if (cptr[c + 1] - cptr[c] > threshold) {
     uint32_t k = atomicAdd(n_long, 1u);
     if (k < cap) long_cols[k] = (uint32_t)c;
   }
@@ -445,6 +475,7 @@ uint32_t build_matrix(Ctx *ctx, MatrixDev &m, const vpin_coo_entry *entries, boo
   m.coo_row.alloc(nnz, st); m.coo_col.alloc(nnz, st); m.coo_val.alloc(nnz, st);
   m.csr_ptr.alloc(num_rows + 1, st); m.csc_ptr.alloc(num_cols + 1, st);
   m.csr_col.alloc(nnz, st); m.csr_val.alloc(nnz, st); m.csc_row.alloc(nnz, st); m.csc_val.alloc(nnz, st);
+  m.csr_code.alloc(std::max<size_t>(nnz, 1), st); m.csc_code.alloc(std::max<size_t>(nnz, 1), st);
   m.csr_ptr.zero(); m.csc_ptr.zero();
   DevVec<unsigned long long> d_err(1, st);
   VPIN_CUDA(cudaMemsetAsync(d_err.p, 0xff, sizeof(unsigned long long), st));
@@ -470,18 +501,36 @@ uint32_t build_matrix(Ctx *ctx, MatrixDev &m, const vpin_coo_entry *entries, boo
   DevVec<uint32_t> row_cur(num_rows + 1, st), col_cur(num_cols + 1, st), n_long(1, st);
   VPIN_CUDA(cudaMemcpyAsync(row_cur.p, m.csr_ptr.p, (num_rows + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   VPIN_CUDA(cudaMemcpyAsync(col_cur.p, m.csc_ptr.p, (num_cols + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  CodeBook cb;
+  {
+    const fl_t one = fl_one(), two = fl_add(one, one);
+    cb.v[0] = one; cb.v[1] = fl_neg(one); cb.v[2] = two; cb.v[3] = fl_neg(two); cb.v[4] = fl_add(two, one);
+  }
   if (nnz)
     ++g_kernel_launches, k_coo_scatter<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(m.coo_row.p, m.coo_col.p, m.coo_val.p, nnz, row_cur.p, col_cur.p,
-                                                                                    m.csr_col.p, m.csr_val.p, m.csc_row.p, m.csc_val.p);
+                                                                                    m.csr_col.p, m.csr_val.p, m.csc_row.p, m.csc_val.p, cb,
+                                                                                    m.csr_code.p, m.csc_code.p);
   const uint32_t cap = 4096;
   m.long_cols.alloc(cap, st);
   n_long.zero();
-  ++g_kernel_launches, k_find_long_cols<<<(unsigned)((num_cols + 255) / 256), 256, 0, st>>>(m.csc_ptr.p, num_cols, m.long_cols.p, n_long.p, cap);
+  ++g_kernel_launches, k_find_long_cols<<<(unsigned)((num_cols + 255) / 256), 256, 0, st>>>(m.csc_ptr.p, num_cols, m.long_cols.p, n_long.p, cap,
+                                                                                            (uint32_t)kLongCol);
   uint32_t h_long = 0;
   VPIN_CUDA(cudaMemcpyAsync(&h_long, n_long.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   ctx->sync();
   VPIN_REQUIRE(h_long <= cap, VPIN_ERR_BAD_ARGUMENT, "too many dense columns");
   m.n_long = h_long;
+  // rows with more than kLongRow entries get a warp each in the SpMV (the capacity grows with the instance: vPIN has one
+  // 128-term row per multiplication)
+  const uint32_t row_cap = (uint32_t)std::max<size_t>(4096, num_rows / 64);
+  m.long_rows.alloc(row_cap, st);
+  n_long.zero();
+  ++g_kernel_launches, k_find_long_cols<<<(unsigned)((num_rows + 255) / 256), 256, 0, st>>>(m.csr_ptr.p, num_rows, m.long_rows.p, n_long.p, row_cap,
+                                                                                            (uint32_t)kLongRow);
+  VPIN_CUDA(cudaMemcpyAsync(&h_long, n_long.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  ctx->sync();
+  // more long rows than the list holds: none of them is listed and the thread-per-row kernel does them all (correct, slower)
+  m.n_long_rows = h_long <= row_cap ? h_long : 0;
   return 0;
 }
 }  // namespace

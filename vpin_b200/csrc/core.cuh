@@ -167,6 +167,7 @@ struct vpin_ctx_impl {
   // multi-GPU (one process per GPU): NCCL communicator over NVLink/NVSwitch, created by vpin_ctx_init_distributed
   int rank = 0, world = 1;
   void *nccl_comm = nullptr;
+  std::shared_ptr<void> host_pool;  // the prover's helper threads (prover.cu HostPool), created with the first proof
   int shard_sumcheck = -1;  // sharded sumcheck rounds of one proof: -1 = VPIN_SHARD_SUMCHECK decides, 0 / 1 = vpin_ctx_set_shard_sumcheck
   DevVec<unsigned long long> d_counters;  // [0] = non-zero MSM digits recoded (= mixed additions executed)
   // sharded sumcheck rounds (one proof on several GPUs, VPIN_SHARD_SUMCHECK=1): device-side result slots of the round kernels
@@ -192,6 +193,7 @@ void dist_allgather_inplace(Ctx *ctx, void *buf, size_t bytes_per_rank);
 void dist_get_unique_id(uint8_t out[128]);
 void dist_init(Ctx *ctx, int rank, int world, const uint8_t id[128]);
 void dist_destroy(Ctx *ctx);
+void dist_abort(Ctx *ctx);  // ncclCommAbort: releases a collective a failed peer will never join
 
 // table_budget: bytes the fixed-base table may take (0 = 30 % of the free HBM). Generators and tables are public parameters:
 // one copy per (device, label) serves every context of the process (a second context proving the same shape neither
@@ -213,6 +215,11 @@ struct MatrixDev {
   DevVec<uint32_t> csc_ptr, csc_row, long_cols;
   DevVec<fl_t> csc_val;
   size_t n_long = 0;
+  // value dictionary (vPIN's R1CS coefficients are +-1, +-2, 3 except for the 2^i of the bit decompositions):
+  // one byte per CSR / CSC entry (kernels_poly.cuh SpmvCode); the SpMV kernels only read the 32-byte value when the code says so
+  DevVec<uint8_t> csr_code, csc_code;
+  DevVec<uint32_t> long_rows;  // rows with more than kLongRow entries (one 128-term bit decomposition per multiplication)
+  size_t n_long_rows = 0;
 };
 struct vpin_instance_impl {
   size_t num_cons = 0, num_vars = 0, num_inputs = 0;  // padded cons / vars (Spartan/src/lib.rs:146-176)

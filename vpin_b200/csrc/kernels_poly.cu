@@ -379,16 +379,46 @@ void launch_bound(const fl_t *Z, const fl_t *L, size_t Lsize, size_t Rsize, fl_t
 }
 
 // ------------------------------------------------------------------------------------------------ SpMV
-__global__ void __launch_bounds__(256) k_spmv_csr(CsrDev m, const fl_t *z, fl_t *out) {
+// acc += coefficient * x with the coefficient given by its dictionary code; the 32-byte value is read only for kCodeGeneral
+__device__ __forceinline__ fl_t spmv_term(const fl_t &acc, uint8_t code, const fl_t *val, uint32_t e, const fl_t &x) {
+  switch (code) {
+    case kCodePlus1: return fl_add(acc, x);
+    case kCodeMinus1: return fl_sub(acc, x);
+    case kCodePlus2: return fl_add(acc, fl_dbl(x));
+    case kCodeMinus2: return fl_sub(acc, fl_dbl(x));
+    case kCodePlus3: return fl_add(acc, fl_add(fl_dbl(x), x));
+    default: return fl_add(acc, fl_mul(ldg_fl(val + e), x));
+  }
+}
+__global__ void __launch_bounds__(256) k_spmv_csr(CsrDev m, const fl_t *z, fl_t *out, int skip_long) {
   size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= m.n) return;
+  uint32_t e = m.ptr[row], end = m.ptr[row + 1];
+  if (skip_long && end - e > (uint32_t)kLongRow) return;  // done by k_spmv_csr_long
   fl_t acc = fl_zero();
-  for (uint32_t e = m.ptr[row], end = m.ptr[row + 1]; e < end; e++)
-    acc = fl_add(acc, fl_mul(ldg_fl(m.val + e), ldg_fl(z + m.idx[e])));
+  for (; e < end; e++) acc = spmv_term(acc, m.code[e], m.val, e, ldg_fl(z + m.idx[e]));
   st_fl(out + row, acc);
 }
+// one warp per long row: lanes stride the entries (coalesced code / index / value loads), shuffle-tree sum
+__global__ void __launch_bounds__(128) k_spmv_csr_long(CsrDev m, const fl_t *z, fl_t *out) {
+  size_t w = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= m.n_long_rows) return;
+  uint32_t row = m.long_rows[w];
+  fl_t acc = fl_zero();
+  for (uint32_t e = m.ptr[row] + lane, end = m.ptr[row + 1]; e < end; e += 32) acc = spmv_term(acc, m.code[e], m.val, e, ldg_fl(z + m.idx[e]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    fl_t o;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o.v[i] = __shfl_down_sync(0xffffffffu, acc.v[i], off);
+    acc = fl_add(acc, o);
+  }
+  if (lane == 0) st_fl(out + row, acc);
+}
 void launch_spmv_csr(const CsrDev &m, const fl_t *z, fl_t *out, cudaStream_t st) {
-  ++g_kernel_launches, k_spmv_csr<<<ew_blocks(m.n), 256, 0, st>>>(m, z, out);
+  ++g_kernel_launches, k_spmv_csr<<<ew_blocks(m.n), 256, 0, st>>>(m, z, out, m.n_long_rows ? 1 : 0);
+  if (m.n_long_rows) ++g_kernel_launches, k_spmv_csr_long<<<(unsigned)((m.n_long_rows + 3) / 4), 128, 0, st>>>(m, z, out);
 }
 __global__ void __launch_bounds__(256) k_spmv_csc(CscDev m, const fl_t *x, const fl_t *d_scale, int accumulate, fl_t *out) {
   size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -396,7 +426,7 @@ __global__ void __launch_bounds__(256) k_spmv_csc(CscDev m, const fl_t *x, const
   uint32_t e = m.ptr[col], end = m.ptr[col + 1];
   if (end - e > (uint32_t)kLongCol) return;  // done by k_spmv_csc_long
   fl_t acc = fl_zero();
-  for (; e < end; e++) acc = fl_add(acc, fl_mul(ldg_fl(x + m.idx[e]), ldg_fl(m.val + e)));
+  for (; e < end; e++) acc = spmv_term(acc, m.code[e], m.val, e, ldg_fl(x + m.idx[e]));
   acc = fl_mul(acc, ld_fl(d_scale));
   if (accumulate) acc = fl_add(acc, ld_fl(out + col));
   st_fl(out + col, acc);
@@ -409,8 +439,7 @@ __global__ void __launch_bounds__(kRedThreads) k_spmv_csc_long(CscDev m, const f
   uint32_t per = (end - beg + gridDim.y - 1) / gridDim.y;
   uint32_t lo = beg + per * blockIdx.y, hi = lo + per < end ? lo + per : end;
   fl_t acc[1] = {fl_zero()};
-  for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x)
-    acc[0] = fl_add(acc[0], fl_mul(ldg_fl(x + m.idx[e]), ldg_fl(m.val + e)));
+  for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) acc[0] = spmv_term(acc[0], m.code[e], m.val, e, ldg_fl(x + m.idx[e]));
   block_sum_store<1>(acc, scratch + (size_t)blockIdx.x * gridDim.y + blockIdx.y);
 }
 __global__ void __launch_bounds__(64) k_spmv_csc_long_fin(CscDev m, const fl_t *scratch, int nsplit, const fl_t *d_scale, int accumulate,

@@ -105,13 +105,19 @@ void launch_dot3(const fl_t *A, const fl_t *B, const fl_t *C, size_t n, fl_t *d_
 // K10: LZ[j] = sum_i L[i] Z[i * R + j] (Spartan/src/dense_mlpoly.rs:220-227). d_tmp: nsplit * R scratch (nsplit <= 64).
 void launch_bound(const fl_t *Z, const fl_t *L, size_t Lsize, size_t Rsize, fl_t *d_out, fl_t *d_tmp, cudaStream_t st);
 
-// K2: CSR SpMV out[row] = sum val * z[col] (Spartan/src/sparse_mlpoly.rs:467-481)
-struct CsrDev { const uint32_t *ptr; const uint32_t *idx; const fl_t *val; size_t n; };
+// Value dictionary of the sparse matrices: code of an entry's coefficient. vPIN's constraint systems use +-1 for 93 % of the
+// entries and +-2, 3 for almost all others; those are additions, not multiplications, and their 32-byte value is never read.
+enum SpmvCode : uint8_t { kCodeGeneral = 0, kCodePlus1 = 1, kCodeMinus1 = 2, kCodePlus2 = 3, kCodeMinus2 = 4, kCodePlus3 = 5 };
+// K2: CSR SpMV out[row] = sum val * z[col] (Spartan/src/sparse_mlpoly.rs:467-481). One thread per row for the short rows
+// (1-3 entries: consecutive threads read consecutive entries, so code / index loads coalesce), one warp per long row
+// (lanes stride the entries, shuffle-tree reduction): a 128-term bit-decomposition row no longer serialises in one thread.
+static const int kLongRow = 16;
+struct CsrDev { const uint32_t *ptr; const uint32_t *idx; const fl_t *val; size_t n; const uint8_t *code; const uint32_t *long_rows; size_t n_long_rows; };
 void launch_spmv_csr(const CsrDev &m, const fl_t *z, fl_t *out, cudaStream_t st);
 // K3: CSC form of M^T x (Spartan/src/sparse_mlpoly.rs:483-498): out[col] = sum x[row] * val, accumulated with a scale:
 // out[col] (+)= scale * sum. Columns with more than kLongCol entries are listed in long_cols and reduced by a block each.
 static const int kLongCol = 256;
-struct CscDev { const uint32_t *ptr; const uint32_t *idx; const fl_t *val; size_t n; const uint32_t *long_cols; size_t n_long; };
+struct CscDev { const uint32_t *ptr; const uint32_t *idx; const fl_t *val; size_t n; const uint32_t *long_cols; size_t n_long; const uint8_t *code; };
 // d_scratch: scratch_elems >= n_long elements (up to 64 slices per long column are used)
 void launch_spmv_csc_scaled(const CscDev &m, const fl_t *x, const fl_t *d_scale, bool accumulate, fl_t *out, fl_t *d_scratch,
                             size_t scratch_elems, cudaStream_t st);

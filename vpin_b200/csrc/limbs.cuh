@@ -205,23 +205,28 @@ template <bool kMerge>
 VPIN_HD void redc_other(uint32_t &w, uint32_t mergeval, uint32_t &m, uint32_t *o, uint32_t &cw) {
 #if defined(__CUDA_ARCH__)
   if (kMerge) {
-    asm("add.cc.u32 %0, %0, %11; mul.lo.u32 %1, %0, %12;"
+    // (m * 2^28, the top limb of l, is two shifts and two additions: IMAD.WIDE is the scarce half-rate instruction)
+    asm("{ .reg .u32 t0, t1;"
+        "add.cc.u32 %0, %0, %11; mul.lo.u32 %1, %0, %12;"
+        "shl.b32 t0, %1, 28; shr.u32 t1, %1, 4;"
         "madc.lo.cc.u32 %2, %1, %13, %2; madc.hi.cc.u32 %3, %1, %13, %3;"
         "madc.lo.cc.u32 %4, %1, %14, %4; madc.hi.cc.u32 %5, %1, %14, %5;"
         "addc.cc.u32 %6, %6, 0; addc.cc.u32 %7, %7, 0;"
-        "madc.lo.cc.u32 %8, %1, %15, %8; madc.hi.cc.u32 %9, %1, %15, %9;"
-        "addc.u32 %10, %10, 0;"
+        "addc.cc.u32 %8, %8, t0; addc.cc.u32 %9, %9, t1;"
+        "addc.u32 %10, %10, 0; }"
         : "+r"(w), "=&r"(m), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(cw)
-        : "r"(mergeval), "n"(VPIN_L_INV32), "n"(VPIN_L_P1), "n"(VPIN_L_P3), "n"(VPIN_L_P7));
+        : "r"(mergeval), "n"(VPIN_L_INV32), "n"(VPIN_L_P1), "n"(VPIN_L_P3));
   } else {
-    asm("mul.lo.u32 %1, %0, %11;"
+    asm("{ .reg .u32 t0, t1;"
+        "mul.lo.u32 %1, %0, %11;"
+        "shl.b32 t0, %1, 28; shr.u32 t1, %1, 4;"
         "mad.lo.cc.u32 %2, %1, %12, %2; madc.hi.cc.u32 %3, %1, %12, %3;"
         "madc.lo.cc.u32 %4, %1, %13, %4; madc.hi.cc.u32 %5, %1, %13, %5;"
         "addc.cc.u32 %6, %6, 0; addc.cc.u32 %7, %7, 0;"
-        "madc.lo.cc.u32 %8, %1, %14, %8; madc.hi.cc.u32 %9, %1, %14, %9;"
-        "addc.u32 %10, %10, 0;"
+        "addc.cc.u32 %8, %8, t0; addc.cc.u32 %9, %9, t1;"
+        "addc.u32 %10, %10, 0; }"
         : "+r"(w), "=&r"(m), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(cw)
-        : "n"(VPIN_L_INV32), "n"(VPIN_L_P1), "n"(VPIN_L_P3), "n"(VPIN_L_P7));
+        : "n"(VPIN_L_INV32), "n"(VPIN_L_P1), "n"(VPIN_L_P3));
   }
 #else
   uint64_t c = 0;
@@ -268,7 +273,7 @@ VPIN_HD void redc_own(uint32_t *s, uint32_t m, uint32_t &cw) {
 }
 
 // r[0..8) = a * b / 2^256 mod l, in [0, 2l): product rows interleaved with reduction rows (word-serial Montgomery),
-// all carries confined to 8-limb windows plus one small carry word. 112 IMAD(.WIDE) in total.
+// all carries confined to 8-limb windows plus one small carry word. 96 IMAD.WIDE (64 product + 32 reduction) + 8 IMAD in total.
 VPIN_HD void mont_mul_l(uint32_t *r, const uint32_t *a, const uint32_t *b) {
   uint32_t ev[18], od[18];  // od[k] has weight 2^(32 (k + 1))
 #pragma unroll

@@ -226,6 +226,7 @@ class HostPool {
   template <class F>
   void run(int i, F &&f) {
     if (slots_.empty()) { f(); return; }  // no helpers (VPIN_HOST_HELPERS=0, or few cores per rank): do it here
+    if (!active_.load(std::memory_order_acquire)) { f(); return; }  // no Scope open: the helpers sleep and would never pick it up
     Slot &s = slots_[i % slots_.size()];
     if (s.state.load(std::memory_order_acquire) != 0) { f(); return; }  // slot busy (fewer helpers than tasks)
     s.fn = std::forward<F>(f);
@@ -251,6 +252,13 @@ class HostPool {
     HostPool &p;
     explicit Scope(HostPool &p_) : p(p_) { p.set_active(true); }
     ~Scope() { p.set_active(false); }
+  };
+  // Declared AFTER the locals a posted task captures by reference: on any exit from the block - normal or by exception - every
+  // task has finished before those locals die (wait() is a no-op for a slot that was already waited for).
+  struct Joiner {
+    HostPool &p;
+    explicit Joiner(HostPool &p_) : p(p_) {}
+    ~Joiner() { for (int i = 0; i < p.size(); i++) p.wait(i); }
   };
 
  private:
@@ -287,13 +295,18 @@ class HostPool {
   std::atomic<bool> active_{false}, stop_{false};
 };
 
+static HostPool &host_pool_of(Ctx *ctx) {
+  if (!ctx->host_pool) ctx->host_pool = std::shared_ptr<void>(new HostPool(HostPool::default_size()), [](void *p) { delete static_cast<HostPool *>(p); });
+  return *static_cast<HostPool *>(ctx->host_pool.get());
+}
+
 struct Prover {
   Ctx *ctx;
   cudaStream_t st;
   MerlinTranscript &t;
   ProverTape &tape;
   const SnarkGens &g;
-  HostPool pool{HostPool::default_size()};
+  HostPool &pool;  // one per context (created with the first proof), not one per proof: no thread spawn / join per proof
   size_t ring = 0;
   // accumulating wall-clock timers (reported next to the phases)
   double t_bullet_gpu = 0, t_bullet_host = 0, t_bullet_pre = 0, t_b_wait = 0, t_b_host = 0, t_b_launch = 0, t_b_small_wait = 0;
@@ -381,8 +394,16 @@ struct Prover {
     *seq_out = seq;
     return RoundCtl{ctx->d_partials.p, ctx->d_round_counters.p, ctx->d_slots + slot, seq};
   }
+  // On a distributed context a result can also stay away because a PEER failed and never joined the collective this rank's
+  // stream is waiting in (cudaStreamQuery then says "not ready" forever): after VPIN_DIST_TIMEOUT_S seconds (default 120) the
+  // communicator is aborted and the call fails instead of hanging.
+  static double dist_timeout_ms() {
+    static const double v = [] { const char *e = getenv("VPIN_DIST_TIMEOUT_S"); double s = e ? atof(e) : 120.0; return (s > 0 ? s : 120.0) * 1e3; }();
+    return v;
+  }
   const fl_t *round_wait(int slot, uint32_t seq) {
     volatile uint32_t *flag = &ctx->h_slots[slot].seq;
+    double t_start = 0;
     for (uint64_t spins = 1;; spins++) {
       if (*flag == seq) break;
       if ((spins & 0x3ff) == 0) {  // a faulted kernel must not hang the host
@@ -392,6 +413,14 @@ struct Prover {
           throw Error(VPIN_ERR_CUDA, "round result never arrived");
         }
         if (e != cudaErrorNotReady) VPIN_CUDA(e);
+        if (ctx->world > 1 && (spins & 0xfffff) == 0) {
+          double now = now_ms();
+          if (t_start == 0) t_start = now;
+          else if (now - t_start > dist_timeout_ms()) {
+            dist_abort(ctx);
+            throw Error(VPIN_ERR_CUDA, "a sumcheck round timed out on a distributed context (a peer rank failed?): communicator aborted");
+          }
+        }
       }
       __builtin_ia32_pause();
     }
@@ -423,6 +452,7 @@ struct Prover {
   // the group element, hence the encoding, does not depend on the order of the additions
   hge_t commit1_par(const PcGens &pc, const fl_t &x, const fl_t &blind) {
     hge_t part = hf::ge_identity(), acc = hf::ge_identity();
+    HostPool::Joiner join(pool);
     pool.run(0, [&] { pc.g1->mul_acc(x, &part); });
     pc.h->mul_acc(blind, &acc);
     pool.wait(0);
@@ -431,6 +461,7 @@ struct Prover {
   hge_t commit_coeffs_par(const std::vector<fl_t> &c, const fl_t &blind) {
     const size_t n = c.size();  // 3 (quadratic round) or 4 (cubic round) coefficients + the blind
     hge_t part[2] = {hf::ge_identity(), hf::ge_identity()}, acc = hf::ge_identity();
+    HostPool::Joiner join(pool);
     pool.run(0, [&] { g.sat_g[0]->mul_acc(c[0], &part[0]); g.sat_g[1]->mul_acc(c[1], &part[0]); });
     pool.run(1, [&] { g.sat_g[2]->mul_acc(c[2], &part[1]); if (n > 3) g.sat_g[3]->mul_acc(c[3], &part[1]); });
     g.sat_g[n]->mul_acc(blind, &acc);
@@ -536,13 +567,15 @@ struct Prover {
     fl_t dot = fl_zero();
     for (size_t i = 0; i < n; i++) dot = dot + a_vec[i] * d_vec[i];
     hge_t p_y = hf::ge_identity(), p_by = hf::ge_identity(), p_dot = hf::ge_identity(), p_rb = hf::ge_identity();
+    Comp beta;
+    hge_t beta_pt;
+    HostPool::Joiner join(pool);
     pool.run(0, [&] { g.sat_pc.g1->mul_acc(y, &p_y); });
     pool.run(1, [&] { g.sat_pc.h->mul_acc(blind_y, &p_by); });
     pool.run(2, [&] { g.sat_pc.g1->mul_acc(dot, &p_dot); });
     g.sat_pc.h->mul_acc(r_beta, &p_rb);
     pool.wait(2);
-    Comp beta;
-    hge_t beta_pt = hf::ge_add(p_dot, p_rb);
+    beta_pt = hf::ge_add(p_dot, p_rb);
     pool.run(2, [&] { beta = compress_host(beta_pt); });
     pool.wait(0);
     pool.wait(1);
@@ -780,6 +813,7 @@ struct Prover {
       // L and R are independent (Horner pass, two fixed-base multiplications, encoding each): R on a helper thread
       hge_t LR[2];
       Comp Lc, Rc;
+      HostPool::Joiner join(pool);
       pool.run(0, [&] {
         LR[1] = horner(vals, 1);
         pc.g1->mul_acc(c[1] * r, &LR[1]);
@@ -1093,7 +1127,7 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   auto phase = [&](const char *name, double start) { ctx->sync(); ctx->phases.push_back({name, now_ms() - start}); };
   MerlinTranscript t(label, label_len);
   ProverTape tape("proof", 5, tape_seed);
-  Prover P{ctx, st, t, tape, g};
+  Prover P{ctx, st, t, tape, g, host_pool_of(ctx)};
   const PcGens &spc = g.sat_pc;
   size_t num_vars = inst.num_vars, num_cons = inst.num_cons, num_inputs = inputs.size();
   VPIN_REQUIRE(wit.n_vars == num_vars && num_inputs < num_vars, VPIN_ERR_SIZE_MISMATCH, "witness size");

@@ -48,9 +48,11 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
                                  const SnarkGens &gens, const uint8_t *label, size_t label_len, const fl_t &tape_seed);
 bool instance_is_sat(Ctx *ctx, const Instance &inst, const uint8_t *vars32, uint64_t n_vars, const uint8_t *inputs32, uint64_t n_inputs);
 
-static inline CsrDev csr_of(const MatrixDev &m, size_t rows) { return CsrDev{m.csr_ptr.p, m.csr_col.p, m.csr_val.p, rows}; }
+static inline CsrDev csr_of(const MatrixDev &m, size_t rows) {
+  return CsrDev{m.csr_ptr.p, m.csr_col.p, m.csr_val.p, rows, m.csr_code.p, m.long_rows.p, m.n_long_rows};
+}
 static inline CscDev csc_of(const MatrixDev &m, size_t cols) {
-  return CscDev{m.csc_ptr.p, m.csc_row.p, m.csc_val.p, cols, m.long_cols.p, m.n_long};
+  return CscDev{m.csc_ptr.p, m.csc_row.p, m.csc_val.p, cols, m.long_cols.p, m.n_long, m.csc_code.p};
 }
 static inline size_t eq_tmp_elems(size_t ell) {
   size_t a = (size_t)3 << ((ell + 1) / 2);

@@ -201,7 +201,9 @@ def witness_json_to_bin(root, tag):
 
 
 def tape_seeds():
-    """Deterministic stand-ins for the two OsRng scalars: 64 B of SHAKE256 -> mod l."""
+    """TEST-ONLY deterministic stand-ins for the two OsRng scalars: 64 B of SHAKE256 -> mod l.
+    They make proofs byte-comparable with the oracle; a real prover passes NULL seeds (the library then draws them from the
+    OS) - reusing a seed for a different witness reuses blinds and nonces and leaks the witness."""
     import hashlib
     L = 2**252 + 27742317777372353535851937790883648493
     q = int.from_bytes(hashlib.shake_256(b"vpin-b200/tape/0x02").digest(64), "little") % L
