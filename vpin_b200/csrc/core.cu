@@ -2,6 +2,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <time.h>
 
 #include <algorithm>
 #include <mutex>
@@ -267,6 +268,24 @@ void dist_abort(Ctx *ctx) {
     ctx->nccl_comm = nullptr;
     ctx->world = 1;
     ctx->rank = 0;
+  }
+}
+void vpin_ctx_impl::sync_distributed() {
+  static const double limit_s = [] { const char *e = getenv("VPIN_DIST_TIMEOUT_S"); double v = e ? atof(e) : 120.0; return v > 0 ? v : 120.0; }();
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (uint64_t spins = 1;; spins++) {
+    cudaError_t e = cudaStreamQuery(st);
+    if (e == cudaSuccess) return;
+    if (e != cudaErrorNotReady) VPIN_CUDA(e);
+    if ((spins & 0xffff) == 0) {
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) > limit_s) {
+        dist_abort(this);
+        throw Error(VPIN_ERR_CUDA, "stream did not drain on a distributed context (a peer rank failed?): communicator aborted");
+      }
+    }
+    __builtin_ia32_pause();
   }
 }
 void dist_allgather_inplace(Ctx *ctx, void *buf, size_t bytes_per_rank) {

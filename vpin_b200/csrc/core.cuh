@@ -174,7 +174,14 @@ struct vpin_ctx_impl {
   // and the all-gather buffer (kRoundSlotVals elements)
   DevVec<RoundSlot> d_dev_slots;
   DevVec<fl_t> d_gather;
-  void sync() { VPIN_CUDA(cudaStreamSynchronize(st)); }
+  // drains the stream. On a distributed context the wait is a poll with a deadline (VPIN_DIST_TIMEOUT_S, default 120 s): a peer
+  // that failed never joins the collective this stream may be waiting in; the communicator is then aborted (dist_abort) and the
+  // call fails instead of hanging.
+  void sync() {
+    if (world > 1 && nccl_comm) sync_distributed();
+    else VPIN_CUDA(cudaStreamSynchronize(st));
+  }
+  void sync_distributed();
   // a marker on the stream that the host can wait for without draining what is queued behind it
   cudaEvent_t ev_marker = nullptr;
   void mark() {
