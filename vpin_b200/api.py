@@ -548,6 +548,47 @@ def dev_commitments_add(ctx, d_c1, d_c2, L, d_out):
     ctx.check(lib().vpin_dev_commitments_add(ctx._h, _dp(d_c1), _dp(d_c2), C.c_uint64(L), _dp(d_out)))
 
 
+def prove_flow_resident(ctx, weights, px, py, seed_q, seed_p, label=b"snark_example", timings=None):
+    """The point-mult driver sequence (vPIN_proof_generation/src/proof_point_mult.rs:24-98) with NOTHING large crossing PCIe:
+    the R1CS instance and the three assignments are expanded on the device from the JSON-level inputs
+    (vpin_build_point_mult_device), committed where they lie (vpin_dev_poly_commit*) and proved resident
+    (vpin_prove_resident). Host traffic: the weights and point coordinates up (80 B per multiplication), the commitments
+    (32 B per Hyrax row) and the proof down. `timings` (a dict) receives the wall time of each call in seconds."""
+    import time
+    import torch
+    T = [time.time()]
+
+    def tick(name):
+        ctx.sync()
+        T.append(time.time())
+        if timings is not None:
+            timings[name] = timings.get(name, 0.0) + T[-1] - T[-2]
+
+    dims, inst, d_para, d_input, d_vars, inputs, n = point_mult_device(ctx, weights, px, py)
+    tick("point_mult (device build + Instance::new)")
+    gens = SNARKGens(ctx, *dims)
+    tick("SNARKGens::new")
+    comm, decomm = SNARK.encode(inst, gens)
+    tick("SNARK::encode")
+    dev = d_vars.device
+    L = gens.L
+    pts = [torch.empty(32 * L, dtype=torch.uint8, device=dev) for _ in range(4)]
+    blinds = [torch.empty(32 * L, dtype=torch.uint8, device=dev) for _ in range(3)]
+    tape = RandomTape(b"\x02", seed_q)
+    dev_poly_commit(ctx, gens, d_para, n, tape, pts[0], blinds[0])
+    dev_poly_commit(ctx, gens, d_input, n, tape, pts[1], blinds[1])
+    dev_poly_commit_with_blinds(ctx, gens, d_vars, n, blinds[0], blinds[1], pts[2], blinds[2])
+    dev_commitments_add(ctx, pts[0], pts[1], L, pts[3])
+    tick("3 commits + combine")
+    wit = DeviceWitness(ctx, gens, d_vars, n, pts[3], blinds[2])
+    proof = my_lib_prove_resident(inst, decomm, wit, inputs, gens, label, seed_p)
+    tick("my_lib_prove")
+    ctx.sync()
+    c_para, c_input, c_vars = (bytes(t.cpu().numpy()) for t in pts[:3])
+    tick("commitments to the host")
+    return dict(proof=proof, comm=comm, comm_vars_para=c_para, comm_vars_input=c_input, comm_vars=c_vars, dims=dims, inputs=inputs)
+
+
 class DeviceWitness(Witness):
     """Witness built from device-resident (vars, comm_vars, blinds_vars)"""
 
