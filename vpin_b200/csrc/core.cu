@@ -299,10 +299,20 @@ namespace {
 std::mutex g_gens_mu;  // held while a table is being built, so that concurrent contexts wait for it instead of building their own
 std::map<std::pair<int, std::string>, std::weak_ptr<LabelGens>> g_gens;
 }  // namespace
-std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n, size_t table_budget, bool *built) {
-  if (built) *built = false;
+// the generators of a label if this context (or another context of the process on the same device) already holds at least n
+std::shared_ptr<LabelGens> find_label_gens(Ctx *ctx, const std::string &label, size_t n) {
   auto it = ctx->label_gens.find(label);
   if (it != ctx->label_gens.end() && it->second->n >= n) return it->second;
+  std::lock_guard<std::mutex> global_lock(g_gens_mu);
+  auto gi = g_gens.find({ctx->device, label});
+  if (gi != g_gens.end())
+    if (auto shared = gi->second.lock())
+      if (shared->n >= n) return ctx->label_gens[label] = shared;
+  return nullptr;
+}
+std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n, size_t table_budget, bool *built) {
+  if (built) *built = false;
+  if (auto have = find_label_gens(ctx, label, n)) return have;
   std::lock_guard<std::mutex> global_lock(g_gens_mu);
   {
     auto gi = g_gens.find({ctx->device, label});

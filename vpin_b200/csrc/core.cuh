@@ -206,6 +206,7 @@ void dist_abort(Ctx *ctx);  // ncclCommAbort: releases a collective a failed pee
 // one copy per (device, label) serves every context of the process (a second context proving the same shape neither
 // rebuilds nor duplicates 30 GB of tables); *built tells whether this call had to build one.
 std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, size_t n, size_t table_budget = 0, bool *built = nullptr);
+std::shared_ptr<LabelGens> find_label_gens(Ctx *ctx, const std::string &label, size_t n);  // nullptr when none is cached yet
 
 // Hyrax rows: out[i] = sum_j Z[i*ld + j] * G_j (+ blind_i * G_{blind_base}). d_points (rows ge_t) and d_comp (rows*32 B)
 // are optional outputs.

@@ -102,21 +102,24 @@ std::unique_ptr<SnarkGens> snark_gens_create(Ctx *ctx, uint64_t num_cons, uint64
   // margin. The tables share what is left: 80 % at most for the evaluation generators (derefs 8 N and comb_ops 16 N
   // scalars go through them), the rest for the satisfiability generators. LeNet layer 5 (N = 2^25) keeps ~115 GB alive:
   // without the plan the first table took 30 % of an empty GPU and the second proof ran out of memory.
-  size_t table_budget_eval = 0, table_budget_sat = 0;
-  {
+  // (the plan - one cudaMemGetInfo, tens of milliseconds on a full device - is only drawn up when a table has to be built)
+  const size_t n_eval = R_max + 2, n_sat = std::max<size_t>(R_sat + 2, 5);
+  g->eval_label = find_label_gens(ctx, "gens_r1cs_eval", n_eval);
+  g->sat_label = find_label_gens(ctx, "gens_r1cs_sat", n_sat);
+  if (!g->eval_label || !g->sat_label) {
     size_t N = (size_t)1 << k, M = (size_t)1 << std::max(nvx, nvy), c = (size_t)1 << nvx, v = num_vars_padded;
     size_t working = (41 * N + 8 * M) * 32 + (16 * N + 2 * M) * 32 + 64 * N + 3 * N * 112 + (8 * v + 5 * c) * 32 + ((size_t)4 << 30);
     size_t free_b = 0, total_b = 0;
     VPIN_CUDA(cudaMemGetInfo(&free_b, &total_b));
     size_t margin = (size_t)6 << 30;
     size_t avail = free_b > working + margin ? free_b - working - margin : 0;
-    table_budget_eval = std::max<size_t>(avail / 5 * 4, 1);
+    size_t table_budget_eval = std::max<size_t>(avail / 5 * 4, 1);
     bool eval_built = false;
-    g->eval_label = get_label_gens(ctx, "gens_r1cs_eval", R_max + 2, table_budget_eval, &eval_built);
+    if (!g->eval_label) g->eval_label = get_label_gens(ctx, "gens_r1cs_eval", n_eval, table_budget_eval, &eval_built);
     size_t eval_bytes = eval_built ? msm_table_entries(g->eval_label->n, g->eval_label->geom) * sizeof(niels_t) : 0;
-    table_budget_sat = std::max<size_t>(avail > eval_bytes ? avail - eval_bytes : 0, 1);
+    size_t table_budget_sat = std::max<size_t>(avail > eval_bytes ? avail - eval_bytes : 0, 1);
+    if (!g->sat_label) g->sat_label = get_label_gens(ctx, "gens_r1cs_sat", n_sat, table_budget_sat);
   }
-  g->sat_label = get_label_gens(ctx, "gens_r1cs_sat", std::max<size_t>(R_sat + 2, 5), table_budget_sat);
   make_pc(ctx, *g->sat_label, ell_sat, &g->sat_pc);
   for (int i = 0; i < 5; i++) g->sat_g[i] = g->sat_label->host_base(i);
   make_pc(ctx, *g->eval_label, ell_ops, &g->ops_pc);
