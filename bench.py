@@ -556,16 +556,16 @@ def run_b200(args):
                      "Instance::new on the device from the JSON-level inputs (weights, point coordinates); not part of `value`"}
     instances = [{"kind": s.kind, "num_cons": s.dims[0], "num_vars": s.dims[1], "nnz_param": s.dims[3], "hyrax_grid": [s.gens.L, s.gens.R]}
                  for s in leg.states]
-    # ---- N > 1: the same sharded proof with the batched product-circuit sumcheck rounds dealt to the ranks as well
-    # (vpin_ctx_set_shard_sumcheck; one NCCL all-gather of <= 3 KB per round). Same bytes; reported beside the headline.
-    sharded_rounds = None
+    # ---- N > 1, beside the headline: the same proof with ONLY the commitment rows sharded (vpin_ctx_set_shard_sumcheck(ctx, 0):
+    # hash layers, product trees and every sumcheck round replicated on all ranks). Same bytes.
+    rows_only = None
     if world > 1:
-        leg.set_shard_sumcheck(1)
+        leg.set_shard_sumcheck(0)
         r2 = leg.time_resident(sample_clocks=False)
         p2 = leg.parity(golden)
-        sharded_rounds = {"value": r2["step_s"], "unit": UNIT, "matches_golden": p2["matches_golden"],
-                          "identical_on_all_ranks": p2["identical_on_all_ranks"], "phases_ms_point_mult": r2["phases"],
-                          "what": "as the headline, plus the instances of the large batched sumcheck layers dealt to the ranks"}
+        rows_only = {"value": r2["step_s"], "unit": UNIT, "matches_golden": p2["matches_golden"],
+                     "identical_on_all_ranks": p2["identical_on_all_ranks"], "phases_ms_point_mult": r2["phases"],
+                     "what": "commitment rows sharded, everything else replicated (the round-1 arrangement)"}
         leg.set_shard_sumcheck(-1)
     leg.close()
 
@@ -655,9 +655,10 @@ def run_b200(args):
                    "l2": "256 MB buffer written between steps; working set ~2 GB >> 126 MB L2",
                    "concurrency": "the network's independent instances are proved concurrently (one context + host thread each)",
                    "parallelism": "1 GPU" if world == 1 else
-                                  f"ONE {tag} proof on {world} GPUs: every rank replays the transcript, the Hyrax commitment rows are split "
-                                  "across the ranks (NCCL all-gather of 32 B per row); sumchecks replicated (sharded rounds: see "
-                                  "one_proof_sharded_rounds)"},
+                                  f"ONE {tag} proof on {world} GPUs: every rank replays the transcript; the Hyrax commitment rows are split "
+                                  "across the ranks (NCCL all-gather of 32 B per row); the product circuits of the memory check are dealt "
+                                  "to the ranks (hash layers, trees, the sumcheck rounds of the large layers: one <= 3 KB all-gather per "
+                                  "round) and the dense evaluations are computed in slices; layers below 2^17 items stay replicated"},
         "host": {"cores": os.cpu_count(), "helpers_per_prover": int(os.environ.get("VPIN_HOST_HELPERS", "2"))},
         "parity": parity,
         "sharded_equals_unsharded": (parity["matches_golden"] is True and parity["identical_on_all_ranks"]) if world > 1 else None,
@@ -673,7 +674,7 @@ def run_b200(args):
         "rooflines": rooflines[:8],
         "imad_peak_forms_tmacs": {"plain_product_plus_alu_combine": imad_forms[0] / 1e12, "single_instruction_mac": imad_forms[1] / 1e12},
         "msm": msm,
-        "one_proof_sharded_rounds": sharded_rounds,
+        "one_proof_rows_only": rows_only,
         "replicas": replicas,
         "concurrent_proofs": concurrent,
         "other_configs": other,

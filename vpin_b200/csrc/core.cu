@@ -190,6 +190,9 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -208,6 +211,9 @@ NcclApi &nccl() {
   VPIN_NCCL_SYM(CommInitRank, "ncclCommInitRank");
   VPIN_NCCL_SYM(AllGather, "ncclAllGather");
   VPIN_NCCL_SYM(AllReduce, "ncclAllReduce");
+  VPIN_NCCL_SYM(Broadcast, "ncclBroadcast");
+  VPIN_NCCL_SYM(GroupStart, "ncclGroupStart");
+  VPIN_NCCL_SYM(GroupEnd, "ncclGroupEnd");
   VPIN_NCCL_SYM(CommDestroy, "ncclCommDestroy");
   VPIN_NCCL_SYM(CommAbort, "ncclCommAbort");
   VPIN_NCCL_SYM(GetErrorString, "ncclGetErrorString");
@@ -269,6 +275,14 @@ void dist_abort(Ctx *ctx) {
     ctx->world = 1;
     ctx->rank = 0;
   }
+}
+// in-place broadcasts of several buffers, each from its own root rank, fused into one NCCL group
+void dist_broadcast_many(Ctx *ctx, void *const *bufs, const size_t *bytes, const int *roots, int count) {
+  VPIN_REQUIRE(ctx->nccl_comm, VPIN_ERR_BAD_ARGUMENT, "context is not distributed");
+  VPIN_NCCL(nccl().GroupStart());
+  for (int i = 0; i < count; i++)
+    VPIN_NCCL(nccl().Broadcast(bufs[i], bufs[i], bytes[i], ncclUint8, roots[i], (ncclComm_t)ctx->nccl_comm, ctx->st));
+  VPIN_NCCL(nccl().GroupEnd());
 }
 void vpin_ctx_impl::sync_distributed() {
   static const double limit_s = [] { const char *e = getenv("VPIN_DIST_TIMEOUT_S"); double v = e ? atof(e) : 120.0; return v > 0 ? v : 120.0; }();

@@ -197,6 +197,7 @@ static const size_t kMinShardRows = 32;
 bool shard_rows(size_t rows, int rank, int world, size_t *r0, size_t *r1);
 // in-place all-gather of `bytes_per_rank` bytes per rank inside buf (rank r's slice at offset r * bytes_per_rank)
 void dist_allgather_inplace(Ctx *ctx, void *buf, size_t bytes_per_rank);
+void dist_broadcast_many(Ctx *ctx, void *const *bufs, const size_t *bytes, const int *roots, int count);
 void dist_get_unique_id(uint8_t out[128]);
 void dist_init(Ctx *ctx, int rank, int world, const uint8_t id[128]);
 void dist_destroy(Ctx *ctx);

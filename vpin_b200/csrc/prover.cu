@@ -193,11 +193,15 @@ std::unique_ptr<Decomm> snark_encode(Ctx *ctx, const Instance &inst, const Snark
 // ------------------------------------------------------------------------------------------------ prover
 namespace {
 
-// Sharded sumcheck rounds of ONE proof across GPUs: opt-in (VPIN_SHARD_SUMCHECK=1) and only for layers of at least this many
-// thread items, see batched_prove.
-static const size_t kShardMinLayer = (size_t)1 << 14;
+// ONE proof on several GPUs beyond the commitment rows: the product circuits of the SPARK memory check (12 over the N ops, 4
+// over the M memory cells, + 6 dot-product instances) are DEALT to the ranks - a rank builds the hash vectors and product trees
+// of its own circuits only, and runs only their instances in the batched sumchecks of the large layers (those of at least
+// kShardMinLayer thread items; one small NCCL all-gather per round, see batched_prove); the short upper layers of every tree are
+// broadcast once by their owners and proved replicated. On by default for a distributed context (VPIN_SHARD_SUMCHECK=0 or
+// vpin_ctx_set_shard_sumcheck(ctx, 0) turn it off); the proof bytes do not change.
+static const size_t kShardMinLayer = (size_t)1 << 17;
 static bool shard_sumcheck_enabled(const Ctx *ctx) {
-  static const bool env_on = [] { const char *e = getenv("VPIN_SHARD_SUMCHECK"); return e && atoi(e) != 0; }();
+  static const bool env_on = [] { const char *e = getenv("VPIN_SHARD_SUMCHECK"); return !e || atoi(e) != 0; }();
   const bool on = ctx->shard_sumcheck < 0 ? env_on : ctx->shard_sumcheck != 0;
   return on && ctx->world > 1 && ctx->nccl_comm != nullptr;
 }
@@ -1316,22 +1320,47 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   const fl_t *d_gt = P.up(r_mem_check);
   phase("network_alloc", t0);
   fl_t *row_init = mem_trees.p, *row_audit = mem_trees.p + 2 * M, *col_init = mem_trees.p + 4 * M, *col_audit = mem_trees.p + 6 * M;
-  {
-    ProfScope ps(ctx, PROF_HASH, 2.0 * M, 2.0 * M * 100, 2);
-    launch_hash_mem(mem_rx.p, dec.row_audit_ts.p, M, d_gt, row_init, row_audit, st);
-    launch_hash_mem(mem_ry.p, dec.col_audit_ts.p, M, d_gt, col_init, col_audit, st);
-  }
   // ops order of the batched proof: row read A,B,C | row write A,B,C | col read A,B,C | col write A,B,C  (:1173-1187)
   std::vector<fl_t *> ops_ptr(12), mem_ptr = {row_init, row_audit, col_init, col_audit};
   for (int i = 0; i < 12; i++) ops_ptr[i] = ops_trees.p + (size_t)i * 2 * N;
+  // several GPUs: circuit i of a set belongs to rank i mod world when the set has layers large enough to be proved sharded
+  // (batched_prove deals instance i to the same rank); everything of a circuit below its short upper layers then exists on
+  // its owner only
+  const int world = ctx->world, rank = ctx->rank;
+  const bool deal_mem = shard_sumcheck_enabled(ctx) && M >= 2 * kShardMinLayer, deal_ops = shard_sumcheck_enabled(ctx) && N >= 2 * kShardMinLayer;
+  auto owns = [&](bool dealt, size_t i) { return !dealt || (int)(i % world) == rank; };
+  {
+    ProfScope ps(ctx, PROF_HASH, 2.0 * M, 2.0 * M * 100, 2);
+    if (owns(deal_mem, 0) || owns(deal_mem, 1)) launch_hash_mem(mem_rx.p, dec.row_audit_ts.p, M, d_gt, row_init, row_audit, st);
+    if (owns(deal_mem, 2) || owns(deal_mem, 3)) launch_hash_mem(mem_ry.p, dec.col_audit_ts.p, M, d_gt, col_init, col_audit, st);
+  }
   for (int k = 0; k < 3; k++) {
     ProfScope ps(ctx, PROF_HASH, 2.0 * N, 2.0 * N * 104, 2);
-    launch_hash_ops(dec.row_addr[k].p, derefs.p + (size_t)k * N, dec.row_read_ts[k].p, N, d_gt, ops_ptr[k], ops_ptr[3 + k], st);
-    launch_hash_ops(dec.col_addr[k].p, derefs.p + (size_t)(3 + k) * N, dec.col_read_ts[k].p, N, d_gt, ops_ptr[6 + k], ops_ptr[9 + k], st);
+    if (owns(deal_ops, k) || owns(deal_ops, 3 + k))
+      launch_hash_ops(dec.row_addr[k].p, derefs.p + (size_t)k * N, dec.row_read_ts[k].p, N, d_gt, ops_ptr[k], ops_ptr[3 + k], st);
+    if (owns(deal_ops, 6 + k) || owns(deal_ops, 9 + k))
+      launch_hash_ops(dec.col_addr[k].p, derefs.p + (size_t)(3 + k) * N, dec.col_read_ts[k].p, N, d_gt, ops_ptr[6 + k], ops_ptr[9 + k], st);
   }
   phase("network_hash", t0);
-  build_trees(ctx, mem_ptr, M, st);
-  build_trees(ctx, ops_ptr, N, st);
+  auto build_dealt = [&](const std::vector<fl_t *> &ptrs, size_t n, bool dealt) {
+    std::vector<fl_t *> mine;
+    for (size_t i = 0; i < ptrs.size(); i++)
+      if (owns(dealt, i)) mine.push_back(ptrs[i]);
+    build_trees(ctx, mine, n, st);
+    if (!dealt) return;
+    // the layers of at most kShardMinLayer elements (the tail of a packed tree) are proved replicated: every owner broadcasts its own
+    std::vector<void *> bufs;
+    std::vector<size_t> bytes;
+    std::vector<int> roots;
+    for (size_t i = 0; i < ptrs.size(); i++) {
+      bufs.push_back(ptrs[i] + 2 * n - 2 * kShardMinLayer);
+      bytes.push_back((2 * kShardMinLayer - 2) * sizeof(fl_t));
+      roots.push_back((int)(i % world));
+    }
+    dist_broadcast_many(ctx, bufs.data(), bytes.data(), roots.data(), (int)bufs.size());
+  };
+  build_dealt(mem_ptr, M, deal_mem);
+  build_dealt(ops_ptr, N, deal_ops);
   phase("build_layered_network", t0);
 
   t0 = now_ms();
@@ -1405,19 +1434,29 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   // HashLayerProof::prove (:740-849)
   t.protocol_name("Sparse polynomial hash layer proof");
   DevVec<fl_t> eq_ops = P.eq_table(rand_ops), eq_mem = P.eq_table(rand_mem);
+  // `count` dot products <table_i, eq> over tables of `len` elements. Several GPUs: every rank takes one contiguous slice of the
+  // index range, the partial sums (count elements per rank) are all-gathered and added on the host in rank order
   auto dots_vs = [&](const fl_t *base, size_t count, size_t len, const fl_t *eq) {
+    const bool split = shard_sumcheck_enabled(ctx) && len >= ((size_t)1 << 18) && len % (size_t)world == 0;
+    const size_t part = split ? len / world : len, o = split ? (size_t)rank * part : 0;
     std::vector<const fl_t *> hp(count);
-    for (size_t i = 0; i < count; i++) hp[i] = base + i * len;
+    for (size_t i = 0; i < count; i++) hp[i] = base + i * len + o;
     DevVec<const fl_t *> dp(count, st);
     dp.upload(hp.data(), count);
-    DevVec<fl_t> dout(count, st);
+    DevVec<fl_t> dout(count * (split ? world : 1), st);
+    fl_t *mine = dout.p + (split ? (size_t)rank * count : 0);
     {
-      ProfScope ps(ctx, PROF_DOT, (double)count * len, 32.0 * (count + 1) * len, 2);
-      launch_dot_multi(dp.p, eq, (int)count, len, dout.p, ctx->d_partials.p, st);
+      ProfScope ps(ctx, PROF_DOT, (double)count * part, 32.0 * (count + 1) * part, 2);
+      launch_dot_multi(dp.p, eq + o, (int)count, part, mine, ctx->d_partials.p, st);
     }
-    std::vector<fl_t> out(count);
-    dout.download(out.data(), count);
+    if (split) dist_allgather_inplace(ctx, dout.p, count * sizeof(fl_t));
+    std::vector<fl_t> all(count * (split ? world : 1)), out(count);
+    dout.download(all.data(), all.size());
     ctx->sync();
+    for (size_t i = 0; i < count; i++) {
+      out[i] = all[i];
+      for (int r = 1; split && r < world; r++) out[i] = out[i] + all[(size_t)r * count + i];
+    }
     return out;
   };
   std::vector<fl_t> eval_derefs = dots_vs(derefs.p, 6, N, eq_ops.p);  // row A,B,C then col A,B,C
