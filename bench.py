@@ -628,8 +628,16 @@ def run_b200(args):
             ent.update(bound="imad", achieved=macs / (p["ms"] * 1e-3) / 1e12, peak=imad_peak / 1e12, unit="TMAC/s",
                        madds_per_step=madds // args.steps, points_per_step=p["units"] / args.steps)
             if facts:
-                # DRAM bytes per mixed addition from the ncu --set full capture x the additions one launch executes here
-                ent["traffic"] = facts["dram_bytes_per_madd"] * (madds / max(1, p["launches"]))
+                if wl["tag"] == "A" and world == 1 and facts.get("step_launches") == p["launches"] // args.steps:
+                    # measured: ncu DRAM bytes of the k_msm_accumulate launches of one CNN-A bench step, averaged per launch
+                    ent["traffic"] = facts["step_dram_bytes_per_launch_avg"]
+                    ent["traffic_how"] = "dram__bytes_read.sum + dram__bytes_write.sum of the %d launches of one step / %d (profiles/r2_msm_step_traffic.csv)" % (
+                        facts["step_launches"], facts["step_launches"])
+                else:
+                    # DRAM bytes per mixed addition from the ncu --set full capture x the additions one launch executes here
+                    ent["traffic"] = facts["dram_bytes_per_madd"] * (madds / max(1, p["launches"]))
+                    ent["traffic_how"] = "bytes per mixed addition of the ncu --set full capture x additions per launch here"
+                ent["algorithmic_bytes_per_launch"] = 98.0 * madds / max(1, p["launches"])  # 96-byte table entry + 2-byte digit per addition
                 ent["traffic_source"] = facts["source"]
                 ent["multiply_pipe_util_ncu"] = facts["fmaheavy_pipe_util"]
         elif p["bytes"] > 0:
