@@ -113,6 +113,13 @@ void vpin_ctx_destroy(vpin_ctx *ctx_) {
   ctx->d_round_counters.release();
   ctx->workspace.release();
   cudaStreamSynchronize(ctx->st);
+  if (ctx->st_side) {
+    cudaStreamSynchronize(ctx->st_side);
+    block_cache_unregister(ctx->st_side);
+    cudaStreamDestroy(ctx->st_side);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+  }
   block_cache_unregister(ctx->st);
   cudaStreamDestroy(ctx->st);
   delete ctx;

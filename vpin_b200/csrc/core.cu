@@ -180,6 +180,29 @@ void prof_drain(Ctx *c) {
   c->prof.pending.clear();
 }
 
+SideScope::SideScope(Ctx *ctx) : c(ctx) {
+  VPIN_REQUIRE(!c->on_side && c->world == 1, VPIN_ERR_BAD_ARGUMENT, "side stream: nested or distributed use");
+  if (!c->st_side) {
+    int prio = 0;
+    VPIN_CUDA(cudaStreamGetPriority(c->st, &prio));
+    VPIN_CUDA(cudaStreamCreateWithPriority(&c->st_side, cudaStreamNonBlocking, prio));
+    block_cache_register(c->st_side);
+    VPIN_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    VPIN_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
+  VPIN_CUDA(cudaEventRecord(c->ev_fork, c->st));
+  VPIN_CUDA(cudaStreamWaitEvent(c->st_side, c->ev_fork, 0));
+  c->st_main = c->st;
+  c->st = c->st_side;
+  c->on_side = true;
+}
+SideScope::~SideScope() {
+  cudaEventRecord(c->ev_join, c->st_side);
+  c->st = c->st_main;
+  c->on_side = false;
+}
+void SideScope::join(Ctx *ctx) { VPIN_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0)); }
+
 // ------------------------------------------------------------------------------------------------ multi-GPU plumbing
 // NCCL is resolved at run time (dlopen) so that the library has no link-time dependency on it and a process that has
 // already loaded torch's bundled libnccl.so.2 shares that copy.
@@ -391,7 +414,7 @@ static void hyrax_rows_local(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_
   size_t segs = msm_num_segments(chunk, cols_total, geom);
   DevVec<uint16_t> digits(msm_digits_count(chunk, cols_total, geom), ctx->st);
   DevVec<ge_t> partial(chunk * geom.group * segs, ctx->st), sums(segs > 1 ? chunk * geom.group : 0, ctx->st);
-  uint32_t *d_wmask = reinterpret_cast<uint32_t *>(ctx->d_counters.p + 2);  // windows in use, per recode launch
+  uint32_t *d_wmask = reinterpret_cast<uint32_t *>(ctx->d_counters.p + (ctx->on_side ? 3 : 2));  // windows in use, per recode launch
   for (size_t r0 = 0; r0 < rows; r0 += chunk) {
     size_t nr = rows - r0 < chunk ? rows - r0 : chunk;
     double pts = (double)nr * cols_total;

@@ -168,6 +168,11 @@ struct vpin_ctx_impl {
   int rank = 0, world = 1;
   void *nccl_comm = nullptr;
   std::shared_ptr<void> host_pool;  // the prover's helper threads (prover.cu HostPool), created with the first proof
+  // A second stream for work of one proof that does not depend on the transcript's next challenges (the row half of the derefs
+  // commitment runs under the second sumcheck): SideScope (below) forks it off the main stream and swaps it in as `st`.
+  cudaStream_t st_main = nullptr, st_side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool on_side = false;
   int shard_sumcheck = -1;  // sharded sumcheck rounds of one proof: -1 = VPIN_SHARD_SUMCHECK decides, 0 / 1 = vpin_ctx_set_shard_sumcheck
   DevVec<unsigned long long> d_counters;  // [0] = non-zero MSM digits recoded (= mixed additions executed)
   // sharded sumcheck rounds (one proof on several GPUs, VPIN_SHARD_SUMCHECK=1): device-side result slots of the round kernels
@@ -191,6 +196,15 @@ struct vpin_ctx_impl {
   void wait_mark() { VPIN_CUDA(cudaEventSynchronize(ev_marker)); }
 };
 
+// While alive, everything the context enqueues (kernels, DevVec allocations, profiling events) goes to the side stream, which
+// starts after what the main stream holds now; join() makes the main stream wait for it. Not for distributed contexts (the
+// communicator's collectives must stay on one stream).
+struct SideScope {
+  Ctx *c;
+  explicit SideScope(Ctx *ctx);
+  ~SideScope();
+  static void join(Ctx *ctx);  // main stream waits for everything the last SideScope enqueued
+};
 // rows [*r0, *r1) of an L-row Hyrax grid that rank `rank` of `world` commits to; the whole range when the grid is too
 // small to shard (fewer than kMinShardRows rows per rank) or not divisible. Returns true when the grid is sharded.
 static const size_t kMinShardRows = 32;

@@ -1208,6 +1208,40 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   fl_t claim_post_phase1 = (Az_claim * Bz_claim - Cz_claim) * tau_claim;
   EqualityS proof_eq_sc_phase1 = P.equality_prove(spc, claim_post_phase1, blind_expected_claim_postsc1, claim_post_phase1, blind_claim_postsc1);
 
+  // ---- early start of SPARK's non-deterministic witness. The row half of the derefs (mem_rx[row_addr], :267-276) depends on
+  // rx only, which is final here; its Hyrax rows (3/8 of the commitment's MSM work, no transcript dependency) run on a side
+  // stream under the second sumcheck and the witness-polynomial evaluation proof, whose latency-bound rounds leave the GPU idle.
+  size_t N = dec.N, M = dec.M;
+  const size_t num_rounds_y_ = math_log2(2 * num_vars);
+  std::vector<fl_t> rx_ext = rx;  // equalize (:1448-1464)
+  if (rx.size() < num_rounds_y_) { rx_ext.assign(num_rounds_y_ - rx.size(), fl_zero()); rx_ext.insert(rx_ext.end(), rx.begin(), rx.end()); }
+  VPIN_REQUIRE(((size_t)1 << rx_ext.size()) == M, VPIN_ERR_SIZE_MISMATCH, "memory size");
+  DevVec<fl_t> mem_rx = P.eq_table(rx_ext);
+  // workspace slab: derefs 8N | mem trees 8M | ops trees 24N | dot-product clones 9N
+  struct WorkspaceBusy {  // keeps the out-of-memory hook (capi.cu) away from the slab until this proof is done with it
+    Ctx *c;
+    explicit WorkspaceBusy(Ctx *c_) : c(c_) { c->workspace_busy = true; }
+    ~WorkspaceBusy() { c->workspace_busy = false; }
+  } workspace_busy(ctx);
+  fl_t *ws = ctx->workspace_reserve(41 * N + 8 * M);
+  struct { fl_t *p; } derefs{ws}, mem_trees{ws + 8 * N}, ops_trees{ws + 8 * N + 8 * M}, dotp_tables{ws + 32 * N + 8 * M};
+  VPIN_CUDA(cudaMemsetAsync(derefs.p, 0, 8 * N * sizeof(fl_t), st));
+  for (int k = 0; k < 3; k++) {
+    ProfScope ps(ctx, PROF_GATHER, 1.0 * N, 1.0 * N * 68, 1);
+    launch_gather(dec.row_addr[k].p, mem_rx.p, N, derefs.p + (size_t)k * N, st);
+  }
+  const PcGens &dpc = g.derefs_pc;
+  VPIN_REQUIRE(dpc.L * dpc.R == 8 * N, VPIN_ERR_SIZE_MISMATCH, "derefs gens");
+  DevVec<uint8_t> derefs_comm(32 * dpc.L, st);
+  const size_t derefs_row_rows = dpc.L / 8 * 3;  // the Hyrax rows that hold row A | row B | row C
+  // (single GPU only: a communicator's collectives stay on one stream; and not for the largest shapes, where the side stream's own
+  // block cache - digits and partial sums of its MSM - would be taken from an HBM that is planned to the last gigabyte)
+  const bool derefs_early = ctx->world == 1 && dpc.L % 8 == 0 && N <= ((size_t)1 << 23);
+  if (derefs_early) {
+    SideScope side(ctx);
+    hyrax_rows(ctx, *g.eval_label, derefs.p, derefs_row_rows, dpc.R, dpc.R, nullptr, 0, nullptr, derefs_comm.p);
+  }
+
   t0 = now_ms();
   fl_t r_A = t.challenge_scalar("challenege_Az"), r_B = t.challenge_scalar("challenege_Bz"), r_C = t.challenge_scalar("challenege_Cz");
   fl_t claim_phase2 = r_A * Az_claim + r_B * Bz_claim + r_C * Cz_claim;
@@ -1274,36 +1308,23 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
 
   // ---------------- R1CSEvalProof::prove -> SparseMatPolyEvalProof::prove (SP/sparse_mlpoly.rs:1466-1533) ----------------
   double t_eval = now_ms();
-  size_t N = dec.N, M = dec.M;
   t.protocol_name("Sparse polynomial evaluation proof");
-  std::vector<fl_t> rx_ext = rx, ry_ext = ry;  // equalize (:1448-1464)
-  if (rx.size() < ry.size()) { rx_ext.assign(ry.size() - rx.size(), fl_zero()); rx_ext.insert(rx_ext.end(), rx.begin(), rx.end()); }
-  else if (rx.size() > ry.size()) { ry_ext.assign(rx.size() - ry.size(), fl_zero()); ry_ext.insert(ry_ext.end(), ry.begin(), ry.end()); }
-  VPIN_REQUIRE(((size_t)1 << rx_ext.size()) == M, VPIN_ERR_SIZE_MISMATCH, "memory size");
-  DevVec<fl_t> mem_rx = P.eq_table(rx_ext), mem_ry = P.eq_table(ry_ext);
+  std::vector<fl_t> ry_ext = ry;  // equalize (:1448-1464); rx_ext, mem_rx and the row derefs exist since the end of phase one
+  if (rx.size() > ry.size()) { ry_ext.assign(rx.size() - ry.size(), fl_zero()); ry_ext.insert(ry_ext.end(), ry.begin(), ry.end()); }
+  VPIN_REQUIRE(ry.size() == num_rounds_y_ && ((size_t)1 << ry_ext.size()) == M, VPIN_ERR_SIZE_MISMATCH, "memory size");
+  DevVec<fl_t> mem_ry = P.eq_table(ry_ext);
   // derefs (:525-530, :267-282) merged as row A,B,C | col A,B,C | 0 | 0 (:61)
-  // workspace slab: derefs 8N | mem trees 8M | ops trees 24N | dot-product clones 9N
-  struct WorkspaceBusy {  // keeps the out-of-memory hook (capi.cu) away from the slab until this proof is done with it
-    Ctx *c;
-    explicit WorkspaceBusy(Ctx *c_) : c(c_) { c->workspace_busy = true; }
-    ~WorkspaceBusy() { c->workspace_busy = false; }
-  } workspace_busy(ctx);
-  fl_t *ws = ctx->workspace_reserve(41 * N + 8 * M);
-  struct { fl_t *p; } derefs{ws}, mem_trees{ws + 8 * N}, ops_trees{ws + 8 * N + 8 * M}, dotp_tables{ws + 32 * N + 8 * M};
-  VPIN_CUDA(cudaMemsetAsync(derefs.p, 0, 8 * N * sizeof(fl_t), st));
   for (int k = 0; k < 3; k++) {
-    ProfScope ps(ctx, PROF_GATHER, 2.0 * N, 2.0 * N * 68, 2);
-    launch_gather(dec.row_addr[k].p, mem_rx.p, N, derefs.p + (size_t)k * N, st);
+    ProfScope ps(ctx, PROF_GATHER, 1.0 * N, 1.0 * N * 68, 1);
     launch_gather(dec.col_addr[k].p, mem_ry.p, N, derefs.p + (size_t)(3 + k) * N, st);
   }
   t0 = now_ms();
-  const PcGens &dpc = g.derefs_pc;
-  VPIN_REQUIRE(dpc.L * dpc.R == 8 * N, VPIN_ERR_SIZE_MISMATCH, "derefs gens");
   std::vector<Comp> comm_derefs(dpc.L);
   {
-    DevVec<uint8_t> dc(32 * dpc.L, st);
-    hyrax_rows(ctx, *g.eval_label, derefs.p, dpc.L, dpc.R, dpc.R, nullptr, 0, nullptr, dc.p);
-    dc.download((uint8_t *)comm_derefs.data(), 32 * dpc.L);
+    const size_t r0 = derefs_early ? derefs_row_rows : 0;  // (the rows before r0 are being committed, or are done, on the side stream)
+    hyrax_rows(ctx, *g.eval_label, derefs.p + r0 * dpc.R, dpc.L - r0, dpc.R, dpc.R, nullptr, 0, nullptr, derefs_comm.p + 32 * r0);
+    if (derefs_early) SideScope::join(ctx);
+    derefs_comm.download((uint8_t *)comm_derefs.data(), 32 * dpc.L);
     ctx->sync();
   }
   // DerefsCommitment::append_to_transcript (:216-222)
