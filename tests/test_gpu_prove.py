@@ -138,6 +138,21 @@ def test_unsatisfied_witness_is_reported(ctx):
     assert inst.is_sat(v, inputs) and not inst.is_sat(bytes(bad), inputs)
 
 
+def test_derefs_row_half_on_the_side_stream(ctx, monkeypatch):
+    """VPIN_DEREFS_EARLY=1: the row half of the derefs commitment is committed on a second stream while the second sumcheck
+    runs (prover.cu, SideScope); the proof bytes must not change."""
+    from vpin_b200 import api
+
+    weights, px, py = W.synth_point_mult(7)
+    dims, inst, vp, vi, v, inputs = api.point_mult(ctx, weights, px, py)
+    sq, sp = W.tape_seeds()
+    base = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp)
+    monkeypatch.setenv("VPIN_DEREFS_EARLY", "1")
+    early = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp)
+    again = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp)
+    assert early["proof"] == base["proof"] == again["proof"] and early["comm"] == base["comm"]
+
+
 def test_null_seeds_draw_fresh_randomness(ctx):
     """NULL tape seeds (the production default): the library draws both init_randomness scalars from the OS like the reference's
     OsRng (SP/random.rs:16-18) - two proofs of one witness then differ in every blinded byte, and both verify."""

@@ -1209,8 +1209,8 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   EqualityS proof_eq_sc_phase1 = P.equality_prove(spc, claim_post_phase1, blind_expected_claim_postsc1, claim_post_phase1, blind_claim_postsc1);
 
   // ---- early start of SPARK's non-deterministic witness. The row half of the derefs (mem_rx[row_addr], :267-276) depends on
-  // rx only, which is final here; its Hyrax rows (3/8 of the commitment's MSM work, no transcript dependency) run on a side
-  // stream under the second sumcheck and the witness-polynomial evaluation proof, whose latency-bound rounds leave the GPU idle.
+  // rx only, which is final here; its Hyrax rows (3/8 of the commitment's MSM work, no transcript dependency) CAN run on a side
+  // stream under the second sumcheck and the witness-polynomial evaluation proof (see derefs_early below).
   size_t N = dec.N, M = dec.M;
   const size_t num_rounds_y_ = math_log2(2 * num_vars);
   std::vector<fl_t> rx_ext = rx;  // equalize (:1448-1464)
@@ -1234,9 +1234,12 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   VPIN_REQUIRE(dpc.L * dpc.R == 8 * N, VPIN_ERR_SIZE_MISMATCH, "derefs gens");
   DevVec<uint8_t> derefs_comm(32 * dpc.L, st);
   const size_t derefs_row_rows = dpc.L / 8 * 3;  // the Hyrax rows that hold row A | row B | row C
-  // (single GPU only: a communicator's collectives stay on one stream; and not for the largest shapes, where the side stream's own
-  // block cache - digits and partial sums of its MSM - would be taken from an HBM that is planned to the last gigabyte)
-  const bool derefs_early = ctx->world == 1 && dpc.L % 8 == 0 && N <= ((size_t)1 << 23);
+  // OFF by default (VPIN_DEREFS_EARLY=1 turns it on): measured on a B200 at CNN A it hides 4 ms of the commitment but the MSM's
+  // resident blocks (256 us each, six per SM) keep the second sumcheck's round kernels waiting for registers - phase two 2.1 ->
+  // 5.8 ms, SNARK::prove 39.5 -> 40.7 ms. Single GPU only (a communicator's collectives stay on one stream) and not for the
+  // largest shapes (the side stream's own block cache would come out of an HBM that is planned to the last gigabyte).
+  const char *early_env = getenv("VPIN_DEREFS_EARLY");
+  const bool derefs_early = early_env && atoi(early_env) != 0 && ctx->world == 1 && dpc.L % 8 == 0 && N <= ((size_t)1 << 23);
   if (derefs_early) {
     SideScope side(ctx);
     hyrax_rows(ctx, *g.eval_label, derefs.p, derefs_row_rows, dpc.R, dpc.R, nullptr, 0, nullptr, derefs_comm.p);
