@@ -197,9 +197,15 @@ namespace {
 // over the M memory cells, + 6 dot-product instances) are DEALT to the ranks - a rank builds the hash vectors and product trees
 // of its own circuits only, and runs only their instances in the batched sumchecks of the large layers (those of at least
 // kShardMinLayer thread items; one small NCCL all-gather per round, see batched_prove); the short upper layers of every tree are
-// broadcast once by their owners and proved replicated. On by default for a distributed context (VPIN_SHARD_SUMCHECK=0 or
-// vpin_ctx_set_shard_sumcheck(ctx, 0) turn it off); the proof bytes do not change.
-static const size_t kShardMinLayer = (size_t)1 << 17;
+// broadcast once by their owners and proved replicated. Mid-size circuit sets (fewer than kDealBuildMin leaves) build every tree
+// everywhere and deal only the rounds of their largest layers (>= kRoundDealMin items): measured on 8 B200s, CNN A loses 10 ms
+// when more is dealt (a per-round exchange costs ~45 us, the broadcast of 16 tree tails 0.5 ms). Inside a sharded layer the
+// rounds go back to replicated once they are short (kUnshardQ items; the owners broadcast their bound tables). On by default for
+// a distributed context (VPIN_SHARD_SUMCHECK=0 or vpin_ctx_set_shard_sumcheck(ctx, 0) turn it off); the proof bytes do not change.
+static const size_t kShardMinLayer = (size_t)1 << 17;  // smallest sharded layer of a circuit set whose BUILD is dealt (thread items)
+static const size_t kRoundDealMin = (size_t)1 << 19;   // smallest sharded layer when only the rounds are dealt (trees replicated)
+static const size_t kDealBuildMin = (size_t)1 << 22;   // leaves from which hash vectors and trees are built by their owners only
+static const size_t kUnshardQ = (size_t)1 << 11;       // a sharded layer goes back to replicated rounds at this many thread items
 static bool shard_sumcheck_enabled(const Ctx *ctx) {
   static const bool env_on = [] { const char *e = getenv("VPIN_SHARD_SUMCHECK"); return !e || atoi(e) != 0; }();
   const bool on = ctx->shard_sumcheck < 0 ? env_on : ctx->shard_sumcheck != 0;
@@ -890,7 +896,7 @@ struct Prover {
   // dotp: optional (left, right, weight) tables of length n/2 each, bound in place.
   struct DotpTables { fl_t *l, *r, *w; fl_t claim; };
   BatchedS batched_prove(const std::vector<fl_t *> &trees, size_t n, std::vector<DotpTables> dotp, const std::vector<fl_t> &tree_evals,
-                         std::vector<fl_t> *rand_out) {
+                         std::vector<fl_t> *rand_out, size_t min_sharded_len_half = kRoundDealMin) {
     BatchedS out;
     size_t num_layers = math_log2(n), nc = trees.size();
     VPIN_REQUIRE(nc + dotp.size() <= (size_t)kMaxBatched, VPIN_ERR_PROVER, "too many batched instances");
@@ -931,7 +937,7 @@ struct Prover {
       // exchanged with one small in-place NCCL all-gather (and the final claims once per layer), then every rank continues
       // with the same transcript. Small layers are not worth the ~15 us of the collective per round and stay replicated.
       const int world = ctx->world, rank = ctx->rank;
-      const bool sharded = shard_sumcheck_enabled(ctx) && len_half >= kShardMinLayer;
+      bool sharded = shard_sumcheck_enabled(ctx) && len_half >= min_sharded_len_half;  // (turns false when the layer un-shards)
       const size_t max_own = (ninst + world - 1) / world;
       std::vector<size_t> own;  // this rank's instances, in order
       BatchedRoundArgs own_args;
@@ -962,6 +968,20 @@ struct Prover {
       auto launch = [&](size_t j, const fl_t &r_prev) {
         size_t q = len_half >> (j + 1);
         args.eq_rest = own_args.eq_rest = eqS.p + q;  // table k = num_rounds - 1 - j of the suffix family (2^k = q elements)
+        if (sharded && j > 0 && q <= kUnshardQ) {
+          // short rounds cost more in exchanges than they save: every owner broadcasts the current (4 q element) tables of its
+          // instances and the layer continues replicated
+          std::vector<void *> bufs;
+          std::vector<size_t> bytes;
+          std::vector<int> roots;
+          for (size_t i = 0; i < ninst; i++) {
+            fl_t *tabs[3] = {args.A[i], args.B[i], i >= nc ? args.Cout[i] : nullptr};
+            for (fl_t *tb : tabs)
+              if (tb) { bufs.push_back(tb); bytes.push_back(4 * q * sizeof(fl_t)); roots.push_back((int)(i % world)); }
+          }
+          dist_broadcast_many(ctx, bufs.data(), bytes.data(), roots.data(), (int)bufs.size());
+          sharded = false;
+        }
         if (sharded) {
           if (!own.empty()) {
             uint32_t dev_seq;
@@ -1347,11 +1367,10 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   // ops order of the batched proof: row read A,B,C | row write A,B,C | col read A,B,C | col write A,B,C  (:1173-1187)
   std::vector<fl_t *> ops_ptr(12), mem_ptr = {row_init, row_audit, col_init, col_audit};
   for (int i = 0; i < 12; i++) ops_ptr[i] = ops_trees.p + (size_t)i * 2 * N;
-  // several GPUs: circuit i of a set belongs to rank i mod world when the set has layers large enough to be proved sharded
-  // (batched_prove deals instance i to the same rank); everything of a circuit below its short upper layers then exists on
-  // its owner only
+  // several GPUs, large circuit sets (>= kDealBuildMin leaves): circuit i of a set belongs to rank i mod world (batched_prove
+  // deals instance i to the same rank); everything of a circuit below its short upper layers then exists on its owner only
   const int world = ctx->world, rank = ctx->rank;
-  const bool deal_mem = shard_sumcheck_enabled(ctx) && M >= 2 * kShardMinLayer, deal_ops = shard_sumcheck_enabled(ctx) && N >= 2 * kShardMinLayer;
+  const bool deal_mem = shard_sumcheck_enabled(ctx) && M >= kDealBuildMin, deal_ops = shard_sumcheck_enabled(ctx) && N >= kDealBuildMin;
   auto owns = [&](bool dealt, size_t i) { return !dealt || (int)(i % world) == rank; };
   {
     ProfScope ps(ctx, PROF_HASH, 2.0 * M, 2.0 * M * 100, 2);
@@ -1448,10 +1467,10 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   std::vector<fl_t> rand_ops, rand_mem;
   phase("product_layer_setup", t0);
   double t1 = now_ms();
-  BatchedS proof_ops = P.batched_prove(ops_ptr, N, dotp, ops_evals, &rand_ops);
+  BatchedS proof_ops = P.batched_prove(ops_ptr, N, dotp, ops_evals, &rand_ops, deal_ops ? kShardMinLayer : kRoundDealMin);
   phase("product_circuits_ops", t1);
   t1 = now_ms();
-  BatchedS proof_mem = P.batched_prove(mem_ptr, M, {}, mem_evals, &rand_mem);
+  BatchedS proof_mem = P.batched_prove(mem_ptr, M, {}, mem_evals, &rand_mem, deal_mem ? kShardMinLayer : kRoundDealMin);
   phase("product_circuits_mem", t1);
   t1 = now_ms();
 
