@@ -3,7 +3,8 @@
 // Every MSM in the prover is over a prefix of one fixed generator stream (Spartan/src/commitments.rs:20-38), and a
 // Hyrax commitment is L independent MSMs over the SAME R generators (Spartan/src/dense_mlpoly.rs:160-175). So instead
 // of per-row Pippenger buckets (rows are only 2^8..2^15 points long) the device keeps, per generator G_j, kMsmSub tables:
-// sub-table t holds the multiples 1..2^(W-1) of 2^(W*geom.group*t) G_j in affine Niels form (96 B each). Scalars are
+// sub-table t holds the multiples 1..2^(W-1) of 2^(W*geom.group*t) G_j in affine Niels form with every coordinate halved,
+// ((y+x)/2, (y-x)/2, d x y) - 96 B each; the mixed addition then uses D = Z1 instead of 2 Z1 (kernels_msm.cu). Scalars are
 // recoded into signed W-bit digits; window w = t*geom.group + w' then contributes table_t[j][|digit|] to the partial sum
 // of "local window" w'. One thread owns one (row, local window, column segment) and adds kMsmSub looked-up multiples per
 // column with 7-multiplication mixed additions (no bucket reduction, no doublings in the hot loop; zero digits —
