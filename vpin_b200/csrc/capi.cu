@@ -85,6 +85,8 @@ vpin_status vpin_ctx_create_ex(int32_t cuda_device, int32_t high_priority, vpin_
     VPIN_CUDA(cudaHostAlloc((void **)&ctx->h_slots, 2 * sizeof(RoundSlot), cudaHostAllocMapped));
     memset(ctx->h_slots, 0, 2 * sizeof(RoundSlot));
     VPIN_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_slots, ctx->h_slots, 0));
+    VPIN_CUDA(cudaHostAlloc((void **)&ctx->h_tail, kTailElems * sizeof(fl_t), cudaHostAllocMapped));
+    VPIN_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_tail, ctx->h_tail, 0));
     ctx->d_round_counters.alloc(1 + kMaxBatched + 13, ctx->st);
     ctx->d_round_counters.zero();
     ctx->sync();
@@ -110,6 +112,7 @@ void vpin_ctx_destroy(vpin_ctx *ctx_) {
   if (ctx->ev_marker) cudaEventDestroy(ctx->ev_marker);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
+  if (ctx->h_tail) cudaFreeHost(ctx->h_tail);
   ctx->d_round_counters.release();
   ctx->workspace.release();
   cudaStreamSynchronize(ctx->st);

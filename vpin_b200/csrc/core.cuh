@@ -147,6 +147,7 @@ struct vpin_ctx_impl {
   // fused sumcheck rounds (kernels_round.cu): two host-mapped result slots used alternately, the counters of the
   // last-block reductions, and the sequence number of the latest launch
   RoundSlot *h_slots = nullptr, *d_slots = nullptr;
+  fl_t *h_tail = nullptr, *d_tail = nullptr;  // host-mapped buffer (kTailElems) for the table heads of a layer's host-finished tail
   DevVec<unsigned> d_round_counters;
   uint32_t round_seq = 0;
   // per-proof workspace for the SPARK tables (derefs, product trees, dot-product clones): one slab that only ever grows, so

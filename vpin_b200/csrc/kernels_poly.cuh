@@ -66,6 +66,9 @@ void launch_round_cubic_additive(fl_t *A, fl_t *B, fl_t *C, fl_t *D, size_t q, b
 void launch_round_r1cs_split(const fl_t *eq_rest, fl_t *B, fl_t *C, fl_t *D, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
 void launch_round_quad(fl_t *A, fl_t *B, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
 void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
+// dst[t * len + i] = p_t[i] for t < a.n, i < len (dst: device address of host-mapped memory), then c.slot->seq = c.seq
+static const int kTailElems = 1024;  // capacity of the mapped tail buffer (elements)
+void launch_tail_copy(const FinalArgs &a, int len, fl_t *d_dst, const RoundCtl &c, cudaStream_t st);
 // vals[k] = p_k[0] + r (p_k[1] - p_k[0]) (bind) or p_k[0]
 void launch_round_final(const FinalArgs &a, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
 // One bullet-reduction round (Spartan/src/nizk/bullet.rs:72-119) in the fixed-base formulation, see kernels_round.cu.

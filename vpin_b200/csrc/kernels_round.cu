@@ -358,6 +358,17 @@ __global__ void __launch_bounds__(kRedThreads) k_bullet_round(BulletRoundArgs p)
   }
   publish<2>(acc, 0, 1, p.ctl.d_partials, p.ctl.d_counters, p.ctl.slot, p.ctl.seq);
 }
+// ---- tail of a batched layer: the first `len` elements of up to kRoundSlotVals tables -> host-mapped memory (the host finishes
+// the last rounds of the layer itself, prover.cu batched_prove), then the sequence number ----
+__global__ void __launch_bounds__(256) k_tail_copy(FinalArgs a, int len, fl_t *dst, RoundSlot *slot, uint32_t seq) {
+  for (int i = threadIdx.x; i < a.n * len; i += blockDim.x) str(dst + i, ldr(a.p[i / len] + (i % len)));
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
+  }
+}
 __global__ void k_publish_seq(RoundSlot *slot, uint32_t seq) {
   __threadfence_system();
   *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
@@ -436,6 +447,9 @@ void launch_publish_vals(const fl_t *src, int count, RoundSlot *slot, uint32_t s
   ++g_kernel_launches, k_publish_vals<<<1, 128, 0, st>>>(src, count, slot, seq);
 }
 void launch_publish_seq(RoundSlot *slot, uint32_t seq, cudaStream_t st) { ++g_kernel_launches, k_publish_seq<<<1, 1, 0, st>>>(slot, seq); }
+void launch_tail_copy(const FinalArgs &a, int len, fl_t *d_dst, const RoundCtl &c, cudaStream_t st) {
+  ++g_kernel_launches, k_tail_copy<<<1, 256, 0, st>>>(a, len, d_dst, c.slot, c.seq);
+}
 void launch_round_final(const FinalArgs &a, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
   ++g_kernel_launches, k_round_final<<<1, 64, 0, st>>>(a, r, bind ? 1 : 0, c.slot, c.seq);
 }

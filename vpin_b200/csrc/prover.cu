@@ -206,6 +206,10 @@ static const size_t kShardMinLayer = (size_t)1 << 17;  // smallest sharded layer
 static const size_t kRoundDealMin = (size_t)1 << 19;   // smallest sharded layer when only the rounds are dealt (trees replicated)
 static const size_t kDealBuildMin = (size_t)1 << 22;   // leaves from which hash vectors and trees are built by their owners only
 static const size_t kUnshardQ = (size_t)1 << 11;       // a sharded layer goes back to replicated rounds at this many thread items
+// The tail of a batched layer on the host: once a round has at most this many thread items the heads of all its tables (4 q
+// elements each) travel to the host in ONE copy and the host binds, evaluates and delivers the final claims itself - ~60 field
+// multiplications per instance instead of 3 - 4 more launch / PCIe round trips of ~20 us each (VPIN_HOST_TAIL_Q overrides, 0 = off)
+static const size_t kHostTailQDefault = 4;
 static bool shard_sumcheck_enabled(const Ctx *ctx) {
   static const bool env_on = [] { const char *e = getenv("VPIN_SHARD_SUMCHECK"); return !e || atoi(e) != 0; }();
   const bool on = ctx->shard_sumcheck < 0 ? env_on : ctx->shard_sumcheck != 0;
@@ -964,9 +968,93 @@ struct Prover {
       auto ungather = [&](const fl_t *g, int per_inst, size_t i, int k) -> const fl_t & {
         return g[(i % world) * (per_inst * max_own) + (i / world) * per_inst + k];
       };
+      // host tail (kHostTailQ): table heads on the host, [instance][A | B | C of a dot-product instance], current length `hlen`
+      static const size_t host_tail_q = [] {
+        const char *e = getenv("VPIN_HOST_TAIL_Q");
+        long v = e ? atol(e) : (long)kHostTailQDefault;
+        return (size_t)(v < 0 ? 0 : (v > 8 ? 8 : v));
+      }();
+      bool host_mode = false, host_pending_bind = false;
+      size_t hlen = 0;
+      std::vector<std::vector<fl_t>> hT;  // 3 * ninst tables (the third one empty for product instances)
+      fl_t host_r_pending = fl_zero();
+      auto host_bind = [&](const fl_t &r) {  // bound_poly_var_top on every host table (SP/dense_mlpoly.rs:229-236)
+        size_t half = hlen / 2;
+        for (auto &T : hT)
+          if (!T.empty()) {
+            for (size_t i = 0; i < half; i++) T[i] = T[i] + r * (T[i + half] - T[i]);
+            T.resize(half);
+          }
+        hlen = half;
+      };
+      // eq(rand[j+1..], x) for x < q on the host (the suffix table the kernels read from eqS)
+      auto host_eq_rest = [&](size_t j, size_t q) {
+        std::vector<fl_t> tb(1, fl_one());
+        for (size_t v = num_rounds; v-- > j + 1;) {  // new variable on top of the index, as k_eq_suffix_small
+          std::vector<fl_t> nx(2 * tb.size());
+          for (size_t x = 0; x < tb.size(); x++) { fl_t hi = tb[x] * rand[v]; nx[x + tb.size()] = hi; nx[x] = tb[x] - hi; }
+          tb.swap(nx);
+        }
+        VPIN_REQUIRE(tb.size() == q, VPIN_ERR_PROVER, "host tail: eq table size");
+        return tb;
+      };
+      // the evaluations of round j from the host tables (length 2 q): what k_round_cubic_batched delivers
+      auto host_eval = [&](size_t j, std::vector<fl_t> &ev_out) {
+        size_t q = hlen / 2;
+        std::vector<fl_t> eqr = host_eq_rest(j, q);
+        for (size_t i = 0; i < ninst; i++) {
+          const std::vector<fl_t> &A = hT[3 * i], &B = hT[3 * i + 1], &Cc = hT[3 * i + 2];
+          fl_t a0s = fl_zero(), a1s = fl_zero(), a2s = fl_zero();
+          for (size_t x = 0; x < q; x++) {
+            if (i < nc) {
+              a0s = a0s + eqr[x] * (A[x] * B[x]);
+              a1s = a1s + eqr[x] * ((A[x + q] - A[x]) * (B[x + q] - B[x]));
+            } else {
+              fl_t da = A[x + q] - A[x], db = B[x + q] - B[x], dc = Cc[x + q] - Cc[x];
+              fl_t a2 = A[x + q] + da, b2 = B[x + q] + db, c2 = Cc[x + q] + dc;
+              a0s = a0s + (A[x] * B[x]) * Cc[x];
+              a1s = a1s + (a2 * b2) * c2;
+              a2s = a2s + ((a2 + da) * (b2 + db)) * (c2 + dc);
+            }
+          }
+          ev_out[3 * i] = a0s; ev_out[3 * i + 1] = a1s; ev_out[3 * i + 2] = a2s;
+        }
+      };
+      // instead of the kernel of round j: one copy of the table heads (4 q elements, or 2 q when no bind is pending)
+      auto start_host_tail = [&](size_t j, const fl_t &r_prev) {
+        size_t q = len_half >> (j + 1);
+        hlen = j > 0 ? 4 * q : 2 * q;
+        FinalArgs fa;
+        fa.n = 0;
+        for (size_t i = 0; i < ninst; i++) {
+          fa.p[fa.n++] = args.A[i];
+          fa.p[fa.n++] = args.B[i];
+          if (i >= nc) fa.p[fa.n++] = args.Cout[i];
+        }
+        VPIN_REQUIRE((size_t)fa.n * hlen <= (size_t)kTailElems, VPIN_ERR_PROVER, "host tail does not fit its buffer");
+        launch_tail_copy(fa, (int)hlen, ctx->d_tail, round_ctl(slot, &seq), st);
+        host_mode = true;
+        host_pending_bind = j > 0;
+        host_r_pending = r_prev;
+      };
+      auto finish_host_tail_copy = [&]() {  // (first use after start_host_tail: the copy has landed)
+        round_wait(slot, seq);
+        hT.assign(3 * ninst, std::vector<fl_t>());
+        const fl_t *src = ctx->h_tail;
+        for (size_t i = 0; i < ninst; i++)
+          for (int tsel = 0; tsel < (i >= nc ? 3 : 2); tsel++) {
+            hT[3 * i + tsel].assign(src, src + hlen);
+            src += hlen;
+          }
+      };
       // round j: bind with r_{j-1} (j > 0) and evaluate over q = len_half >> (j+1) thread items
       auto launch = [&](size_t j, const fl_t &r_prev) {
         size_t q = len_half >> (j + 1);
+        if (host_mode) { host_pending_bind = true; host_r_pending = r_prev; return; }
+        if (!sharded && host_tail_q && q <= host_tail_q && (2 * ninst + (ninst - nc)) * 4 * q <= (size_t)kTailElems) {
+          start_host_tail(j, r_prev);
+          return;
+        }
         args.eq_rest = own_args.eq_rest = eqS.p + q;  // table k = num_rounds - 1 - j of the suffix family (2^k = q elements)
         if (sharded && j > 0 && q <= kUnshardQ) {
           // short rounds cost more in exchanges than they save: every owner broadcasts the current (4 q element) tables of its
@@ -1009,7 +1097,11 @@ struct Prover {
       fl_t E = fl_one();
       for (size_t j = 0; j < num_rounds; j++) {
         double tw0 = now_ms();
-        {
+        if (host_mode) {
+          if (hT.empty()) finish_host_tail_copy();
+          if (host_pending_bind) { host_bind(host_r_pending); host_pending_bind = false; }
+          host_eval(j, ev);
+        } else {
           const fl_t *got = round_wait(slot, seq);
           if (sharded) {
             for (size_t i = 0; i < ninst; i++)
@@ -1058,7 +1150,16 @@ struct Prover {
         for (size_t k = 0; k < dotp.size(); k++) { fa.p[fa.n++] = dotp[k].l; fa.p[fa.n++] = dotp[k].r; fa.p[fa.n++] = dotp[k].w; }
       VPIN_REQUIRE(fa.n <= kRoundSlotVals, VPIN_ERR_PROVER, "too many final claims");
       std::vector<fl_t> fin(fa.n);
-      if (sharded) {  // three final claims per own instance (left, right, third factor), exchanged like the round sums
+      if (host_mode) {  // the last bind on the host; fin layout as below: (left, right) per circuit | eq claim slot | (l, r, w) per dot product
+        if (hT.empty()) finish_host_tail_copy();
+        if (num_rounds > 0) host_bind(r_j);
+        VPIN_REQUIRE(hlen == 1, VPIN_ERR_PROVER, "host tail: table length");
+        for (size_t c = 0; c < nc; c++) { fin[2 * c] = hT[3 * c][0]; fin[2 * c + 1] = hT[3 * c + 1][0]; }
+        fin[2 * nc] = fl_zero();
+        if (with_dotp)
+          for (size_t k = 0; k < dotp.size(); k++)
+            for (int x = 0; x < 3; x++) fin[2 * nc + 1 + 3 * k + x] = hT[3 * (nc + k) + x][0];
+      } else if (sharded) {  // three final claims per own instance (left, right, third factor), exchanged like the round sums
         FinalArgs fo;
         fo.n = 0;
         for (size_t k = 0; k < own.size(); k++) {
