@@ -319,7 +319,11 @@ class Leg:
                 # the point-mult proof is the critical path of the step: its stream gets the urgent priority, so the point-add
                 # instance's kernels fill the gaps instead of delaying its latency-bound rounds
                 c = api.Context(self.local_rank, high_priority=prio and kind == "point_mult")
-                if distributed:
+                # ONE communicator per process: the point-mult proof (the critical path, > 95 % of the work) is the one that is
+                # sharded; the small point-add proof runs beside it on every rank without a communicator. Two NCCL communicators
+                # driven concurrently from two host threads may issue their collectives in different orders on different ranks,
+                # which NCCL does not tolerate (observed: a hang at N = 2).
+                if distributed and kind == "point_mult":
                     c.init_distributed(self.rank, self.world, dist)
                 self.states.append(InstanceState(c, kind, build(c), torch, device_built=device_built and kind == "point_mult"))
         self.states.sort(key=lambda s_: s_.kind)  # point_add before point_mult (the order the JSON line lists them in)
