@@ -5,6 +5,6 @@ cd "$(dirname "$0")/.."
 for tool in memcheck racecheck initcheck synccheck; do
   echo "== $tool"
   sel="point_add_flow"
-  [ "$tool" = memcheck ] && sel="point_add_flow or device_builder or flow_m7"
-  compute-sanitizer --tool "$tool" --error-exitcode 99 --print-limit 5 python -m pytest tests/test_gpu_prove.py -x -q -k "$sel" 2>&1 | tail -6
+  [ "$tool" = memcheck ] && sel="point_add_flow or device_builder or flow_m7 or side_stream or spmv_and_transpose"
+  compute-sanitizer --tool "$tool" --error-exitcode 99 --print-limit 5 python -m pytest tests/test_gpu_prove.py tests/test_gpu_kernels.py -x -q -k "$sel" 2>&1 | tail -6
 done
