@@ -114,7 +114,7 @@ def make_workload(tag, replica=0):
 class InstanceState:
     """One R1CS instance of the workload with everything the two timed legs need, host and device side."""
 
-    def __init__(self, ctx, kind, built, torch, device_built=False):
+    def __init__(self, ctx, kind, built, torch, device_built=False, high_priority=False):
         """built: what api.point_mult / api.point_addition return (host assignments) or, with device_built, what
         api.point_mult_device returns (assignments expanded on the device, already in Montgomery form: no large host buffer
         exists at all - only the resident leg can then be timed)"""
@@ -156,6 +156,15 @@ class InstanceState:
                 torch.cuda.synchronize()
                 api.dev_to_mont(ctx, d, self.n, d)
                 self.d_assign.append(d)
+        # SNARK::encode does not depend on the witness: on one GPU it runs on a second context (own stream and scratch) from a
+        # helper thread while this thread commits to the three assignments (ctypes releases the GIL; a Rust shim would use
+        # std::thread::scope). VPIN_BENCH_OVERLAP_ENCODE=0 keeps the calls strictly sequential. On a
+        # distributed context encode's commitments are sharded by the context's communicator, so it stays where it is.
+        self.aux = self.enc_pool = None
+        if getattr(ctx, "world", 1) == 1 and os.environ.get("VPIN_BENCH_OVERLAP_ENCODE", "1") == "1":
+            from concurrent.futures import ThreadPoolExecutor
+            self.aux = api.Context(ctx.device, high_priority=high_priority)
+            self.enc_pool = ThreadPoolExecutor(max_workers=1)
         L = self.gens.L
         self.d_pts = [torch.empty(32 * L, dtype=torch.uint8, device=dev) for _ in range(4)]
         self.d_blinds = [torch.empty(32 * L, dtype=torch.uint8, device=dev) for _ in range(3)]
@@ -166,16 +175,32 @@ class InstanceState:
         L = self.gens.L
         return sum(a.nbytes for a in self.coo) + 4 * 32 * self.n + 2 * 32 * L * 2 + 64 * L + len(self.inputs)
 
-    def step_resident(self, ctx, seeds):
+    def encode(self, overlap=True, inst=None, gens=None):
+        """SNARK::encode of the step: a future when it runs beside the commitments, else the result itself"""
+        from vpin_b200 import api
+        inst, gens = inst or self.inst, gens or self.gens
+        if overlap and self.aux is not None:
+            return self.enc_pool.submit(api.SNARK.encode, inst, gens, self.aux)
+        return api.SNARK.encode(inst, gens)
+
+    def close(self):
+        if self.enc_pool is not None:
+            self.enc_pool.shutdown()
+        if self.aux is not None:
+            self.aux.close()
+        self.aux = self.enc_pool = None
+
+    def step_resident(self, ctx, seeds, overlap=True):
         from vpin_b200 import api
         sq, sp = seeds
-        comm, decomm = api.SNARK.encode(self.inst, self.gens)
+        enc = self.encode(overlap)
         tape = api.RandomTape(b"\x02", sq)
         api.dev_poly_commit(ctx, self.gens, self.d_assign[0], self.n, tape, self.d_pts[0], self.d_blinds[0])
         api.dev_poly_commit(ctx, self.gens, self.d_assign[1], self.n, tape, self.d_pts[1], self.d_blinds[1])
         api.dev_poly_commit_with_blinds(ctx, self.gens, self.d_assign[2], self.n, self.d_blinds[0], self.d_blinds[1], self.d_pts[2],
                                         self.d_blinds[2])
         api.dev_commitments_add(ctx, self.d_pts[0], self.d_pts[1], self.gens.L, self.d_pts[3])
+        comm, decomm = enc.result() if hasattr(enc, "result") else enc
         wit = api.DeviceWitness(ctx, self.gens, self.d_assign[2], self.n, self.d_pts[3], self.d_blinds[2])
         proof = api.my_lib_prove_resident(self.inst, decomm, wit, self.inputs, self.gens, TRANSCRIPT_LABEL, sp)
         return comm, proof
@@ -190,12 +215,13 @@ class InstanceState:
         vp, vi, v = (t.numpy() for t in self.h_assign)
         sq, sp = seeds
         gens = api.SNARKGens(ctx, *self.dims); T.append(time.time())
-        comm, decomm = api.SNARK.encode(inst, gens); T.append(time.time())
+        enc = self.encode(True, inst, gens); T.append(time.time())
         tape = api.RandomTape(b"\x02", sq)
         c_para, b_para = api.dense_mlpoly_commit(ctx, gens, api._buf(vp), tape, n=self.n)
         c_input, b_input = api.dense_mlpoly_commit(ctx, gens, api._buf(vi), tape, n=self.n)
         c_vars, b_vars = api.my_dense_mlpoly_commit(ctx, gens, api._buf(v), b_para, b_input, n=self.n)
-        combined = ctx.commitments_add(c_para, c_input); T.append(time.time())
+        combined = ctx.commitments_add(c_para, c_input)
+        comm, decomm = enc.result() if hasattr(enc, "result") else enc; T.append(time.time())
         proof = api.my_lib_prove(inst, decomm, api._buf(v), self.inputs, gens, TRANSCRIPT_LABEL, combined, b_vars, sp, n=self.n); T.append(time.time())
         del inst, decomm, gens
         T.append(time.time())
@@ -325,7 +351,8 @@ class Leg:
                 # which NCCL does not tolerate (observed: a hang at N = 2).
                 if distributed and kind == "point_mult":
                     c.init_distributed(self.rank, self.world, dist)
-                self.states.append(InstanceState(c, kind, build(c), torch, device_built=device_built and kind == "point_mult"))
+                self.states.append(InstanceState(c, kind, build(c), torch, device_built=device_built and kind == "point_mult",
+                                                 high_priority=prio and kind == "point_mult"))
         self.states.sort(key=lambda s_: s_.kind)  # point_add before point_mult (the order the JSON line lists them in)
         self.ctx = self.states[-1].ctx  # a point-mult context
         self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
@@ -376,7 +403,8 @@ class Leg:
         import gc
         gc.collect()
         gc.disable()  # the harness is Python: keep its cyclic collector (7 ms pauses) out of the timed steps
-        l0 = sum(s_.ctx.kernel_launches for s_ in self.states)
+        launches = lambda: sum(s_.ctx.kernel_launches + (s_.aux.kernel_launches if s_.aux is not None else 0) for s_ in self.states)
+        l0 = launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record(self.stream)  # the device is idle here (barrier) ...
@@ -388,7 +416,7 @@ class Leg:
         wall = time.time() - t0
         gc.enable()
         dev_ms = e0.elapsed_time(e1)
-        out = {"launches": sum(s_.ctx.kernel_launches for s_ in self.states) - l0, "phases": self.ctx.phase_times(),
+        out = {"launches": launches() - l0, "phases": self.ctx.phase_times(),
                "clocks": clocks.stop() if clocks else None,
                "step_s": self.max_over_ranks(dev_ms / 1e3 / args.steps), "wall_step_s": self.max_over_ranks(wall / args.steps)}
         assert [p for _, p in self.last] == [p for _, p in self.first], "proof bytes changed between steps (must be deterministic)"
@@ -409,7 +437,7 @@ class Leg:
         for _ in range(args.steps):
             self.flush.zero_()
             torch.cuda.synchronize()
-            prof_out = [s_.step_resident(s_.ctx, seeds) for s_ in self.states]
+            prof_out = [s_.step_resident(s_.ctx, seeds, overlap=False) for s_ in self.states]
         self.sync_all()
         p1.record(self.stream)
         self.barrier()
@@ -486,6 +514,8 @@ class Leg:
         import gc
         ctxs = [s_.ctx for s_ in self.states]
         self.pool.shutdown()
+        for s_ in self.states:
+            s_.close()
         self.states = self.first = self.last = None
         self.ctx = None
         gc.collect()
@@ -693,7 +723,8 @@ def run_b200(args):
         "clocks": res["clocks"],
         "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_ms": e2e_steps_ms,
                 "slowest_step_calls_ms": e2e_slowest_calls,
-                "calls": ["Instance::new", "SNARKGens::new", "SNARK::encode", "3 commits + combine", "my_lib_prove", "release"]},
+                "calls": ["Instance::new", "SNARKGens::new", "SNARK::encode (submitted to the second context)",
+                          "3 commits + combine, then the join with SNARK::encode", "my_lib_prove", "release"]},
         "roofline": top,
         "roofline_pass": {"ms_per_step": prof_ms / args.steps if prof_ms else None,
                           "how": "same K steps repeated after the timed region with CUDA-event scopes on the launching stream, instances sequential"},

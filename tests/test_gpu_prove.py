@@ -204,6 +204,77 @@ def test_two_contexts_prove_concurrently():
             assert proof == ref.proof, name
 
 
+def test_encode_on_a_second_context_beside_the_commitments(ctx):
+    """SNARK::encode run on a second context from a helper thread while the first context commits to the assignments (what
+    bench.py's step does on one GPU): the same computation commitment, and the proof made with that decommitment is the oracle's."""
+    from concurrent.futures import ThreadPoolExecutor
+    from vpin_b200 import api
+
+    sq, sp = W.tape_seeds()
+    weights, mx, my = W.synth_point_mult(7)
+    built = O.build_point_mult(weights, mx, my)
+    ref = O.Flow(built, sq, sp, verify=True)
+    dims, inst, vp, vi, v, inputs = api.point_mult(ctx, weights, mx, my)
+    gens = api.SNARKGens(ctx, *dims)
+    aux = api.Context(0)
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        for _ in range(2):
+            fut = pool.submit(api.SNARK.encode, inst, gens, aux)
+            tape = api.RandomTape(b"\x02", sq)
+            p_para, p_input, p_vars = inst.pad(vp), inst.pad(vi), inst.pad(v)
+            c_para, b_para = api.dense_mlpoly_commit(ctx, gens, p_para, tape)
+            c_input, b_input = api.dense_mlpoly_commit(ctx, gens, p_input, tape)
+            c_vars, b_vars = api.my_dense_mlpoly_commit(ctx, gens, p_vars, b_para, b_input)
+            combined = ctx.commitments_add(c_para, c_input)
+            comm, decomm = fut.result()
+            proof = api.my_lib_prove(inst, decomm, p_vars, inputs, gens, b"snark_example", combined, b_vars, sp)
+            assert comm == ref.comm and c_vars == ref.comm_vars
+            assert proof == ref.proof
+            del decomm
+    del gens, inst
+    aux.close()
+
+
+def _mailbox_worker(env):
+    import json
+    import os
+    import subprocess
+    import sys
+
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "mailbox_worker.py")], env=e,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+    return json.loads(line[len("RESULT "):])
+
+
+def test_prelaunch_on_and_off_give_the_same_bytes():
+    """Rounds enqueued before their challenge exists (the kernel waits for the host's post in mapped memory) against challenges
+    passed as kernel parameters: the same proof bytes, and both equal to the committed oracle digest of the m = 7 flow."""
+    import json
+    import os
+
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_flows.json")))
+    want = [c for c in gold["cases"] if c["kind"] == "point_mult" and c["args"] == {"m": 7}]
+    on = _mailbox_worker({"VPIN_PRELAUNCH_Q": "1048576"})
+    off = _mailbox_worker({"VPIN_PRELAUNCH_Q": "0"})
+    assert [r["proof"] for r in on] == [r["proof"] for r in off] and on[0]["proof"] == on[1]["proof"]
+    assert on[0]["comm"] == off[0]["comm"]
+    if want:
+        assert on[0]["proof"] == want[0]["proof_sha256"]
+
+
+def test_prelaunch_lost_post_times_out_and_the_proof_is_redone():
+    """A host that never posts a challenge (VPIN_TEST_DROP_POST loses the 40th post): the waiting kernel gives up after
+    VPIN_MAILBOX_TIMEOUT_MS, the context stops pre-launching and redoes the proof - same bytes, and the context keeps working."""
+    ok = _mailbox_worker({})
+    lost = _mailbox_worker({"VPIN_TEST_DROP_POST": "40", "VPIN_MAILBOX_TIMEOUT_MS": "200"})
+    assert [r["proof"] for r in lost] == [r["proof"] for r in ok]
+    assert lost[0]["s"] < 30
+
+
 @pytest.mark.parametrize("tag", ["conv3", "conv5", "A"])
 def test_named_vpin_shapes_verify(ctx, tag):
     """BASELINE.json's named shapes at full size (point-mult instance): too large for the CPU prover inside a test, so the

@@ -409,9 +409,12 @@ class RandomTape:
 
 class SNARK:
     @staticmethod
-    def encode(inst, gens):
-        """SNARK::encode(&inst, &gens) -> (ComputationCommitment as bincode bytes, ComputationDecommitment handle)"""
-        ctx = inst.ctx
+    def encode(inst, gens, ctx=None):
+        """SNARK::encode(&inst, &gens) -> (ComputationCommitment as bincode bytes, ComputationDecommitment handle).
+        ctx: the context (stream, scratch) the call runs on, the instance's own by default. Encoding does not depend on the
+        witness, so a driver may run it on a SECOND context from a second host thread while the first one commits to the
+        assignments (bench.py): the decommitment can be handed to a proof on any context of the device."""
+        ctx = ctx or inst.ctx
         cap = 64 + 32 * (1 << 16) * 2
         out = getattr(ctx, "_comm_buf", None)  # one 4 MB output buffer per context, reused (no mmap / munmap per call)
         if out is None:

@@ -29,6 +29,13 @@ using namespace vpin;
   return VPIN_OK;
 
 namespace {
+// true when a pre-launched round kernel of the context gave up waiting for its challenge (kernels_poly.cuh ChalLatch::abort)
+bool mailbox_timed_out(Ctx *ctx) {
+  uint32_t flag = 0;
+  if (!ctx->d_chal_latch.p || cudaStreamSynchronize(ctx->st) != cudaSuccess) return false;
+  if (cudaMemcpy(&flag, &ctx->d_chal_latch.p->abort, sizeof(flag), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+  return flag != 0;
+}
 // canonical LE bytes -> Montgomery table in HBM (rejects values >= l like Scalar::from_bytes)
 DevVec<fl_t> upload_scalars(Ctx *ctx, const uint8_t *b, size_t n) {
   DevVec<fl_t> d(n, ctx->st);
@@ -89,6 +96,11 @@ vpin_status vpin_ctx_create_ex(int32_t cuda_device, int32_t high_priority, vpin_
     VPIN_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_tail, ctx->h_tail, 0));
     ctx->d_round_counters.alloc(1 + kMaxBatched + 13, ctx->st);
     ctx->d_round_counters.zero();
+    VPIN_CUDA(cudaHostAlloc((void **)&ctx->h_chal, kChalRing * sizeof(ChalSlot), cudaHostAllocMapped));
+    memset(ctx->h_chal, 0, kChalRing * sizeof(ChalSlot));
+    VPIN_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_chal, ctx->h_chal, 0));
+    ctx->d_chal_latch.alloc(1, ctx->st);
+    ctx->d_chal_latch.zero();
     ctx->sync();
   } catch (const std::exception &) {
     delete ctx;
@@ -110,9 +122,11 @@ void vpin_ctx_destroy(vpin_ctx *ctx_) {
   for (auto &p : ctx->prof.pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
   if (ctx->ev_marker) cudaEventDestroy(ctx->ev_marker);
-  if (ctx->h_small) cudaFreeHost(ctx->h_small);
-  if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
-  if (ctx->h_tail) cudaFreeHost(ctx->h_tail);
+  if (ctx->h_small) gated_cuda_free_host(ctx->h_small);
+  if (ctx->h_slots) gated_cuda_free_host(ctx->h_slots);
+  if (ctx->h_tail) gated_cuda_free_host(ctx->h_tail);
+  if (ctx->h_chal) gated_cuda_free_host(ctx->h_chal);
+  ctx->d_chal_latch.release();
   ctx->d_round_counters.release();
   ctx->workspace.release();
   cudaStreamSynchronize(ctx->st);
@@ -384,8 +398,20 @@ vpin_status vpin_prove_resident(vpin_ctx *ctx, const vpin_instance *inst, const 
   for (size_t i = 0; i < n_inputs; i++) VPIN_REQUIRE(fl_from_bytes(inputs32 + 32 * i, &inputs[i]), VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
   fl_t seed;
   VPIN_REQUIRE(tape_seed_from(tape_seed32, &seed), VPIN_ERR_INVALID_SCALAR, "InvalidScalar");
-  std::vector<uint8_t> proof = snark_prove(c_, *I, *reinterpret_cast<const Decomm *>(decomm), *reinterpret_cast<const Witness *>(w), inputs,
-                                           *reinterpret_cast<const SnarkGens *>(gens), transcript_label, label_len, seed);
+  // A pre-launched round kernel whose challenge never came (its host thread was held up for seconds: a device-synchronising call
+  // of another library in the process, a stopped process) times out, and the proof fails with a drained stream. The context then
+  // stops pre-launching and the proof is redone once - same inputs, same tape seed, hence the same bytes.
+  std::vector<uint8_t> proof;
+  for (int attempt = 0;; attempt++) {
+    try {
+      proof = snark_prove(c_, *I, *reinterpret_cast<const Decomm *>(decomm), *reinterpret_cast<const Witness *>(w), inputs,
+                          *reinterpret_cast<const SnarkGens *>(gens), transcript_label, label_len, seed);
+      break;
+    } catch (const vpin::Error &) {
+      if (attempt > 0 || c_->no_prelaunch || !mailbox_timed_out(c_)) throw;
+      c_->no_prelaunch = true;
+    }
+  }
   *proof_len = proof.size();
   VPIN_REQUIRE(proof_out && proof_cap >= proof.size(), VPIN_ERR_BUFFER_TOO_SMALL, "proof_out too small");
   memcpy(proof_out, proof.data(), proof.size());

@@ -30,6 +30,18 @@ size_t round_block(size_t bytes) {
   return r;
 }
 }  // namespace
+std::shared_mutex &device_sync_gate() {
+  static std::shared_mutex mu;
+  return mu;
+}
+void gated_cuda_free(void *p) {
+  std::unique_lock<std::shared_mutex> g(device_sync_gate());
+  cudaFree(p);
+}
+void gated_cuda_free_host(void *p) {
+  std::unique_lock<std::shared_mutex> g(device_sync_gate());
+  cudaFreeHost(p);
+}
 BlockCache *block_cache_of(cudaStream_t st) {
   std::lock_guard<std::mutex> g(g_cache_mu);
   auto it = g_caches.find(st);
@@ -55,7 +67,7 @@ void block_cache_unregister(cudaStream_t st) {
     for (auto &kv : c->live_) g_orphans.insert(kv);  // still owned by some handle: freed when it lets go
   }
   for (auto &kv : c->free_)
-    for (void *p : kv.second) cudaFree(p);
+    for (void *p : kv.second) gated_cuda_free(p);
 }
 void *block_cache_alloc(BlockCache *c, size_t bytes) {
   size_t r = round_block(bytes);
@@ -80,17 +92,19 @@ void *block_cache_alloc(BlockCache *c, size_t bytes) {
     if (attempt == 1 && !(c->pressure && c->pressure())) break;
     for (;;) {
       size_t freed = 0;
+      std::vector<void *> give_back;  // (freed outside the cache lock: the free waits for the device-synchronisation gate)
       {
         std::lock_guard<std::mutex> g(c->mu);
         for (auto it = c->free_.rbegin(); it != c->free_.rend() && freed < r; ++it) {
           while (!it->second.empty() && freed < r) {
-            cudaFree(it->second.back());
+            give_back.push_back(it->second.back());
             it->second.pop_back();
             freed += it->first;
           }
         }
         for (auto it = c->free_.begin(); it != c->free_.end();) it = it->second.empty() ? c->free_.erase(it) : std::next(it);
       }
+      for (void *q : give_back) gated_cuda_free(q);
       e = cudaMalloc(&p, r);
       if (e == cudaSuccess || freed == 0) break;  // done, or nothing left to give back
       cudaGetLastError();
@@ -99,6 +113,7 @@ void *block_cache_alloc(BlockCache *c, size_t bytes) {
   if (e != cudaSuccess) {  // last resort: the idle blocks of every other context of the process (concurrent proofs share the GPU)
     cudaGetLastError();
     std::vector<BlockCache *> others;
+    std::vector<void *> give_back;
     {
       std::lock_guard<std::mutex> g(g_cache_mu);
       for (auto &kv : g_caches)
@@ -106,10 +121,11 @@ void *block_cache_alloc(BlockCache *c, size_t bytes) {
       for (BlockCache *o : others) {  // (under g_cache_mu: a cache cannot be unregistered meanwhile)
         std::lock_guard<std::mutex> go(o->mu);
         for (auto &kv : o->free_)
-          for (void *q : kv.second) cudaFree(q);
+          for (void *q : kv.second) give_back.push_back(q);
         o->free_.clear();
       }
     }
+    for (void *q : give_back) gated_cuda_free(q);
     e = cudaMalloc(&p, r);
   }
   if (e != cudaSuccess) {
@@ -139,7 +155,7 @@ void block_cache_free(BlockCache *c, void *p) {
     std::lock_guard<std::mutex> g(g_cache_mu);
     g_orphans.erase(p);
   }
-  cudaFree(p);  // implicit device synchronisation: nothing can still be using it
+  gated_cuda_free(p);  // implicit device synchronisation: nothing can still be using it
 }
 
 // ------------------------------------------------------------------------------------------------ profiling

@@ -8,6 +8,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -52,6 +53,17 @@ void block_cache_unregister(cudaStream_t st);           // frees every cached bl
 // `hook` is called (without the cache lock) when the driver is out of memory even after the idle blocks went back to it;
 // it releases whatever the owner can spare (the context's idle SPARK workspace) and returns true if that was anything.
 void block_cache_set_pressure_hook(cudaStream_t st, std::function<bool()> hook);
+
+// Device-synchronisation gate. cudaFree / cudaFreeHost wait for the whole device to go idle and keep other threads' launches
+// out while they do. A pre-launched round kernel (kernels_poly.cuh ChalSlot) idles only after its HOST thread has posted a
+// challenge, and that thread may be sitting in exactly such a blocked launch: measured as a 20 s stall (until the mailbox timed
+// out) when one context was destroyed while another context's proof was in a pre-launch window. Every freeing call of the
+// library therefore takes the gate exclusively and a prover holds it shared while one of its kernels may be waiting for a
+// post (prover.cu ChalGuard). Frees of other libraries in the process are not covered: the mailbox time-out and the retry of
+// vpin_prove without pre-launch (capi.cu) are the backstop for those.
+std::shared_mutex &device_sync_gate();
+void gated_cuda_free(void *p);
+void gated_cuda_free_host(void *p);
 
 // HBM array owned through the stream's block cache
 template <class T>
@@ -150,6 +162,11 @@ struct vpin_ctx_impl {
   fl_t *h_tail = nullptr, *d_tail = nullptr;  // host-mapped buffer (kTailElems) for the table heads of a layer's host-finished tail
   DevVec<unsigned> d_round_counters;
   uint32_t round_seq = 0;
+  // challenge mailbox of the pre-launched round kernels (kernels_poly.cuh ChalSlot): a ring of host-mapped slots the host posts
+  // challenges into, and the device-side latch that relays a posted challenge to the other blocks of a grid
+  ChalSlot *h_chal = nullptr, *d_chal = nullptr;
+  DevVec<ChalLatch> d_chal_latch;
+  bool no_prelaunch = false;  // set after a mailbox time-out: the context keeps proving with challenges as kernel parameters
   // per-proof workspace for the SPARK tables (derefs, product trees, dot-product clones): one slab that only ever grows, so
   // a steady-state proof allocates nothing large (multi-GB cudaMallocAsync calls were measured at 10-150 ms when the pool
   // has to grow or is fragmented)

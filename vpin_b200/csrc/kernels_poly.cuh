@@ -49,6 +49,18 @@ struct RoundCtl {
   RoundSlot *slot;                 // device-visible address of the slot
   uint32_t seq;
 };
+// Challenge mailbox: a round kernel can be launched BEFORE the challenge it binds with is known - it then waits for the host to
+// post the challenge in host-mapped memory instead of receiving it as a kernel parameter. The launch latency (API call + front
+// end, ~6 us of a ~15 us round trip) leaves the critical path of the latency-bound rounds; the Fiat-Shamir transcript stays on
+// the host. A slot is eight 8-byte atoms (limb, tag): each atom validates itself, so one 64-byte read is a complete poll no
+// matter in which order the host's stores land. In a multi-block grid the first block to arrive polls the host and relays the
+// value through a device-side latch (one PCIe poller per kernel). A poll that outlives ChalRef::timeout_ms (the host died, or
+// was held up for seconds) sets the latch's sticky abort word: that kernel and every later mailbox kernel of the context
+// returns without publishing, which the host's round_wait reports as an error.
+struct ChalSlot { uint32_t w[16]; };                                   // host-mapped
+struct ChalLatch { uint32_t owner, ready, abort, pad[5]; uint32_t r[8]; };  // device memory, one per context, zero at creation
+struct ChalRef { const ChalSlot *slot; ChalLatch *latch; uint32_t tag, timeout_ms; };  // slot == nullptr: the challenge is the kernel parameter
+static const int kChalRing = 64;
 static const int kMaxBatched = 18;  // 12 product circuits + 6 dot-product halves (Spartan/src/sparse_mlpoly.rs:1173-1197)
 struct BatchedRoundArgs {
   fl_t *A[kMaxBatched], *B[kMaxBatched];  // bound in place
@@ -65,12 +77,14 @@ void launch_round_cubic_additive(fl_t *A, fl_t *B, fl_t *C, fl_t *D, size_t q, b
 // delivers t(0) = sum eq_rest (B C - D) at X = 0 and the leading coefficient t(inf) = sum eq_rest (B1 - B0)(C1 - C0)
 void launch_round_r1cs_split(const fl_t *eq_rest, fl_t *B, fl_t *C, fl_t *D, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
 void launch_round_quad(fl_t *A, fl_t *B, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
-void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
+void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st,
+                                const ChalRef &ch = ChalRef{nullptr, nullptr, 0, 0});
 // dst[t * len + i] = p_t[i] for t < a.n, i < len (dst: device address of host-mapped memory), then c.slot->seq = c.seq
 static const int kTailElems = 1024;  // capacity of the mapped tail buffer (elements)
 void launch_tail_copy(const FinalArgs &a, int len, fl_t *d_dst, const RoundCtl &c, cudaStream_t st);
 // vals[k] = p_k[0] + r (p_k[1] - p_k[0]) (bind) or p_k[0]
-void launch_round_final(const FinalArgs &a, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st);
+void launch_round_final(const FinalArgs &a, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st,
+                        const ChalRef &ch = ChalRef{nullptr, nullptr, 0, 0});
 // One bullet-reduction round (Spartan/src/nizk/bullet.rs:72-119) in the fixed-base formulation, see kernels_round.cu.
 struct BulletRoundArgs {
   const fl_t *a_old, *b_old;  // vectors before the pending fold (length 2 * len when fold, len otherwise)

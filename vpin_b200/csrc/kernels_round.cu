@@ -114,6 +114,83 @@ __device__ __forceinline__ void publish(fl_t (&acc)[K], int inst, int ninst, fl_
 
 __device__ __forceinline__ fl_t bind1(const fl_t &lo, const fl_t &hi, const fl_t &r) { return fl_add(lo, fl_mul(r, fl_sub(hi, lo))); }
 
+// ---- challenge mailbox (kernels_poly.cuh): the pre-launched kernel's wait for the challenge the host has not derived yet ----
+// one 64-byte poll of a host-mapped slot; true when all eight (limb, tag) atoms carry `tag`
+__device__ __forceinline__ bool chal_poll_host(const ChalSlot *slot, uint32_t tag, uint32_t (&v)[8]) {
+  uint32_t t[8];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[2 * k]), "=r"(t[2 * k]), "=r"(v[2 * k + 1]), "=r"(t[2 * k + 1])
+                 : "l"(reinterpret_cast<const char *>(slot) + 16 * k)
+                 : "memory");
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 8; k++) ok = ok && t[k] == tag;
+  return ok;
+}
+// Replaces r by the posted challenge when the launch carries a mailbox reference. Block-uniform result; false = the mailbox
+// was aborted and NO thread of the grid may publish anything (the host then sees a drained stream without a result).
+__device__ __forceinline__ bool chal_fetch(const ChalRef &c, fl_t &r) {
+  if (!c.slot) return true;
+  __shared__ uint32_t s_r[8];
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int ok = 0;
+    ChalLatch *L = c.latch;
+    volatile uint32_t *owner = &L->owner, *ready = &L->ready, *abortw = &L->abort;
+    const bool single = gridDim.x * gridDim.y * gridDim.z == 1;
+    bool poller = single;
+    if (!single) {  // the first block of the grid to arrive polls the host for everybody
+      uint32_t old = *owner;
+      while ((int32_t)(c.tag - old) > 0) {
+        uint32_t prev = atomicCAS(&L->owner, old, c.tag);
+        if (prev == old) { poller = true; break; }
+        old = prev;
+      }
+    }
+    const long long t0 = clock64(), limit = (long long)c.timeout_ms << 21;  // ~2.1 M cycles per millisecond
+    if (poller) {
+      for (;;) {
+        if (*abortw) break;
+        if (chal_poll_host(c.slot, c.tag, v)) { ok = 1; break; }
+        if (clock64() - t0 > limit) { *abortw = 1; break; }
+      }
+      if (!single) {
+        if (ok) {
+          volatile uint32_t *dst = L->r;
+#pragma unroll
+          for (int k = 0; k < 8; k++) dst[k] = v[k];
+        }
+        __threadfence();
+        *ready = c.tag;
+      }
+    } else {
+      for (;;) {
+        if (*ready == c.tag) {
+          __threadfence();
+          if (!*abortw) {
+            const volatile uint32_t *src = L->r;
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = src[k];
+            ok = 1;
+          }
+          break;
+        }
+        if (clock64() - t0 > 2 * limit) break;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) s_r[k] = v[k];
+    s_ok = ok;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; k++) r.v[k] = s_r[k];
+  return s_ok != 0;
+}
+
 // loads the evaluation pair (lo, hi) of thread item i; with kBind the table is first bound in place with r
 template <bool kBind>
 __device__ __forceinline__ void load_pair(fl_t *T, size_t i, size_t q, const fl_t &r, fl_t &lo, fl_t &hi) {
@@ -209,8 +286,9 @@ __device__ __forceinline__ void batched_item_dotp(const fl_t &a0, const fl_t &a1
   acc[2] = fl_add(acc[2], fl_mul(fl_mul(a3, b3), c3));
 }
 template <bool kBind>
-__global__ void __launch_bounds__(kRedThreads, 2) k_round_cubic_batched(BatchedRoundArgs a, size_t q, fl_t r, fl_t *partials, unsigned *counters,
-                                                                     RoundSlot *slot, uint32_t seq) {
+__global__ void __launch_bounds__(kRedThreads, 2) k_round_cubic_batched(BatchedRoundArgs a, size_t q, fl_t r, ChalRef ch, fl_t *partials,
+                                                                     unsigned *counters, RoundSlot *slot, uint32_t seq) {
+  if (kBind && !chal_fetch(ch, r)) return;
   const int inst = blockIdx.y;
   fl_t *A = a.A[inst], *B = a.B[inst];
   fl_t acc[3] = {fl_zero(), fl_zero(), fl_zero()};
@@ -242,8 +320,9 @@ __global__ void __launch_bounds__(kRedThreads, 2) k_round_cubic_batched(BatchedR
 static const size_t kSmallQ = 64;         // what the kernel supports
 static const size_t kSmallQDefault = 16;  // measured on a B200: 16 beats 64 by 0.6 ms per CNN-A proof (a lane then has one item)
 template <bool kBind>
-__global__ void __launch_bounds__(16 * kMaxBatched + 16) k_round_cubic_batched_small(BatchedRoundArgs a, int ninst, size_t q, fl_t r,
+__global__ void __launch_bounds__(16 * kMaxBatched + 16) k_round_cubic_batched_small(BatchedRoundArgs a, int ninst, size_t q, fl_t r, ChalRef ch,
                                                                                     RoundSlot *slot, uint32_t seq) {
+  if (kBind && !chal_fetch(ch, r)) return;
   const int inst = threadIdx.x >> 4, lane = threadIdx.x & 15;
   fl_t acc[3] = {fl_zero(), fl_zero(), fl_zero()};
   if (inst < ninst) {
@@ -291,7 +370,8 @@ __global__ void __launch_bounds__(16 * kMaxBatched + 16) k_round_cubic_batched_s
 }
 
 // ---- final claims: vals[k] = p_k[0] + r (p_k[1] - p_k[0])  (or p_k[0] when nothing is left to bind) ----
-__global__ void __launch_bounds__(64) k_round_final(FinalArgs a, fl_t r, int bind, RoundSlot *slot, uint32_t seq) {
+__global__ void __launch_bounds__(64) k_round_final(FinalArgs a, fl_t r, ChalRef ch, int bind, RoundSlot *slot, uint32_t seq) {
+  if (bind && !chal_fetch(ch, r)) return;
   int k = threadIdx.x;
   if (k < a.n) {
     const fl_t *p = a.p[k];
@@ -423,18 +503,19 @@ static size_t small_q_threshold() {  // VPIN_SMALL_Q overrides (experiments)
   }();
   return v;
 }
-void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
+void launch_round_cubic_batched(const BatchedRoundArgs &a, int ninst, size_t q, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st,
+                                const ChalRef &ch) {
   ++g_kernel_launches;
   if (q <= small_q_threshold()) {
     int threads = (16 * ninst + 31) / 32 * 32;
-    if (bind) k_round_cubic_batched_small<true><<<1, threads, 0, st>>>(a, ninst, q, r, c.slot, c.seq);
-    else k_round_cubic_batched_small<false><<<1, threads, 0, st>>>(a, ninst, q, r, c.slot, c.seq);
+    if (bind) k_round_cubic_batched_small<true><<<1, threads, 0, st>>>(a, ninst, q, r, ch, c.slot, c.seq);
+    else k_round_cubic_batched_small<false><<<1, threads, 0, st>>>(a, ninst, q, r, ch, c.slot, c.seq);
     return;
   }
   int nb = round_blocks(q, ninst > 4 ? kRedBlocks / 4 : kRedBlocks);
   dim3 grid(nb, ninst);
-  if (bind) k_round_cubic_batched<true><<<grid, kRedThreads, 0, st>>>(a, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
-  else k_round_cubic_batched<false><<<grid, kRedThreads, 0, st>>>(a, q, r, c.d_partials, c.d_counters, c.slot, c.seq);
+  if (bind) k_round_cubic_batched<true><<<grid, kRedThreads, 0, st>>>(a, q, r, ch, c.d_partials, c.d_counters, c.slot, c.seq);
+  else k_round_cubic_batched<false><<<grid, kRedThreads, 0, st>>>(a, q, r, ch, c.d_partials, c.d_counters, c.slot, c.seq);
 }
 void launch_bullet_round(const BulletRoundArgs &p, cudaStream_t st) {
   unsigned nb = (unsigned)((p.stride + kRedThreads - 1) / kRedThreads);
@@ -450,8 +531,8 @@ void launch_publish_seq(RoundSlot *slot, uint32_t seq, cudaStream_t st) { ++g_ke
 void launch_tail_copy(const FinalArgs &a, int len, fl_t *d_dst, const RoundCtl &c, cudaStream_t st) {
   ++g_kernel_launches, k_tail_copy<<<1, 256, 0, st>>>(a, len, d_dst, c.slot, c.seq);
 }
-void launch_round_final(const FinalArgs &a, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st) {
-  ++g_kernel_launches, k_round_final<<<1, 64, 0, st>>>(a, r, bind ? 1 : 0, c.slot, c.seq);
+void launch_round_final(const FinalArgs &a, bool bind, const fl_t &r, const RoundCtl &c, cudaStream_t st, const ChalRef &ch) {
+  ++g_kernel_launches, k_round_final<<<1, 64, 0, st>>>(a, r, ch, bind ? 1 : 0, c.slot, c.seq);
 }
 
 }  // namespace vpin

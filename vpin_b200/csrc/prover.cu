@@ -2,6 +2,7 @@
 // Host side: Merlin transcript, random tape, O(1)-size sigma protocols, bincode. Device side: everything whose cost
 // grows with the instance (tables in HBM, see kernels_poly.cu / kernels_msm.cu).
 #include "prover.cuh"
+#include <shared_mutex>
 
 #include <time.h>
 
@@ -405,6 +406,53 @@ struct Prover {
     fl_t l_at(const fl_t &r) const { fl_t l0 = fl_one() - w; return l0 + r * (w - l0); }   // eq(w, r)
     fl_t t_at(const fl_t &r) const { return t0 + r * ((t1 - t0 - a) + r * a); }          // the next scaled claim
   };
+  // ---- challenge mailbox of the pre-launched rounds (kernels_poly.cuh ChalSlot) ----
+  // eight 8-byte atoms (limb, tag); x86 keeps the stores in order and each atom validates itself on the device side
+  void chal_write(uint32_t tag, const fl_t &r) {
+    volatile uint64_t *w = reinterpret_cast<volatile uint64_t *>(ctx->h_chal + tag % kChalRing);
+    for (int k = 0; k < 8; k++) w[k] = (uint64_t)r.v[k] | ((uint64_t)tag << 32);
+  }
+  // Tags some enqueued kernel still waits for; an unwinding layer releases them with a dummy value. From the first pre-launch of
+  // a layer until the guard dies the device-synchronisation gate (core.cuh) is held shared: no cudaFree of this library can
+  // stall this thread's launches while a kernel depends on this thread's next post.
+  struct ChalGuard {
+    Prover *P;
+    std::vector<uint32_t> tags;
+    std::shared_lock<std::shared_mutex> gate;
+    ~ChalGuard() {
+      for (uint32_t tg : tags) P->chal_write(tg, fl_zero());
+    }
+  };
+  void chal_post(uint32_t tag, const fl_t &r, ChalGuard *g) {
+    if (!test_drop_post()) chal_write(tag, r);
+    for (size_t i = 0; i < g->tags.size(); i++)
+      if (g->tags[i] == tag) { g->tags.erase(g->tags.begin() + i); break; }
+  }
+  // how long a pre-launched kernel waits for its challenge before it gives up (VPIN_MAILBOX_TIMEOUT_MS, default 2 s; the proof
+  // is then redone without pre-launch, capi.cu)
+  static uint32_t mailbox_timeout_ms() {
+    static const uint32_t v = [] {
+      const char *e = getenv("VPIN_MAILBOX_TIMEOUT_MS");
+      long x = e ? atol(e) : 2000;
+      return (uint32_t)(x < 1 ? 1 : (x > 600000 ? 600000 : x));
+    }();
+    return v;
+  }
+  // test hook: VPIN_TEST_DROP_POST=n loses the n-th post of the process (a host that never answers), once
+  static bool test_drop_post() {
+    static std::atomic<long> left{[] { const char *e = getenv("VPIN_TEST_DROP_POST"); return e ? atol(e) : 0; }()};
+    if (left.load(std::memory_order_relaxed) <= 0) return false;
+    return left.fetch_sub(1) == 1;
+  }
+  // largest round (thread items) whose kernel is enqueued before its challenge exists; VPIN_PRELAUNCH_Q=0 turns pre-launch off
+  static size_t prelaunch_q() {
+    static const size_t v = [] {
+      const char *e = getenv("VPIN_PRELAUNCH_Q");
+      long long x = e ? atoll(e) : (1ll << 14);
+      return (size_t)(x < 0 ? 0 : x);
+    }();
+    return v;
+  }
   // ---- fused rounds: results arrive in host-mapped slots (kernels_round.cu) ----
   RoundCtl round_ctl(int slot, uint32_t *seq_out) {
     uint32_t seq = ++ctx->round_seq;
@@ -935,6 +983,17 @@ struct Prover {
       double tables = 2.0 * nc + 1 + (with_dotp ? 3.0 * dotp.size() : 0);
       uint32_t seq = 0;
       int slot = 0;
+      // Per round (index num_rounds = the final-claims kernel): sequence number of its result and, for a PRE-LAUNCHED round, the
+      // mailbox tag its kernel waits for (0: the challenge travelled as a kernel parameter). Rounds [0, launched) are enqueued.
+      // Pre-launch (kernels_poly.cuh ChalSlot): up to kAhead rounds are enqueued before their challenge exists; the kernel of
+      // round j + 1 is already resident and polling when the host posts r_j, so neither the launch call nor the front-end
+      // latency sits between two rounds. The transcript stays on the host. Only for layers that are not dealt to other ranks,
+      // rounds of at most prelaunch_q() thread items (longer kernels hide their launch anyway) and never while the per-class
+      // profiler brackets the launches with events.
+      std::vector<uint32_t> rseq(num_rounds + 1, 0), rtag(num_rounds + 1, 0);
+      size_t launched = 0, host_from = SIZE_MAX;  // host_from: first round the host evaluates itself (host tail)
+      static const size_t kAhead = 3;
+      ChalGuard outstanding{this, {}, {}};  // posts a dummy value to every tag still waited for if the layer unwinds
       // One proof on several GPUs (opt-in, VPIN_SHARD_SUMCHECK=1): the instances of a LARGE layer are dealt round-robin to the
       // ranks. Every layer starts from tree data that all ranks hold, and nothing outside the layer's sumcheck reads its
       // tables, so a rank only ever evaluates and binds its own instances; per round the 3 sums of every instance are
@@ -974,7 +1033,7 @@ struct Prover {
         long v = e ? atol(e) : (long)kHostTailQDefault;
         return (size_t)(v < 0 ? 0 : (v > 8 ? 8 : v));
       }();
-      bool host_mode = false, host_pending_bind = false;
+      bool host_pending_bind = false;
       size_t hlen = 0;
       std::vector<std::vector<fl_t>> hT;  // 3 * ninst tables (the third one empty for product instances)
       fl_t host_r_pending = fl_zero();
@@ -1021,7 +1080,7 @@ struct Prover {
         }
       };
       // instead of the kernel of round j: one copy of the table heads (4 q elements, or 2 q when no bind is pending)
-      auto start_host_tail = [&](size_t j, const fl_t &r_prev) {
+      auto start_host_tail = [&](size_t j) {
         size_t q = len_half >> (j + 1);
         hlen = j > 0 ? 4 * q : 2 * q;
         FinalArgs fa;
@@ -1033,12 +1092,10 @@ struct Prover {
         }
         VPIN_REQUIRE((size_t)fa.n * hlen <= (size_t)kTailElems, VPIN_ERR_PROVER, "host tail does not fit its buffer");
         launch_tail_copy(fa, (int)hlen, ctx->d_tail, round_ctl(slot, &seq), st);
-        host_mode = true;
-        host_pending_bind = j > 0;
-        host_r_pending = r_prev;
+        host_from = j;  // (the bind with r_{j-1} is delivered by `deliver` once that challenge exists)
       };
       auto finish_host_tail_copy = [&]() {  // (first use after start_host_tail: the copy has landed)
-        round_wait(slot, seq);
+        round_wait((int)(host_from & 1), rseq[host_from]);
         hT.assign(3 * ninst, std::vector<fl_t>());
         const fl_t *src = ctx->h_tail;
         for (size_t i = 0; i < ninst; i++)
@@ -1048,13 +1105,28 @@ struct Prover {
           }
       };
       // round j: bind with r_{j-1} (j > 0) and evaluate over q = len_half >> (j+1) thread items
-      auto launch = [&](size_t j, const fl_t &r_prev) {
+      const bool pre_ok = !sharded && prelaunch_q() > 0 && !ctx->prof.on && !ctx->no_prelaunch;
+      auto is_host_tail = [&](size_t q) {
+        return !sharded && host_tail_q && q <= host_tail_q && (2 * ninst + (ninst - nc)) * 4 * q <= (size_t)kTailElems;
+      };
+      auto new_tag = [&](size_t j) {
+        if (!outstanding.gate.owns_lock()) outstanding.gate = std::shared_lock<std::shared_mutex>(device_sync_gate());
+        uint32_t tag = ++ctx->round_seq;
+        rtag[j] = tag;
+        outstanding.tags.push_back(tag);
+        return ChalRef{ctx->d_chal + tag % kChalRing, ctx->d_chal_latch.p, tag, mailbox_timeout_ms()};
+      };
+      // enqueues round j (launched == j). pre: the kernel takes r_{j-1} from the mailbox (r_prev is ignored)
+      auto launch = [&](size_t j, const fl_t &r_prev, bool pre) {
         size_t q = len_half >> (j + 1);
-        if (host_mode) { host_pending_bind = true; host_r_pending = r_prev; return; }
-        if (!sharded && host_tail_q && q <= host_tail_q && (2 * ninst + (ninst - nc)) * 4 * q <= (size_t)kTailElems) {
-          start_host_tail(j, r_prev);
+        slot = (int)(j & 1);
+        if (is_host_tail(q)) {
+          start_host_tail(j);
+          rseq[j] = seq;
+          launched = num_rounds + 1;  // nothing else of this layer runs on the device
           return;
         }
+        launched = j + 1;
         args.eq_rest = own_args.eq_rest = eqS.p + q;  // table k = num_rounds - 1 - j of the suffix family (2^k = q elements)
         if (sharded && j > 0 && q <= kUnshardQ) {
           // short rounds cost more in exchanges than they save: every owner broadcasts the current (4 q element) tables of its
@@ -1079,29 +1151,83 @@ struct Prover {
             launch_round_cubic_batched(own_args, (int)own.size(), q, j > 0, r_prev, ctl, st);
           }
           exchange(3);
+          rseq[j] = seq;
           return;
         }
         ProfScope ps(ctx, PROF_SC_BATCHED, (double)ninst * q, tables * (j > 0 ? 6 : 2) * q * 32);
-        launch_round_cubic_batched(args, (int)ninst, q, j > 0, r_prev, round_ctl(slot, &seq), st);
+        ChalRef ch = pre ? new_tag(j) : ChalRef{nullptr, nullptr, 0, 0};
+        launch_round_cubic_batched(args, (int)ninst, q, j > 0, r_prev, round_ctl(slot, &seq), st, ch);
+        rseq[j] = seq;
+      };
+      // final claims: every table bound with the last challenge (in the kernel; the tables themselves are done with)
+      FinalArgs fa;
+      fa.n = 0;
+      for (size_t c = 0; c < nc; c++) { fa.p[fa.n++] = args.A[c]; fa.p[fa.n++] = args.B[c]; }
+      fa.p[fa.n++] = args.A[0];  // (slot of the eq claim eq(rand, r): equal to E below, not needed by the prover)
+      if (with_dotp)
+        for (size_t k = 0; k < dotp.size(); k++) { fa.p[fa.n++] = dotp[k].l; fa.p[fa.n++] = dotp[k].r; fa.p[fa.n++] = dotp[k].w; }
+      VPIN_REQUIRE(fa.n <= kRoundSlotVals, VPIN_ERR_PROVER, "too many final claims");
+      auto launch_final = [&](const fl_t &r_last, bool pre) {
+        slot = (int)(num_rounds & 1);
+        ProfScope ps(ctx, PROF_FINAL, (double)fa.n, 0);
+        ChalRef ch = pre ? new_tag(num_rounds) : ChalRef{nullptr, nullptr, 0, 0};
+        launch_round_final(fa, num_rounds > 0, r_last, round_ctl(slot, &seq), st, ch);
+        rseq[num_rounds] = seq;
+        launched = num_rounds + 1;
+      };
+      // enqueues, ahead of their challenges, the rounds before `upto` (and the final-claims kernel after the last round)
+      auto launch_ahead = [&](size_t upto) {
+        if (!pre_ok) return;
+        while (launched < upto && launched <= num_rounds) {
+          size_t jj = launched;
+          if (jj == num_rounds) { launch_final(fl_zero(), true); break; }
+          size_t q = len_half >> (jj + 1);
+          bool tail = is_host_tail(q);
+          if (!tail && q > prelaunch_q()) break;
+          launch(jj, fl_zero(), !tail);
+        }
+      };
+      // r = r_{next-1} has been drawn: hand it to round `next` (next == num_rounds: the final claims)
+      auto deliver = [&](size_t next, const fl_t &r) {
+        if (next >= host_from) {  // the host binds its own tables
+          if (next < num_rounds) { host_pending_bind = true; host_r_pending = r; }
+          return;
+        }
+        if (next < launched) {  // pre-launched: its kernel is waiting for the tag (or about to)
+          if (rtag[next]) chal_post(rtag[next], r, &outstanding);
+          return;
+        }
+        if (next < num_rounds) {
+          launch(next, r, false);
+          if (next >= host_from) { host_pending_bind = true; host_r_pending = r; }  // (the launch started the host tail)
+        }
       };
       fl_t r_j = fl_zero();
-      if (num_rounds) launch(0, r_j);
+      if (num_rounds) launch(0, r_j, false);
       // the first round's kernel needs neither the coefficients nor the claim: both are drawn / formed while it runs
       std::vector<fl_t> coeffs = t.challenge_vector("rand_coeffs_next_layer", claims_to_verify.size());
       fl_t e = fl_zero();
       for (size_t i = 0; i < coeffs.size(); i++) e = e + claims_to_verify[i] * coeffs[i];
       std::vector<fl_t> ev(3 * ninst);
-      // split-eq bookkeeping of the product instances (SplitEq): E = eq(rand_<j, r_<j), sc[c] = claim of instance c / E
-      std::vector<fl_t> winv = batch_invert(rand), sc(claims_to_verify.begin(), claims_to_verify.begin() + nc);
-      std::vector<SplitEq> keep(nc);
+      // split-eq bookkeeping of the product instances (SplitEq): E = eq(rand_<j, r_<j). Every product instance has the same
+      // factor E l(X), so the coefficients are folded in BEFORE the split is undone: with T = sum_c coeffs[c] t_c (a quadratic)
+      // sum_c coeffs[c] s_c(X) = E l(X) T(X), and one SplitEq (on T(0), T(inf) and the scaled claim SC = sum_c coeffs[c] sc_c)
+      // replaces one per instance: ~36 instead of ~200 host multiplications per round. Exact field arithmetic (linearity).
+      std::vector<fl_t> winv = batch_invert(rand);
+      fl_t SC = fl_zero();
+      for (size_t c = 0; c < nc; c++) SC = SC + claims_to_verify[c] * coeffs[c];
+      SplitEq keep;
       fl_t E = fl_one();
       for (size_t j = 0; j < num_rounds; j++) {
+        launch_ahead(j + 1 + kAhead);
         double tw0 = now_ms();
-        if (host_mode) {
+        if (j >= host_from) {
           if (hT.empty()) finish_host_tail_copy();
           if (host_pending_bind) { host_bind(host_r_pending); host_pending_bind = false; }
           host_eval(j, ev);
         } else {
+          slot = (int)(j & 1);
+          seq = rseq[j];
           const fl_t *got = round_wait(slot, seq);
           if (sharded) {
             for (size_t i = 0; i < ninst; i++)
@@ -1110,16 +1236,21 @@ struct Prover {
             memcpy(ev.data(), got, 3 * ninst * sizeof(fl_t));
           }
         }
-        for (size_t c = 0; c < nc; c++) {  // (t(0), t(inf)) of the cofactor -> the evaluations at 0, 2, 3 the reference computes
-          fl_t t0 = ev[3 * c], a = ev[3 * c + 1];
-          SplitEq::evals(E, rand[j], winv[j], sc[c], t0, a, &ev[3 * c], &keep[c]);
-        }
         double tw1 = now_ms();
         t_b_wait += tw1 - tw0;
         n_b_rounds++;
         if ((len_half >> (j + 1)) <= 64) { t_b_small_wait += tw1 - tw0; n_b_small++; }
         fl_t c0 = fl_zero(), c2 = fl_zero(), c3 = fl_zero();
-        for (size_t i = 0; i < ninst; i++) {
+        if (nc) {  // (T(0), T(inf)) of the combined cofactor -> the combined evaluations at 0, 2, 3 the reference computes
+          fl_t T0 = fl_zero(), Ainf = fl_zero(), out3[3];
+          for (size_t c = 0; c < nc; c++) {
+            T0 = T0 + ev[3 * c] * coeffs[c];
+            Ainf = Ainf + ev[3 * c + 1] * coeffs[c];
+          }
+          SplitEq::evals(E, rand[j], winv[j], SC, T0, Ainf, out3, &keep);
+          c0 = out3[0]; c2 = out3[1]; c3 = out3[2];
+        }
+        for (size_t i = nc; i < ninst; i++) {
           c0 = c0 + ev[3 * i] * coeffs[i];
           c2 = c2 + ev[3 * i + 1] * coeffs[i];
           c3 = c3 + ev[3 * i + 2] * coeffs[i];
@@ -1131,26 +1262,17 @@ struct Prover {
         t.message("poly", "UniPoly_end");
         r_j = t.challenge_scalar("challenge_nextround");
         rand_prod.push_back(r_j);
-        slot ^= 1;
         double tw2 = now_ms();
         t_b_host += tw2 - tw1;
-        if (j + 1 < num_rounds) launch(j + 1, r_j);
+        deliver(j + 1, r_j);
         t_b_launch += now_ms() - tw2;
-        for (size_t c = 0; c < nc; c++) sc[c] = keep[c].t_at(r_j);
-        if (nc) E = E * keep[0].l_at(r_j);
+        if (nc) { SC = keep.t_at(r_j); E = E * keep.l_at(r_j); }
         e = unipoly_eval(poly, r_j);
         layer.polys.push_back({poly[0], poly[2], poly[3]});  // CompressedUniPoly (SP/unipoly.rs:80-87)
       }
-      // final claims: every table bound with the last challenge (in the kernel; the tables themselves are done with)
-      FinalArgs fa;
-      fa.n = 0;
-      for (size_t c = 0; c < nc; c++) { fa.p[fa.n++] = args.A[c]; fa.p[fa.n++] = args.B[c]; }
-      fa.p[fa.n++] = args.A[0];  // (slot of the eq claim eq(rand, r): equal to E above, not needed by the prover)
-      if (with_dotp)
-        for (size_t k = 0; k < dotp.size(); k++) { fa.p[fa.n++] = dotp[k].l; fa.p[fa.n++] = dotp[k].r; fa.p[fa.n++] = dotp[k].w; }
-      VPIN_REQUIRE(fa.n <= kRoundSlotVals, VPIN_ERR_PROVER, "too many final claims");
       std::vector<fl_t> fin(fa.n);
-      if (host_mode) {  // the last bind on the host; fin layout as below: (left, right) per circuit | eq claim slot | (l, r, w) per dot product
+      slot = (int)(num_rounds & 1);
+      if (host_from != SIZE_MAX) {  // the last bind on the host; fin layout as below: (left, right) per circuit | eq claim slot | (l, r, w) per dot product
         if (hT.empty()) finish_host_tail_copy();
         if (num_rounds > 0) host_bind(r_j);
         VPIN_REQUIRE(hlen == 1, VPIN_ERR_PROVER, "host tail: table length");
@@ -1181,9 +1303,8 @@ struct Prover {
           for (size_t k = 0; k < dotp.size(); k++)
             for (int x = 0; x < 3; x++) fin[2 * nc + 1 + 3 * k + x] = ungather(got, 3, nc + k, x);
       } else {
-        ProfScope ps(ctx, PROF_FINAL, (double)fa.n, 0);
-        launch_round_final(fa, num_rounds > 0, r_j, round_ctl(slot, &seq), st);
-        memcpy(fin.data(), round_wait(slot, seq), fa.n * sizeof(fl_t));
+        if (launched <= num_rounds) launch_final(r_j, false);
+        memcpy(fin.data(), round_wait((int)(num_rounds & 1), rseq[num_rounds]), fa.n * sizeof(fl_t));
       }
       for (size_t c = 0; c < nc; c++) { layer.left.push_back(fin[2 * c]); layer.right.push_back(fin[2 * c + 1]); }
       for (size_t c = 0; c < nc; c++) {
@@ -1256,6 +1377,8 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   MerlinTranscript t(label, label_len);
   ProverTape tape("proof", 5, tape_seed);
   Prover P{ctx, st, t, tape, g, host_pool_of(ctx)};
+  // a mailbox time-out of an earlier, failed call must not fail this one (the abort word of the latch is sticky)
+  VPIN_CUDA(cudaMemsetAsync(&ctx->d_chal_latch.p->abort, 0, sizeof(uint32_t), st));
   const PcGens &spc = g.sat_pc;
   size_t num_vars = inst.num_vars, num_cons = inst.num_cons, num_inputs = inputs.size();
   VPIN_REQUIRE(wit.n_vars == num_vars && num_inputs < num_vars, VPIN_ERR_SIZE_MISMATCH, "witness size");
