@@ -132,7 +132,12 @@ VPIN_HD fp_t fp_mul(const fp_t &a, const fp_t &b) {
   limb::mul_8x8(t, a.v, b.v);
   return fp_reduce_wide(t);
 }
-VPIN_HD fp_t fp_sqr(const fp_t &a) { return fp_mul(a, a); }
+// a * a with the dedicated squaring of limbs.cuh (36 + 8 IMAD.WIDE instead of 64 + 8); same value as fp_mul(a, a)
+VPIN_HD fp_t fp_sqr(const fp_t &a) {
+  uint32_t t[16];
+  limb::sqr_8x8(t, a.v);
+  return fp_reduce_wide(t);
+}
 // fp_mul with the accumulation of chosen product rows moved to the ALU pipe (limbs.cuh mul_8x8_p); same value
 template <uint32_t kAluRows>
 VPIN_HD fp_t fp_mul_p(const fp_t &a, const fp_t &b) {

@@ -138,22 +138,30 @@ __device__ __forceinline__ uint32_t recode_one(const fl_t *src, const MsmGeom &g
   x.v[0] = lo.x; x.v[1] = lo.y; x.v[2] = lo.z; x.v[3] = lo.w; x.v[4] = hi.x; x.v[5] = hi.y; x.v[6] = hi.z; x.v[7] = hi.w;
   return msm_recode_value(x, g, dst, plane, used);
 }
+// Grid-stride: a block recodes several 256-scalar tiles and reports its window mask and its non-zero count ONCE. (One atomic
+// per warp - 524 288 same-address atomics for CNN A's comb_ops commitment - kept this kernel at 1.1 TB/s: the L2 serialises them.)
 __global__ void __launch_bounds__(256) k_recode(const fl_t *scalars, size_t rows, size_t cols, size_t ld, const fl_t *extra, MsmGeom g,
                                                 size_t stride, uint16_t *digits, unsigned long long *nonzero, uint32_t *wmask) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nz = 0, used = 0;
-  if (idx < rows * stride) {
+  const size_t total = rows * stride, step = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {
     size_t row = idx / stride, col = idx % stride;
     const fl_t *src = col < cols ? scalars + row * ld + col : (col == cols && extra ? extra + row : nullptr);
-    nz = recode_one(src, g, digits + row * stride + col, rows * stride, &used);
+    uint32_t u = 0;
+    nz += recode_one(src, g, digits + row * stride + col, total, &u);
+    used |= u;
   }
-  if (wmask) {  // windows that hold a non-zero digit anywhere in this launch (the accumulate kernel skips the others)
-    used = __reduce_or_sync(0xffffffffu, used);
-    if ((threadIdx.x & 31) == 0 && used) atomicOr(wmask, used);
-  }
-  if (nonzero) {
-    nz = __reduce_add_sync(0xffffffffu, nz);
-    if ((threadIdx.x & 31) == 0 && nz) atomicAdd(nonzero, (unsigned long long)nz);
+  if (!wmask && !nonzero) return;
+  __shared__ uint32_t s_nz[8], s_used[8];
+  nz = __reduce_add_sync(0xffffffffu, nz);
+  used = __reduce_or_sync(0xffffffffu, used);
+  if ((threadIdx.x & 31) == 0) { s_nz[threadIdx.x >> 5] = nz; s_used[threadIdx.x >> 5] = used; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    nz = used = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) { nz += s_nz[k]; used |= s_used[k]; }
+    if (wmask && used) atomicOr(wmask, used);  // windows that hold a non-zero digit anywhere in this launch (the accumulate kernel skips the others)
+    if (nonzero && nz) atomicAdd(nonzero, (unsigned long long)nz);
   }
 }
 void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, const fl_t *d_extra, const MsmGeom &g, uint16_t *d_digits,
@@ -161,8 +169,10 @@ void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, c
   size_t stride = msm_col_stride(cols + (d_extra ? 1 : 0));
   size_t total = rows * stride;
   if (d_wmask) cudaMemsetAsync(d_wmask, 0, sizeof(uint32_t), st);
-  ++g_kernel_launches, k_recode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_scalars, rows, cols, ld, d_extra, g, stride, d_digits, d_nonzero,
-                                                                                 d_wmask);
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)148 * 32;  // 4 resident blocks per SM x 8 waves
+  if (blocks > cap) blocks = cap;
+  ++g_kernel_launches, k_recode<<<(unsigned)blocks, 256, 0, st>>>(d_scalars, rows, cols, ld, d_extra, g, stride, d_digits, d_nonzero, d_wmask);
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate
@@ -344,31 +354,35 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
 #undef VPIN_MSM_LAUNCH
 }
 
-// finish, step 1 (only when a row was split into segments): one warp per (row, local window) adds the segment partials
-// (lane-strided, then a shuffle tree) -> sums[row][w'].
+// finish, step 1 (only when a row was split into segments): `lanes` lanes per (row, local window) add the segment partials
+// (lane-strided, then a shuffle tree) -> sums[row][w']. The kernel is bound by the multiply pipe, and a warp-wide addition costs
+// the same whether 1 or 32 of its lanes hold data: with a whole warp per pair the tree's five levels were 5 of the 6 warp-wide
+// additions a pair of 45 segments cost (23 % of the lanes useful, 344 us for CNN A's comb_ops commitment). `lanes` now comes from
+// a small cost model (msm_segsum_lanes): 2 - 4 lanes for the 20480 pairs x 45 segments of that commitment, a full tree for the
+// 10 pairs of a bullet-reduction round.
 // publish: optional {counter, host-mapped sequence word, value}: the last block to finish stores the value there (system scope),
 // which tells the host that every window sum has landed in its mapped slot — saves the separate one-thread launch
 struct SegsumPublish { unsigned *counter; volatile uint32_t *seq_word; uint32_t seq; };
-__global__ void __launch_bounds__(128) k_msm_segsum(const ge_t *partial, size_t pairs, size_t segs, ge_t *sums, SegsumPublish pub) {
-  size_t pair = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);  // (row, w') flattened
-  const int lane = threadIdx.x & 31;
-  if (pair < pairs) {
-    const ge_t *p = partial + pair * segs;
+__global__ void __launch_bounds__(128) k_msm_segsum(const ge_t *partial, size_t pairs, size_t segs, int lanes, ge_t *sums, SegsumPublish pub) {
+  const int lane = threadIdx.x & 31, sub = lane & (lanes - 1);
+  const size_t warp = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const size_t pair = warp * (32 / lanes) + lane / lanes;  // (row, w') flattened
+  const bool live = pair < pairs;
+  {
+    const ge_t *p = partial + (live ? pair : 0) * segs;
     ge_t acc = ge_identity();
     bool first = true;
-    for (size_t s = lane; s < segs; s += 32) {
-      ge_t q = ld_ge(p + s);
-      acc = first ? q : ge_add(acc, q);
-      first = false;
-    }
-    int width = segs >= 32 ? 32 : (int)segs;
-    for (int off = 16; off > 0; off >>= 1) {
-      if (off < width) {  // warp-uniform; lanes beyond the data hold the identity
-        ge_t o = shfl_down_ge(acc, off);
-        acc = ge_add(acc, o);
+    if (live)
+      for (size_t s = sub; s < segs; s += lanes) {
+        ge_t q = ld_ge(p + s);
+        acc = first ? q : ge_add(acc, q);
+        first = false;
       }
+    for (int off = lanes >> 1; off > 0; off >>= 1) {  // (lanes beyond the data hold the identity; a read across the group's end
+      ge_t o = shfl_down_ge(acc, off);               //  only reaches lanes whose sums nobody uses)
+      acc = ge_add(acc, o);
     }
-    if (lane == 0) st_ge(sums + pair, acc);
+    if (live && sub == 0) st_ge(sums + pair, acc);
   }
   if (pub.counter) {
     __threadfence_system();
@@ -379,6 +393,31 @@ __global__ void __launch_bounds__(128) k_msm_segsum(const ge_t *partial, size_t 
       *pub.seq_word = pub.seq;
     }
   }
+}
+// lanes per pair: the power of two that minimises depth x max(latency of one addition, multiply-pipe time of all warps' additions)
+// with depth = ceil(segs / lanes) - 1 serial additions + log2(lanes) tree levels. Few pairs (the two rows of a bullet-reduction
+// round) are latency-bound and get a wide tree; thousands of pairs are pipe-bound and get few lanes.
+static int msm_segsum_lanes(size_t pairs, size_t segs) {
+  static const int forced = [] { const char *e = getenv("VPIN_SEGSUM_LANES"); return e ? atoi(e) : 0; }();  // (experiments: 1, 2, .., 32)
+  if (forced >= 1 && forced <= 32 && (forced & (forced - 1)) == 0) return forced;
+  const double add_latency = 5000.0;             // cycles of one dependent extended addition in a lone warp
+  const double pipe_per_warp_add = 2592.0 / 592;  // 9 x 72 IMAD.WIDE x 4 cycles, spread over 148 x 4 sub-partitions
+  int best = 1;
+  double best_cost = 0;
+  for (int lanes = 1, lg = 0; lanes <= 32; lanes <<= 1, lg++) {
+    double depth = (double)((segs + lanes - 1) / lanes) - 1 + lg;
+    if (depth < 1) depth = 1;
+    double warps = (double)pairs * lanes / 32.0;
+    double per_add = warps * pipe_per_warp_add > add_latency ? warps * pipe_per_warp_add : add_latency;
+    double cost = depth * per_add;
+    if (lanes == 1 || cost < best_cost) { best = lanes; best_cost = cost; }
+    if ((size_t)lanes >= segs) break;
+  }
+  return best;
+}
+static unsigned msm_segsum_blocks(size_t pairs, int lanes) {
+  size_t per_block = (size_t)4 * (32 / lanes);
+  return (unsigned)((pairs + per_block - 1) / per_block);
 }
 // finish, step 2: one thread per row runs the Horner pass over the kMsmGroup window sums and encodes the point
 __global__ void __launch_bounds__(32) k_msm_horner(const ge_t *sums, size_t rows, MsmGeom g, ge_t *out, uint8_t *comp) {
@@ -401,21 +440,110 @@ __global__ void __launch_bounds__(32) k_msm_horner(const ge_t *sums, size_t rows
     q[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
+// The same pass with FOUR lanes per row. A commitment ends with this kernel and the host waits for its bytes, so what counts
+// is the length of the dependent chain, not the work: a doubling is two rounds of four independent multiplications (the
+// squares of X, Y, Z, X + Y, then E F, G H, F G, E H), an addition likewise, and lane q of a quad computes the q-th product of
+// each round; the products travel between the lanes by shuffles. 2 multiplications deep per doubling instead of 8, 3 per
+// addition instead of 9. The encoding's inverse square root is a chain of squarings that cannot be split; lane 0 runs it.
+__device__ __forceinline__ fp_t quad_from(const fp_t &v, int src) {
+  fp_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], src, 4);
+  return r;
+}
+__device__ __forceinline__ fp_t quad_xor1(const fp_t &v) {
+  fp_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, v.v[i], 1, 4);
+  return r;
+}
+__device__ __forceinline__ fp_t fp_sel(bool c, const fp_t &a, const fp_t &b) {
+  fp_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = c ? a.v[i] : b.v[i];
+  return r;
+}
+// second round of a doubling / addition: lane 0 E F (X3), lane 1 G H (Y3), lane 2 F G (Z3), lane 3 E H (T3)
+__device__ __forceinline__ fp_t quad_efgh(int q, const fp_t &e, const fp_t &f, const fp_t &g, const fp_t &h) {
+  fp_t m1 = fp_sel(q == 1, g, fp_sel(q == 2, f, e));
+  fp_t m2 = fp_sel(q == 0, f, fp_sel(q == 2, g, h));
+  return fp_mul(m1, m2);
+}
+// c: coordinate q of the point (lane 0 X, 1 Y, 2 Z, 3 T) -> coordinate q of its double
+__device__ __forceinline__ fp_t quad_dbl(int q, const fp_t &c) {
+  fp_t x = quad_from(c, 0), y = quad_from(c, 1);
+  fp_t s = fp_sqr(fp_sel(q == 3, fp_add(x, y), c));
+  fp_t a = quad_from(s, 0), b = quad_from(s, 1), cc = quad_from(s, 2), xy2 = quad_from(s, 3);
+  cc = fp_add(cc, cc);
+  fp_t e = fp_sub(fp_sub(xy2, a), b), g = fp_sub(b, a), f = fp_sub(g, cc), h = fp_sub(fp_neg(a), b);
+  return quad_efgh(q, e, f, g, h);
+}
+// coordinate q of P + Q; Q is read from memory (all lanes see the same point), t2d = Q.T * 2d
+__device__ __forceinline__ fp_t quad_add(int q, const fp_t &c, const ge_t &Q, const fp_t &t2d) {
+  fp_t o = quad_xor1(c);  // lane 0: Y1, lane 1: X1, lane 2: T1, lane 3: Z1
+  fp_t m1 = fp_sel(q == 0, fp_sub(o, c), fp_sel(q == 1, fp_add(c, o), o));
+  fp_t m2 = fp_sel(q == 0, fp_sub(Q.Y, Q.X), fp_sel(q == 1, fp_add(Q.Y, Q.X), fp_sel(q == 2, t2d, Q.Z)));
+  fp_t s = fp_mul(m1, m2);
+  fp_t a = quad_from(s, 0), b = quad_from(s, 1), cc = quad_from(s, 2), d = quad_from(s, 3);
+  d = fp_add(d, d);
+  fp_t e = fp_sub(b, a), f = fp_sub(d, cc), g = fp_add(d, cc), h = fp_add(b, a);
+  return quad_efgh(q, e, f, g, h);
+}
+__global__ void __launch_bounds__(128) k_msm_horner_quad(const ge_t *sums, size_t rows, MsmGeom g, ge_t *out, uint8_t *comp) {
+  const int q = threadIdx.x & 3;
+  size_t row = (size_t)blockIdx.x * 32 + (threadIdx.x >> 2);
+  const bool live = row < rows;
+  if (!live) row = rows - 1;  // (whole quads stay in step for the shuffles)
+  const ge_t *p = sums + row * g.group;
+  const fp_t *first = &p[g.group - 1].X;
+  fp_t c = ld_fp(first + q);
+  for (int w = g.group - 2; w >= 0; w--) {
+    ge_t Q = ld_ge(p + w);
+    fp_t t2d = fp_mul(Q.T, fp_d2());
+#pragma unroll 1
+    for (int i = 0; i < g.W; i++) c = quad_dbl(q, c);
+    c = quad_add(q, c, Q, t2d);
+  }
+  ge_t h;
+  h.X = quad_from(c, 0); h.Y = quad_from(c, 1); h.Z = quad_from(c, 2); h.T = quad_from(c, 3);
+  if (!live || q != 0) return;
+  if (out) st_ge(out + row, h);
+  if (comp) {
+    uint8_t b[32];
+    ge_compress(h, b);
+    uint4 *o4 = reinterpret_cast<uint4 *>(comp + 32 * row);
+    uint32_t w[8];
+    for (int k = 0; k < 8; k++) w[k] = (uint32_t)b[4 * k] | ((uint32_t)b[4 * k + 1] << 8) | ((uint32_t)b[4 * k + 2] << 16) | ((uint32_t)b[4 * k + 3] << 24);
+    o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+static bool horner_quad() {  // VPIN_HORNER_QUAD=0: the one-thread-per-row pass (for comparison)
+  static const bool v = [] { const char *e = getenv("VPIN_HORNER_QUAD"); return !e || atoi(e) != 0; }();
+  return v;
+}
+static void launch_horner(const ge_t *sums, size_t rows, const MsmGeom &g, ge_t *d_out, uint8_t *d_comp, cudaStream_t st) {
+  ++g_kernel_launches;
+  if (horner_quad()) k_msm_horner_quad<<<(unsigned)((rows + 31) / 32), 128, 0, st>>>(sums, rows, g, d_out, d_comp);
+  else k_msm_horner<<<(unsigned)((rows + 31) / 32), 32, 0, st>>>(sums, rows, g, d_out, d_comp);
+}
 void launch_msm_segsum(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, cudaStream_t st, unsigned *d_counter,
                        uint32_t *d_seq_word, uint32_t seq) {
   size_t pairs = rows * g.group;
   SegsumPublish pub{d_counter, d_seq_word, seq};
-  ++g_kernel_launches, k_msm_segsum<<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(d_partial, pairs, segs, d_sums, pub);
+  const int lanes = msm_segsum_lanes(pairs, segs);
+  ++g_kernel_launches, k_msm_segsum<<<msm_segsum_blocks(pairs, lanes), 128, 0, st>>>(d_partial, pairs, segs, lanes, d_sums, pub);
 }
 void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, ge_t *d_out, uint8_t *d_comp,
                        cudaStream_t st) {
   const ge_t *sums = d_partial;
   if (segs > 1) {
     size_t pairs = rows * g.group;
-    ++g_kernel_launches, k_msm_segsum<<<(unsigned)((pairs + 3) / 4), 128, 0, st>>>(d_partial, pairs, segs, d_sums, SegsumPublish{nullptr, nullptr, 0});
+    const int lanes = msm_segsum_lanes(pairs, segs);
+    ++g_kernel_launches, k_msm_segsum<<<msm_segsum_blocks(pairs, lanes), 128, 0, st>>>(d_partial, pairs, segs, lanes, d_sums, SegsumPublish{nullptr, nullptr, 0});
     sums = d_sums;
   }
-  ++g_kernel_launches, k_msm_horner<<<(unsigned)((rows + 31) / 32), 32, 0, st>>>(sums, rows, g, d_out, d_comp);
+  launch_horner(sums, rows, g, d_out, d_comp, st);
 }
 
 // ------------------------------------------------------------------------------------------------ encodings

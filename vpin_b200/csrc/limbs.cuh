@@ -191,6 +191,146 @@ VPIN_HD void mul_8x8_p(uint32_t *t, const uint32_t *a, const uint32_t *b) {
 #endif
 }
 
+// r[0..2n) += (a[0], a[2], .., a[2n-2]) * b with one carry chain, cw += carry out (n = 1, 2, 3; n = 4 is mad_row)
+VPIN_HD void mad_chain3(uint32_t *r, const uint32_t *a, uint32_t b, uint32_t &cw) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %7, %10, %0; madc.hi.cc.u32 %1, %7, %10, %1;"
+      "madc.lo.cc.u32 %2, %8, %10, %2; madc.hi.cc.u32 %3, %8, %10, %3;"
+      "madc.lo.cc.u32 %4, %9, %10, %4; madc.hi.cc.u32 %5, %9, %10, %5;"
+      "addc.u32 %6, %6, 0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(cw)
+      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(b));
+#else
+  uint64_t c = 0;
+  for (int k = 0; k < 3; k++) {
+    uint64_t p = (uint64_t)a[2 * k] * b;
+    uint64_t lo = (uint64_t)r[2 * k] + (uint32_t)p + c;
+    r[2 * k] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)r[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+    r[2 * k + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+  cw += (uint32_t)c;
+#endif
+}
+VPIN_HD void mad_chain2(uint32_t *r, const uint32_t *a, uint32_t b, uint32_t &cw) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %5, %7, %0; madc.hi.cc.u32 %1, %5, %7, %1;"
+      "madc.lo.cc.u32 %2, %6, %7, %2; madc.hi.cc.u32 %3, %6, %7, %3;"
+      "addc.u32 %4, %4, 0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(cw)
+      : "r"(a[0]), "r"(a[2]), "r"(b));
+#else
+  uint64_t c = 0;
+  for (int k = 0; k < 2; k++) {
+    uint64_t p = (uint64_t)a[2 * k] * b;
+    uint64_t lo = (uint64_t)r[2 * k] + (uint32_t)p + c;
+    r[2 * k] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)r[2 * k + 1] + (uint32_t)(p >> 32) + (lo >> 32);
+    r[2 * k + 1] = (uint32_t)hi;
+    c = hi >> 32;
+  }
+  cw += (uint32_t)c;
+#endif
+}
+VPIN_HD void mad_chain1(uint32_t *r, const uint32_t *a, uint32_t b, uint32_t &cw) {
+#if defined(__CUDA_ARCH__)
+  asm("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(cw)
+      : "r"(a[0]), "r"(b));
+#else
+  uint64_t p = (uint64_t)a[0] * b;
+  uint64_t lo = (uint64_t)r[0] + (uint32_t)p;
+  r[0] = (uint32_t)lo;
+  uint64_t hi = (uint64_t)r[1] + (uint32_t)(p >> 32) + (lo >> 32);
+  r[1] = (uint32_t)hi;
+  cw += (uint32_t)(hi >> 32);
+#endif
+}
+
+// t[0..16) = a * a. The 28 products a_i a_j (i < j) are accumulated once - row i is two carry chains, the factors a_j with
+// j - i odd into the odd accumulator and those with j - i even into the even one, each chain's carry word a limb no later row
+// has filled yet - then doubled with funnel shifts and the eight squares a_i^2 (disjoint 64-bit slots) are added:
+// 36 IMAD.WIDE instead of the 64 of mul_8x8(t, a, a). The dependent chains that end a commitment (60 doublings of the window
+// Horner pass, 254 squarings of the ristretto encoding's inverse square root) are latency-bound on exactly this count.
+VPIN_HD void sqr_8x8(uint32_t *t, const uint32_t *a) {
+  uint32_t ev[16], od[16];  // od[k] has weight 2^(32 (k + 1))
+#pragma unroll
+  for (int k = 0; k < 16; k++) ev[k] = od[k] = 0;
+  mad_row(od + 0, a + 1, a[0], od[8]);       // a0 * (a1, a3, a5, a7)
+  mad_chain3(ev + 2, a + 2, a[0], ev[8]);    // a0 * (a2, a4, a6)
+  mad_chain3(od + 2, a + 2, a[1], od[8]);    // a1 * (a2, a4, a6)
+  mad_chain3(ev + 4, a + 3, a[1], ev[10]);   // a1 * (a3, a5, a7)
+  mad_chain3(od + 4, a + 3, a[2], od[10]);   // a2 * (a3, a5, a7)
+  mad_chain2(ev + 6, a + 4, a[2], ev[10]);   // a2 * (a4, a6)
+  mad_chain2(od + 6, a + 4, a[3], od[10]);   // a3 * (a4, a6)
+  mad_chain2(ev + 8, a + 5, a[3], ev[12]);   // a3 * (a5, a7)
+  mad_chain2(od + 8, a + 5, a[4], od[12]);   // a4 * (a5, a7)
+  mad_chain1(ev + 10, a + 6, a[4], ev[12]);  // a4 * a6
+  mad_chain1(od + 10, a + 6, a[5], od[12]);  // a5 * a6
+  mad_chain1(ev + 12, a + 7, a[5], ev[14]);  // a5 * a7
+  mad_chain1(od + 12, a + 7, a[6], od[14]);  // a6 * a7
+  // s = ev + (od << 32) < 2^511
+  uint32_t s[16];
+  s[0] = ev[0];
+#if defined(__CUDA_ARCH__)
+  uint32_t cy;
+  asm("add.cc.u32 %0, %8, %15; addc.cc.u32 %1, %9, %16; addc.cc.u32 %2, %10, %17; addc.cc.u32 %3, %11, %18;"
+      "addc.cc.u32 %4, %12, %19; addc.cc.u32 %5, %13, %20; addc.cc.u32 %6, %14, %21; addc.u32 %7, 0, 0;"
+      : "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(cy)
+      : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+        "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]));
+  asm("add.cc.u32 %8, %8, 0xffffffff;"
+      "addc.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20;"
+      "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.u32 %7, %16, %24;"
+      : "=r"(s[8]), "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12]), "=r"(s[13]), "=r"(s[14]), "=r"(s[15]), "+r"(cy)
+      : "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
+        "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+#else
+  {
+    uint64_t c = 0;
+    for (int k = 1; k < 16; k++) {
+      c += (uint64_t)ev[k] + od[k - 1];
+      s[k] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+#endif
+  // t = 2 s + sum_i a_i^2 2^(64 i)
+  uint32_t sh[16], dg[16];
+  sh[0] = s[0] << 1;
+#pragma unroll
+  for (int k = 1; k < 16; k++) sh[k] = (s[k] << 1) | (s[k - 1] >> 31);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int i = 0; i < 8; i++) asm("mul.lo.u32 %0, %2, %2; mul.hi.u32 %1, %2, %2;" : "=r"(dg[2 * i]), "=r"(dg[2 * i + 1]) : "r"(a[i]));
+  uint32_t cz;
+  asm("add.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20;"
+      "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.cc.u32 %7, %16, %24; addc.u32 %8, 0, 0;"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(cz)
+      : "r"(sh[0]), "r"(sh[1]), "r"(sh[2]), "r"(sh[3]), "r"(sh[4]), "r"(sh[5]), "r"(sh[6]), "r"(sh[7]),
+        "r"(dg[0]), "r"(dg[1]), "r"(dg[2]), "r"(dg[3]), "r"(dg[4]), "r"(dg[5]), "r"(dg[6]), "r"(dg[7]));
+  asm("add.cc.u32 %8, %8, 0xffffffff;"
+      "addc.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20;"
+      "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.u32 %7, %16, %24;"
+      : "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]), "+r"(cz)
+      : "r"(sh[8]), "r"(sh[9]), "r"(sh[10]), "r"(sh[11]), "r"(sh[12]), "r"(sh[13]), "r"(sh[14]), "r"(sh[15]),
+        "r"(dg[8]), "r"(dg[9]), "r"(dg[10]), "r"(dg[11]), "r"(dg[12]), "r"(dg[13]), "r"(dg[14]), "r"(dg[15]));
+#else
+  for (int i = 0; i < 8; i++) {
+    uint64_t p = (uint64_t)a[i] * a[i];
+    dg[2 * i] = (uint32_t)p;
+    dg[2 * i + 1] = (uint32_t)(p >> 32);
+  }
+  uint64_t c = 0;
+  for (int k = 0; k < 16; k++) {
+    c += (uint64_t)sh[k] + dg[k];
+    t[k] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+}
+
 // ---- Montgomery reduction rows for l = 2^252 + 27742317777372353535851937790883648493 (limbs P0..P3, 0, 0, 0, 2^28) ----
 #define VPIN_L_P0 0x5cf5d3edu
 #define VPIN_L_P1 0x5812631au
