@@ -218,7 +218,10 @@ struct Acc8 {
   }
 };
 // grid (ceil(rows / 128), kMsmGroup, segs), block 128: thread = (row, local window w', column segment)
-template <class Acc>
+// kPrefetch: 1 = the table entries of the NEXT column are requested into L2 (prefetch.global.L2) while the current column's
+// additions run: the entry address depends on a digit load, and that two-step chain to DRAM is what the loop's long-scoreboard
+// stalls wait for (2.7 of 13.4 stall cycles per issue in profiles/r2_ncu_msm_accumulate_summary.csv)
+template <class Acc, int kPrefetch = 0>
 __device__ __forceinline__ void msm_accumulate_body(const niels_t *table, const MsmGeom &g, const uint16_t *digits, size_t rows, size_t cols,
                                                     size_t cols_total, size_t extra_base, size_t stride, size_t n_bases, size_t seg_len,
                                                     ge_t *partial, const uint32_t *wmask) {
@@ -243,6 +246,21 @@ __device__ __forceinline__ void msm_accumulate_body(const niels_t *table, const 
   acc.init();
   for (size_t col = c0; col < c1; col++) {
     size_t base = col < cols ? col : extra_base;
+    if (kPrefetch && col + 1 < c1) {
+      size_t nbase = col + 1 < cols ? col + 1 : extra_base;
+#pragma unroll
+      for (int t = 0; t < kMsmSub; t++) {
+        int w = t * g.group + wl;
+        if (w < g.windows) {
+          uint32_t d = dg[(size_t)w * plane + col + 1];
+          if (d) {
+            const char *e = reinterpret_cast<const char *>(table + ((size_t)t * n_bases + nbase) * g.table + ((d & 0x7fffu) - 1u));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(e));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(e + 64));  // (a 96-byte entry at 32-byte alignment can straddle a 128-byte line)
+          }
+        }
+      }
+    }
 #pragma unroll 1
     for (int t = 0; t < kMsmSub; t++) {  // not unrolled: one copy of the 7-multiplication body keeps the loop inside the I-cache
       int w = t * g.group + wl;
@@ -257,6 +275,7 @@ __device__ __forceinline__ void msm_accumulate_body(const niels_t *table, const 
                           size_t stride, size_t n_bases, size_t seg_len, ge_t *partial, const uint32_t *wmask
 #define VPIN_MSM_ACC_PASS table, g, digits, rows, cols, cols_total, extra_base, stride, n_bases, seg_len, partial, wmask
 __global__ void __launch_bounds__(kMsmRowsPerBlock, 6) k_msm_accumulate(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<0>>(VPIN_MSM_ACC_PASS); }
+__global__ void __launch_bounds__(kMsmRowsPerBlock, 6) k_msm_accumulate_pf(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<0>, 1>(VPIN_MSM_ACC_PASS); }
 // 0x8888: the odd-column products of rows 1, 3, 5, 7 accumulate on the ALU pipe (the best of the row patterns tried)
 __global__ void __launch_bounds__(kMsmRowsPerBlock, 5) k_msm_accumulate_a2(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc8<0x8888u>>(VPIN_MSM_ACC_PASS); }
 __global__ void __launch_bounds__(kMsmRowsPerBlock, 4) k_msm_accumulate_f9p0(VPIN_MSM_ACC_ARGS) { msm_accumulate_body<Acc9<0>>(VPIN_MSM_ACC_PASS); }
@@ -349,6 +368,7 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
     case 1: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p0); break;
     case 2: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p1); break;
     case 12: VPIN_MSM_LAUNCH(k_msm_accumulate_a2); break;
+    case 20: VPIN_MSM_LAUNCH(k_msm_accumulate_pf); break;
     default: VPIN_MSM_LAUNCH(k_msm_accumulate); break;
   }
 #undef VPIN_MSM_LAUNCH

@@ -14,7 +14,22 @@ namespace vpin {
 
 class Keccak {
  public:
+  // The permutation is compiled twice: plain x86-64, and with BMI1/BMI2 (ANDN for chi, RORX for rho: 0.33 instead of 0.46 - 0.67 us
+  // per permutation on the development host) - chosen once at run time. A CNN-A proof absorbs ~0.5 MB through ~4500 permutations
+  // on the host's critical path.
   static void permute(uint64_t a[25]) {
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const bool bmi = __builtin_cpu_supports("bmi") && __builtin_cpu_supports("bmi2");
+    if (bmi) { permute_bmi(a); return; }
+#endif
+    permute_body(a);
+  }
+
+ private:
+#if defined(__x86_64__) && defined(__GNUC__)
+  __attribute__((target("bmi,bmi2"))) static void permute_bmi(uint64_t a[25]) { permute_body(a); }
+#endif
+  __attribute__((always_inline)) static inline void permute_body(uint64_t a[25]) {
     static const uint64_t kRound[24] = {
         0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
         0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
@@ -47,9 +62,7 @@ class Keccak {
     a[10] = a10; a[11] = a11; a[12] = a12; a[13] = a13; a[14] = a14; a[15] = a15; a[16] = a16; a[17] = a17; a[18] = a18; a[19] = a19;
     a[20] = a20; a[21] = a21; a[22] = a22; a[23] = a23; a[24] = a24;
   }
-
- private:
-  static uint64_t rotl(uint64_t v, int n) { return n == 0 ? v : (v << n) | (v >> (64 - n)); }
+  __attribute__((always_inline)) static inline uint64_t rotl(uint64_t v, int n) { return n == 0 ? v : (v << n) | (v >> (64 - n)); }
 };
 
 // SHAKE256 extendable-output function (rate 136 bytes)
@@ -123,12 +136,18 @@ class Strobe {
     cursor_ = 0;
     op_start_ = 0;
   }
-  void mix(const void *d, size_t n) {
+  void mix(const void *d, size_t n) {  // (run by run up to the end of the rate: the inner loop has no branch and vectorises)
     const uint8_t *p = (const uint8_t *)d;
     uint8_t *s = bytes();
-    for (size_t i = 0; i < n; i++) {
-      s[cursor_] ^= p[i];
-      if (++cursor_ == kRate) flush();
+    while (n) {
+      size_t run = (size_t)kRate - cursor_;
+      if (run > n) run = n;
+      uint8_t *dst = s + cursor_;
+      for (size_t i = 0; i < run; i++) dst[i] ^= p[i];
+      p += run;
+      n -= run;
+      cursor_ = (uint8_t)(cursor_ + run);
+      if (cursor_ == kRate) flush();
     }
   }
   void start(uint8_t flags) {
