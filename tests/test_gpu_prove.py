@@ -139,16 +139,18 @@ def test_unsatisfied_witness_is_reported(ctx):
 
 
 def test_derefs_row_half_on_the_side_stream(ctx, monkeypatch):
-    """VPIN_DEREFS_EARLY=1: the row half of the derefs commitment is committed on a second stream while the second sumcheck
-    runs (prover.cu, SideScope); the proof bytes must not change."""
+    """The row half of the derefs commitment is committed on a second, low-priority stream while the second sumcheck runs
+    (prover.cu, SideScope; the default on one GPU, VPIN_DEREFS_EARLY=0 keeps everything on one stream); the proof bytes must
+    not depend on it."""
     from vpin_b200 import api
 
     weights, px, py = W.synth_point_mult(7)
     dims, inst, vp, vi, v, inputs = api.point_mult(ctx, weights, px, py)
     sq, sp = W.tape_seeds()
+    early = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp)
+    monkeypatch.setenv("VPIN_DEREFS_EARLY", "0")
     base = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp)
     monkeypatch.setenv("VPIN_DEREFS_EARLY", "1")
-    early = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp)
     again = api.prove_flow(ctx, dims, inst, vp, vi, v, inputs, sq, sp)
     assert early["proof"] == base["proof"] == again["proof"] and early["comm"] == base["comm"]
 

@@ -76,7 +76,8 @@ vpin_status vpin_ctx_create_ex(int32_t cuda_device, int32_t high_priority, vpin_
     {
       int lo = 0, hi = 0;  // (numerically lower = more urgent; default streams sit at `lo`)
       VPIN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      VPIN_CUDA(cudaStreamCreateWithPriority(&ctx->st, cudaStreamNonBlocking, high_priority ? hi : lo));
+      // (a default context sits one step above the lowest priority: its side stream - SideScope - runs below it)
+      VPIN_CUDA(cudaStreamCreateWithPriority(&ctx->st, cudaStreamNonBlocking, high_priority ? hi : (lo - 1 >= hi ? lo - 1 : lo)));
     }
     block_cache_register(ctx->st);
     block_cache_set_pressure_hook(ctx->st, [ctx]() {

@@ -196,12 +196,18 @@ void prof_drain(Ctx *c) {
   c->prof.pending.clear();
 }
 
+// resident MSM blocks per SM while a commitment runs on the side stream (VPIN_SIDE_MSM_BLOCKS, default 3 of the usual 6)
+int side_msm_blocks_per_sm() {
+  static const int v = [] { const char *e = getenv("VPIN_SIDE_MSM_BLOCKS"); int x = e ? atoi(e) : 3; return x < 0 ? 0 : x; }();
+  return v;
+}
 SideScope::SideScope(Ctx *ctx) : c(ctx) {
   VPIN_REQUIRE(!c->on_side && c->world == 1, VPIN_ERR_BAD_ARGUMENT, "side stream: nested or distributed use");
   if (!c->st_side) {
-    int prio = 0;
-    VPIN_CUDA(cudaStreamGetPriority(c->st, &prio));
-    VPIN_CUDA(cudaStreamCreateWithPriority(&c->st_side, cudaStreamNonBlocking, prio));
+    // the LOWEST priority of the device: what runs here fills gaps, the main stream's round kernels take free resources first
+    int lo = 0, hi = 0;
+    VPIN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    VPIN_CUDA(cudaStreamCreateWithPriority(&c->st_side, cudaStreamNonBlocking, lo));
     block_cache_register(c->st_side);
     VPIN_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     VPIN_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -440,7 +446,8 @@ static void hyrax_rows_local(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_
     }
     {
       ProfScope ps(ctx, PROF_MSM_ACCUMULATE, pts, 0);
-      launch_msm_accumulate(g.table(), digits.p, nr, cols, d_blinds != nullptr, blind_base, segs, partial.p, ctx->st, d_wmask);
+      launch_msm_accumulate(g.table(), digits.p, nr, cols, d_blinds != nullptr, blind_base, segs, partial.p, ctx->st, d_wmask,
+                            ctx->on_side ? side_msm_blocks_per_sm() : 0);
     }
     ProfScope ps(ctx, PROF_MSM_FINISH, pts, 0);
     launch_msm_finish(partial.p, nr, segs, geom, sums.p, d_points ? d_points + r0 : nullptr, d_comp ? d_comp + 32 * r0 : nullptr, ctx->st);

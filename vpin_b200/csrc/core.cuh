@@ -217,6 +217,7 @@ struct vpin_ctx_impl {
 // While alive, everything the context enqueues (kernels, DevVec allocations, profiling events) goes to the side stream, which
 // starts after what the main stream holds now; join() makes the main stream wait for it. Not for distributed contexts (the
 // communicator's collectives must stay on one stream).
+int side_msm_blocks_per_sm();
 struct SideScope {
   Ctx *c;
   explicit SideScope(Ctx *ctx);

@@ -351,7 +351,7 @@ size_t msm_num_segments(size_t rows, size_t cols_total, const MsmGeom &g) {
   return segs;
 }
 void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t rows, size_t cols, bool has_extra, size_t extra_base,
-                           size_t segs, ge_t *d_partial, cudaStream_t st, const uint32_t *d_wmask) {
+                           size_t segs, ge_t *d_partial, cudaStream_t st, const uint32_t *d_wmask, int blocks_per_sm) {
   size_t cols_total = cols + (has_extra ? 1 : 0);
   size_t stride = msm_col_stride(cols_total);
   size_t seg_len = (cols_total + segs - 1) / segs;
@@ -363,6 +363,14 @@ void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t r
   }
   dim3 grid((unsigned)((rows + kMsmRowsPerBlock - 1) / kMsmRowsPerBlock), t.geom.group, (unsigned)segs);
   ++g_kernel_launches;
+  if (blocks_per_sm > 0 && blocks_per_sm < 6) {  // occupancy cap: 227 KB of shared memory per SM / blocks_per_sm, minus a margin
+    static const bool ok = cudaFuncSetAttribute(k_msm_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+    size_t smem = ok ? (size_t)(220 * 1024) / (blocks_per_sm + 1) + 1024 : 0;  // more than a (cap + 1)-th of the SM: cap + 1 blocks cannot fit
+    if (smem > 200 * 1024) smem = 200 * 1024;
+    k_msm_accumulate<<<grid, kMsmRowsPerBlock, smem, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride, t.n_bases, seg_len,
+                                                          d_partial, d_wmask);
+    return;
+  }
 #define VPIN_MSM_LAUNCH(K) K<<<grid, kMsmRowsPerBlock, 0, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride, t.n_bases, seg_len, d_partial, d_wmask)
   switch (msm_variant()) {
     case 1: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p0); break;

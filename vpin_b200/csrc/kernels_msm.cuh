@@ -69,8 +69,11 @@ void launch_recode(const fl_t *d_scalars, size_t rows, size_t cols, size_t ld, c
 size_t msm_num_segments(size_t rows, size_t cols_total, const MsmGeom &g);
 // partial[(row * geom.group + w') * segs + seg] = sum over the segment's columns and the kMsmSub sub-tables; the optional extra
 // column (index cols) uses table base `extra_base`
+// blocks_per_sm (0 = as many as fit, six): a cap on the kernel's resident blocks per SM, enforced with a dynamic shared-memory
+// request nobody reads. A commitment that runs on a low-priority side stream UNDER latency-bound round kernels (the row half of
+// the derefs, prover.cu) must leave registers free on every SM, or those kernels' blocks wait for several 256-us blocks to retire.
 void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t rows, size_t cols, bool has_extra, size_t extra_base,
-                           size_t segs, ge_t *d_partial, cudaStream_t st, const uint32_t *d_wmask = nullptr);
+                           size_t segs, ge_t *d_partial, cudaStream_t st, const uint32_t *d_wmask = nullptr, int blocks_per_sm = 0);
 // out[row] = sum_w' 2^(W*w') sum_seg partial[row][w'][seg]; d_sums: rows * geom.group scratch points (used when segs > 1);
 // d_out (points) and d_comp (32-byte encodings) are optional
 void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, ge_t *d_out, uint8_t *d_comp,

@@ -1478,12 +1478,16 @@ std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &d
   VPIN_REQUIRE(dpc.L * dpc.R == 8 * N, VPIN_ERR_SIZE_MISMATCH, "derefs gens");
   DevVec<uint8_t> derefs_comm(32 * dpc.L, st);
   const size_t derefs_row_rows = dpc.L / 8 * 3;  // the Hyrax rows that hold row A | row B | row C
-  // OFF by default (VPIN_DEREFS_EARLY=1 turns it on): measured on a B200 at CNN A it hides 4 ms of the commitment but the MSM's
-  // resident blocks (256 us each, six per SM) keep the second sumcheck's round kernels waiting for registers - phase two 2.1 ->
-  // 5.8 ms, SNARK::prove 39.5 -> 40.7 ms. Single GPU only (a communicator's collectives stay on one stream) and not for the
-  // largest shapes (the side stream's own block cache would come out of an HBM that is planned to the last gigabyte).
+  // ON by default (VPIN_DEREFS_EARLY=0 turns it off). The side stream has the device's lowest priority and its MSM kernel is capped
+  // at three resident blocks per SM (kernels_msm.cuh): without both - first measurement of round 2 - the MSM's resident blocks
+  // (256 us each, six per SM, no registers left) kept the second sumcheck's round kernels waiting, phase two 2.1 -> 5.8 ms, a net
+  // loss. With them, CNN A on a B200: phase two 1.8 -> 2.9 ms, evaluation proof 1.6 -> 2.6 ms, derefs commitment 8.7 -> 4.8 ms,
+  // SNARK::prove 34.2 -> 31.9 ms (profiles/r2_derefs_early.log). Single GPU only (a communicator's collectives stay on one
+  // stream) and not for the largest shapes (the side stream's own block cache would come out of an HBM that is planned to the
+  // last gigabyte).
   const char *early_env = getenv("VPIN_DEREFS_EARLY");
-  const bool derefs_early = early_env && atoi(early_env) != 0 && ctx->world == 1 && dpc.L % 8 == 0 && N <= ((size_t)1 << 23);
+  const bool derefs_early = !(early_env && atoi(early_env) == 0) && ctx->world == 1 && !ctx->prof.on && dpc.L % 8 == 0 &&
+                            derefs_row_rows >= 48 && N <= ((size_t)1 << 23);
   if (derefs_early) {
     SideScope side(ctx);
     hyrax_rows(ctx, *g.eval_label, derefs.p, derefs_row_rows, dpc.R, dpc.R, nullptr, 0, nullptr, derefs_comm.p);
