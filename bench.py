@@ -156,14 +156,20 @@ class InstanceState:
                 torch.cuda.synchronize()
                 api.dev_to_mont(ctx, d, self.n, d)
                 self.d_assign.append(d)
-        # SNARK::encode does not depend on the witness: on one GPU it runs on a second context (own stream and scratch) from a
-        # helper thread while this thread commits to the three assignments (ctypes releases the GIL; a Rust shim would use
-        # std::thread::scope). VPIN_BENCH_OVERLAP_ENCODE=0 keeps the calls strictly sequential. On a
-        # distributed context encode's commitments are sharded by the context's communicator, so it stays where it is.
-        self.aux = self.enc_pool = None
-        if getattr(ctx, "world", 1) == 1 and os.environ.get("VPIN_BENCH_OVERLAP_ENCODE", "1") == "1":
+        # SNARK::encode does not depend on the witness: on one GPU a helper thread runs it on a second context (own stream and
+        # scratch, this instance's priority) while this thread commits to the three assignments (ctypes releases the GIL; a Rust
+        # shim would use std::thread::scope). VPIN_BENCH_OVERLAP_ENCODE=0 keeps the calls strictly
+        # sequential. On a distributed context encode's commitments are sharded by the context's communicator, so it stays there.
+        # Mode "1" is a measured alternative that lost: vPIN's my_lib_prove reads only encode's dense tables (the computation
+        # commitment never enters the prover's transcript, VP/commit_test.rs:75), so the commitment's MSMs can run on a BACKGROUND
+        # context (lowest stream priority, one MSM block per SM) underneath the proof - but 4.5 ms of MSM moved there slowed the
+        # multiplier-bound round kernels of the proof by 7 ms (CNN A step 45.2 against 41.3 ms, profiles/r2_encode_overlap_modes.log).
+        self.aux = self.bg = self.enc_pool = None
+        self.enc_mode = os.environ.get("VPIN_BENCH_OVERLAP_ENCODE", "2")
+        if getattr(ctx, "world", 1) == 1 and self.enc_mode in ("1", "2"):
             from concurrent.futures import ThreadPoolExecutor
             self.aux = api.Context(ctx.device, high_priority=high_priority)
+            self.bg = api.Context(ctx.device, background=True) if self.enc_mode == "1" else None
             self.enc_pool = ThreadPoolExecutor(max_workers=1)
         L = self.gens.L
         self.d_pts = [torch.empty(32 * L, dtype=torch.uint8, device=dev) for _ in range(4)]
@@ -176,33 +182,47 @@ class InstanceState:
         return sum(a.nbytes for a in self.coo) + 4 * 32 * self.n + 2 * 32 * L * 2 + 64 * L + len(self.inputs)
 
     def encode(self, overlap=True, inst=None, gens=None):
-        """SNARK::encode of the step: a future when it runs beside the commitments, else the result itself"""
+        """SNARK::encode of the step -> (decommitment, commitment), each a callable that waits for its half: on the helper
+        thread the tables are made first and the commitment right behind them (one worker), else both are ready at once"""
         from vpin_b200 import api
         inst, gens = inst or self.inst, gens or self.gens
+        if overlap and self.aux is not None and self.enc_mode == "2":
+            f = self.enc_pool.submit(api.SNARK.encode, inst, gens, self.aux)
+            return (lambda: f.result()[1]), (lambda: f.result()[0])
         if overlap and self.aux is not None:
-            return self.enc_pool.submit(api.SNARK.encode, inst, gens, self.aux)
-        return api.SNARK.encode(inst, gens)
+            f_tab = self.enc_pool.submit(api.encode_tables, inst, gens, self.aux)
+            box = {}
+
+            def get_decomm():  # called when the witness commitments are done: the commitment's MSMs start now, under the proof
+                d = f_tab.result()
+                box["f"] = self.enc_pool.submit(api.encode_commit, d, gens, self.bg)
+                return d
+            return get_decomm, (lambda: box["f"].result())
+        comm, decomm = api.SNARK.encode(inst, gens)
+        return (lambda: decomm), (lambda: comm)
 
     def close(self):
         if self.enc_pool is not None:
             self.enc_pool.shutdown()
-        if self.aux is not None:
-            self.aux.close()
-        self.aux = self.enc_pool = None
+        for c in (self.aux, self.bg):
+            if c is not None:
+                c.close()
+        self.aux = self.bg = self.enc_pool = None
 
     def step_resident(self, ctx, seeds, overlap=True):
         from vpin_b200 import api
         sq, sp = seeds
-        enc = self.encode(overlap)
+        get_decomm, get_comm = self.encode(overlap)
         tape = api.RandomTape(b"\x02", sq)
         api.dev_poly_commit(ctx, self.gens, self.d_assign[0], self.n, tape, self.d_pts[0], self.d_blinds[0])
         api.dev_poly_commit(ctx, self.gens, self.d_assign[1], self.n, tape, self.d_pts[1], self.d_blinds[1])
         api.dev_poly_commit_with_blinds(ctx, self.gens, self.d_assign[2], self.n, self.d_blinds[0], self.d_blinds[1], self.d_pts[2],
                                         self.d_blinds[2])
         api.dev_commitments_add(ctx, self.d_pts[0], self.d_pts[1], self.gens.L, self.d_pts[3])
-        comm, decomm = enc.result() if hasattr(enc, "result") else enc
+        decomm = get_decomm()
         wit = api.DeviceWitness(ctx, self.gens, self.d_assign[2], self.n, self.d_pts[3], self.d_blinds[2])
         proof = api.my_lib_prove_resident(self.inst, decomm, wit, self.inputs, self.gens, TRANSCRIPT_LABEL, sp)
+        comm = get_comm()
         return comm, proof
 
     def step_e2e(self, ctx, seeds):
@@ -215,15 +235,16 @@ class InstanceState:
         vp, vi, v = (t.numpy() for t in self.h_assign)
         sq, sp = seeds
         gens = api.SNARKGens(ctx, *self.dims); T.append(time.time())
-        enc = self.encode(True, inst, gens); T.append(time.time())
+        get_decomm, get_comm = self.encode(True, inst, gens); T.append(time.time())
         tape = api.RandomTape(b"\x02", sq)
         c_para, b_para = api.dense_mlpoly_commit(ctx, gens, api._buf(vp), tape, n=self.n)
         c_input, b_input = api.dense_mlpoly_commit(ctx, gens, api._buf(vi), tape, n=self.n)
         c_vars, b_vars = api.my_dense_mlpoly_commit(ctx, gens, api._buf(v), b_para, b_input, n=self.n)
         combined = ctx.commitments_add(c_para, c_input)
-        comm, decomm = enc.result() if hasattr(enc, "result") else enc; T.append(time.time())
-        proof = api.my_lib_prove(inst, decomm, api._buf(v), self.inputs, gens, TRANSCRIPT_LABEL, combined, b_vars, sp, n=self.n); T.append(time.time())
-        del inst, decomm, gens
+        decomm = get_decomm(); T.append(time.time())
+        proof = api.my_lib_prove(inst, decomm, api._buf(v), self.inputs, gens, TRANSCRIPT_LABEL, combined, b_vars, sp, n=self.n)
+        comm = get_comm(); T.append(time.time())
+        del inst, decomm, gens, get_decomm, get_comm
         T.append(time.time())
         # per-call wall times of this step (Instance::new, SNARKGens::new, encode, commits, prove, handle release), kept for the
         # slowest step of the leg (bench line: e2e.slowest_step_calls_ms)
@@ -403,7 +424,7 @@ class Leg:
         import gc
         gc.collect()
         gc.disable()  # the harness is Python: keep its cyclic collector (7 ms pauses) out of the timed steps
-        launches = lambda: sum(s_.ctx.kernel_launches + (s_.aux.kernel_launches if s_.aux is not None else 0) for s_ in self.states)
+        launches = lambda: sum(s_.ctx.kernel_launches + sum(c.kernel_launches for c in (s_.aux, s_.bg) if c is not None) for s_ in self.states)
         l0 = launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
@@ -709,7 +730,8 @@ def run_b200(args):
         "dtype": "u32 limbs (8x32 Montgomery F_l, 8x32 F_p; IMAD.WIDE)", "data": "synthetic",
         "config": {"workload": tag, "point_mults": wl["m"], "point_adds": wl["n_add"], "instances": instances,
                    "l2": "256 MB buffer written between steps; working set ~2 GB >> 126 MB L2",
-                   "concurrency": "the network's independent instances are proved concurrently (one context + host thread each)",
+                   "concurrency": "the network's independent instances are proved concurrently (one context + host thread each); on one GPU "
+                                  "SNARK::encode runs on a second context of its instance beside the three witness commitments",
                    "parallelism": "1 GPU" if world == 1 else
                                   f"ONE {tag} proof on {world} GPUs: every rank replays the transcript; the Hyrax commitment rows are split "
                                   "across the ranks (NCCL all-gather of 32 B per row); the product circuits of the memory check are dealt "

@@ -66,6 +66,8 @@ vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out);
  * contexts share a GPU (a network's independent instances are proved concurrently, one context each) the thread blocks
  * of this one are scheduled first — give it to the instance on the critical path (the point-mult proof). */
 vpin_status vpin_ctx_create_ex(int32_t cuda_device, int32_t high_priority, vpin_ctx **out);
+/* high_priority < 0: a BACKGROUND context - the device's lowest stream priority and at most one resident MSM block per SM.
+ * For work nothing waits for: vpin_encode_commit (below) while my_lib_prove runs on another context of the same device. */
 void vpin_ctx_destroy(vpin_ctx *ctx);
 /* Multi-GPU, one process (and one context) per GPU. Rank 0 calls vpin_nccl_unique_id and ships the 128 bytes to the other
  * ranks by any means (bench.py: a torch.distributed broadcast); every rank then calls vpin_ctx_init_distributed. After
@@ -114,6 +116,16 @@ vpin_status vpin_instance_export_coo(vpin_ctx *ctx, const vpin_instance *inst, u
  * comm_out receives bincode(ComputationCommitment); *decomm keeps the dense representation in HBM. */
 vpin_status vpin_encode(vpin_ctx *ctx, const vpin_instance *inst, const vpin_gens *gens, uint8_t *comm_out,
                         uint64_t comm_cap, uint64_t *comm_len, vpin_decomm **decomm);
+/* The two halves of SNARK::encode, for a driver that overlaps them with the rest of its flow:
+ *  vpin_encode_tables: the dense representation my_lib_prove reads (SP/sparse_mlpoly.rs:382-438 MultiSparseMatPolynomialAsDense,
+ *    AddrTimestamps::new :232-265) - no commitment. The handle may be used by a proof on any context of the device.
+ *  vpin_encode_commit: the two Hyrax commitments over it (SP/sparse_mlpoly.rs:500-520) -> bincode(ComputationCommitment).
+ * vPIN's my_lib_prove never appends the computation commitment to its transcript (VP/commit_test.rs:75, unlike SP/lib.rs:377), so
+ * the proof does not wait for the second half: run it on a background context (vpin_ctx_create_ex(.., -1, ..)) under the proof.
+ * vpin_encode == vpin_encode_tables + vpin_encode_commit on one context. */
+vpin_status vpin_encode_tables(vpin_ctx *ctx, const vpin_instance *inst, const vpin_gens *gens, vpin_decomm **decomm);
+vpin_status vpin_encode_commit(vpin_ctx *ctx, const vpin_decomm *decomm, const vpin_gens *gens, uint8_t *comm_out,
+                               uint64_t comm_cap, uint64_t *comm_len);
 void vpin_decomm_destroy(vpin_decomm *decomm);
 
 /* ---- DensePolynomial::commit(&gens.gens_r1cs_sat.gens_pc, Some(&mut tape))   SP/dense_mlpoly.rs:193-218 ----------

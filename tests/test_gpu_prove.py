@@ -206,9 +206,11 @@ def test_two_contexts_prove_concurrently():
             assert proof == ref.proof, name
 
 
-def test_encode_on_a_second_context_beside_the_commitments(ctx):
-    """SNARK::encode run on a second context from a helper thread while the first context commits to the assignments (what
-    bench.py's step does on one GPU): the same computation commitment, and the proof made with that decommitment is the oracle's."""
+def test_encode_on_a_background_context_under_the_commitments_and_the_proof(ctx):
+    """What bench.py's step does on one GPU: a helper thread runs SNARK::encode on a background context - the dense tables while
+    the first context commits to the assignments, the computation commitment's MSMs while it proves (my_lib_prove reads the
+    tables only). The same computation commitment as the one-call encode, and the proof made with that decommitment is the
+    oracle's."""
     from concurrent.futures import ThreadPoolExecutor
     from vpin_b200 import api
 
@@ -218,21 +220,27 @@ def test_encode_on_a_second_context_beside_the_commitments(ctx):
     ref = O.Flow(built, sq, sp, verify=True)
     dims, inst, vp, vi, v, inputs = api.point_mult(ctx, weights, mx, my)
     gens = api.SNARKGens(ctx, *dims)
-    aux = api.Context(0)
+    aux = api.Context(0, background=True)
     with ThreadPoolExecutor(max_workers=1) as pool:
         for _ in range(2):
-            fut = pool.submit(api.SNARK.encode, inst, gens, aux)
+            f_tab = pool.submit(api.encode_tables, inst, gens, aux)
+            f_comm = pool.submit(lambda: api.encode_commit(f_tab.result(), gens, aux))
             tape = api.RandomTape(b"\x02", sq)
             p_para, p_input, p_vars = inst.pad(vp), inst.pad(vi), inst.pad(v)
             c_para, b_para = api.dense_mlpoly_commit(ctx, gens, p_para, tape)
             c_input, b_input = api.dense_mlpoly_commit(ctx, gens, p_input, tape)
             c_vars, b_vars = api.my_dense_mlpoly_commit(ctx, gens, p_vars, b_para, b_input)
             combined = ctx.commitments_add(c_para, c_input)
-            comm, decomm = fut.result()
+            decomm = f_tab.result()
             proof = api.my_lib_prove(inst, decomm, p_vars, inputs, gens, b"snark_example", combined, b_vars, sp)
+            comm = f_comm.result()
             assert comm == ref.comm and c_vars == ref.comm_vars
             assert proof == ref.proof
             del decomm
+        # the one-call form on a second, ordinary context
+        comm2, decomm2 = api.SNARK.encode(inst, gens, aux)
+        assert comm2 == ref.comm
+        del decomm2
     del gens, inst
     aux.close()
 

@@ -67,10 +67,12 @@ def _buf(b):
 class Context:
     """One per host thread (the reference API is single-threaded: &mut Transcript, &mut RandomTape)."""
 
-    def __init__(self, device=0, high_priority=False):
+    def __init__(self, device=0, high_priority=False, background=False):
+        """high_priority: the device's most urgent stream priority (the proof on the critical path); background: the lowest
+        priority and one resident MSM block per SM (work nothing waits for, see SNARK.encode_commit)"""
         self._h = C.c_void_p()
         self.device = device
-        st = lib().vpin_ctx_create_ex(C.c_int32(device), C.c_int32(1 if high_priority else 0), C.byref(self._h))
+        st = lib().vpin_ctx_create_ex(C.c_int32(device), C.c_int32(-1 if background else (1 if high_priority else 0)), C.byref(self._h))
         if st != 0:
             raise VpinError(st, "vpin_ctx_create failed (no usable CUDA device?)")
 
@@ -424,6 +426,31 @@ class SNARK:
         st = lib().vpin_encode(ctx._h, inst._h, gens._h, out, C.c_uint64(cap), C.byref(n), C.byref(d))
         ctx.check(st)
         return C.string_at(out, n.value), Decommitment(d)
+
+
+def _comm_buffer(ctx):
+    cap = 64 + 32 * (1 << 16) * 2
+    out = getattr(ctx, "_comm_buf", None)  # one 4 MB output buffer per context, reused (no mmap / munmap per call)
+    if out is None:
+        out = ctx._comm_buf = C.create_string_buffer(cap)
+    return out, cap
+
+
+def encode_tables(inst, gens, ctx=None):
+    """First half of SNARK::encode: the dense representation my_lib_prove reads (no commitment) -> Decommitment handle"""
+    ctx = ctx or inst.ctx
+    d = C.c_void_p()
+    ctx.check(lib().vpin_encode_tables(ctx._h, inst._h, gens._h, C.byref(d)))
+    return Decommitment(d)
+
+
+def encode_commit(decomm, gens, ctx):
+    """Second half: the ComputationCommitment (bincode bytes) of a Decommitment. Nothing in my_lib_prove depends on it: run it on
+    a background context (Context(device, background=True)) from a helper thread while the proof is under way."""
+    out, cap = _comm_buffer(ctx)
+    n = C.c_uint64()
+    ctx.check(lib().vpin_encode_commit(ctx._h, decomm._h, gens._h, out, C.c_uint64(cap), C.byref(n)))
+    return C.string_at(out, n.value)
 
 
 class Decommitment:

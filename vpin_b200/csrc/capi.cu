@@ -77,7 +77,9 @@ vpin_status vpin_ctx_create_ex(int32_t cuda_device, int32_t high_priority, vpin_
       int lo = 0, hi = 0;  // (numerically lower = more urgent; default streams sit at `lo`)
       VPIN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       // (a default context sits one step above the lowest priority: its side stream - SideScope - runs below it)
-      VPIN_CUDA(cudaStreamCreateWithPriority(&ctx->st, cudaStreamNonBlocking, high_priority ? hi : (lo - 1 >= hi ? lo - 1 : lo)));
+      ctx->background = high_priority < 0;
+      VPIN_CUDA(cudaStreamCreateWithPriority(&ctx->st, cudaStreamNonBlocking,
+                                             high_priority > 0 ? hi : (high_priority < 0 ? lo : (lo - 1 >= hi ? lo - 1 : lo))));
     }
     block_cache_register(ctx->st);
     block_cache_set_pressure_hook(ctx->st, [ctx]() {
@@ -267,6 +269,23 @@ vpin_status vpin_encode(vpin_ctx *ctx, const vpin_instance *inst, const vpin_gen
   VPIN_REQUIRE(comm_out && comm_cap >= comm.size(), VPIN_ERR_BUFFER_TOO_SMALL, "comm_out too small");
   memcpy(comm_out, comm.data(), comm.size());
   *decomm = reinterpret_cast<vpin_decomm *>(d.release());
+  VPIN_CATCH
+}
+vpin_status vpin_encode_tables(vpin_ctx *ctx, const vpin_instance *inst, const vpin_gens *gens, vpin_decomm **decomm) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE(inst && gens && decomm, VPIN_ERR_BAD_ARGUMENT, "null argument");
+  auto d = snark_encode_tables(c_, *reinterpret_cast<const Instance *>(inst), *reinterpret_cast<const SnarkGens *>(gens));
+  *decomm = reinterpret_cast<vpin_decomm *>(d.release());
+  VPIN_CATCH
+}
+vpin_status vpin_encode_commit(vpin_ctx *ctx, const vpin_decomm *decomm, const vpin_gens *gens, uint8_t *comm_out, uint64_t comm_cap,
+                               uint64_t *comm_len) {
+  VPIN_TRY(reinterpret_cast<Ctx *>(ctx))
+  VPIN_REQUIRE(decomm && gens && comm_len, VPIN_ERR_BAD_ARGUMENT, "null argument");
+  std::vector<uint8_t> comm = snark_encode_commit(c_, *reinterpret_cast<const Decomm *>(decomm), *reinterpret_cast<const SnarkGens *>(gens));
+  *comm_len = comm.size();
+  VPIN_REQUIRE(comm_out && comm_cap >= comm.size(), VPIN_ERR_BUFFER_TOO_SMALL, "comm_out too small");
+  memcpy(comm_out, comm.data(), comm.size());
   VPIN_CATCH
 }
 void vpin_decomm_destroy(vpin_decomm *d) { delete reinterpret_cast<Decomm *>(d); }

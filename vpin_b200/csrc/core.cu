@@ -196,9 +196,10 @@ void prof_drain(Ctx *c) {
   c->prof.pending.clear();
 }
 
-// resident MSM blocks per SM while a commitment runs on the side stream (VPIN_SIDE_MSM_BLOCKS, default 3 of the usual 6)
+// resident MSM blocks per SM while a commitment runs on the side stream (VPIN_SIDE_MSM_BLOCKS, default 2 of the usual 6: with the
+// single block of a background context's MSM that still leaves the registers of one 256-thread round-kernel block on every SM)
 int side_msm_blocks_per_sm() {
-  static const int v = [] { const char *e = getenv("VPIN_SIDE_MSM_BLOCKS"); int x = e ? atoi(e) : 3; return x < 0 ? 0 : x; }();
+  static const int v = [] { const char *e = getenv("VPIN_SIDE_MSM_BLOCKS"); int x = e ? atoi(e) : 2; return x < 0 ? 0 : x; }();
   return v;
 }
 SideScope::SideScope(Ctx *ctx) : c(ctx) {
@@ -447,7 +448,7 @@ static void hyrax_rows_local(Ctx *ctx, const LabelGens &g, const fl_t *dZ, size_
     {
       ProfScope ps(ctx, PROF_MSM_ACCUMULATE, pts, 0);
       launch_msm_accumulate(g.table(), digits.p, nr, cols, d_blinds != nullptr, blind_base, segs, partial.p, ctx->st, d_wmask,
-                            ctx->on_side ? side_msm_blocks_per_sm() : 0);
+                            ctx->background ? 1 : (ctx->on_side ? side_msm_blocks_per_sm() : 0));
     }
     ProfScope ps(ctx, PROF_MSM_FINISH, pts, 0);
     launch_msm_finish(partial.p, nr, segs, geom, sums.p, d_points ? d_points + r0 : nullptr, d_comp ? d_comp + 32 * r0 : nullptr, ctx->st);

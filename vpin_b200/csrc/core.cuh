@@ -166,6 +166,9 @@ struct vpin_ctx_impl {
   // challenges into, and the device-side latch that relays a posted challenge to the other blocks of a grid
   ChalSlot *h_chal = nullptr, *d_chal = nullptr;
   DevVec<ChalLatch> d_chal_latch;
+  // background context (vpin_ctx_create_ex(.., -1, ..)): lowest stream priority and at most one resident MSM block per SM - for
+  // work nothing waits for (the commitment half of SNARK::encode while the proof runs on another context of the device)
+  bool background = false;
   bool no_prelaunch = false;  // set after a mailbox time-out: the context keeps proving with challenges as kernel parameters
   // per-proof workspace for the SPARK tables (derefs, product trees, dot-product clones): one slab that only ever grows, so
   // a steady-state proof allocates nothing large (multi-GB cudaMallocAsync calls were measured at 10-150 ms when the pool

@@ -132,8 +132,14 @@ std::unique_ptr<SnarkGens> snark_gens_create(Ctx *ctx, uint64_t num_cons, uint64
 // ------------------------------------------------------------------------------------------------ encode
 // SP/lib.rs:347-358 -> SP/r1csinstance.rs:309-321 -> SP/sparse_mlpoly.rs:500-520, :382-438, AddrTimestamps::new :232-265
 std::unique_ptr<Decomm> snark_encode(Ctx *ctx, const Instance &inst, const SnarkGens &gens, std::vector<uint8_t> *comm_bytes) {
+  auto d = snark_encode_tables(ctx, inst, gens);
+  *comm_bytes = snark_encode_commit(ctx, *d, gens);
+  return d;
+}
+std::unique_ptr<Decomm> snark_encode_tables(Ctx *ctx, const Instance &inst, const SnarkGens &gens) {
   cudaStream_t st = ctx->st;
   auto d = std::make_unique<Decomm>();
+  d->num_cons = inst.num_cons; d->num_vars = inst.num_vars; d->num_inputs = inst.num_inputs;
   size_t N = 1;
   for (int k = 0; k < 3; k++) N = std::max(N, next_pow2(inst.M[k].nnz));
   size_t nvx = math_log2(inst.num_cons), nvy = math_log2(2 * inst.num_vars);
@@ -171,6 +177,15 @@ std::unique_ptr<Decomm> snark_encode(Ctx *ctx, const Instance &inst, const Snark
   d->comb_mem.alloc(2 * M, st);
   launch_u32_to_fl(d->row_audit_ts.p, M, d->comb_mem.p, st);
   launch_u32_to_fl(d->col_audit_ts.p, M, d->comb_mem.p + M, st);
+  ctx->sync();  // the tables may be read from any stream once this returns
+  return d;
+}
+std::vector<uint8_t> snark_encode_commit(Ctx *ctx, const Decomm &dec, const SnarkGens &gens) {
+  cudaStream_t st = ctx->st;
+  const Decomm *d = &dec;
+  const size_t N = dec.N, M = dec.M;
+  VPIN_REQUIRE(math_log2(16 * N) == gens.ops_pc.ell && math_log2(2 * M) == gens.mem_pc.ell, VPIN_ERR_SIZE_MISMATCH,
+               "gens do not match the decommitment");
   // two Hyrax commitments without blinds (:507-508)
   const PcGens &po = gens.ops_pc, &pm = gens.mem_pc;
   DevVec<uint8_t> c_ops(32 * po.L, st), c_mem(32 * pm.L, st);
@@ -183,12 +198,11 @@ std::unique_ptr<Decomm> snark_encode(Ctx *ctx, const Instance &inst, const Snark
   // bincode(ComputationCommitment { comm: R1CSCommitment { num_cons, num_vars, num_inputs, comm: SparseMatPolyCommitment {
   //   batch_size, num_ops, num_mem_cells, comm_comb_ops, comm_comb_mem } } })   SP/r1csinstance.rs:53-58, sparse_mlpoly.rs:332-338
   Bin o;
-  o.u64(inst.num_cons); o.u64(inst.num_vars); o.u64(inst.num_inputs);
+  o.u64(dec.num_cons); o.u64(dec.num_vars); o.u64(dec.num_inputs);
   o.u64(3); o.u64(N); o.u64(M);
   o.comps(h_ops);
   o.comps(h_mem);
-  *comm_bytes = std::move(o.b);
-  return d;
+  return std::move(o.b);
 }
 
 // ------------------------------------------------------------------------------------------------ prover

@@ -25,6 +25,7 @@ typedef vpin_gens_impl SnarkGens;
 // MultiSparseMatPolynomialAsDense (Spartan/src/sparse_mlpoly.rs:285-292) resident in HBM
 struct vpin_decomm_impl {
   size_t N = 0, M = 0;  // ops per matrix (padded nnz), memory cells
+  size_t num_cons = 0, num_vars = 0, num_inputs = 0;  // of the instance (the commitment's bincode carries them)
   struct U32View { uint32_t *p = nullptr; };
   DevVec<uint32_t> row_addr_all, col_addr_all, row_read_ts_all, col_read_ts_all;  // 3N each: matrices A | B | C
   U32View row_addr[3], col_addr[3], row_read_ts[3], col_read_ts[3];                // views into the arrays above
@@ -44,6 +45,12 @@ typedef vpin_witness_impl Witness;
 
 std::unique_ptr<SnarkGens> snark_gens_create(Ctx *ctx, uint64_t num_cons, uint64_t num_vars, uint64_t num_inputs, uint64_t num_nz_entries);
 std::unique_ptr<Decomm> snark_encode(Ctx *ctx, const Instance &inst, const SnarkGens &gens, std::vector<uint8_t> *comm_bytes);
+// the two halves of SNARK::encode: the dense representation (timestamps by a radix sort, comb_ops, comb_mem: everything
+// my_lib_prove reads - vPIN's prover never appends the computation commitment to its transcript, VP/commit_test.rs:75) and the two
+// Hyrax commitments over it (the ComputationCommitment the verifier gets). The second half depends on nothing but the first and
+// nothing in the proof depends on it, so a driver may run it on a background context while the proof is under way.
+std::unique_ptr<Decomm> snark_encode_tables(Ctx *ctx, const Instance &inst, const SnarkGens &gens);
+std::vector<uint8_t> snark_encode_commit(Ctx *ctx, const Decomm &decomm, const SnarkGens &gens);
 std::vector<uint8_t> snark_prove(Ctx *ctx, const Instance &inst, const Decomm &decomm, const Witness &w, const std::vector<fl_t> &inputs,
                                  const SnarkGens &gens, const uint8_t *label, size_t label_len, const fl_t &tape_seed);
 bool instance_is_sat(Ctx *ctx, const Instance &inst, const uint8_t *vars32, uint64_t n_vars, const uint8_t *inputs32, uint64_t n_inputs);
