@@ -179,10 +179,16 @@ VPIN_HD fl_t fl_sqr(const fl_t &a) { return fl_mul(a, a); }
 
 // canonical (non-Montgomery) limbs of a: a * 1 / R
 VPIN_HD fl_t fl_from_mont(const fl_t &a) {
+#if defined(__CUDA_ARCH__)
+  fl_t r;
+  limb::mont_redc_l(r.v, a.v);  // the reduction rows of a multiplication by one, without its product rows
+  return fl_cond_sub(r);
+#else
   fl_t one;
   for (int i = 0; i < 8; i++) one.v[i] = 0;
   one.v[0] = 1;
   return fl_mul(a, one);
+#endif
 }
 VPIN_HD fl_t fl_to_mont(const fl_t &a) { return fl_mul(a, fl_r2()); }
 VPIN_HD fl_t fl_from_u64(uint64_t x) {

@@ -459,5 +459,44 @@ VPIN_HD void mont_mul_l(uint32_t *r, const uint32_t *a, const uint32_t *b) {
 #endif
 }
 
+// r[0..8) = a / 2^256 mod l, in [0, 2l): mont_mul_l(r, a, 1) without its 64 product multiplications - the eight reduction rows
+// only (32 IMAD.WIDE + 8 IMAD). The MSM recode kernels leave Montgomery form once per scalar and were throttled by the
+// multiply pipe doing it with a full multiplication by one.
+VPIN_HD void mont_redc_l(uint32_t *r, const uint32_t *a) {
+  uint32_t ev[18], od[18];  // od[k] has weight 2^(32 (k + 1))
+#pragma unroll
+  for (int k = 0; k < 18; k++) ev[k] = od[k] = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { ev[2 * k] = a[2 * k]; od[2 * k] = a[2 * k + 1]; }
+  uint32_t m;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if (i == 0) {
+      redc_other<false>(ev[0], 0u, m, od, od[8]);
+      redc_own(ev, m, ev[8]);
+    } else if (i & 1) {
+      redc_other<true>(od[i - 1], ev[i], m, ev + i + 1, ev[i + 9]);
+      redc_own(od + i - 1, m, od[i + 7]);
+    } else {
+      redc_other<true>(ev[i], od[i - 1], m, od + i, od[i + 8]);
+      redc_own(ev + i, m, ev[i + 8]);
+    }
+  }
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, %17; addc.cc.u32 %2, %10, %18; addc.cc.u32 %3, %11, %19;"
+      "addc.cc.u32 %4, %12, %20; addc.cc.u32 %5, %13, %21; addc.cc.u32 %6, %14, %22; addc.u32 %7, %15, %23;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
+        "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+#else
+  uint64_t c = 0;
+  for (int k = 0; k < 8; k++) {
+    c += (uint64_t)ev[8 + k] + od[7 + k];
+    r[k] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+}
+
 }  // namespace limb
 }  // namespace vpin
