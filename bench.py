@@ -158,7 +158,7 @@ class InstanceState:
                 self.d_assign.append(d)
         # SNARK::encode does not depend on the witness: on one GPU a helper thread runs it on a second context (own stream and
         # scratch, this instance's priority) while this thread commits to the three assignments (ctypes releases the GIL; a Rust
-        # shim would use std::thread::scope, INTEGRATION.md section 4). VPIN_BENCH_OVERLAP_ENCODE=0 keeps the calls strictly
+        # shim would use std::thread::scope, INTEGRATION.md section 3c). VPIN_BENCH_OVERLAP_ENCODE=0 keeps the calls strictly
         # sequential. On a distributed context encode's commitments are sharded by the context's communicator, so it stays there.
         # Mode "1" is a measured alternative that lost: vPIN's my_lib_prove reads only encode's dense tables (the computation
         # commitment never enters the prover's transcript, VP/commit_test.rs:75), so the commitment's MSMs can run on a BACKGROUND

@@ -116,7 +116,7 @@ vpin_status vpin_instance_export_coo(vpin_ctx *ctx, const vpin_instance *inst, u
  * comm_out receives bincode(ComputationCommitment); *decomm keeps the dense representation in HBM. */
 vpin_status vpin_encode(vpin_ctx *ctx, const vpin_instance *inst, const vpin_gens *gens, uint8_t *comm_out,
                         uint64_t comm_cap, uint64_t *comm_len, vpin_decomm **decomm);
-/* The two halves of SNARK::encode, for a driver that overlaps them with the rest of its flow (INTEGRATION.md section 4):
+/* The two halves of SNARK::encode, for a driver that overlaps them with the rest of its flow (INTEGRATION.md section 3c):
  *  vpin_encode_tables: the dense representation my_lib_prove reads (SP/sparse_mlpoly.rs:382-438 MultiSparseMatPolynomialAsDense,
  *    AddrTimestamps::new :232-265) - no commitment. The handle may be used by a proof on any context of the device.
  *  vpin_encode_commit: the two Hyrax commitments over it (SP/sparse_mlpoly.rs:500-520) -> bincode(ComputationCommitment).

@@ -415,7 +415,7 @@ class SNARK:
         """SNARK::encode(&inst, &gens) -> (ComputationCommitment as bincode bytes, ComputationDecommitment handle).
         ctx: the context (stream, scratch) the call runs on, the instance's own by default. Encoding does not depend on the
         witness, so a driver may run it on a SECOND context from a second host thread while the first one commits to the
-        assignments (bench.py, INTEGRATION.md section 4): the decommitment can be handed to a proof on any context of the device."""
+        assignments (bench.py, INTEGRATION.md section 3c): the decommitment can be handed to a proof on any context of the device."""
         ctx = ctx or inst.ctx
         cap = 64 + 32 * (1 << 16) * 2
         out = getattr(ctx, "_comm_buf", None)  # one 4 MB output buffer per context, reused (no mmap / munmap per call)
