@@ -405,13 +405,23 @@ std::shared_ptr<LabelGens> get_label_gens(Ctx *ctx, const std::string &label, si
     size_t free_b = 0, total_b = 0;
     VPIN_CUDA(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = std::min<size_t>(table_budget ? std::min(table_budget, free_b) : free_b / 10 * 3, (size_t)64 << 30);
-    int W = kMsmMinW;
-    while (W < kMsmMaxW && msm_table_bytes_per_base(W + 1) * n <= budget) W++;
-    if (const char *e = getenv("VPIN_MSM_W")) {
+    // fewest windows (= mixed additions per scalar) whose table fits; at equal windows four sub-tables (the shorter Horner pass)
+    int W = kMsmMinW, sub = kMsmSub;
+    for (int w = kMsmMinW; w <= kMsmMaxW; w++)
+      for (int sb = 2; sb <= 4; sb += 2) {
+        if (msm_table_bytes_per_base(w, sb) * n > budget) continue;
+        int have = msm_geom(W, sub).windows, cand = msm_geom(w, sb).windows;
+        if (cand < have || (cand == have && sb > sub)) { W = w; sub = sb; }
+      }
+    if (const char *e = getenv("VPIN_MSM_W")) {  // VPIN_MSM_W / VPIN_MSM_SUB pin the geometry (tests, experiments)
       int w = atoi(e);
       if (w >= kMsmMinW && w <= kMsmMaxW) W = w;
     }
-    g->geom = msm_geom(W);
+    if (const char *e = getenv("VPIN_MSM_SUB")) {
+      int sb = atoi(e);
+      if (sb == 2 || sb == 4) sub = sb;
+    }
+    g->geom = msm_geom(W, sub);
   }
   g->d_table.alloc(msm_table_entries(n, g->geom), ctx->st);
   {

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128) k_points_dbl_n(const ge_t *in, size_t n, 
 void launch_table_build(const ge_t *d_bases, size_t n, const MsmGeom &g, niels_t *d_table, ge_t *d_scratch, cudaStream_t st) {
   const ge_t *cur = d_bases;
   size_t threads = n * (g.table / kTblChunk);
-  for (int t = 0; t < kMsmSub; t++) {
+  for (int t = 0; t < g.sub; t++) {
     if (t > 0) {
       ++g_kernel_launches, k_points_dbl_n<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cur, n, g.W * g.group, d_scratch);
       cur = d_scratch;
@@ -233,7 +233,7 @@ __device__ __forceinline__ void msm_accumulate_body(const niels_t *table, const 
   // 128-bit weights) is finished at once; its digits are not even read
   {
     uint32_t live = wmask ? *wmask : 0xffffffffu, mine = 0;
-    for (int t = 0; t < kMsmSub; t++) mine |= (t * g.group + wl) < g.windows ? (live >> (t * g.group + wl)) & 1u : 0u;
+    for (int t = 0; t < g.sub; t++) mine |= (t * g.group + wl) < g.windows ? (live >> (t * g.group + wl)) & 1u : 0u;
     if (!mine) {
       st_ge(partial + (row * g.group + wl) * segs + seg, ge_identity());
       return;
@@ -249,7 +249,7 @@ __device__ __forceinline__ void msm_accumulate_body(const niels_t *table, const 
     if (kPrefetch && col + 1 < c1) {
       size_t nbase = col + 1 < cols ? col + 1 : extra_base;
 #pragma unroll
-      for (int t = 0; t < kMsmSub; t++) {
+      for (int t = 0; t < g.sub; t++) {
         int w = t * g.group + wl;
         if (w < g.windows) {
           uint32_t d = dg[(size_t)w * plane + col + 1];
@@ -262,7 +262,7 @@ __device__ __forceinline__ void msm_accumulate_body(const niels_t *table, const 
       }
     }
 #pragma unroll 1
-    for (int t = 0; t < kMsmSub; t++) {  // not unrolled: one copy of the 7-multiplication body keeps the loop inside the I-cache
+    for (int t = 0; t < g.sub; t++) {  // not unrolled: one copy of the 7-multiplication body keeps the loop inside the I-cache
       int w = t * g.group + wl;
       if (w >= g.windows) break;
       uint32_t d = dg[(size_t)w * plane + col];
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(32) k_msm_accumulate_small(const niels_t *tabl
   for (size_t col = c0 + lane; col < c1; col += 32) {
     size_t base = col < cols ? col : extra_base;
 #pragma unroll 1
-    for (int t = 0; t < kMsmSub; t++) {
+    for (int t = 0; t < g.sub; t++) {
       int w = t * g.group + wl;
       if (w >= g.windows) break;
       uint32_t d = dg[(size_t)w * plane + col];

@@ -19,37 +19,43 @@
 
 namespace vpin {
 
-static const int kMsmSub = 4;                      // sub-tables per generator
+static const int kMsmSub = 4;                      // sub-tables per generator (the default; MsmGeom::sub is what a table was built with)
 static const int kMsmColsPerBlock = 64;            // digit rows are padded to a multiple of this many columns
 static const int kMsmRowsPerBlock = 128;           // threads per accumulate block (consecutive rows)
 static const int kMsmMinW = 12, kMsmMaxW = 15;     // window widths the kernels support (digit = 15-bit magnitude | sign)
-static const int kMsmMaxGroup = 6;                 // Horner length at the narrowest window
+static const int kMsmMaxGroup = 10;                // longest Horner pass: two sub-tables at W = 13 (20 windows)
 
 // Window geometry of one generator stream. The window width is chosen per stream when its table is built: the widest
 // one whose table fits the memory budget (a wider window means fewer mixed additions per scalar — 22 at W = 12, 17 at
 // W = 15 — for a table that doubles with every bit: 786 KB per generator at W = 12, 6.3 MB at W = 15).
+// Sub-tables trade memory against the Horner pass: with `sub` tables per generator a row needs group = ceil(windows / sub) local
+// windows and (group - 1) W doublings at the end. TWO sub-tables of width W + 1 take the memory of four of width W and save a
+// window's worth of additions per scalar (W = 12 -> 13: 22 -> 20, 14 -> 15: 19 -> 17) for a Horner pass twice as long - the
+// better deal whenever the HBM plan of a shape cannot afford four sub-tables of the wider window (LeNet layer 5).
 struct MsmGeom {
   int W;        // window width (bits)
   int windows;  // signed digits of |s| <= (l-1)/2 < 2^252
   int group;    // local windows per sub-table (Horner length)
   int table;    // multiples 1..2^(W-1) per generator and sub-table
+  int sub;      // sub-tables per generator (2 or 4)
 };
-static inline MsmGeom msm_geom(int W) {
+static inline MsmGeom msm_geom(int W, int sub = kMsmSub) {
   MsmGeom g;
   g.W = W;
   g.windows = 252 / W + 1;
-  g.group = (g.windows + kMsmSub - 1) / kMsmSub;
+  g.sub = sub;
+  g.group = (g.windows + sub - 1) / sub;
   g.table = 1 << (W - 1);
   return g;
 }
-static inline size_t msm_table_bytes_per_base(int W) { return (size_t)kMsmSub * ((size_t)1 << (W - 1)) * sizeof(niels_t); }
+static inline size_t msm_table_bytes_per_base(int W, int sub = kMsmSub) { return (size_t)sub * ((size_t)1 << (W - 1)) * sizeof(niels_t); }
 
 struct MsmTable {
-  niels_t *d_table;   // [kMsmSub][n_bases][geom.table]
+  niels_t *d_table;   // [geom.sub][n_bases][geom.table]
   size_t n_bases;
   MsmGeom geom;
 };
-static inline size_t msm_table_entries(size_t n_bases, const MsmGeom &g) { return (size_t)kMsmSub * n_bases * g.table; }
+static inline size_t msm_table_entries(size_t n_bases, const MsmGeom &g) { return (size_t)g.sub * n_bases * g.table; }
 
 // bases: n extended points on device. Builds the kMsmSub sub-tables (msm_table_entries(n, g) entries). d_scratch: n points.
 void launch_table_build(const ge_t *d_bases, size_t n, const MsmGeom &g, niels_t *d_table, ge_t *d_scratch, cudaStream_t st);
