@@ -428,7 +428,9 @@ vpin_status vpin_prove_resident(vpin_ctx *ctx, const vpin_instance *inst, const 
                           *reinterpret_cast<const SnarkGens *>(gens), transcript_label, label_len, seed);
       break;
     } catch (const vpin::Error &) {
-      if (attempt > 0 || c_->no_prelaunch || !mailbox_timed_out(c_)) throw;
+      // (not on a distributed context: the other ranks are half-way through the collectives of the first attempt - there the
+      // time-out is ten times longer and a time-out fails the call on this rank like a failed peer does on the others)
+      if (attempt > 0 || c_->no_prelaunch || c_->world > 1 || !mailbox_timed_out(c_)) throw;
       c_->no_prelaunch = true;
     }
   }

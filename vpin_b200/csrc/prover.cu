@@ -462,6 +462,9 @@ struct Prover {
   static size_t prelaunch_q() {
     static const size_t v = [] {
       const char *e = getenv("VPIN_PRELAUNCH_Q");
+      // Nsight Compute serialises kernels and holds the launching thread until each one has finished: a kernel that waits for
+      // that thread's next post could only time out. Its injection sets NV_COMPUTE_PROFILER_PERFWORKS_DIR in the target process.
+      if (!e && getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) return (size_t)0;
       long long x = e ? atoll(e) : (1ll << 14);
       return (size_t)(x < 0 ? 0 : x);
     }();
@@ -1128,7 +1131,7 @@ struct Prover {
         uint32_t tag = ++ctx->round_seq;
         rtag[j] = tag;
         outstanding.tags.push_back(tag);
-        return ChalRef{ctx->d_chal + tag % kChalRing, ctx->d_chal_latch.p, tag, mailbox_timeout_ms()};
+        return ChalRef{ctx->d_chal + tag % kChalRing, ctx->d_chal_latch.p, tag, mailbox_timeout_ms() * (ctx->world > 1 ? 10u : 1u)};
       };
       // enqueues round j (launched == j). pre: the kernel takes r_{j-1} from the mailbox (r_prev is ignored)
       auto launch = [&](size_t j, const fl_t &r_prev, bool pre) {
