@@ -357,10 +357,14 @@ __global__ void __launch_bounds__(128) k_bound(const fl_t *Z, const fl_t *L, siz
   size_t per = (Lsize + gridDim.y - 1) / gridDim.y;
   size_t lo = per * blockIdx.y, hi = lo + per < Lsize ? lo + per : Lsize;
   fl_t acc = fl_zero();
-  for (size_t i = lo; i < hi; i++) {
-    fl_t l = ldg_fl(L + i);
-    acc = fl_add(acc, fl_mul(l, ldg_fl(Z + i * Rsize + j)));
+  size_t i = lo;
+  for (; i + 4 <= hi; i += 4) {  // four rows' loads in flight before the first multiplication (the chain through acc hid none of them)
+    fl_t z0 = ldg_fl(Z + i * Rsize + j), z1 = ldg_fl(Z + (i + 1) * Rsize + j), z2 = ldg_fl(Z + (i + 2) * Rsize + j),
+         z3 = ldg_fl(Z + (i + 3) * Rsize + j);
+    fl_t l0 = ldg_fl(L + i), l1 = ldg_fl(L + i + 1), l2 = ldg_fl(L + i + 2), l3 = ldg_fl(L + i + 3);
+    acc = fl_add(acc, fl_add(fl_add(fl_mul(l0, z0), fl_mul(l1, z1)), fl_add(fl_mul(l2, z2), fl_mul(l3, z3))));
   }
+  for (; i < hi; i++) acc = fl_add(acc, fl_mul(ldg_fl(L + i), ldg_fl(Z + i * Rsize + j)));
   st_fl(tmp + (size_t)blockIdx.y * Rsize + j, acc);
 }
 __global__ void __launch_bounds__(128) k_bound_finish(const fl_t *tmp, int nsplit, size_t Rsize, fl_t *out) {
