@@ -300,179 +300,6 @@ __device__ __forceinline__ ge_t shfl_down_ge(const ge_t &g, int off) {
   }
   return r;
 }
-// Few rows (the bullet-reduction L / R rows, single Pedersen commitments): rows cannot fill a warp, so the lanes of a warp
-// take the COLUMNS of one (row, local window, segment) instead and the 32 partial sums are added by a shuffle tree.
-// grid (segs, kMsmGroup, rows), one warp per block.
-__global__ void __launch_bounds__(32) k_msm_accumulate_small(const niels_t *table, MsmGeom g, const uint16_t *digits, size_t rows, size_t cols,
-                                                             size_t cols_total, size_t extra_base, size_t stride, size_t n_bases,
-                                                             size_t seg_len, ge_t *partial) {
-  const size_t row = blockIdx.z, seg = blockIdx.x, segs = gridDim.x;
-  const int wl = blockIdx.y, lane = threadIdx.x;
-  size_t c0 = seg * seg_len, c1 = c0 + seg_len < cols_total ? c0 + seg_len : cols_total;
-  const size_t plane = rows * stride;
-  const uint16_t *dg = digits + row * stride;
-  Acc8<0> a8;
-  a8.init();
-  for (size_t col = c0 + lane; col < c1; col += 32) {
-    size_t base = col < cols ? col : extra_base;
-#pragma unroll 1
-    for (int t = 0; t < g.sub; t++) {
-      int w = t * g.group + wl;
-      if (w >= g.windows) break;
-      uint32_t d = dg[(size_t)w * plane + col];
-      if (d) a8.madd(table + ((size_t)t * n_bases + base) * g.table + ((d & 0x7fffu) - 1u), d >> 15);
-    }
-  }
-  ge_t acc = a8.get();
-#pragma unroll 1
-  for (int off = 16; off > 0; off >>= 1) {
-    ge_t o = shfl_down_ge(acc, off);
-    acc = ge_add(acc, o);
-  }
-  if (lane == 0) st_ge(partial + (row * g.group + wl) * segs + seg, acc);
-}
-static const size_t kMsmSmallRows = 16;
-size_t msm_num_segments(size_t rows, size_t cols_total, const MsmGeom &g) {
-  if (rows <= kMsmSmallRows) {
-    const size_t want_warps = (size_t)148 * 16;
-    size_t per = rows * g.group;
-    size_t segs = (want_warps + per - 1) / per;
-    size_t max_segs = (cols_total + 63) / 64;  // at least two columns per lane
-    if (segs > max_segs) segs = max_segs;
-    return segs < 1 ? 1 : segs;
-  }
-  const size_t want_threads = (size_t)148 * 6144;  // ~6 waves of blocks: short blocks balance the SMs (measured: 610 -> 736 Mpoints/s from 1024)
-  size_t per = rows * g.group;
-  size_t segs = (want_threads + per - 1) / per;
-  size_t max_segs = (cols_total + 7) / 8;  // at least 8 columns per thread
-  if (segs > max_segs) segs = max_segs;
-  if (segs < 1) segs = 1;
-  if (segs > 65535) segs = 65535;
-  return segs;
-}
-void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t rows, size_t cols, bool has_extra, size_t extra_base,
-                           size_t segs, ge_t *d_partial, cudaStream_t st, const uint32_t *d_wmask, int blocks_per_sm) {
-  size_t cols_total = cols + (has_extra ? 1 : 0);
-  size_t stride = msm_col_stride(cols_total);
-  size_t seg_len = (cols_total + segs - 1) / segs;
-  if (rows <= kMsmSmallRows) {
-    dim3 grid((unsigned)segs, t.geom.group, (unsigned)rows);
-    ++g_kernel_launches, k_msm_accumulate_small<<<grid, 32, 0, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride,
-                                                                      t.n_bases, seg_len, d_partial);
-    return;
-  }
-  dim3 grid((unsigned)((rows + kMsmRowsPerBlock - 1) / kMsmRowsPerBlock), t.geom.group, (unsigned)segs);
-  ++g_kernel_launches;
-  if (blocks_per_sm > 0 && blocks_per_sm < 6) {  // occupancy cap: 227 KB of shared memory per SM / blocks_per_sm, minus a margin
-    static const bool ok = cudaFuncSetAttribute(k_msm_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
-    size_t smem = ok ? (size_t)(220 * 1024) / (blocks_per_sm + 1) + 1024 : 0;  // more than a (cap + 1)-th of the SM: cap + 1 blocks cannot fit
-    if (smem > 200 * 1024) smem = 200 * 1024;
-    k_msm_accumulate<<<grid, kMsmRowsPerBlock, smem, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride, t.n_bases, seg_len,
-                                                          d_partial, d_wmask);
-    return;
-  }
-#define VPIN_MSM_LAUNCH(K) K<<<grid, kMsmRowsPerBlock, 0, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride, t.n_bases, seg_len, d_partial, d_wmask)
-  switch (msm_variant()) {
-    case 1: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p0); break;
-    case 2: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p1); break;
-    case 12: VPIN_MSM_LAUNCH(k_msm_accumulate_a2); break;
-    case 20: VPIN_MSM_LAUNCH(k_msm_accumulate_pf); break;
-    default: VPIN_MSM_LAUNCH(k_msm_accumulate); break;
-  }
-#undef VPIN_MSM_LAUNCH
-}
-
-// finish, step 1 (only when a row was split into segments): `lanes` lanes per (row, local window) add the segment partials
-// (lane-strided, then a shuffle tree) -> sums[row][w']. The kernel is bound by the multiply pipe, and a warp-wide addition costs
-// the same whether 1 or 32 of its lanes hold data: with a whole warp per pair the tree's five levels were 5 of the 6 warp-wide
-// additions a pair of 45 segments cost (23 % of the lanes useful, 344 us for CNN A's comb_ops commitment). `lanes` now comes from
-// a small cost model (msm_segsum_lanes): 2 - 4 lanes for the 20480 pairs x 45 segments of that commitment, a full tree for the
-// 10 pairs of a bullet-reduction round.
-// publish: optional {counter, host-mapped sequence word, value}: the last block to finish stores the value there (system scope),
-// which tells the host that every window sum has landed in its mapped slot — saves the separate one-thread launch
-struct SegsumPublish { unsigned *counter; volatile uint32_t *seq_word; uint32_t seq; };
-__global__ void __launch_bounds__(128) k_msm_segsum(const ge_t *partial, size_t pairs, size_t segs, int lanes, ge_t *sums, SegsumPublish pub) {
-  const int lane = threadIdx.x & 31, sub = lane & (lanes - 1);
-  const size_t warp = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  const size_t pair = warp * (32 / lanes) + lane / lanes;  // (row, w') flattened
-  const bool live = pair < pairs;
-  {
-    const ge_t *p = partial + (live ? pair : 0) * segs;
-    ge_t acc = ge_identity();
-    bool first = true;
-    if (live)
-      for (size_t s = sub; s < segs; s += lanes) {
-        ge_t q = ld_ge(p + s);
-        acc = first ? q : ge_add(acc, q);
-        first = false;
-      }
-    for (int off = lanes >> 1; off > 0; off >>= 1) {  // (lanes beyond the data hold the identity; a read across the group's end
-      ge_t o = shfl_down_ge(acc, off);               //  only reaches lanes whose sums nobody uses)
-      acc = ge_add(acc, o);
-    }
-    if (live && sub == 0) st_ge(sums + pair, acc);
-  }
-  if (pub.counter) {
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(pub.counter, 1u) == gridDim.x - 1) {
-      *pub.counter = 0;
-      __threadfence_system();
-      *pub.seq_word = pub.seq;
-    }
-  }
-}
-// lanes per pair: the power of two that minimises depth x max(latency of one addition, multiply-pipe time of all warps' additions)
-// with depth = ceil(segs / lanes) - 1 serial additions + log2(lanes) tree levels. Few pairs (the two rows of a bullet-reduction
-// round) are latency-bound and get a wide tree; thousands of pairs are pipe-bound and get few lanes.
-static int msm_segsum_lanes(size_t pairs, size_t segs) {
-  static const int forced = [] { const char *e = getenv("VPIN_SEGSUM_LANES"); return e ? atoi(e) : 0; }();  // (experiments: 1, 2, .., 32)
-  if (forced >= 1 && forced <= 32 && (forced & (forced - 1)) == 0) return forced;
-  const double add_latency = 5000.0;             // cycles of one dependent extended addition in a lone warp
-  const double pipe_per_warp_add = 2592.0 / 592;  // 9 x 72 IMAD.WIDE x 4 cycles, spread over 148 x 4 sub-partitions
-  int best = 1;
-  double best_cost = 0;
-  for (int lanes = 1, lg = 0; lanes <= 32; lanes <<= 1, lg++) {
-    double depth = (double)((segs + lanes - 1) / lanes) - 1 + lg;
-    if (depth < 1) depth = 1;
-    double warps = (double)pairs * lanes / 32.0;
-    double per_add = warps * pipe_per_warp_add > add_latency ? warps * pipe_per_warp_add : add_latency;
-    double cost = depth * per_add;
-    if (lanes == 1 || cost < best_cost) { best = lanes; best_cost = cost; }
-    if ((size_t)lanes >= segs) break;
-  }
-  return best;
-}
-static unsigned msm_segsum_blocks(size_t pairs, int lanes) {
-  size_t per_block = (size_t)4 * (32 / lanes);
-  return (unsigned)((pairs + per_block - 1) / per_block);
-}
-// finish, step 2: one thread per row runs the Horner pass over the kMsmGroup window sums and encodes the point
-__global__ void __launch_bounds__(32) k_msm_horner(const ge_t *sums, size_t rows, MsmGeom g, ge_t *out, uint8_t *comp) {
-  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= rows) return;
-  const ge_t *p = sums + row * g.group;
-  ge_t h = ld_ge(p + g.group - 1);
-  for (int w = g.group - 2; w >= 0; w--) {
-    for (int i = 0; i < g.W; i++) h = ge_dbl(h);
-    h = ge_add(h, ld_ge(p + w));
-  }
-  if (out) st_ge(out + row, h);
-  if (comp) {
-    uint8_t b[32];
-    ge_compress(h, b);
-    uint4 *q = reinterpret_cast<uint4 *>(comp + 32 * row);
-    uint32_t w[8];
-    for (int k = 0; k < 8; k++) w[k] = (uint32_t)b[4 * k] | ((uint32_t)b[4 * k + 1] << 8) | ((uint32_t)b[4 * k + 2] << 16) | ((uint32_t)b[4 * k + 3] << 24);
-    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
-  }
-}
-// The same pass with FOUR lanes per row. A commitment ends with this kernel and the host waits for its bytes, so what counts
-// is the length of the dependent chain, not the work: a doubling is two rounds of four independent multiplications (the
-// squares of X, Y, Z, X + Y, then E F, G H, F G, E H), an addition likewise, and lane q of a quad computes the q-th product of
-// each round; the products travel between the lanes by shuffles. 2 multiplications deep per doubling instead of 8, 3 per
-// addition instead of 9. The encoding's inverse square root is a chain of squarings that cannot be split; lane 0 runs it.
 __device__ __forceinline__ fp_t quad_from(const fp_t &v, int src) {
   fp_t r;
 #pragma unroll
@@ -517,6 +344,252 @@ __device__ __forceinline__ fp_t quad_add(int q, const fp_t &c, const ge_t &Q, co
   fp_t e = fp_sub(b, a), f = fp_sub(d, cc), g = fp_add(d, cc), h = fp_add(b, a);
   return quad_efgh(q, e, f, g, h);
 }
+__device__ __forceinline__ ge_t shfl_ge(const ge_t &g, int src) {
+  ge_t r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.X.v[i] = __shfl_sync(0xffffffffu, g.X.v[i], src);
+    r.Y.v[i] = __shfl_sync(0xffffffffu, g.Y.v[i], src);
+    r.Z.v[i] = __shfl_sync(0xffffffffu, g.Z.v[i], src);
+    r.T.v[i] = __shfl_sync(0xffffffffu, g.T.v[i], src);
+  }
+  return r;
+}
+// Sum of the points held by each group of `lanes` consecutive lanes (a power of two), left in the group's first lane - the
+// shuffle tree of the small-row MSM and of the segment sum, with every addition done by FOUR lanes (the quad of lanes
+// 4k .. 4k + 3 takes the k-th addition of a pass): three multiplications deep instead of nine, and a level of fewer than eight
+// additions no longer costs a warp-wide one. A bullet-reduction round is 9 - 11 such levels on the proof's critical path.
+// Every lane of the warp must call it; lanes without data hold the identity.
+__device__ __forceinline__ ge_t warp_tree_sum_quad(ge_t acc, int lanes) {
+  const int lane = threadIdx.x & 31, q = lane & 3, quad = lane >> 2;
+  for (int s = lanes >> 1; s > 0; s >>= 1) {
+    const int adds = (32 / lanes) * s;  // additions of this level: (a, a + s) with a = group * lanes + i, i < s
+    for (int p0 = 0; p0 < adds; p0 += 8) {
+      int j = p0 + quad;
+      if (j >= adds) j = adds - 1;  // (idle quads repeat the last addition; nobody takes their result)
+      const int a = (j / s) * lanes + (j % s);
+      ge_t P = shfl_ge(acc, a), Q = shfl_ge(acc, a + s);
+      fp_t m1 = fp_sel(q == 0, fp_sub(P.Y, P.X), fp_sel(q == 1, fp_add(P.Y, P.X), fp_sel(q == 2, P.T, P.Z)));
+      fp_t m2 = fp_sel(q == 0, fp_sub(Q.Y, Q.X), fp_sel(q == 1, fp_add(Q.Y, Q.X), fp_sel(q == 2, Q.T, Q.Z)));
+      fp_t sres = fp_mul(m1, m2);
+      fp_t sc = fp_mul(sres, fp_d2());  // lane 2: C = 2 d T1 T2
+      sres = fp_sel(q == 2, sc, sres);
+      fp_t a_ = quad_from(sres, 0), b_ = quad_from(sres, 1), c_ = quad_from(sres, 2), d_ = quad_from(sres, 3);
+      d_ = fp_add(d_, d_);
+      fp_t e = fp_sub(b_, a_), f = fp_sub(d_, c_), gg = fp_add(d_, c_), h = fp_add(b_, a_);
+      fp_t r = quad_efgh(q, e, f, gg, h);  // lane q: coordinate q of P + Q
+      // the lane that holds the first operand takes the whole sum: addition j of this pass sits in quad j - p0
+      const int i = lane % lanes, mine = (lane / lanes) * s + i;
+      const bool dest = i < s && mine >= p0 && mine < p0 + 8 && mine < adds;
+      const int src = dest ? 4 * (mine - p0) : lane & ~3;
+      ge_t sum;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        sum.X.v[k] = __shfl_sync(0xffffffffu, r.v[k], src);
+        sum.Y.v[k] = __shfl_sync(0xffffffffu, r.v[k], src + 1);
+        sum.Z.v[k] = __shfl_sync(0xffffffffu, r.v[k], src + 2);
+        sum.T.v[k] = __shfl_sync(0xffffffffu, r.v[k], src + 3);
+      }
+      if (dest) acc = sum;
+    }
+  }
+  return acc;
+}
+// Few rows (the bullet-reduction L / R rows, single Pedersen commitments): rows cannot fill a warp, so the lanes of a warp
+// take the COLUMNS of one (row, local window, segment) instead and the 32 partial sums are added by a shuffle tree.
+// grid (segs, kMsmGroup, rows), one warp per block.
+__global__ void __launch_bounds__(32) k_msm_accumulate_small(const niels_t *table, MsmGeom g, const uint16_t *digits, size_t rows, size_t cols,
+                                                             size_t cols_total, size_t extra_base, size_t stride, size_t n_bases,
+                                                             size_t seg_len, ge_t *partial, int quad_tree) {
+  const size_t row = blockIdx.z, seg = blockIdx.x, segs = gridDim.x;
+  const int wl = blockIdx.y, lane = threadIdx.x;
+  size_t c0 = seg * seg_len, c1 = c0 + seg_len < cols_total ? c0 + seg_len : cols_total;
+  const size_t plane = rows * stride;
+  const uint16_t *dg = digits + row * stride;
+  Acc8<0> a8;
+  a8.init();
+  for (size_t col = c0 + lane; col < c1; col += 32) {
+    size_t base = col < cols ? col : extra_base;
+#pragma unroll 1
+    for (int t = 0; t < g.sub; t++) {
+      int w = t * g.group + wl;
+      if (w >= g.windows) break;
+      uint32_t d = dg[(size_t)w * plane + col];
+      if (d) a8.madd(table + ((size_t)t * n_bases + base) * g.table + ((d & 0x7fffu) - 1u), d >> 15);
+    }
+  }
+  ge_t acc = quad_tree ? warp_tree_sum_quad(a8.get(), 32) : a8.get();
+  if (!quad_tree) {
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+      ge_t o = shfl_down_ge(acc, off);
+      acc = ge_add(acc, o);
+    }
+  }
+  if (lane == 0) st_ge(partial + (row * g.group + wl) * segs + seg, acc);
+}
+static bool tree_quad() {  // VPIN_TREE_QUAD=0: one lane per addition in the shuffle trees (for comparison)
+  static const bool v = [] { const char *e = getenv("VPIN_TREE_QUAD"); return !e || atoi(e) != 0; }();
+  return v;
+}
+static const size_t kMsmSmallRows = 16;
+size_t msm_num_segments(size_t rows, size_t cols_total, const MsmGeom &g) {
+  if (rows <= kMsmSmallRows) {
+    const size_t want_warps = (size_t)148 * 16;
+    size_t per = rows * g.group;
+    size_t segs = (want_warps + per - 1) / per;
+    size_t max_segs = (cols_total + 63) / 64;  // at least two columns per lane
+    if (segs > max_segs) segs = max_segs;
+    return segs < 1 ? 1 : segs;
+  }
+  const size_t want_threads = (size_t)148 * 6144;  // ~6 waves of blocks: short blocks balance the SMs (measured: 610 -> 736 Mpoints/s from 1024)
+  size_t per = rows * g.group;
+  size_t segs = (want_threads + per - 1) / per;
+  size_t max_segs = (cols_total + 7) / 8;  // at least 8 columns per thread
+  if (segs > max_segs) segs = max_segs;
+  if (segs < 1) segs = 1;
+  if (segs > 65535) segs = 65535;
+  return segs;
+}
+void launch_msm_accumulate(const MsmTable &t, const uint16_t *d_digits, size_t rows, size_t cols, bool has_extra, size_t extra_base,
+                           size_t segs, ge_t *d_partial, cudaStream_t st, const uint32_t *d_wmask, int blocks_per_sm) {
+  size_t cols_total = cols + (has_extra ? 1 : 0);
+  size_t stride = msm_col_stride(cols_total);
+  size_t seg_len = (cols_total + segs - 1) / segs;
+  if (rows <= kMsmSmallRows) {
+    dim3 grid((unsigned)segs, t.geom.group, (unsigned)rows);
+    ++g_kernel_launches, k_msm_accumulate_small<<<grid, 32, 0, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride,
+                                                                      t.n_bases, seg_len, d_partial, tree_quad() ? 1 : 0);
+    return;
+  }
+  dim3 grid((unsigned)((rows + kMsmRowsPerBlock - 1) / kMsmRowsPerBlock), t.geom.group, (unsigned)segs);
+  ++g_kernel_launches;
+  if (blocks_per_sm > 0 && blocks_per_sm < 6) {  // occupancy cap: 227 KB of shared memory per SM / blocks_per_sm, minus a margin
+    static const bool ok = cudaFuncSetAttribute(k_msm_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+    size_t smem = ok ? (size_t)(220 * 1024) / (blocks_per_sm + 1) + 1024 : 0;  // more than a (cap + 1)-th of the SM: cap + 1 blocks cannot fit
+    if (smem > 200 * 1024) smem = 200 * 1024;
+    k_msm_accumulate<<<grid, kMsmRowsPerBlock, smem, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride, t.n_bases, seg_len,
+                                                          d_partial, d_wmask);
+    return;
+  }
+#define VPIN_MSM_LAUNCH(K) K<<<grid, kMsmRowsPerBlock, 0, st>>>(t.d_table, t.geom, d_digits, rows, cols, cols_total, extra_base, stride, t.n_bases, seg_len, d_partial, d_wmask)
+  switch (msm_variant()) {
+    case 1: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p0); break;
+    case 2: VPIN_MSM_LAUNCH(k_msm_accumulate_f9p1); break;
+    case 12: VPIN_MSM_LAUNCH(k_msm_accumulate_a2); break;
+    case 20: VPIN_MSM_LAUNCH(k_msm_accumulate_pf); break;
+    default: VPIN_MSM_LAUNCH(k_msm_accumulate); break;
+  }
+#undef VPIN_MSM_LAUNCH
+}
+
+// finish, step 1 (only when a row was split into segments): `lanes` lanes per (row, local window) add the segment partials
+// (lane-strided, then a shuffle tree) -> sums[row][w']. The kernel is bound by the multiply pipe, and a warp-wide addition costs
+// the same whether 1 or 32 of its lanes hold data: with a whole warp per pair the tree's five levels were 5 of the 6 warp-wide
+// additions a pair of 45 segments cost (23 % of the lanes useful, 344 us for CNN A's comb_ops commitment). `lanes` now comes from
+// a small cost model (msm_segsum_lanes): 2 - 4 lanes for the 20480 pairs x 45 segments of that commitment, a full tree for the
+// 10 pairs of a bullet-reduction round.
+// publish: optional {counter, host-mapped sequence word, value}: the last block to finish stores the value there (system scope),
+// which tells the host that every window sum has landed in its mapped slot — saves the separate one-thread launch
+struct SegsumPublish { unsigned *counter; volatile uint32_t *seq_word; uint32_t seq; };
+__global__ void __launch_bounds__(128) k_msm_segsum(const ge_t *partial, size_t pairs, size_t segs, int lanes, int quad_tree, ge_t *sums,
+                                                    SegsumPublish pub) {
+  const int lane = threadIdx.x & 31, sub = lane & (lanes - 1);
+  const size_t warp = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const size_t pair = warp * (32 / lanes) + lane / lanes;  // (row, w') flattened
+  const bool live = pair < pairs;
+  {
+    const ge_t *p = partial + (live ? pair : 0) * segs;
+    ge_t acc = ge_identity();
+    bool first = true;
+    if (live)
+      for (size_t s = sub; s < segs; s += lanes) {
+        ge_t q = ld_ge(p + s);
+        acc = first ? q : ge_add(acc, q);
+        first = false;
+      }
+    if (quad_tree) acc = warp_tree_sum_quad(acc, lanes);
+    else
+      for (int off = lanes >> 1; off > 0; off >>= 1) {  // (lanes beyond the data hold the identity; a read across the group's end
+        ge_t o = shfl_down_ge(acc, off);               //  only reaches lanes whose sums nobody uses)
+        acc = ge_add(acc, o);
+      }
+    if (live && sub == 0) st_ge(sums + pair, acc);
+  }
+  if (pub.counter) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(pub.counter, 1u) == gridDim.x - 1) {
+      *pub.counter = 0;
+      __threadfence_system();
+      *pub.seq_word = pub.seq;
+    }
+  }
+}
+// lanes per pair: the power of two that minimises (multiplications in sequence) x max(latency of one, multiply-pipe time of one
+// for all warps) with ceil(segs / lanes) - 1 serial additions of nine multiplications and the passes of the quad tree
+// (warp_tree_sum_quad: three in sequence, four executed). Few pairs (the two rows of a bullet-reduction round) are latency-bound
+// and get a wide tree; thousands of pairs are pipe-bound and get few lanes.
+static int msm_segsum_lanes(size_t pairs, size_t segs) {
+  static const int forced = [] { const char *e = getenv("VPIN_SEGSUM_LANES"); return e ? atoi(e) : 0; }();  // (experiments: 1, 2, .., 32)
+  if (forced >= 1 && forced <= 32 && (forced & (forced - 1)) == 0) return forced;
+  const double mul_latency = 650.0;          // cycles of one dependent F_p multiplication in a lone warp
+  const double pipe_per_warp_mul = 288.0 / 592;  // 72 IMAD.WIDE x 4 cycles, spread over 148 x 4 sub-partitions
+  const bool quad = tree_quad();
+  int best = 1;
+  double best_cost = 0;
+  for (int lanes = 1; lanes <= 32; lanes <<= 1) {
+    double serial = (double)((segs + lanes - 1) / lanes) - 1;
+    double seq = serial * 9, work = serial * 9;
+    for (int s = lanes >> 1; s > 0; s >>= 1) {
+      if (quad) {
+        int passes = ((32 / lanes) * s + 7) / 8;
+        seq += 3.0 * passes;
+        work += 4.0 * passes;
+      } else {
+        seq += 9;
+        work += 9;
+      }
+    }
+    if (seq < 1) seq = 1;
+    double warps = (double)pairs * lanes / 32.0;
+    double per_mul = warps * pipe_per_warp_mul > mul_latency ? warps * pipe_per_warp_mul : mul_latency;
+    double cost = (warps * pipe_per_warp_mul > mul_latency ? work : seq) * per_mul;  // pipe-bound: what is executed counts
+    if (lanes == 1 || cost < best_cost) { best = lanes; best_cost = cost; }
+    if ((size_t)lanes >= segs) break;
+  }
+  return best;
+}
+static unsigned msm_segsum_blocks(size_t pairs, int lanes) {
+  size_t per_block = (size_t)4 * (32 / lanes);
+  return (unsigned)((pairs + per_block - 1) / per_block);
+}
+// finish, step 2: one thread per row runs the Horner pass over the kMsmGroup window sums and encodes the point
+__global__ void __launch_bounds__(32) k_msm_horner(const ge_t *sums, size_t rows, MsmGeom g, ge_t *out, uint8_t *comp) {
+  size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const ge_t *p = sums + row * g.group;
+  ge_t h = ld_ge(p + g.group - 1);
+  for (int w = g.group - 2; w >= 0; w--) {
+    for (int i = 0; i < g.W; i++) h = ge_dbl(h);
+    h = ge_add(h, ld_ge(p + w));
+  }
+  if (out) st_ge(out + row, h);
+  if (comp) {
+    uint8_t b[32];
+    ge_compress(h, b);
+    uint4 *q = reinterpret_cast<uint4 *>(comp + 32 * row);
+    uint32_t w[8];
+    for (int k = 0; k < 8; k++) w[k] = (uint32_t)b[4 * k] | ((uint32_t)b[4 * k + 1] << 8) | ((uint32_t)b[4 * k + 2] << 16) | ((uint32_t)b[4 * k + 3] << 24);
+    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+// The same pass with FOUR lanes per row. A commitment ends with this kernel and the host waits for its bytes, so what counts
+// is the length of the dependent chain, not the work: a doubling is two rounds of four independent multiplications (the
+// squares of X, Y, Z, X + Y, then E F, G H, F G, E H), an addition likewise, and lane q of a quad computes the q-th product of
+// each round; the products travel between the lanes by shuffles. 2 multiplications deep per doubling instead of 8, 3 per
+// addition instead of 9. The encoding's inverse square root is a chain of squarings that cannot be split; lane 0 runs it.
 __global__ void __launch_bounds__(128) k_msm_horner_quad(const ge_t *sums, size_t rows, MsmGeom g, ge_t *out, uint8_t *comp) {
   const int q = threadIdx.x & 3;
   size_t row = (size_t)blockIdx.x * 32 + (threadIdx.x >> 2);
@@ -560,7 +633,7 @@ void launch_msm_segsum(const ge_t *d_partial, size_t rows, size_t segs, const Ms
   size_t pairs = rows * g.group;
   SegsumPublish pub{d_counter, d_seq_word, seq};
   const int lanes = msm_segsum_lanes(pairs, segs);
-  ++g_kernel_launches, k_msm_segsum<<<msm_segsum_blocks(pairs, lanes), 128, 0, st>>>(d_partial, pairs, segs, lanes, d_sums, pub);
+  ++g_kernel_launches, k_msm_segsum<<<msm_segsum_blocks(pairs, lanes), 128, 0, st>>>(d_partial, pairs, segs, lanes, tree_quad() ? 1 : 0, d_sums, pub);
 }
 void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, const MsmGeom &g, ge_t *d_sums, ge_t *d_out, uint8_t *d_comp,
                        cudaStream_t st) {
@@ -568,7 +641,7 @@ void launch_msm_finish(const ge_t *d_partial, size_t rows, size_t segs, const Ms
   if (segs > 1) {
     size_t pairs = rows * g.group;
     const int lanes = msm_segsum_lanes(pairs, segs);
-    ++g_kernel_launches, k_msm_segsum<<<msm_segsum_blocks(pairs, lanes), 128, 0, st>>>(d_partial, pairs, segs, lanes, d_sums, SegsumPublish{nullptr, nullptr, 0});
+    ++g_kernel_launches, k_msm_segsum<<<msm_segsum_blocks(pairs, lanes), 128, 0, st>>>(d_partial, pairs, segs, lanes, tree_quad() ? 1 : 0, d_sums, SegsumPublish{nullptr, nullptr, 0});
     sums = d_sums;
   }
   launch_horner(sums, rows, g, d_out, d_comp, st);
