@@ -553,7 +553,7 @@ def load_golden():
     return {(c["tag"], c["kind"]): c for c in d["cases"]}
 
 
-def short_leg(args, torch, dist, tag, distributed, golden, steps=5, warmup=3):
+def short_leg(args, torch, dist, tag, distributed, golden, steps=10, warmup=3):
     """another named shape, same measurement (steps / warm-up reduced): seconds per step + parity against the golden digests"""
     import copy
     a2 = copy.copy(args)
