@@ -553,7 +553,27 @@ def load_golden():
     return {(c["tag"], c["kind"]): c for c in d["cases"]}
 
 
-def short_leg(args, torch, dist, tag, distributed, golden, steps=10, warmup=3):
+def class_rooflines(prof, madds, prof_ms, steps, imad_peak, hbm_peak):
+    """per-kernel-class roofline entries of a profile pass (Leg.profile_pass): the MSM against the live IMAD.WIDE peak (executed
+    additions x 504), everything else its algorithmic bytes against the measured HBM copy rate"""
+    out = []
+    for name, p in prof.items():
+        if p["ms"] <= 0:
+            continue
+        ent = {"kernel": name, "launches": p["launches"] // steps, "ms_per_step": p["ms"] / steps, "share_of_step": p["ms"] / prof_ms}
+        if name == "msm_accumulate":
+            ent.update(bound="imad", achieved=madds * 504.0 / (p["ms"] * 1e-3) / 1e12, peak=imad_peak / 1e12, unit="TMAC/s")
+        elif p["bytes"] > 0:
+            ent.update(bound="hbm", achieved=p["bytes"] / (p["ms"] * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s")
+        else:
+            continue
+        ent["frac"] = ent["achieved"] / ent["peak"]
+        out.append(ent)
+    out.sort(key=lambda e: -e["ms_per_step"])
+    return out
+
+
+def short_leg(args, torch, dist, tag, distributed, golden, steps=10, warmup=3, rooflines_with=None):
     """another named shape, same measurement (steps / warm-up reduced): seconds per step + parity against the golden digests"""
     import copy
     a2 = copy.copy(args)
@@ -568,6 +588,14 @@ def short_leg(args, torch, dist, tag, distributed, golden, steps=10, warmup=3):
            "instances": [{"kind": s_.kind, "num_cons": s_.dims[0], "nnz_param": s_.dims[3], "hyrax_grid": [s_.gens.L, s_.gens.R]} for s_ in leg.states],
            "matches_golden": par["matches_golden"], "identical_on_all_ranks": par["identical_on_all_ranks"],
            "snark_prove_ms_point_mult": ph.get("SNARK::prove")}
+    if rooflines_with and not distributed:
+        # the per-kernel-class rooflines at a size where the F_l kernels stream instead of waiting for launches (CNN E: 2^22
+        # constraints) - same scopes, same byte counts as the headline's `rooflines`
+        try:
+            prof, madds, prof_ms = leg.profile_pass()
+            out["rooflines"] = class_rooflines(prof, madds, prof_ms, a2.steps, *rooflines_with)[:8]
+        except Exception as e:  # noqa: BLE001
+            out["rooflines"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     leg.close()
     return out
 
@@ -677,7 +705,8 @@ def run_b200(args):
     extra = os.environ.get("VPIN_BENCH_OTHER", "conv3,conv5,conv7,E" + (",L5" if world >= 8 else ""))
     for tag in [t for t in extra.split(",") if t and t != args.workload]:
         try:
-            other[tag] = short_leg(args, torch, dist, tag, world > 1, golden)
+            other[tag] = short_leg(args, torch, dist, tag, world > 1, golden,
+                                   rooflines_with=(imad_peak, hbm_peak) if tag == "E" and not args.no_profile else None)
         except Exception as e:  # noqa: BLE001  (an auxiliary leg must never cost the headline line)
             other[tag] = {"error": f"{type(e).__name__}: {e}"[:300]}
             if world > 1:
