@@ -241,6 +241,12 @@ def test_encode_on_a_background_context_under_the_commitments_and_the_proof(ctx)
         comm2, decomm2 = api.SNARK.encode(inst, gens, aux)
         assert comm2 == ref.comm
         del decomm2
+        # Instance::new and SNARK::encode both on the second context, the proof on the first (bench.py's e2e step)
+        inst2 = api.Instance(aux, dims[0], dims[1], dims[2], *inst.export_coo(dims[1]))
+        comm3, decomm3 = api.SNARK.encode(inst2, gens, aux)
+        proof3 = api.my_lib_prove(inst2, decomm3, p_vars, inputs, gens, b"snark_example", combined, b_vars, sp, ctx=ctx)
+        assert comm3 == ref.comm and proof3 == ref.proof
+        del decomm3, inst2
     del gens, inst
     aux.close()
 

@@ -507,10 +507,11 @@ def _proof_buffer(ctx):
     return buf
 
 
-def my_lib_prove(inst, decomm, vars_bytes, inputs_bytes, gens, transcript_label, comm_vars, blinds_vars, tape_seed, n=None):
+def my_lib_prove(inst, decomm, vars_bytes, inputs_bytes, gens, transcript_label, comm_vars, blinds_vars, tape_seed, n=None, ctx=None):
     """my_lib_prove (vPIN_proof_generation/src/commit_test.rs:59-133): host buffers in, bincode(SNARK) out.
-    `vars_bytes` doubles as poly_vars (DensePolynomial::new(padded_vars.assignment))."""
-    ctx = inst.ctx
+    `vars_bytes` doubles as poly_vars (DensePolynomial::new(padded_vars.assignment)). ctx: the context the proof runs on (the
+    instance's own by default; an instance or decommitment made on another context of the device may be proved on any)."""
+    ctx = ctx or inst.ctx
     out = _proof_buffer(ctx)
     n_vars = len(vars_bytes) // 32 if n is None else n
     n = C.c_uint64()
