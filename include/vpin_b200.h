@@ -62,7 +62,7 @@ typedef struct vpin_coo_entry {
 
 /* ---- context ---------------------------------------------------------------------------------------------- */
 vpin_status vpin_ctx_create(int32_t cuda_device, vpin_ctx **out);
-/* high_priority != 0: the context's stream is created at the device's most urgent stream priority, so that when several
+/* high_priority > 0: the context's stream is created at the device's most urgent stream priority, so that when several
  * contexts share a GPU (a network's independent instances are proved concurrently, one context each) the thread blocks
  * of this one are scheduled first — give it to the instance on the critical path (the point-mult proof). */
 vpin_status vpin_ctx_create_ex(int32_t cuda_device, int32_t high_priority, vpin_ctx **out);
