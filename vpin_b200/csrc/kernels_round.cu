@@ -360,8 +360,10 @@ __global__ void __launch_bounds__(16 * kMaxBatched + 16) k_round_cubic_batched_s
   if (lane == 0 && inst < ninst) {
 #pragma unroll
     for (int k = 0; k < 3; k++) str(slot->vals + inst * 3 + k, acc[k]);
-    __threadfence_system();
   }
+  // ONE system-scope fence for the block: the barrier orders every lane's stores before thread 0's fence, and a fence is
+  // cumulative - what thread 0 has synchronised with is visible before what it writes next (a fence per storing lane as well
+  // cost a second PCIe flush on the critical path of every small round)
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
@@ -379,8 +381,7 @@ __global__ void __launch_bounds__(64) k_round_final(FinalArgs a, fl_t r, ChalRef
     if (bind) v = bind1(v, ldr(p + 1), r);
     str(slot->vals + k, v);
   }
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();  // (one fence for the block, by the thread that publishes: see k_round_cubic_batched_small)
   if (threadIdx.x == 0) {
     __threadfence_system();
     *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
@@ -442,8 +443,7 @@ __global__ void __launch_bounds__(kRedThreads) k_bullet_round(BulletRoundArgs p)
 // the last rounds of the layer itself, prover.cu batched_prove), then the sequence number ----
 __global__ void __launch_bounds__(256) k_tail_copy(FinalArgs a, int len, fl_t *dst, RoundSlot *slot, uint32_t seq) {
   for (int i = threadIdx.x; i < a.n * len; i += blockDim.x) str(dst + i, ldr(a.p[i / len] + (i % len)));
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();  // (one fence for the block, by the thread that publishes: see k_round_cubic_batched_small)
   if (threadIdx.x == 0) {
     __threadfence_system();
     *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
@@ -461,8 +461,7 @@ __global__ void k_stage_vals(const fl_t *src, int n_valid, int n_total, fl_t *ds
 __global__ void k_publish_vals(const fl_t *src, int count, RoundSlot *slot, uint32_t seq) {
   int k = threadIdx.x;
   if (k < count) str(slot->vals + k, ldr(src + k));
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();  // (one fence for the block, by the thread that publishes: see k_round_cubic_batched_small)
   if (threadIdx.x == 0) {
     __threadfence_system();
     *reinterpret_cast<volatile uint32_t *>(&slot->seq) = seq;
