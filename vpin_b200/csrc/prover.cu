@@ -465,6 +465,8 @@ struct Prover {
       // Nsight Compute serialises kernels and holds the launching thread until each one has finished: a kernel that waits for
       // that thread's next post could only time out. Its injection sets NV_COMPUTE_PROFILER_PERFWORKS_DIR in the target process.
       if (!e && getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) return (size_t)0;
+      const char *blocking = getenv("CUDA_LAUNCH_BLOCKING");  // every launch then waits for its kernel: same situation
+      if (!e && blocking && atoi(blocking) != 0) return (size_t)0;
       long long x = e ? atoll(e) : (1ll << 14);
       return (size_t)(x < 0 ? 0 : x);
     }();
